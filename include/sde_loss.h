@@ -1,0 +1,103 @@
+/*
+ * sde_loss.h -- C ABI of libsde_loss.so: the B200 (sm_100a) view-synthesis loss path
+ * of SimpleDepthEstimation (MonoDepth2 / PackNet / MotionLearning self-supervision).
+ *
+ * The reference has no FFI: its operator API for this path is Python.  Each entry
+ * point below states the reference symbol (file:line in zzzxxxttt/SimpleDepthEstimation)
+ * whose arithmetic it replaces; INTEGRATION.md shows the ctypes binding a maintainer
+ * adds on the reference side.
+ *
+ * Conventions (all entry points):
+ *   - return 0 (SDE_OK) or a negative sde_status; never throws, never exits;
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never
+ *     allocates, frees or synchronises; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*, NULL = legacy default stream);
+ *   - device pointers, fp32, contiguous NCHW, 4-byte aligned; intrinsics [B,3,3]
+ *     row-major; poses [B,4,4] row-major (R = [:3,:3], t = [:3,3]);
+ *   - workspaces must be zero-filled ONCE after allocation; every call leaves them
+ *     zeroed again, so they can be reused call after call on the same stream;
+ *   - re-entrant for distinct (stream, workspace) pairs; no mutable globals;
+ *   - results are deterministic: fixed-order reductions, no floating-point atomics.
+ */
+#ifndef SDE_LOSS_H_
+#define SDE_LOSS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDE_ABI_VERSION 1
+#define SDE_MAX_SCALES 6
+#define SDE_MAX_SOURCES 4
+
+typedef enum sde_status {
+  SDE_OK = 0,
+  SDE_ERR_INVALID_ARG = -1,   /* NULL pointer, non-positive size, h or w < 2, too many scales/sources */
+  SDE_ERR_UNSUPPORTED = -2,   /* option not implemented by the fused path (e.g. CLIP > 0) */
+  SDE_ERR_CUDA = -3,          /* a CUDA runtime call failed; see sde_last_cuda_error() */
+  SDE_ERR_NO_DEVICE = -4      /* no sm_100 device / driver */
+} sde_status;
+
+/* flags of sde_mono_desc.flags */
+#define SDE_MONO_AUTOMASK 1u       /* LOSS.AUTOMASK (MonoDepth2.py:96-101) */
+#define SDE_MONO_REDUCE_MEAN 2u    /* LOSS.PHOTOMETRIC_REDUCE == 'mean' (MonoDepth2.py:116-117); default 'min' */
+
+int sde_version(void);
+const char* sde_strerror(int status);
+/* text of the last CUDA error seen by this thread ("" if none) */
+const char* sde_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * MonoDepth2 multi-scale loss (fused).  Replaces the loss loop of
+ * MonoDepth2Model.forward, detectron2/modeling/meta_arch/MonoDepth2.py:78-124, i.e. per
+ * scale and source: view_synthesis (geometry/camera.py:166-202) -> SSIM
+ * (modeling/losses/ssim_loss.py:34-53) + L1 (MonoDepth2.py:130-151) -> identity automask
+ * candidates -> per-pixel min (MonoDepth2.py:116-119) -> mean; plus smoothness_loss
+ * (modeling/losses/smoothness_loss.py:42-80) with the scale weights of MonoDepth2.py:80,103-105.
+ * The image pyramid (resize_img, camera.py:40-46) is an input: target[i], source[i][j].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sde_mono_desc {
+  int32_t batch;                    /* B */
+  int32_t n_scales;                 /* len(depth_pred), 1..SDE_MAX_SCALES, finest first */
+  int32_t n_sources;                /* S = len(ctx_img), 1..SDE_MAX_SOURCES */
+  int32_t height[SDE_MAX_SCALES];   /* depth_pred[i].shape[-2] */
+  int32_t width[SDE_MAX_SCALES];    /* depth_pred[i].shape[-1] */
+  int32_t full_height, full_width;  /* image.shape[-2:]; intrinsics are given at this size */
+  float ssim_weight;                /* LOSS.SSIM_WEIGHT (0.85); 0 -> pure L1 */
+  float c1, c2;                     /* LOSS.C1, LOSS.C2 */
+  float smooth_weight;              /* LOSS.SMOOTHNESS_WEIGHT (1e-3); 0 -> smooth_loss = 0 */
+  uint32_t flags;                   /* SDE_MONO_* */
+} sde_mono_desc;
+
+typedef struct sde_mono_buffers {
+  /* inputs */
+  const float* target[SDE_MAX_SCALES];                   /* [B,3,h_i,w_i] */
+  const float* source[SDE_MAX_SCALES][SDE_MAX_SOURCES];  /* [B,3,h_i,w_i] */
+  const float* depth[SDE_MAX_SCALES];                    /* [B,1,h_i,w_i] */
+  const float* intrinsics;                               /* [B,3,3] at full_height x full_width */
+  const float* pose[SDE_MAX_SOURCES];                    /* [B,4,4] target->source_j */
+  /* forward outputs */
+  float* losses;                      /* [2]: rec_loss, smooth_loss */
+  uint8_t* argmin[SDE_MAX_SCALES];    /* [B,h_i,w_i] winning candidate index (warp0,ident0,warp1,ident1..) */
+  float* saved_stats;                 /* [n_scales*B*2] per-image (mean inverse depth, smoothness) for backward */
+  /* backward inputs / outputs */
+  const float* grad_losses;           /* [2] upstream d/d rec_loss, d/d smooth_loss (device) */
+  float* grad_depth[SDE_MAX_SCALES];  /* [B,1,h_i,w_i] */
+  float* grad_pose[SDE_MAX_SOURCES];  /* [B,4,4]; last row written as zeros */
+  /* scratch */
+  void* workspace;                    /* sde_mono_workspace_bytes(), zero-filled once */
+} sde_mono_buffers;
+
+size_t sde_mono_workspace_bytes(const sde_mono_desc* desc);
+/* writes losses, argmin, saved_stats */
+int sde_mono_loss_forward(const sde_mono_desc* desc, const sde_mono_buffers* buf, void* stream);
+/* reads argmin, saved_stats, grad_losses; recomputes the warp; writes grad_depth, grad_pose */
+int sde_mono_loss_backward(const sde_mono_desc* desc, const sde_mono_buffers* buf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDE_LOSS_H_ */

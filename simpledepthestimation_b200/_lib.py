@@ -1,0 +1,85 @@
+"""ctypes binding of libsde_loss.so (include/sde_loss.h).  No fallback: if the library is
+missing or a call fails, an exception is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+MAX_SCALES = 6
+MAX_SOURCES = 4
+FLAG_AUTOMASK = 1
+FLAG_REDUCE_MEAN = 2
+
+_f32p = C.c_void_p  # device pointers travel as integers
+
+
+class MonoDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("n_scales", C.c_int32), ("n_sources", C.c_int32),
+        ("height", C.c_int32 * MAX_SCALES), ("width", C.c_int32 * MAX_SCALES),
+        ("full_height", C.c_int32), ("full_width", C.c_int32),
+        ("ssim_weight", C.c_float), ("c1", C.c_float), ("c2", C.c_float), ("smooth_weight", C.c_float),
+        ("flags", C.c_uint32),
+    ]
+
+
+class MonoBuffers(C.Structure):
+    _fields_ = [
+        ("target", _f32p * MAX_SCALES),
+        ("source", (_f32p * MAX_SOURCES) * MAX_SCALES),
+        ("depth", _f32p * MAX_SCALES),
+        ("intrinsics", _f32p),
+        ("pose", _f32p * MAX_SOURCES),
+        ("losses", _f32p),
+        ("argmin", _f32p * MAX_SCALES),
+        ("saved_stats", _f32p),
+        ("grad_losses", _f32p),
+        ("grad_depth", _f32p * MAX_SCALES),
+        ("grad_pose", _f32p * MAX_SOURCES),
+        ("workspace", _f32p),
+    ]
+
+
+class SdeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsde_loss.so")
+
+
+def load():
+    """Loads the shared library once.  Raises if it has not been built
+    (python -m simpledepthestimation_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise SdeError(f"{path} not found: build it with `python -m simpledepthestimation_b200.build` "
+                       "(there is no CPU or PyTorch fallback)")
+    lib = C.CDLL(path)
+    lib.sde_version.restype = C.c_int
+    lib.sde_strerror.restype = C.c_char_p
+    lib.sde_strerror.argtypes = [C.c_int]
+    lib.sde_last_cuda_error.restype = C.c_char_p
+    lib.sde_mono_workspace_bytes.restype = C.c_size_t
+    lib.sde_mono_workspace_bytes.argtypes = [C.POINTER(MonoDesc)]
+    for name in ("sde_mono_loss_forward", "sde_mono_loss_backward"):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(MonoDesc), C.POINTER(MonoBuffers), C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        lib = load()
+        msg = lib.sde_strerror(status).decode()
+        if status == -3:
+            msg += ": " + lib.sde_last_cuda_error().decode()
+        raise SdeError(f"{what} failed: {msg} (status {status})")

@@ -1,0 +1,82 @@
+// Kernel-side parameter block of the fused MonoDepth2 loss (one launch covers every scale).
+#pragma once
+#include "sde_common.cuh"
+
+namespace sde {
+
+constexpr int kTileW = 64;   // 32 lanes x 2 pixels (one f2 per lane)
+constexpr int kTileH = 16;   // 4 warps x 4 rows
+constexpr int kThreads = 128;
+constexpr int kRowsPerWarp = 4;
+// backward: a CTA recomputes SSIM on a kTileW x kTileH block of window centres and emits
+// gradients for its interior (the 3x3 adjoint needs one ring of neighbours)
+constexpr int kBwdW = kTileW - 2;   // 62
+constexpr int kBwdH = kTileH - 2;   // 14
+
+struct MonoParams {
+  int B, n_scales, S;
+  int h[SDE_MAX_SCALES], w[SDE_MAX_SCALES];
+  int tiles_x[SDE_MAX_SCALES], tiles_y[SDE_MAX_SCALES];
+  int tile_start[SDE_MAX_SCALES + 1];  // CTA index where scale s starts; [n_scales] = grid size
+  float sx[SDE_MAX_SCALES], sy[SDE_MAX_SCALES];  // w_i / W, h_i / H
+  const float* target[SDE_MAX_SCALES];
+  const float* source[SDE_MAX_SCALES][SDE_MAX_SOURCES];
+  const float* depth[SDE_MAX_SCALES];
+  const float* K;
+  const float* pose[SDE_MAX_SOURCES];
+  uint8_t* argmin[SDE_MAX_SCALES];
+  float* losses;
+  float* stats;           // [n_scales*B][2] = (mean inverse depth, per-image smoothness)
+  float ssim_w, l1_w, c1, c2;
+  float smooth_scale[SDE_MAX_SCALES];  // scale_w * SMOOTHNESS_WEIGHT / n_scales (MonoDepth2.py:80,103-105)
+  unsigned flags;
+  // forward workspace
+  float* partials;        // [grid][4]
+  double* fin;            // [n_scales*B][2]
+  unsigned* counter;
+  // backward
+  const float* grad_losses;
+  float* grad_depth[SDE_MAX_SCALES];
+  float* grad_pose[SDE_MAX_SOURCES];
+  float* pose_partials;   // [bwd grid][S][12]
+  unsigned* counter_bwd;
+  int btiles_x[SDE_MAX_SCALES], btiles_y[SDE_MAX_SCALES];
+  int btile_start[SDE_MAX_SCALES + 1];
+};
+
+struct TileCoord {
+  int s, b, x0, y0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const MonoParams& p, int bid) {
+  int s = 0;
+  while (s + 1 < p.n_scales && bid >= p.tile_start[s + 1]) ++s;
+  int t = bid - p.tile_start[s];
+  const int tx = t % p.tiles_x[s];
+  t /= p.tiles_x[s];
+  const int ty = t % p.tiles_y[s];
+  TileCoord c;
+  c.s = s;
+  c.b = t / p.tiles_y[s];
+  c.x0 = tx * kTileW;
+  c.y0 = ty * kTileH;
+  return c;
+}
+
+// backward tiles: (x0, y0) is the first pixel of the gradient (interior) region
+__device__ __forceinline__ TileCoord decode_btile(const MonoParams& p, int bid) {
+  int s = 0;
+  while (s + 1 < p.n_scales && bid >= p.btile_start[s + 1]) ++s;
+  int t = bid - p.btile_start[s];
+  const int tx = t % p.btiles_x[s];
+  t /= p.btiles_x[s];
+  const int ty = t % p.btiles_y[s];
+  TileCoord c;
+  c.s = s;
+  c.b = t / p.btiles_y[s];
+  c.x0 = tx * kBwdW;
+  c.y0 = ty * kBwdH;
+  return c;
+}
+
+}  // namespace sde

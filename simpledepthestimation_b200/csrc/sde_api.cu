@@ -1,0 +1,163 @@
+// C ABI of libsde_loss.so (see include/sde_loss.h): argument validation, parameter-block
+// construction and kernel launches.  No torch types, no allocation, no synchronisation.
+#include <string.h>
+
+#include "mono_params.cuh"
+
+namespace sde {
+cudaError_t launch_mono_fwd(const MonoParams& p, cudaStream_t stream);
+cudaError_t launch_mono_bwd(const MonoParams& p, cudaStream_t stream);
+
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e) {
+  strncpy(g_cuda_err, cudaGetErrorString(e), sizeof(g_cuda_err) - 1);
+  g_cuda_err[sizeof(g_cuda_err) - 1] = 0;
+  return SDE_ERR_CUDA;
+}
+
+static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+struct MonoLayout {
+  int grid, bgrid;
+  size_t off_fin, off_partials, off_pose, total;
+};
+
+static int mono_check(const sde_mono_desc* d) {
+  if (!d) return SDE_ERR_INVALID_ARG;
+  if (d->batch < 1 || d->n_scales < 1 || d->n_scales > SDE_MAX_SCALES) return SDE_ERR_INVALID_ARG;
+  if (d->n_sources < 1 || d->n_sources > SDE_MAX_SOURCES) return SDE_ERR_INVALID_ARG;
+  if (d->full_height < 2 || d->full_width < 2) return SDE_ERR_INVALID_ARG;
+  for (int i = 0; i < d->n_scales; ++i)
+    if (d->height[i] < 2 || d->width[i] < 2) return SDE_ERR_INVALID_ARG;  // reflect pad needs >= 2
+  if (!(d->ssim_weight >= 0.0f) || !(d->smooth_weight >= 0.0f)) return SDE_ERR_INVALID_ARG;
+  return SDE_OK;
+}
+
+static MonoLayout mono_layout(const sde_mono_desc* d) {
+  MonoLayout L;
+  L.grid = 0;
+  L.bgrid = 0;
+  for (int i = 0; i < d->n_scales; ++i) {
+    L.grid += d->batch * ((d->width[i] + kTileW - 1) / kTileW) * ((d->height[i] + kTileH - 1) / kTileH);
+    L.bgrid += d->batch * ((d->width[i] + kBwdW - 1) / kBwdW) * ((d->height[i] + kBwdH - 1) / kBwdH);
+  }
+  size_t off = 16;  // two counters
+  L.off_fin = off;
+  off = align16(off + (size_t)d->n_scales * d->batch * 2 * sizeof(double));
+  L.off_partials = off;
+  off = align16(off + (size_t)L.grid * 4 * sizeof(float));
+  L.off_pose = off;
+  off = align16(off + (size_t)L.bgrid * d->n_sources * 12 * sizeof(float));
+  L.total = off;
+  return L;
+}
+
+static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool backward, MonoParams& p) {
+  int st = mono_check(d);
+  if (st != SDE_OK) return st;
+  if (!b || !b->intrinsics || !b->workspace || !b->saved_stats) return SDE_ERR_INVALID_ARG;
+  memset(&p, 0, sizeof(p));
+  p.B = d->batch; p.n_scales = d->n_scales; p.S = d->n_sources;
+  int start = 0, bstart = 0;
+  for (int i = 0; i < d->n_scales; ++i) {
+    if (!b->target[i] || !b->depth[i]) return SDE_ERR_INVALID_ARG;
+    p.h[i] = d->height[i]; p.w[i] = d->width[i];
+    p.tiles_x[i] = (p.w[i] + kTileW - 1) / kTileW;
+    p.tiles_y[i] = (p.h[i] + kTileH - 1) / kTileH;
+    p.tile_start[i] = start;
+    start += p.B * p.tiles_x[i] * p.tiles_y[i];
+    p.btiles_x[i] = (p.w[i] + kBwdW - 1) / kBwdW;
+    p.btiles_y[i] = (p.h[i] + kBwdH - 1) / kBwdH;
+    p.btile_start[i] = bstart;
+    bstart += p.B * p.btiles_x[i] * p.btiles_y[i];
+    // x_scale = w_i / W as the reference forms it (MonoDepth2.py:83-85), then cast to fp32 by the multiply
+    p.sx[i] = (float)((double)p.w[i] / (double)d->full_width);
+    p.sy[i] = (float)((double)p.h[i] / (double)d->full_height);
+    p.target[i] = b->target[i]; p.depth[i] = b->depth[i];
+    p.argmin[i] = b->argmin[i];
+    p.grad_depth[i] = b->grad_depth[i];
+    for (int j = 0; j < d->n_sources; ++j) {
+      if (!b->source[i][j]) return SDE_ERR_INVALID_ARG;
+      p.source[i][j] = b->source[i][j];
+    }
+    const double scale_w = 1.0 / (double)(1 << (d->n_scales - i - 1));
+    p.smooth_scale[i] = d->smooth_weight > 0.0f ? (float)(scale_w * (double)d->smooth_weight / d->n_scales) : 0.0f;
+  }
+  for (int i = d->n_scales; i <= SDE_MAX_SCALES; ++i) {
+    p.tile_start[i] = start;
+    p.btile_start[i] = bstart;
+  }
+  for (int j = 0; j < d->n_sources; ++j) {
+    if (!b->pose[j]) return SDE_ERR_INVALID_ARG;
+    p.pose[j] = b->pose[j];
+    p.grad_pose[j] = b->grad_pose[j];
+  }
+  p.K = b->intrinsics;
+  p.losses = b->losses; p.stats = b->saved_stats;
+  p.ssim_w = d->ssim_weight;
+  p.l1_w = d->ssim_weight > 0.0f ? 1.0f - d->ssim_weight : 1.0f;  // MonoDepth2.py:137-144
+  p.c1 = d->c1; p.c2 = d->c2;
+  p.flags = d->flags;
+  const MonoLayout L = mono_layout(d);
+  char* ws = static_cast<char*>(b->workspace);
+  p.counter = reinterpret_cast<unsigned*>(ws);
+  p.counter_bwd = reinterpret_cast<unsigned*>(ws) + 1;
+  p.fin = reinterpret_cast<double*>(ws + L.off_fin);
+  p.partials = reinterpret_cast<float*>(ws + L.off_partials);
+  p.pose_partials = reinterpret_cast<float*>(ws + L.off_pose);
+  p.grad_losses = b->grad_losses;
+  if (!backward) {
+    if (!b->losses) return SDE_ERR_INVALID_ARG;
+  } else {
+    if (!b->grad_losses) return SDE_ERR_INVALID_ARG;
+    for (int i = 0; i < d->n_scales; ++i)
+      if (!b->grad_depth[i] || (!(d->flags & SDE_MONO_REDUCE_MEAN) && !b->argmin[i])) return SDE_ERR_INVALID_ARG;
+    for (int j = 0; j < d->n_sources; ++j)
+      if (!b->grad_pose[j]) return SDE_ERR_INVALID_ARG;
+  }
+  return SDE_OK;
+}
+}  // namespace sde
+
+using namespace sde;
+
+extern "C" {
+
+int sde_version(void) { return SDE_ABI_VERSION; }
+
+const char* sde_strerror(int status) {
+  switch (status) {
+    case SDE_OK: return "ok";
+    case SDE_ERR_INVALID_ARG: return "invalid argument";
+    case SDE_ERR_UNSUPPORTED: return "option not supported by the fused path";
+    case SDE_ERR_CUDA: return "CUDA runtime error (see sde_last_cuda_error)";
+    case SDE_ERR_NO_DEVICE: return "no CUDA device";
+    default: return "unknown status";
+  }
+}
+
+const char* sde_last_cuda_error(void) { return g_cuda_err; }
+
+size_t sde_mono_workspace_bytes(const sde_mono_desc* desc) {
+  if (mono_check(desc) != SDE_OK) return 0;
+  return mono_layout(desc).total;
+}
+
+int sde_mono_loss_forward(const sde_mono_desc* desc, const sde_mono_buffers* buf, void* stream) {
+  MonoParams p;
+  int st = mono_params(desc, buf, false, p);
+  if (st != SDE_OK) return st;
+  cudaError_t e = launch_mono_fwd(p, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SDE_OK : cuda_fail(e);
+}
+
+int sde_mono_loss_backward(const sde_mono_desc* desc, const sde_mono_buffers* buf, void* stream) {
+  MonoParams p;
+  int st = mono_params(desc, buf, true, p);
+  if (st != SDE_OK) return st;
+  cudaError_t e = launch_mono_bwd(p, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SDE_OK : cuda_fail(e);
+}
+
+}  // extern "C"

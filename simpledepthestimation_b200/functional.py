@@ -1,0 +1,177 @@
+"""torch.autograd.Function wrappers over the C ABI (libsde_loss.so).
+
+PyTorch is plumbing here: it owns device memory and the stream; the arithmetic is the
+hand-written sm_100a kernels.  There is no CPU / eager fallback -- calling these on a CPU
+tensor or without the built library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+__all__ = ["MonoLossPlan", "mono_photometric_smoothness_loss"]
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.SdeError(f"{name} must be a CUDA tensor: the view-synthesis loss has no CPU path")
+    if t.dtype != torch.float32:
+        raise _lib.SdeError(f"{name} must be float32, got {t.dtype}")
+
+
+def _contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class MonoLossPlan:
+    """Shape-specialised launcher of the fused MonoDepth2 loss (forward + backward).
+
+    Holds the descriptor, the zero-initialised workspace and the output buffers for one
+    (B, scales, S, sizes, loss options) signature so that a training step costs two kernel
+    launches and no allocation.  Mirrors the options read by the reference's
+    MonoDepth2Model.__init__ (detectron2/modeling/meta_arch/MonoDepth2.py:26-46).
+    """
+
+    def __init__(self, batch: int, sizes: Sequence[Sequence[int]], n_sources: int, full_size: Sequence[int],
+                 device, ssim_weight=0.85, c1=1e-4, c2=9e-4, smooth_weight=1e-3, automask=True, reduce="min"):
+        if reduce not in ("min", "mean"):
+            raise NotImplementedError(reduce)  # same as MonoDepth2.py:120-121
+        if len(sizes) > _lib.MAX_SCALES or n_sources > _lib.MAX_SOURCES:
+            raise _lib.SdeError("too many scales / sources")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.batch, self.sizes, self.n_sources = batch, [tuple(s) for s in sizes], n_sources
+        self.full_size = tuple(full_size)
+        d = _lib.MonoDesc()
+        d.batch, d.n_scales, d.n_sources = batch, len(sizes), n_sources
+        for i, (h, w) in enumerate(self.sizes):
+            d.height[i], d.width[i] = h, w
+        d.full_height, d.full_width = self.full_size
+        d.ssim_weight, d.c1, d.c2, d.smooth_weight = ssim_weight, c1, c2, smooth_weight
+        d.flags = (_lib.FLAG_AUTOMASK if automask else 0) | (_lib.FLAG_REDUCE_MEAN if reduce == "mean" else 0)
+        self.desc = d
+        nbytes = self.lib.sde_mono_workspace_bytes(C.byref(d))
+        if nbytes == 0:
+            raise _lib.SdeError("invalid loss descriptor (sizes must be >= 2, 1..6 scales, 1..4 sources)")
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self.stats = torch.empty(len(sizes) * batch * 2, dtype=torch.float32, device=self.device)
+
+    # ---------------------------------------------------------------------------------
+    def _buffers(self, target, source, depth, K, pose) -> _lib.MonoBuffers:
+        b = _lib.MonoBuffers()
+        for i in range(len(self.sizes)):
+            b.target[i] = target[i].data_ptr()
+            b.depth[i] = depth[i].data_ptr()
+            for j in range(self.n_sources):
+                b.source[i][j] = source[i][j].data_ptr()
+        for j in range(self.n_sources):
+            b.pose[j] = pose[j].data_ptr()
+        b.intrinsics = K.data_ptr()
+        b.saved_stats = self.stats.data_ptr()
+        b.workspace = self.workspace.data_ptr()
+        return b
+
+    def _check(self, target, source, depth, K, pose):
+        B = self.batch
+        for i, (h, w) in enumerate(self.sizes):
+            _require_cuda(target[i], "target"); _require_cuda(depth[i], "depth")
+            if tuple(target[i].shape) != (B, 3, h, w) or tuple(depth[i].shape) != (B, 1, h, w):
+                raise _lib.SdeError(f"scale {i}: expected target [B,3,{h},{w}] and depth [B,1,{h},{w}]")
+            for j in range(self.n_sources):
+                _require_cuda(source[i][j], "source")
+                if tuple(source[i][j].shape) != (B, 3, h, w):
+                    raise _lib.SdeError(f"scale {i} source {j}: expected [B,3,{h},{w}]")
+        _require_cuda(K, "intrinsics")
+        if tuple(K.shape) != (B, 3, 3):
+            raise _lib.SdeError("intrinsics must be [B,3,3]")
+        for j in range(self.n_sources):
+            _require_cuda(pose[j], "pose")
+            if tuple(pose[j].shape) != (B, 4, 4):
+                raise _lib.SdeError("pose must be [B,4,4]")
+
+    def forward(self, target, source, depth, K, pose, want_argmin=True, out=None):
+        """Runs the forward kernel.  Returns (losses[2], argmin list).  All inputs contiguous fp32 CUDA."""
+        self._check(target, source, depth, K, pose)
+        b = self._buffers(target, source, depth, K, pose)
+        losses = out if out is not None else torch.empty(2, dtype=torch.float32, device=self.device)
+        b.losses = losses.data_ptr()
+        argmin = []
+        if want_argmin:
+            for i, (h, w) in enumerate(self.sizes):
+                a = torch.empty(self.batch, h, w, dtype=torch.uint8, device=self.device)
+                argmin.append(a)
+                b.argmin[i] = a.data_ptr()
+        st = self.lib.sde_mono_loss_forward(C.byref(self.desc), C.byref(b), torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "sde_mono_loss_forward")
+        return losses, argmin
+
+    def backward(self, target, source, depth, K, pose, argmin, grad_losses, grad_depth=None, grad_pose=None):
+        """Runs the backward kernel (recomputes the warp).  Returns (grad_depth list, grad_pose list)."""
+        b = self._buffers(target, source, depth, K, pose)
+        b.grad_losses = grad_losses.data_ptr()
+        if grad_depth is None:
+            grad_depth = [torch.empty_like(d) for d in depth]
+        if grad_pose is None:
+            grad_pose = [torch.empty_like(p) for p in pose]
+        for i in range(len(self.sizes)):
+            b.grad_depth[i] = grad_depth[i].data_ptr()
+            if argmin:
+                b.argmin[i] = argmin[i].data_ptr()
+        for j in range(self.n_sources):
+            b.grad_pose[j] = grad_pose[j].data_ptr()
+        st = self.lib.sde_mono_loss_backward(C.byref(self.desc), C.byref(b), torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "sde_mono_loss_backward")
+        return grad_depth, grad_pose
+
+
+class _MonoLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: MonoLossPlan, K, n_scales, n_sources, *tensors):
+        depth = [_contig(t) for t in tensors[:n_scales]]
+        pose = [_contig(t) for t in tensors[n_scales:n_scales + n_sources]]
+        rest = tensors[n_scales + n_sources:]
+        target = [_contig(t) for t in rest[:n_scales]]
+        source = [[_contig(rest[n_scales + i * n_sources + j]) for j in range(n_sources)] for i in range(n_scales)]
+        K = _contig(K)
+        losses, argmin = plan.forward(target, source, depth, K, pose)
+        ctx.plan, ctx.n_scales, ctx.n_sources = plan, n_scales, n_sources
+        ctx.save_for_backward(K, *depth, *pose, *target, *[s for row in source for s in row], *argmin)
+        ctx.stats = plan.stats.clone()  # the plan may be reused before backward runs
+        for a in argmin:
+            ctx.mark_non_differentiable(a)
+        return (losses[0], losses[1], *argmin)
+
+    @staticmethod
+    def backward(ctx, g_rec, g_smooth, *_):
+        n, S, plan = ctx.n_scales, ctx.n_sources, ctx.plan
+        saved = ctx.saved_tensors
+        K = saved[0]
+        depth = list(saved[1:1 + n])
+        pose = list(saved[1 + n:1 + n + S])
+        target = list(saved[1 + n + S:1 + 2 * n + S])
+        flat = saved[1 + 2 * n + S:1 + 2 * n + S + n * S]
+        source = [[flat[i * S + j] for j in range(S)] for i in range(n)]
+        argmin = list(saved[1 + 2 * n + S + n * S:])
+        zero = torch.zeros((), dtype=torch.float32, device=K.device)
+        g = torch.stack([g_rec if g_rec is not None else zero, g_smooth if g_smooth is not None else zero]).float()
+        plan.stats.copy_(ctx.stats)
+        grad_depth, grad_pose = plan.backward(target, source, depth, K, pose, argmin, g.contiguous())
+        return (None, None, None, None, *grad_depth, *grad_pose, *([None] * (n + n * S)))
+
+
+def mono_photometric_smoothness_loss(plan: MonoLossPlan, target: List[torch.Tensor],
+                                     source: List[List[torch.Tensor]], depth: List[torch.Tensor],
+                                     K: torch.Tensor, pose: List[torch.Tensor]):
+    """Differentiable fused loss: returns (rec_loss, smooth_loss, argmin_maps).
+
+    target[i] [B,3,h_i,w_i], source[i][j] likewise, depth[i] [B,1,h_i,w_i] (requires_grad),
+    K [B,3,3] at full resolution, pose[j] [B,4,4] (requires_grad).  Gradients flow to depth
+    and pose only (images and intrinsics are data, as in the reference)."""
+    n, S = len(depth), len(pose)
+    flat_src = [source[i][j] for i in range(n) for j in range(S)]
+    out = _MonoLossFn.apply(plan, K, n, S, *depth, *pose, *target, *flat_src)
+    return out[0], out[1], list(out[2:])
