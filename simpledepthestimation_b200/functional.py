@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["MonoLossPlan", "mono_photometric_smoothness_loss"]
+__all__ = ["MonoLossPlan", "HostLossRunner", "mono_photometric_smoothness_loss"]
 
 
 def _require_cuda(t: torch.Tensor, name: str):
@@ -93,14 +93,18 @@ class MonoLossPlan:
             if tuple(pose[j].shape) != (B, 4, 4):
                 raise _lib.SdeError("pose must be [B,4,4]")
 
-    def forward(self, target, source, depth, K, pose, want_argmin=True, out=None):
+    def forward(self, target, source, depth, K, pose, want_argmin=True, out=None, argmin_out=None):
         """Runs the forward kernel.  Returns (losses[2], argmin list).  All inputs contiguous fp32 CUDA."""
         self._check(target, source, depth, K, pose)
         b = self._buffers(target, source, depth, K, pose)
         losses = out if out is not None else torch.empty(2, dtype=torch.float32, device=self.device)
         b.losses = losses.data_ptr()
         argmin = []
-        if want_argmin:
+        if argmin_out is not None:
+            argmin = argmin_out
+            for i in range(len(self.sizes)):
+                b.argmin[i] = argmin[i].data_ptr()
+        elif want_argmin:
             for i, (h, w) in enumerate(self.sizes):
                 a = torch.empty(self.batch, h, w, dtype=torch.uint8, device=self.device)
                 argmin.append(a)
@@ -175,3 +179,65 @@ def mono_photometric_smoothness_loss(plan: MonoLossPlan, target: List[torch.Tens
     flat_src = [source[i][j] for i in range(n) for j in range(S)]
     out = _MonoLossFn.apply(plan, K, n, S, *depth, *pose, *target, *flat_src)
     return out[0], out[1], list(out[2:])
+
+
+class HostLossRunner:
+    """End-to-end step through HOST buffers: pinned host inputs -> device (H2D on the compute
+    stream), fused forward + backward, losses and gradients -> pinned host (D2H), then one
+    stream synchronise.  This is the call a host-side integration (data on the CPU side of the
+    C ABI) makes; `h2d_bytes` / `d2h_bytes` count exactly the tensors copied per step."""
+
+    def __init__(self, plan: MonoLossPlan, device):
+        self.plan, self.device = plan, torch.device(device)
+        B, S = plan.batch, plan.n_sources
+        new = lambda *shape, dt=torch.float32: torch.empty(*shape, dtype=dt, device=self.device)  # noqa: E731
+        self.target = [new(B, 3, h, w) for h, w in plan.sizes]
+        self.source = [[new(B, 3, h, w) for _ in range(S)] for h, w in plan.sizes]
+        self.depth = [new(B, 1, h, w) for h, w in plan.sizes]
+        self.K = new(B, 3, 3)
+        self.pose = [new(B, 4, 4) for _ in range(S)]
+        self.losses = new(2)
+        self.argmin = [new(B, h, w, dt=torch.uint8) for h, w in plan.sizes]
+        self.grad_depth = [torch.empty_like(d) for d in self.depth]
+        self.grad_pose = [torch.empty_like(p) for p in self.pose]
+        self.ones = torch.ones(2, device=self.device)
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
+        self.h_losses = pin(self.losses)
+        self.h_grad_depth = [pin(t) for t in self.grad_depth]
+        self.h_grad_pose = [pin(t) for t in self.grad_pose]
+        dev_in = self.target + [s for row in self.source for s in row] + self.depth + [self.K] + self.pose
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in dev_in)
+        outs = [self.losses] + self.grad_depth + self.grad_pose
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in outs)
+
+    @staticmethod
+    def pin(host_set):
+        """Pins a (target, source, depth, K, pose) tuple of CPU tensors."""
+        tgt, src, depth, K, pose = host_set
+        p = lambda t: t.contiguous().pin_memory()  # noqa: E731
+        return ([p(t) for t in tgt], [[p(x) for x in row] for row in src], [p(d) for d in depth], p(K),
+                [p(x) for x in pose])
+
+    def step(self, host_set):
+        tgt, src, depth, K, pose = host_set
+        for d, h in zip(self.target, tgt):
+            d.copy_(h, non_blocking=True)
+        for drow, hrow in zip(self.source, src):
+            for d, h in zip(drow, hrow):
+                d.copy_(h, non_blocking=True)
+        for d, h in zip(self.depth, depth):
+            d.copy_(h, non_blocking=True)
+        self.K.copy_(K, non_blocking=True)
+        for d, h in zip(self.pose, pose):
+            d.copy_(h, non_blocking=True)
+        self.plan.forward(self.target, self.source, self.depth, self.K, self.pose, out=self.losses,
+                          argmin_out=self.argmin)
+        self.plan.backward(self.target, self.source, self.depth, self.K, self.pose, self.argmin, self.ones,
+                           self.grad_depth, self.grad_pose)
+        self.h_losses.copy_(self.losses, non_blocking=True)
+        for h, d in zip(self.h_grad_depth, self.grad_depth):
+            h.copy_(d, non_blocking=True)
+        for h, d in zip(self.h_grad_pose, self.grad_pose):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.h_losses, self.h_grad_depth, self.h_grad_pose

@@ -1,0 +1,86 @@
+"""MonoDepth2Model: drop-in for the reference meta-architecture
+(detectron2/modeling/meta_arch/MonoDepth2.py:20-128).  Same constructor (cfg), same batch-dict
+contract, same output keys (`rec_loss`, `smooth_loss`, eval: `depth_pred`), same LOSS.* config
+keys -- but the multi-scale loss loop (MonoDepth2.py:78-124) is two fused CUDA launches."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ...functional import MonoLossPlan, mono_photometric_smoothness_loss
+from ...geometry.camera import resize_img
+from ...utils.memory import to_cuda
+from ..nets import build_depth_net, build_pose_net
+from .build import META_ARCH_REGISTRY
+
+
+@META_ARCH_REGISTRY.register()
+class MonoDepth2Model(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.depth_net = build_depth_net(cfg)
+        self.pose_net = build_pose_net(cfg)
+
+        self.ssim_loss_weight = cfg.LOSS.SSIM_WEIGHT
+        self.c1, self.c2 = cfg.LOSS.C1, cfg.LOSS.C2
+        self.photometric_reduce = cfg.LOSS.PHOTOMETRIC_REDUCE
+        self.use_automask = cfg.LOSS.AUTOMASK
+        self.clip_loss = cfg.LOSS.CLIP
+        self.var_loss_w = cfg.LOSS.VAR_LOSS_WEIGHT
+        self.sup_loss_w = cfg.LOSS.SUPERVISED_WEIGHT
+        self.smooth_loss_w = cfg.LOSS.SMOOTHNESS_WEIGHT
+        if self.photometric_reduce not in ("min", "mean"):
+            raise NotImplementedError(self.photometric_reduce)
+        if self.clip_loss > 0.0 or self.sup_loss_w > 0.0 or self.var_loss_w > 0.0:
+            # off in every shipped config (Base.yaml:8,12,14); not part of the fused path yet
+            raise NotImplementedError("LOSS.CLIP / SUPERVISED_WEIGHT / VAR_LOSS_WEIGHT > 0 are not supported "
+                                      "by the fused B200 loss path")
+
+        self.register_buffer("pixel_mean", torch.Tensor(cfg.MODEL.PIXEL_MEAN).view(1, -1, 1, 1))
+        self.register_buffer("pixel_std", torch.Tensor(cfg.MODEL.PIXEL_STD).view(1, -1, 1, 1))
+        self._plans = {}
+
+    @property
+    def device(self):
+        return self.pixel_mean.device
+
+    def _plan(self, batch, sizes, n_sources, full_size):
+        key = (batch, tuple(sizes), n_sources, tuple(full_size), str(self.device))
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = MonoLossPlan(batch, sizes, n_sources, full_size, self.device,
+                                ssim_weight=self.ssim_loss_weight, c1=self.c1, c2=self.c2,
+                                smooth_weight=self.smooth_loss_w, automask=self.use_automask,
+                                reduce=self.photometric_reduce)
+            self._plans[key] = plan
+        return plan
+
+    def forward(self, batch):
+        batch = to_cuda(batch, self.device)
+        output = {}
+        batch["depth_net_input"] = (batch["img"] - self.pixel_mean) / self.pixel_std
+        batch = self.depth_net(batch)
+
+        if self.training:
+            batch["pose_net_input"] = torch.cat([batch["img"]] + batch["ctx_img"], 1)
+            batch = self.pose_net(batch)  # num_ctx * [B, 4, 4]
+
+            image = batch["img_orig"]
+            contexts = batch["ctx_img_orig"]
+            depth_pred = batch["depth_pred"]
+            pose_pred = list(batch["pose_pred"])
+            sizes = [tuple(d.shape[-2:]) for d in depth_pred]
+
+            # image pyramid (resize_img, MonoDepth2.py:82,88); sources resized once per scale
+            target = [resize_img(image, s) for s in sizes]
+            source = [[resize_img(c, s) for c in contexts] for s in sizes]
+
+            plan = self._plan(image.shape[0], sizes, len(contexts), tuple(image.shape[-2:]))
+            rec, smooth, _ = mono_photometric_smoothness_loss(plan, target, source, list(depth_pred),
+                                                              batch["intrinsics"].float(), pose_pred)
+            output["rec_loss"] = rec
+            if self.smooth_loss_w > 0.0:
+                output["smooth_loss"] = smooth
+        else:
+            output["depth_pred"] = batch["depth_pred"][0]
+        return output

@@ -1,0 +1,2 @@
+from .build import META_ARCH_REGISTRY, build_model  # noqa: F401
+from .MonoDepth2 import MonoDepth2Model  # noqa: F401
