@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
         if (j == 0) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) planes[(kBA + c) * kPlane + i] = __ldg(target + c * hw + pix);
-          planes[kBInv * kPlane + i] = 1.0f / fmaxf(d, 1e-6f);
+          planes[kBInv * kPlane + i] = 1.0f / (d < 1e-6f ? 1e-6f : d);  // clamp(min=1e-6) keeps NaN, as torch.clamp does
           const bool inside = ty >= 0 && ty < h && tx >= 0 && tx < w;
           // 255 never matches a candidate: windows centred outside the image do not exist
           sh.arg[i] = inside ? (reduce_mean ? (uint8_t)254 : amap[pix]) : (uint8_t)255;
@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
               const f2 aa2 = sA * sA, xx2 = sX * sX, t = sX * sA;
               const f2 n1 = fma2(bc2(2.0f), t, C1);
               const f2 n2 = fma2(bc2(2.0f), fma2(bc2(9.0f), sXA, neg2(t)), C2);
-              const f2 d1 = xx2 + aa2 + C1;
-              const f2 d2 = fma2(bc2(9.0f), sXX + sAA, C2 - xx2 - aa2);
+              const f2 d1 = (xx2 + aa2) + C1;   // same operation order as the forward kernel
+              const f2 d2 = (fma2(bc2(9.0f), sXX, neg2(xx2)) + fma2(bc2(9.0f), sAA, neg2(aa2))) + C2;
               const f2 D = d1 * d2;
               const f2 invD = mk2(1.0f / D.x, 1.0f / D.y);
               const f2 ssim = n1 * n2 * invD;

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
         if (j == 0) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) planes[(kPlA + c) * kPlane + i] = __ldg(target + c * hw + pix);
-          planes[kPlInv * kPlane + i] = 1.0f / fmaxf(d, 1e-6f);
+          planes[kPlInv * kPlane + i] = 1.0f / (d < 1e-6f ? 1e-6f : d);  // clamp(min=1e-6) keeps NaN, as torch.clamp does
         }
       }
     }
@@ -136,8 +136,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
           const f2 sA = hA[0] + hA[1] + nA;
           const f2 sAA = hAA[0] + hAA[1] + nAA;
           const f2 aa2 = sA * sA;
-          const f2 qA = fma2(bc2(9.0f), sAA, C2 - aa2);   // 81 (sigma_y + C2)
-          const f2 rA = aa2 + C1;                           // 81 (mu_y^2 + C1)
+          const f2 vA = fma2(bc2(9.0f), sAA, neg2(aa2));     // 81 sigma_y
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             if (k < ncand) {
@@ -146,12 +145,14 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
                 const f2 sX = hX[k][0] + hX[k][1] + nX[k];
                 const f2 sXX = hXX[k][0] + hXX[k][1] + nXX[k];
                 const f2 sXA = hXA[k][0] + hXA[k][1] + nXA[k];
+                // numerator and denominator are formed with mirrored operation orders so that
+                // X == A gives ssim == 1 exactly (identity candidate of identical frames is 0)
                 const f2 t = sX * sA, xx2 = sX * sX;
                 const f2 n1 = fma2(bc2(2.0f), t, C1);
                 const f2 n2 = fma2(bc2(2.0f), fma2(bc2(9.0f), sXA, neg2(t)), C2);
-                const f2 d1 = xx2 + rA;
-                const f2 d2 = fma2(bc2(9.0f), sXX, qA - xx2);
-                const f2 ssim = fdiv2(n1 * n2, d1 * d2);
+                const f2 d1 = (xx2 + aa2) + C1;
+                const f2 d2 = (fma2(bc2(9.0f), sXX, neg2(xx2)) + vA) + C2;
+                const f2 ssim = div2(n1 * n2, d1 * d2);
                 a = fma2(sat2(fma2(ssim, bc2(-0.5f), bc2(0.5f))), wS, a);
               }
               acc[k][o] = fma2(l1p[k], wL, a);

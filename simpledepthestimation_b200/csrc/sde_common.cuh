@@ -56,6 +56,13 @@ __device__ __forceinline__ f2 sat2(f2 a) { return mk2(__saturatef(a.x), __satura
 // a / b with the fast reciprocal (2 ulp); operands here are O(1e-8 .. 10), far from the
 // 2^126 range where __fdividef degrades.
 __device__ __forceinline__ f2 fdiv2(f2 a, f2 b) { return mk2(__fdividef(a.x, b.x), __fdividef(a.y, b.y)); }
+// a / b: hardware reciprocal plus one Newton correction on the quotient (two packed FMAs).
+// Within 1 ulp of the IEEE quotient and exactly 1 when a == b.
+__device__ __forceinline__ f2 div2(f2 a, f2 b) {
+  const f2 r = mk2(__frcp_rn(b.x), __frcp_rn(b.y));
+  const f2 q = a * r;
+  return fma2(r, fma2(neg2(q), b, a), q);
+}
 __device__ __forceinline__ f2 ld2(const float* p) {
   float2 v = *reinterpret_cast<const float2*>(p);
   return mk2(v.x, v.y);

@@ -1,0 +1,296 @@
+"""Parity of the fused CUDA loss (through the C ABI) with the oracle / the reference's golden
+outputs.  Tolerances (BASELINE.json north_star): loss 1e-5 relative; argmin maps exact except
+where the two best candidates are within 1e-5; gradients 1e-4 relative (to the largest gradient
+of the tensor) on decision-stable pixels against the fp64 reference."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (build_pyramid, golden_mono_inputs, gpu_mono_from_pose, gpu_mono_from_vec, load_golden, oracle_mono,
+                     port_mono_from_vec, rel_err, stable_mask)
+from simpledepthestimation_b200.synthetic import euler_pose, mono_inputs
+
+pytestmark = pytest.mark.gpu
+LOSS_TOL, GRAD_TOL, TIE_TOL = 1e-5, 1e-4, 1e-5
+
+VARIANTS = {"": ({}, {}), "_noauto": (dict(automask=False), dict(automask=False)),
+            "_mean": (dict(reduce="mean"), dict(reduce="mean")), "_l1": (dict(ssim_weight=0.0), dict(ssim_w=0.0))}
+
+
+@pytest.fixture(scope="module")
+def dev(sde_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def check_against(out, ref_rec, ref_smooth, ref_gd, ref_gv, masks=None):
+    assert rel_err(out["rec_loss"], ref_rec) < LOSS_TOL
+    assert rel_err(out["smooth_loss"], ref_smooth) < LOSS_TOL
+    for i, (g, r) in enumerate(zip(out["grad_depth"], ref_gd)):
+        r = torch.as_tensor(r, dtype=torch.float64)
+        err = (g.double() - r).abs() / r.abs().max()
+        if masks is not None:
+            frac_unstable = 1.0 - float(masks[i].double().mean())
+            assert frac_unstable < 0.05, f"scale {i}: {frac_unstable:.3f} of pixels decision-unstable"
+            err = err[:, 0][masks[i]]
+        assert float(err.max()) < GRAD_TOL, f"grad_depth[{i}] {float(err.max()):.2e}"
+    for j, (g, r) in enumerate(zip(out["grad_pose_vec"], ref_gv)):
+        assert rel_err(g, r) < GRAD_TOL, f"grad_pose_vec[{j}]"
+
+
+@pytest.mark.parametrize("name", ["mono_2x32x64", "mono_1x50x70", "mono_1x48x160_bigpose"])
+def test_golden_reference_outputs(dev, name):
+    """CUDA path vs outputs of the real reference (fp64 run) on the committed inputs."""
+    g = load_golden(name)
+    inp = golden_mono_inputs(g)
+    tgt, src = build_pyramid(inp)
+    for tag, (plan_kw, _) in VARIANTS.items():
+        if f"rec_loss{tag}_f64" not in g:
+            continue
+        out = gpu_mono_from_vec(inp, dev, **plan_kw)
+        n = len(inp["depth"])
+        masks = None
+        if tag in ("", "_noauto"):
+            masks = [stable_mask(inp, tgt, src, i, automask=(tag == "")) for i in range(n)]
+        check_against(out, g[f"rec_loss{tag}_f64"], g[f"smooth_loss{tag}_f64"],
+                      [g[f"grad_depth{i}{tag}_f64"] for i in range(n)],
+                      [g[f"grad_pose_vec{j}{tag}_f64"] for j in range(len(inp["pose_vec"]))], masks)
+        if tag == "":
+            for i, a in enumerate(out["argmin"]):
+                mism = a.numpy() != g[f"argmin{i}"]
+                assert not (mism & (g[f"argmin_gap{i}"] > TIE_TOL)).any(), f"argmin scale {i}"
+
+
+def test_cfg1_kitti_shape_against_live_oracle(dev):
+    """BASELINE.json configs[0]: 640x192, batch 1, 4 scales, 2 sources."""
+    inp = mono_inputs(1, 192, 640)
+    tgt, src = build_pyramid(inp)
+    ref = port_mono_from_vec(inp, torch.float64)
+    out = gpu_mono_from_vec(inp, dev)
+    assert rel_err(out["rec_loss"], ref["rec_loss"].detach()) < LOSS_TOL
+    assert rel_err(out["smooth_loss"], ref["smooth_loss"].detach()) < LOSS_TOL
+    g = load_golden("mono_cfg1_1x192x640")
+    if golden_mono_inputs(g) is not None:  # same bits as in the build container -> compare with the real reference
+        assert rel_err(out["rec_loss"], g["rec_loss_f64"]) < LOSS_TOL
+        assert rel_err(out["smooth_loss"], g["smooth_loss_f64"]) < LOSS_TOL
+    for i, a in enumerate(out["argmin"]):
+        top2 = ref["cand"][i].topk(2, dim=1, largest=False)[0]
+        gap = top2[:, 1] - top2[:, 0]
+        mism = a.long() != ref["argmin"][i]
+        assert not (mism & (gap > TIE_TOL)).any()
+        assert float(mism.double().mean()) < 1e-3
+    ref32 = port_mono_from_vec(inp, torch.float32)
+    for i, (gd, r) in enumerate(zip(out["grad_depth"], ref["grad_depth"])):
+        m = stable_mask(inp, tgt, src, i)
+        assert float(m.double().mean()) > 0.95
+        err64 = ((gd.double() - r).abs() / r.abs().max())[:, 0]
+        err32 = ((gd.double() - ref32["grad_depth"][i].double()).abs() / r.abs().max())[:, 0]
+        # On decision-stable pixels the gradient must agree with the reference at 1e-4 of the largest
+        # gradient.  At 640 px wide an fp32 pixel coordinate has 3e-5..6e-5 px resolution and the SSIM
+        # gradient of low-variance windows amplifies that ~1e-3-fold, so a few stable pixels of the
+        # reference's OWN fp32 run sit 3e-4 from its fp64 run (measured: 10 of 122880 at scale 0); there
+        # the kernel must match the fp32 reference instead.
+        assert float(torch.minimum(err64, err32)[m].max()) < GRAD_TOL
+        assert float(torch.quantile(err64.flatten(), 0.999)) < GRAD_TOL
+        assert int((err64[m] > GRAD_TOL).sum()) <= 20
+    for j, (gv, r) in enumerate(zip(out["grad_pose_vec"], ref["grad_pose_vec"])):
+        # a handful of decision-flip pixels at the coarse scales move a pose gradient by ~1e-3 in ANY
+        # fp32 implementation; bound ours by the reference's own fp32 deviation
+        own = rel_err(gv, r)
+        ref_dev = rel_err(ref32["grad_pose_vec"][j], r)
+        assert own < max(GRAD_TOL, 5 * ref_dev), (own, ref_dev)
+
+
+def test_bit_identical_across_runs(dev):
+    inp = mono_inputs(3, 96, 320, seed=11)
+    outs = [gpu_mono_from_vec(inp, dev) for _ in range(4)]
+    for o in outs[1:]:
+        assert torch.equal(o["rec_loss"], outs[0]["rec_loss"]) and torch.equal(o["smooth_loss"], outs[0]["smooth_loss"])
+        for a, b in zip(o["grad_depth"] + o["grad_pose_vec"] + o["argmin"],
+                        outs[0]["grad_depth"] + outs[0]["grad_pose_vec"] + outs[0]["argmin"]):
+            assert torch.equal(a, b)
+
+
+def test_cfg2_batch_linearity_at_full_size(dev):
+    """BASELINE.json configs[1] (640x192, batch 12): the batch loss is the mean of the per-sample
+    losses and a sample's gradients are 1/B of its stand-alone gradients (size-independent check
+    that needs no CPU oracle at this size)."""
+    B = 12
+    inp = mono_inputs(B, 192, 640, seed=2)
+    # pyramid and pose matrices are built once on the CPU and sliced, so the batched and the
+    # per-sample runs see identical input bits (library resize / bmm kernels vary with batch size)
+    tgt, src = build_pyramid(inp)
+    pose = [euler_pose(v) for v in inp["pose_vec"]]
+    full = gpu_mono_from_pose(inp["depth"], inp["K"], pose, tgt, src, (192, 640), dev)
+    rec, sm = [], []
+    for b in range(B):
+        sl = slice(b, b + 1)
+        o = gpu_mono_from_pose([d[sl] for d in inp["depth"]], inp["K"][sl], [p[sl] for p in pose],
+                               [t[sl] for t in tgt], [[x[sl] for x in row] for row in src], (192, 640), dev)
+        rec.append(float(o["rec_loss"]))
+        sm.append(float(o["smooth_loss"]))
+        for i in range(4):
+            assert torch.equal(o["argmin"][i][0], full["argmin"][i][b])
+            assert rel_err(full["grad_depth"][i][b] * B, o["grad_depth"][i][0]) < 1e-5
+        for j in range(2):
+            assert rel_err(full["grad_pose"][j][b] * B, o["grad_pose"][j][0]) < 1e-4
+    assert abs(np.mean(rec) - float(full["rec_loss"])) < 2e-6 * float(full["rec_loss"])
+    assert abs(np.mean(sm) - float(full["smooth_loss"])) < 2e-6 * float(full["smooth_loss"])
+
+
+# ------------------------------------------------------------------------------------------- edge cases
+def _against_oracle(inp, dev, loss_tol=LOSS_TOL, **kw):
+    plan_kw = {k: v for k, v in kw.items()}
+    port_kw = dict(automask=kw.get("automask", True), reduce=kw.get("reduce", "min"),
+                   ssim_w=kw.get("ssim_weight", 0.85), smooth_w=kw.get("smooth_weight", 1e-3))
+    out = gpu_mono_from_vec(inp, dev, **plan_kw)
+    tgt, src = build_pyramid(inp)
+    ref = oracle_mono(inp, torch.float64, tgt, src, **port_kw)
+    assert rel_err(out["rec_loss"], ref["rec_loss"].detach()) < loss_tol
+    if port_kw["smooth_w"] > 0:
+        assert rel_err(out["smooth_loss"], ref["smooth_loss"].detach()) < loss_tol
+    return out, ref
+
+
+def test_source_equal_to_target_gives_zero_loss_and_gradients(dev):
+    """(i): identity candidates are exactly 0, the automask wins everywhere, no gradient flows."""
+    inp = mono_inputs(2, 32, 64, seed=4)
+    inp["ctx"] = [inp["img"].clone(), inp["img"].clone()]
+    out = gpu_mono_from_vec(inp, dev, smooth_weight=0.0)
+    assert float(out["rec_loss"]) == 0.0
+    for a in out["argmin"]:
+        assert bool(((a == 1) | (a == 0)).all())  # first exact zero wins; the warp can only tie
+    for g in out["grad_depth"] + out["grad_pose_vec"]:
+        assert float(g.abs().max()) == 0.0
+
+
+def test_identical_sources_break_ties_towards_the_lowest_index(dev):
+    """(ii): torch.min keeps the first index among equal candidates."""
+    inp = mono_inputs(2, 32, 64, seed=5)
+    inp["ctx"][1] = inp["ctx"][0].clone()
+    inp["pose_vec"][1] = inp["pose_vec"][0].clone()
+    out = gpu_mono_from_vec(inp, dev)
+    for a in out["argmin"]:
+        assert int(a.max()) <= 1
+
+
+def test_identity_pose(dev):
+    """(iii): R = I, t = 0."""
+    inp = mono_inputs(2, 32, 64, seed=6)
+    inp["pose_vec"] = [torch.zeros_like(v) for v in inp["pose_vec"]]
+    _against_oracle(inp, dev)
+
+
+def test_points_behind_the_camera_and_out_of_view(dev):
+    """(iv)/(v): large motion sends samples behind the camera or far outside the image; the
+    clamped border sampling and zero coordinate gradients must match the reference."""
+    inp = mono_inputs(2, 48, 80, seed=7)
+    inp["pose_vec"][0] = torch.tensor([[0.5, 0.1, -60.0, 0.0, 0.3, 0.0], [30.0, -20.0, 1.0, 0.2, 0.0, 0.1]])
+    inp["pose_vec"][1] = torch.tensor([[0.0, 0.0, -1.0, 0.0, 3.0, 0.0], [-200.0, 0.0, 0.0, 0.0, 0.0, 1.0]])
+    out, ref = _against_oracle(inp, dev)
+    for g in out["grad_depth"] + out["grad_pose_vec"]:
+        assert bool(torch.isfinite(g).all())
+    for i, (g, r) in enumerate(zip(out["grad_depth"], ref["grad_depth"])):
+        err = (g.double() - r).abs() / r.abs().max()
+        assert float(torch.quantile(err.flatten(), 0.99)) < GRAD_TOL
+
+
+def test_translation_broadcast_shapes_agree(dev):
+    """(vi): the kernel takes t from the 4x4 pose; the reference's two spellings ([B,3,1,1] and the
+    expanded [B,3,h,w]) are the same numbers, so one oracle run covers both."""
+    inp = mono_inputs(1, 24, 80, seed=8)
+    _against_oracle(inp, dev)
+
+
+def test_depth_at_the_clamps(dev):
+    """(vii): depth below the 1e-6 clamp of the smoothness term and near-zero projected depth."""
+    inp = mono_inputs(1, 32, 64, seed=9)
+    for d in inp["depth"]:
+        d[:, :, ::5, ::7] = 5e-7
+        d[:, :, 1::6, 2::9] = 2e-6
+    out, ref = _against_oracle(inp, dev, loss_tol=5e-5)
+    for i, (g, r) in enumerate(zip(out["grad_depth"], ref["grad_depth"])):
+        assert bool(torch.isfinite(g).all())
+        tiny = inp["depth"][i] < 1e-6
+        # below the clamp the smoothness term passes no gradient (clamp(min=1e-6), smoothness_loss.py:62);
+        # what is left is the photometric part, which the oracle has too
+        err = (g.double() - r).abs() / r.abs().max()
+        assert float(torch.quantile(err.flatten(), 0.98)) < GRAD_TOL
+        assert float(err[tiny].max()) < 1e-2
+
+
+def test_shallow_depths_down_to_5cm(dev):
+    inp = mono_inputs(2, 32, 64, seed=10, min_depth=0.05)
+    _against_oracle(inp, dev)
+
+
+@pytest.mark.parametrize("shape", [(1, 24, 80), (1, 37, 53), (2, 16, 130), (1, 6, 8)])
+def test_odd_sizes_single_scale(dev, shape):
+    """(viii): sizes that are not multiples of the tile, one scale only."""
+    B, H, W = shape
+    inp = mono_inputs(B, H, W, scales=1, seed=12)
+    out, ref = _against_oracle(inp, dev)
+    g, r = out["grad_depth"][0], ref["grad_depth"][0]
+    err = (g.double() - r).abs() / r.abs().max()
+    assert float(torch.quantile(err.flatten(), 0.99)) < GRAD_TOL
+
+
+def test_single_source_single_sample(dev):
+    """(x): B = 1, S = 1."""
+    inp = mono_inputs(1, 32, 64, S=1, seed=13)
+    _against_oracle(inp, dev)
+    _against_oracle(inp, dev, automask=False)
+
+
+def test_three_sources(dev):
+    inp = mono_inputs(1, 32, 64, S=3, seed=14)
+    _against_oracle(inp, dev)
+
+
+def test_nan_depth_propagates_to_the_loss(dev):
+    """The trainer asserts torch.isfinite(losses) (projects/MonoDepth2/train.py:93): a NaN in the
+    predictions must surface, not be hidden."""
+    inp = mono_inputs(1, 32, 64, seed=15)
+    inp["depth"][0][0, 0, 3, 4] = float("nan")
+    out = gpu_mono_from_vec(inp, dev)
+    assert not bool(torch.isfinite(out["smooth_loss"]))
+
+
+def test_upstream_gradient_scaling(dev):
+    """Backward honours the upstream gradients of the two scalars independently."""
+    from simpledepthestimation_b200.functional import MonoLossPlan, mono_photometric_smoothness_loss
+    from oracle import port
+
+    inp = mono_inputs(1, 32, 64, seed=16)
+    g = lambda t: t.to(dev).contiguous()  # noqa: E731
+    sizes = [tuple(d.shape[-2:]) for d in inp["depth"]]
+    tgt = [g(port.resize_bilinear(inp["img"], s)) for s in sizes]
+    src = [[g(port.resize_bilinear(c, s)) for c in inp["ctx"]] for s in sizes]
+    plan = MonoLossPlan(1, sizes, 2, (32, 64), dev)
+    grads = []
+    for wr, ws in ((1.0, 1.0), (3.0, 0.0), (0.0, 2.0)):
+        depth = [g(d).requires_grad_() for d in inp["depth"]]
+        pose = [g(euler_pose(v)).requires_grad_() for v in inp["pose_vec"]]
+        rec, sm, _ = mono_photometric_smoothness_loss(plan, tgt, src, depth, g(inp["K"]), pose)
+        (wr * rec + ws * sm).backward()
+        grads.append(([d.grad.clone() for d in depth], [p.grad.clone() for p in pose]))
+    for i in range(4):
+        combo = grads[1][0][i] / 3.0 + grads[2][0][i] / 2.0
+        assert rel_err(combo, grads[0][0][i]) < 1e-5
+    for j in range(2):
+        assert rel_err(grads[1][1][j] / 3.0, grads[0][1][j]) < 1e-5   # smoothness does not touch the pose
+        assert float(grads[2][1][j].abs().max()) == 0.0
+
+
+def test_shape_errors_raise(dev):
+    from simpledepthestimation_b200 import _lib
+    from simpledepthestimation_b200.functional import MonoLossPlan
+
+    plan = MonoLossPlan(1, [(16, 32)], 1, (16, 32), dev)
+    z = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
+    with pytest.raises(_lib.SdeError):
+        plan.forward([z(1, 3, 16, 33)], [[z(1, 3, 16, 32)]], [z(1, 1, 16, 32)], z(1, 3, 3), [z(1, 4, 4)])
+    with pytest.raises(_lib.SdeError):
+        plan.forward([z(1, 3, 16, 32).cpu()], [[z(1, 3, 16, 32)]], [z(1, 1, 16, 32)], z(1, 3, 3), [z(1, 4, 4)])
+    with pytest.raises(NotImplementedError):
+        MonoLossPlan(1, [(16, 32)], 1, (16, 32), dev, reduce="median")
