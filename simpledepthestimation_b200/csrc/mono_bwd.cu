@@ -34,7 +34,7 @@ struct BwdShared {
   Proj proj[SDE_MAX_SOURCES];
   float red[12][kThreads / 32];
   unsigned ticket;
-  uint8_t arg[kPlane];
+  __align__(8) uint8_t arg[kPlane];
 };
 
 __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_constant__ MonoParams p) {
@@ -49,6 +49,9 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
   const bool use_ssim = p.ssim_w > 0.0f;
   // plane (yy, xx) <-> image (oy + yy, ox + xx); Q = plane [1..16]x[1..64]; P = plane [2..15]x[2..63]
   const int ox = tc.x0 - 2, oy = tc.y0 - 2;
+  const bool interior = ox >= 0 && oy >= 0 && ox + kHW <= w && oy + kHH <= h;
+  // reflect-pad adjoint: pixels next to the image border also receive the mirrored pad position
+  const bool lr_border = ox + 2 <= 1 || ox + kHW - 3 >= w - 2;
 
   if (tid < p.S) {
     Cam cam;
@@ -62,7 +65,9 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
   __syncthreads();
 
   const float* __restrict__ depth = p.depth[s] + (size_t)b * hw;
-  const float* __restrict__ target = p.target[s] + (size_t)b * 3 * hw;
+  const float* __restrict__ tg0 = p.target[s] + (size_t)b * 3 * hw;
+  const float* __restrict__ tg1 = tg0 + hw;
+  const float* __restrict__ tg2 = tg1 + hw;
   const uint8_t* __restrict__ amap = reduce_mean ? nullptr : p.argmin[s] + (size_t)b * hw;
 
   const float g_rec = __ldg(p.grad_losses), g_smooth = __ldg(p.grad_losses + 1);
@@ -77,11 +82,10 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
   const int c0 = 2 * lane;
   const f2 C1 = bc2(81.0f * p.c1), C2 = bc2(81.0f * p.c2);
 
-  // image coordinates of this lane's pixel pair and its four rows (as centre q and as pixel p)
+  // image columns of this lane's pixel pair; extra multiplicities of the reflect-pad adjoint
   const int px0 = ox + c0 + 1, px1 = px0 + 1;
-  // reflect-pad adjoint weights: a border-adjacent pixel also receives the mirrored pad position
-  const f2 wL = mk2(px0 == 1 ? 2.0f : 1.0f, px1 == 1 ? 2.0f : 1.0f);
-  const f2 wR = mk2(px0 == w - 2 ? 2.0f : 1.0f, px1 == w - 2 ? 2.0f : 1.0f);
+  const float eL0 = px0 == 1 ? 1.0f : 0.0f, eL1 = px1 == 1 ? 1.0f : 0.0f;
+  const float eR0 = px0 == w - 2 ? 1.0f : 0.0f, eR1 = px1 == w - 2 ? 1.0f : 0.0f;
 
   float gd[kPosPerThread];
 #pragma unroll
@@ -89,30 +93,44 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
 
   for (int j = 0; j < p.S; ++j) {
     const int cand = automask ? 2 * j : j;
+    const Cam cam = sh.cam;
+    const Proj pj = sh.proj[j];
+    const float* __restrict__ sc0 = p.source[s][j] + (size_t)b * 3 * hw;
+    const float* __restrict__ sc1 = sc0 + hw;
+    const float* __restrict__ sc2 = sc1 + hw;
     // ---------------------------------------------------------------- phase 1
     {
-      const Cam cam = sh.cam;
-      const Proj pj = sh.proj[j];
-      const float* __restrict__ src = p.source[s][j] + (size_t)b * 3 * hw;
-      for (int i = tid; i < kPlane; i += kThreads) {
-        const int yy = i / kHW, xx = i - yy * kHW;
+      int yy = tid / kHW, xx = tid - yy * kHW;
+      for (int i = tid; i < kPositions; i += kThreads) {
         const int ty = oy + yy, tx = ox + xx;
-        const int gy = reflect_clamp(ty, h), gx = reflect_clamp(tx, w);
+        int gy = ty, gx = tx;
+        if (!interior) {
+          gy = reflect_clamp(ty, h);
+          gx = reflect_clamp(tx, w);
+        }
         const int pix = gy * w + gx;
         const float d = __ldg(depth + pix);
-        float X, Y, sv[3];
-        project_px(cam, pj, (float)gx, (float)gy, d, X, Y);
-        bilinear3(src, hw, w, h, X, Y, sv);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) planes[(kBS + c) * kPlane + i] = sv[c];
+        float P[3], den, X, Y;
+        project_full(cam, pj, (float)gx, (float)gy, d, P, den, X, Y);
+        const Cell cell = bilinear_cell(X, Y, w, h);
+        const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
+        const float w00 = bx * by, w01 = cell.ax * by, w10 = bx * cell.ay, w11 = cell.ax * cell.ay;
+        float* dst = planes + plane_index(yy, xx);
+        dst[(kBS + 0) * kPlane] = tap4(sc0, cell.off, w, w00, w01, w10, w11);
+        dst[(kBS + 1) * kPlane] = tap4(sc1, cell.off, w, w00, w01, w10, w11);
+        dst[(kBS + 2) * kPlane] = tap4(sc2, cell.off, w, w00, w01, w10, w11);
         if (j == 0) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) planes[(kBA + c) * kPlane + i] = __ldg(target + c * hw + pix);
-          planes[kBInv * kPlane + i] = 1.0f / (d < 1e-6f ? 1e-6f : d);  // clamp(min=1e-6) keeps NaN, as torch.clamp does
+          dst[(kBA + 0) * kPlane] = __ldg(tg0 + pix);
+          dst[(kBA + 1) * kPlane] = __ldg(tg1 + pix);
+          dst[(kBA + 2) * kPlane] = __ldg(tg2 + pix);
+          dst[kBInv * kPlane] = 1.0f / (d < 1e-6f ? 1e-6f : d);  // clamp(min=1e-6) keeps NaN, as torch.clamp does
           const bool inside = ty >= 0 && ty < h && tx >= 0 && tx < w;
           // 255 never matches a candidate: windows centred outside the image do not exist
-          sh.arg[i] = inside ? (reduce_mean ? (uint8_t)254 : amap[pix]) : (uint8_t)255;
+          sh.arg[plane_index(yy, xx)] = inside ? (reduce_mean ? (uint8_t)254 : amap[pix]) : (uint8_t)255;
         }
+        xx += kThreads - kHW;
+        yy += 1;
+        if (xx >= kHW) { xx -= kHW; yy += 1; }
       }
     }
     __syncthreads();
@@ -121,50 +139,50 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     for (int c = 0; c < 3; ++c) {
       // -------------------------------------------------------------- phase 2: SSIM coefficients on Q
       if (use_ssim) {
-        const float* pa = planes + (kBA + c) * kPlane + r0 * kHW + c0;
-        const float* px = planes + (kBS + c) * kPlane + r0 * kHW + c0;
+        const float* pa = planes + (kBA + c) * kPlane + plane_index(r0, c0);
         f2 hA[2], hAA[2], hX[2], hXX[2], hXA[2];
 #pragma unroll
         for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
-          const f2 alo = ld2(pa + rr * kHW), ahi = ld2(pa + rr * kHW + 2);
-          const f2 xlo = ld2(px + rr * kHW), xhi = ld2(px + rr * kHW + 2);
-          const f2 aC = mk2(alo.y, ahi.x), aO = mk2(alo.x, ahi.y);
-          const f2 xC = mk2(xlo.y, xhi.x), xO = mk2(xlo.x, xhi.y);
-          const f2 aa = aC * aC, xx = xC * xC, xa = xC * aC;
-          const f2 nA = aC + swp(aC) + aO, nAA = fma2(aO, aO, aa + swp(aa));
-          const f2 nX = xC + swp(xC) + xO, nXX = fma2(xO, xO, xx + swp(xx)), nXA = fma2(xO, aO, xa + swp(xa));
+          const Row4 a = ld_row(pa + rr * kPitch);
+          const Row4 x = ld_row(pa + (kBS - kBA) * kPlane + rr * kPitch);
+          const f2 aa = a.c * a.c, xx2 = x.c * x.c, xa = x.c * a.c;
+          const f2 nA = (a.c + swp(a.c)) + a.o, nAA = fma2(a.o, a.o, aa + swp(aa));
+          const f2 nX = (x.c + swp(x.c)) + x.o, nXX = fma2(x.o, x.o, xx2 + swp(xx2));
+          const f2 nXA = fma2(x.o, a.o, xa + swp(xa));
           if (rr >= 2) {
             const int row = r0 + rr - 1;  // plane row of the window centre
-            const uint8_t* pm = sh.arg + row * kHW + c0 + 1;
-            const int m0 = pm[0], m1 = pm[1];
-            const bool sel0 = reduce_mean ? (m0 != 255) : (m0 == cand);
-            const bool sel1 = reduce_mean ? (m1 != 255) : (m1 == cand);
+            const uchar2 m = *reinterpret_cast<const uchar2*>(sh.arg + plane_index(row, c0 + 1));
+            const bool sel0 = reduce_mean ? (m.x != 255) : (m.x == cand);
+            const bool sel1 = reduce_mean ? (m.y != 255) : (m.y == cand);
             f2 ca = bc2(0.0f), cb = bc2(0.0f), cc = bc2(0.0f);
             if (__any_sync(0xffffffffu, sel0 || sel1)) {
-              const f2 sA = hA[0] + hA[1] + nA, sAA = hAA[0] + hAA[1] + nAA;
-              const f2 sX = hX[0] + hX[1] + nX, sXX = hXX[0] + hXX[1] + nXX, sXA = hXA[0] + hXA[1] + nXA;
-              const f2 aa2 = sA * sA, xx2 = sX * sX, t = sX * sA;
+              const f2 sA = (hA[0] + hA[1]) + nA, sAA = (hAA[0] + hAA[1]) + nAA;
+              const f2 sX = (hX[0] + hX[1]) + nX, sXX = (hXX[0] + hXX[1]) + nXX, sXA = (hXA[0] + hXA[1]) + nXA;
+              // same operation order as the forward kernel
+              const f2 aa2 = sA * sA, xs = sX * sX, t = sX * sA;
+              const f2 vA = fma2(aa2, bc2(-1.0f), sAA * bc2(9.0f));
               const f2 n1 = fma2(bc2(2.0f), t, C1);
-              const f2 n2 = fma2(bc2(2.0f), fma2(bc2(9.0f), sXA, neg2(t)), C2);
-              const f2 d1 = (xx2 + aa2) + C1;   // same operation order as the forward kernel
-              const f2 d2 = (fma2(bc2(9.0f), sXX, neg2(xx2)) + fma2(bc2(9.0f), sAA, neg2(aa2))) + C2;
-              const f2 D = d1 * d2;
-              const f2 invD = mk2(1.0f / D.x, 1.0f / D.y);
-              const f2 ssim = n1 * n2 * invD;
+              const f2 n2 = fma2(bc2(2.0f), fma2(t, bc2(-1.0f), sXA * bc2(9.0f)), C2);
+              const f2 d1 = (xs + aa2) + C1;
+              const f2 d2 = (fma2(xs, bc2(-1.0f), sXX * bc2(9.0f)) + vA) + C2;
+              const f2 N = n1 * n2, D = d1 * d2;
+              const f2 ssim = div2(N, D);
+              const f2 invD = div2(bc2(1.0f), D);
               // torch.clamp passes the gradient on the closed interval 0 <= (1-ssim)/2 <= 1
-              const f2 half = fma2(ssim, bc2(-0.5f), bc2(0.5f));
-              const f2 g = mk2((sel0 && half.x >= 0.0f && half.x <= 1.0f) ? g_ss : 0.0f,
-                               (sel1 && half.y >= 0.0f && half.y <= 1.0f) ? g_ss : 0.0f);
+              const float h0 = fmaf(lo(ssim), -0.5f, 0.5f), h1 = fmaf(hi(ssim), -0.5f, 0.5f);
+              const f2 g = mk2((sel0 && h0 >= 0.0f && h0 <= 1.0f) ? g_ss : 0.0f,
+                               (sel1 && h1 >= 0.0f && h1 <= 1.0f) ? g_ss : 0.0f);
               const f2 gi = g * invD;
-              // d ssim / d(sum S), d(sum S^2), d(sum S A)
-              ca = gi * fma2(bc2(2.0f) * sA, n2 - n1, neg2(bc2(2.0f) * sX * ssim * (d2 - d1)));
-              cb = gi * bc2(-18.0f) * ssim * d1;   // 2 * (-9 ssim / d2)
-              cc = gi * bc2(18.0f) * n1;
+              // d ssim / d(sum S), d(sum S^2), d(sum S A)   (SURVEY.md A.6 in window-sum form)
+              const f2 u = (sA * (n2 - n1)) - ((sX * ssim) * (d2 - d1));
+              ca = (gi * bc2(2.0f)) * u;
+              cb = (gi * bc2(-18.0f)) * (ssim * d1);
+              cc = (gi * bc2(18.0f)) * n1;
             }
-            float* pc = planes + kBCoef * kPlane + row * kHW + c0 + 1;
-            pc[0] = ca.x; pc[1] = ca.y;
-            pc[kPlane] = cb.x; pc[kPlane + 1] = cb.y;
-            pc[2 * kPlane] = cc.x; pc[2 * kPlane + 1] = cc.y;
+            float* pc = planes + kBCoef * kPlane + plane_index(row, c0 + 1);
+            *reinterpret_cast<unsigned long long*>(pc) = ca.v;
+            *reinterpret_cast<unsigned long long*>(pc + kPlane) = cb.v;
+            *reinterpret_cast<unsigned long long*>(pc + 2 * kPlane) = cc.v;
           }
           hA[0] = hA[1]; hA[1] = nA; hAA[0] = hAA[1]; hAA[1] = nAA;
           hX[0] = hX[1]; hX[1] = nX; hXX[0] = hXX[1]; hXX[1] = nXX; hXA[0] = hXA[1]; hXA[1] = nXA;
@@ -173,43 +191,44 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       __syncthreads();
       // -------------------------------------------------------------- phase 3: adjoint gather -> gS_c on P
       {
-        f2 hq[3][2];  // horizontal (weighted) 3-sums of a, b, c for the two previous coefficient rows
+        f2 hq[3][2];  // horizontal 3-sums of a, b, c for the two previous coefficient rows
 #pragma unroll
         for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
           f2 nq[3];
           if (use_ssim) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              const float* pc = planes + (kBCoef + k) * kPlane + (r0 + rr) * kHW + c0;
-              const f2 lo = ld2(pc), hi = ld2(pc + 2);
-              nq[k] = fma2(wL, lo, fma2(wR, hi, mk2(lo.y, hi.x)));
+              const Row4 q = ld_row(planes + (kBCoef + k) * kPlane + plane_index(r0 + rr, c0));
+              f2 hsum = (q.c + swp(q.c)) + q.o;
+              if (lr_border) {   // block-uniform: only tiles on the left / right image border
+                hsum = hsum + mk2(eL0 * lo(q.o) + eR0 * hi(q.c), eL1 * lo(q.c) + eR1 * hi(q.o));
+              }
+              nq[k] = hsum;
             }
           }
           if (rr >= 2) {
             const int row = r0 + rr - 1;        // plane row of pixel p
             const int py = oy + row;
-            const float wu = py == 1 ? 2.0f : 1.0f, wd = py == h - 2 ? 2.0f : 1.0f;
-            const f2 Sp = mk2(planes[(kBS + c) * kPlane + row * kHW + c0 + 1],
-                              planes[(kBS + c) * kPlane + row * kHW + c0 + 2]);
-            const f2 Ap = mk2(planes[(kBA + c) * kPlane + row * kHW + c0 + 1],
-                              planes[(kBA + c) * kPlane + row * kHW + c0 + 2]);
+            const f2 wu = bc2(py == 1 ? 2.0f : 1.0f), wd = bc2(py == h - 2 ? 2.0f : 1.0f);
+            const f2 Sp = ld2(planes + (kBS + c) * kPlane + plane_index(row, c0 + 1));
+            const f2 Ap = ld2(planes + (kBA + c) * kPlane + plane_index(row, c0 + 1));
             f2 gS = bc2(0.0f);
             if (use_ssim) {
-              const f2 va = fma2(bc2(wu), hq[0][0], fma2(bc2(wd), nq[0], hq[0][1]));
-              const f2 vb = fma2(bc2(wu), hq[1][0], fma2(bc2(wd), nq[1], hq[1][1]));
-              const f2 vc = fma2(bc2(wu), hq[2][0], fma2(bc2(wd), nq[2], hq[2][1]));
+              const f2 va = fma2(wu, hq[0][0], fma2(wd, nq[0], hq[0][1]));
+              const f2 vb = fma2(wu, hq[1][0], fma2(wd, nq[1], hq[1][1]));
+              const f2 vc = fma2(wu, hq[2][0], fma2(wd, nq[2], hq[2][1]));
               gS = fma2(Sp, vb, fma2(Ap, vc, va));
             }
             // L1 term on the pixel itself: sign(S - A) where this candidate was selected
-            const uint8_t* pm = sh.arg + row * kHW + c0 + 1;
-            const int m0 = pm[0], m1 = pm[1];
-            const bool sel0 = reduce_mean ? (m0 != 255) : (m0 == cand);
-            const bool sel1 = reduce_mean ? (m1 != 255) : (m1 == cand);
+            const uchar2 m = *reinterpret_cast<const uchar2*>(sh.arg + plane_index(row, c0 + 1));
+            const bool sel0 = reduce_mean ? (m.x != 255) : (m.x == cand);
+            const bool sel1 = reduce_mean ? (m.y != 255) : (m.y == cand);
             const f2 df = Sp - Ap;
-            if (sel0) gS.x += df.x > 0.0f ? g_l1 : (df.x < 0.0f ? -g_l1 : 0.0f);
-            if (sel1) gS.y += df.y > 0.0f ? g_l1 : (df.y < 0.0f ? -g_l1 : 0.0f);
-            float* pg = planes + (kBG + c) * kPlane + row * kHW + c0 + 1;
-            pg[0] = gS.x; pg[1] = gS.y;
+            const float d0 = lo(df), d1 = hi(df);
+            const float l0 = sel0 ? (d0 > 0.0f ? g_l1 : (d0 < 0.0f ? -g_l1 : 0.0f)) : 0.0f;
+            const float l1 = sel1 ? (d1 > 0.0f ? g_l1 : (d1 < 0.0f ? -g_l1 : 0.0f)) : 0.0f;
+            gS = gS + mk2(l0, l1);
+            *reinterpret_cast<unsigned long long*>(planes + (kBG + c) * kPlane + plane_index(row, c0 + 1)) = gS.v;
           }
           if (use_ssim) {
 #pragma unroll
@@ -222,9 +241,6 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
 
     // ---------------------------------------------------------------- phase 4: warp backward on P
     {
-      const Cam cam = sh.cam;
-      const Proj pj = sh.proj[j];
-      const float* __restrict__ src = p.source[s][j] + (size_t)b * 3 * hw;
       float acc[12];
 #pragma unroll
       for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
@@ -234,45 +250,31 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
         const int ly = i / kBwdW, lx = i - ly * kBwdW;
         const int gy = tc.y0 + ly, gx = tc.x0 + lx;
         if (i < kBwdW * kBwdH && gy < h && gx < w) {
-          const int pl = (ly + 2) * kHW + lx + 2;
+          const int pl = plane_index(ly + 2, lx + 2);
           const float g0 = planes[kBG * kPlane + pl], g1 = planes[(kBG + 1) * kPlane + pl],
                       g2 = planes[(kBG + 2) * kPlane + pl];
           if (g0 != 0.0f || g1 != 0.0f || g2 != 0.0f) {
             const float d = __ldg(depth + gy * w + gx);
             const float fxp = (float)gx, fyp = (float)gy;
-            // ray = K^-1 [x,y,1], P = K^-1 [x d, y d, d]  (camera.py:125-138)
-            const float xd = fxp * d, yd = fyp * d;
-            const float Px = cam.ki[0] * xd + cam.ki[1] * yd + cam.ki[2] * d;
-            const float Py = cam.ki[3] * xd + cam.ki[4] * yd + cam.ki[5] * d;
-            const float Pz = cam.ki[6] * xd + cam.ki[7] * yd + cam.ki[8] * d;
-            const float p0 = pj.m[0] * Px + pj.m[1] * Py + pj.m[2] * Pz + pj.tau[0];
-            const float p1 = pj.m[3] * Px + pj.m[4] * Py + pj.m[5] * Pz + pj.tau[1];
-            const float p2 = pj.m[6] * Px + pj.m[7] * Py + pj.m[8] * Pz + pj.tau[2];
-            const float den = p2 + 1e-6f;
-            const float X = p0 / den, Y = p1 / den;
+            float P[3], den, X, Y;
+            project_full(cam, pj, fxp, fyp, d, P, den, X, Y);
             const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
             // gradient gates of nan_to_num and clamp (closed interval), camera.py:184-188
             const bool gate_x = (X >= 0.0f) && (X <= wm1);   // false for NaN / +-inf
             const bool gate_y = (Y >= 0.0f) && (Y <= hm1);
             if (gate_x || gate_y) {
-              const float ix = fminf(fmaxf(X, 0.0f), wm1), iy = fminf(fmaxf(Y, 0.0f), hm1);
-              const float x0f = floorf(ix), y0f = floorf(iy);
-              const int x0 = (int)x0f, y0 = (int)y0f;
-              const float wx1 = ix - x0f, wx0 = (x0f + 1.0f) - ix, wy1 = iy - y0f, wy0 = (y0f + 1.0f) - iy;
-              const bool inx = x0 + 1 <= w - 1, iny = y0 + 1 <= h - 1;  // out-of-range taps contribute 0
-              const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
-              const int o00 = y0 * w + x0, o01 = y0 * w + x1, o10 = y1 * w + x0, o11 = y1 * w + x1;
+              const Cell cell = bilinear_cell(X, Y, w, h);
+              const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
               float gX = 0.0f, gY = 0.0f;
               const float gs[3] = {g0, g1, g2};
+              const float* pls[3] = {sc0, sc1, sc2};
 #pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                const float* plc = src + c * hw;
-                const float v00 = __ldg(plc + o00);
-                const float v01 = inx ? __ldg(plc + o01) : 0.0f;
-                const float v10 = iny ? __ldg(plc + o10) : 0.0f;
-                const float v11 = (inx && iny) ? __ldg(plc + o11) : 0.0f;
-                gX += gs[c] * ((v01 - v00) * wy0 + (v11 - v10) * wy1);
-                gY += gs[c] * ((v10 - v00) * wx0 + (v11 - v01) * wx1);
+              for (int cc = 0; cc < 3; ++cc) {
+                const float* q0 = pls[cc] + cell.off;
+                const float* q1 = q0 + w;
+                const float v00 = __ldg(q0), v01 = __ldg(q0 + 1), v10 = __ldg(q1), v11 = __ldg(q1 + 1);
+                gX += gs[cc] * ((v01 - v00) * by + (v11 - v10) * cell.ay);
+                gY += gs[cc] * ((v10 - v00) * bx + (v11 - v01) * cell.ax);
               }
               if (!gate_x) gX = 0.0f;
               if (!gate_y) gY = 0.0f;
@@ -283,9 +285,9 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
               const float gc0 = cam.fx * u0;
               const float gc1 = cam.sk * u0 + cam.fy * u1;
               const float gc2 = -(gX * dx + gY * dy) * q;
-              acc[0] += gc0 * Px; acc[1] += gc0 * Py; acc[2] += gc0 * Pz; acc[3] += gc0;
-              acc[4] += gc1 * Px; acc[5] += gc1 * Py; acc[6] += gc1 * Pz; acc[7] += gc1;
-              acc[8] += gc2 * Px; acc[9] += gc2 * Py; acc[10] += gc2 * Pz; acc[11] += gc2;
+              acc[0] += gc0 * P[0]; acc[1] += gc0 * P[1]; acc[2] += gc0 * P[2]; acc[3] += gc0;
+              acc[4] += gc1 * P[0]; acc[5] += gc1 * P[1]; acc[6] += gc1 * P[2]; acc[7] += gc1;
+              acc[8] += gc2 * P[0]; acc[9] += gc2 * P[1]; acc[10] += gc2 * P[2]; acc[11] += gc2;
               // d/d depth: (R^T K^T g_p) . K^-1 [x,y,1]
               const float gP0 = pj.r[0] * gc0 + pj.r[3] * gc1 + pj.r[6] * gc2;
               const float gP1 = pj.r[1] * gc0 + pj.r[4] * gc1 + pj.r[7] * gc2;
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       if (i < kBwdW * kBwdH && gy < h && gx < w) {
         float g = gd[it];
         if (sscale > 0.0f) {
-          const int pl = (ly + 2) * kHW + lx + 2;
+          const int pl = plane_index(ly + 2, lx + 2);
           const float* pi = planes + kBInv * kPlane + pl;
           const float ic = pi[0];
           float el = 0.0f, er = 0.0f, eu = 0.0f, edn = 0.0f;
@@ -340,14 +342,14 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
             const float* pa = planes + (kBA + c) * kPlane + pl;
             const float a = pa[0];
             el += fabsf(pa[-1] - a); er += fabsf(a - pa[1]);
-            eu += fabsf(pa[-kHW] - a); edn += fabsf(a - pa[kHW]);
+            eu += fabsf(pa[-kPitch] - a); edn += fabsf(a - pa[kPitch]);
           }
           float G = 0.0f;
           auto sgn = [](float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); };
           if (gx + 1 < w) G += sgn(ic - pi[1]) * expf(-er * (1.0f / 3.0f)) * inx;
           if (gx >= 1) G -= sgn(pi[-1] - ic) * expf(-el * (1.0f / 3.0f)) * inx;
-          if (gy + 1 < h) G += sgn(ic - pi[kHW]) * expf(-edn * (1.0f / 3.0f)) * iny;
-          if (gy >= 1) G -= sgn(pi[-kHW] - ic) * expf(-eu * (1.0f / 3.0f)) * iny;
+          if (gy + 1 < h) G += sgn(ic - pi[kPitch]) * expf(-edn * (1.0f / 3.0f)) * iny;
+          if (gy >= 1) G -= sgn(pi[-kPitch] - ic) * expf(-eu * (1.0f / 3.0f)) * iny;
           const float d = __ldg(depth + gy * w + gx);
           const float g_inv = G / mbar - homog;
           if (d >= 1e-6f) g += -ic * ic * g_inv * (g_smooth * sscale);

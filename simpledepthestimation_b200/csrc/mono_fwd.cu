@@ -31,14 +31,15 @@ struct FwdShared {
   unsigned ticket;
 };
 
+template <bool AUTOMASK>
 __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_constant__ MonoParams p) {
   extern __shared__ __align__(16) float planes[];  // [kFwdPlanes][kPlane]
   __shared__ FwdShared sh;
+  constexpr int NC = AUTOMASK ? 2 : 1;             // candidates per source: warp [+ identity]
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const TileCoord tc = decode_tile(p, blockIdx.x);
   const int s = tc.s, b = tc.b, h = p.h[s], w = p.w[s], hw = h * w;
-  const bool automask = (p.flags & SDE_MONO_AUTOMASK) != 0;
   const bool reduce_mean = (p.flags & SDE_MONO_REDUCE_MEAN) != 0;
 
   if (tid < p.S) {
@@ -51,20 +52,24 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
   __syncthreads();
 
   const float* __restrict__ depth = p.depth[s] + (size_t)b * hw;
-  const float* __restrict__ target = p.target[s] + (size_t)b * 3 * hw;
+  const float* __restrict__ tg0 = p.target[s] + (size_t)b * 3 * hw;
+  const float* __restrict__ tg1 = tg0 + hw;
+  const float* __restrict__ tg2 = tg1 + hw;
+  // tiles whose halo lies inside the image need no reflection / clamping of the staged positions
+  const bool interior = tc.x0 >= 1 && tc.y0 >= 1 && tc.x0 + kTileW + 1 <= w && tc.y0 + kTileH + 1 <= h;
 
   // phase-2 ownership: rows r0..r0+3 of the tile, columns 2*lane, 2*lane+1
   const int r0 = wid * kRowsPerWarp;
-  const int c0 = 2 * lane;  // plane column of the left halo of this lane's pair
-  const f2 wS = bc2(p.ssim_w * (1.0f / 3.0f)), wL = bc2(p.l1_w * (1.0f / 3.0f));
+  const int c0 = 2 * lane;  // halo'd column of the left neighbour of this lane's pair
+  const float wS = p.ssim_w * (1.0f / 3.0f), wL = p.l1_w * (1.0f / 3.0f);
   const f2 C1 = bc2(81.0f * p.c1), C2 = bc2(81.0f * p.c2);
   const bool use_ssim = p.ssim_w > 0.0f;
 
-  f2 best[kRowsPerWarp];
+  float best[kRowsPerWarp][2];
   int arg[kRowsPerWarp][2];
 #pragma unroll
   for (int o = 0; o < kRowsPerWarp; ++o) {
-    best[o] = reduce_mean ? bc2(0.0f) : bc2(__int_as_float(0x7f800000));
+    best[o][0] = best[o][1] = reduce_mean ? 0.0f : __int_as_float(0x7f800000);
     arg[o][0] = arg[o][1] = 0;
   }
 
@@ -73,120 +78,129 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
     {
       const Cam cam = sh.cam;
       const Proj pj = sh.proj[j];
-      const float* __restrict__ src = p.source[s][j] + (size_t)b * 3 * hw;
-      for (int i = tid; i < kPlane; i += kThreads) {
-        const int yy = i / kHW, xx = i - yy * kHW;
-        const int gy = reflect_clamp(tc.y0 - 1 + yy, h), gx = reflect_clamp(tc.x0 - 1 + xx, w);
+      const float* __restrict__ sc0 = p.source[s][j] + (size_t)b * 3 * hw;
+      const float* __restrict__ sc1 = sc0 + hw;
+      const float* __restrict__ sc2 = sc1 + hw;
+      int yy = tid / kHW, xx = tid - yy * kHW;
+      for (int i = tid; i < kPositions; i += kThreads) {
+        int gy = tc.y0 - 1 + yy, gx = tc.x0 - 1 + xx;
+        if (!interior) {
+          gy = reflect_clamp(gy, h);
+          gx = reflect_clamp(gx, w);
+        }
         const int pix = gy * w + gx;
         const float d = __ldg(depth + pix);
-        float X, Y, sv[3];
-        project_px(cam, pj, (float)gx, (float)gy, d, X, Y);
-        bilinear3(src, hw, w, h, X, Y, sv);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          planes[(kPlS + c) * kPlane + i] = sv[c];
-          planes[(kPlI + c) * kPlane + i] = __ldg(src + c * hw + pix);
+        float P[3], den, X, Y;
+        project_full(cam, pj, (float)gx, (float)gy, d, P, den, X, Y);
+        const Cell cell = bilinear_cell(X, Y, w, h);
+        const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
+        const float w00 = bx * by, w01 = cell.ax * by, w10 = bx * cell.ay, w11 = cell.ax * cell.ay;
+        float* dst = planes + plane_index(yy, xx);
+        dst[(kPlS + 0) * kPlane] = tap4(sc0, cell.off, w, w00, w01, w10, w11);
+        dst[(kPlS + 1) * kPlane] = tap4(sc1, cell.off, w, w00, w01, w10, w11);
+        dst[(kPlS + 2) * kPlane] = tap4(sc2, cell.off, w, w00, w01, w10, w11);
+        if (AUTOMASK) {
+          dst[(kPlI + 0) * kPlane] = __ldg(sc0 + pix);
+          dst[(kPlI + 1) * kPlane] = __ldg(sc1 + pix);
+          dst[(kPlI + 2) * kPlane] = __ldg(sc2 + pix);
         }
         if (j == 0) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) planes[(kPlA + c) * kPlane + i] = __ldg(target + c * hw + pix);
-          planes[kPlInv * kPlane + i] = 1.0f / (d < 1e-6f ? 1e-6f : d);  // clamp(min=1e-6) keeps NaN, as torch.clamp does
+          dst[(kPlA + 0) * kPlane] = __ldg(tg0 + pix);
+          dst[(kPlA + 1) * kPlane] = __ldg(tg1 + pix);
+          dst[(kPlA + 2) * kPlane] = __ldg(tg2 + pix);
+          dst[kPlInv * kPlane] = 1.0f / (d < 1e-6f ? 1e-6f : d);  // clamp(min=1e-6) keeps NaN, as torch.clamp does
         }
+        // next position: i + 128 = one row down and 62 columns right (mod 66)
+        xx += kThreads - kHW;
+        yy += 1;
+        if (xx >= kHW) { xx -= kHW; yy += 1; }
       }
     }
     __syncthreads();
 
     // ---------------------------------------------------------------- phase 2
-    f2 acc[2][kRowsPerWarp];
+    f2 acc[NC][kRowsPerWarp];
 #pragma unroll
-    for (int o = 0; o < kRowsPerWarp; ++o) acc[0][o] = acc[1][o] = bc2(0.0f);
-    const int ncand = automask ? 2 : 1;
+    for (int k = 0; k < NC; ++k)
+#pragma unroll
+      for (int o = 0; o < kRowsPerWarp; ++o) acc[k][o] = bc2(0.0f);
 
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
-      const float* pa = planes + (kPlA + c) * kPlane + r0 * kHW + c0;
+      const float* pa = planes + (kPlA + c) * kPlane + plane_index(r0, c0);
       f2 hA[2], hAA[2];                 // horizontal 3-sums of the two previous rows
-      f2 hX[2][2], hXX[2][2], hXA[2][2];
-      f2 l1p[2];                        // |X - A| of the previous row's centre pair
+      f2 hX[NC][2], hXX[NC][2], hXA[NC][2];
+      f2 dXA[NC];                       // X - A of the previous row's centre pair
 #pragma unroll
       for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
-        const f2 alo = ld2(pa + rr * kHW), ahi = ld2(pa + rr * kHW + 2);
-        const f2 aC = mk2(alo.y, ahi.x), aO = mk2(alo.x, ahi.y);
-        const f2 aa = aC * aC;
-        const f2 nA = aC + swp(aC) + aO;
-        const f2 nAA = fma2(aO, aO, aa + swp(aa));
-        f2 nX[2], nXX[2], nXA[2], l1n[2];
+        const Row4 a = ld_row(pa + rr * kPitch);
+        const f2 aa = a.c * a.c;
+        const f2 nA = (a.c + swp(a.c)) + a.o;
+        const f2 nAA = fma2(a.o, a.o, aa + swp(aa));
+        f2 nX[NC], nXX[NC], nXA[NC], dn[NC];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (k < ncand) {
-            const float* px = planes + ((k == 0 ? kPlS : kPlI) + c) * kPlane + (r0 + rr) * kHW + c0;
-            const f2 xlo = ld2(px), xhi = ld2(px + 2);
-            const f2 xC = mk2(xlo.y, xhi.x), xO = mk2(xlo.x, xhi.y);
-            const f2 xx = xC * xC, xa = xC * aC;
-            nX[k] = xC + swp(xC) + xO;
-            nXX[k] = fma2(xO, xO, xx + swp(xx));
-            nXA[k] = fma2(xO, aO, xa + swp(xa));
-            l1n[k] = abs2(xC - aC);
-          }
+        for (int k = 0; k < NC; ++k) {
+          const Row4 x = ld_row(pa + ((k == 0 ? kPlS : kPlI) - kPlA) * kPlane + rr * kPitch);
+          const f2 xx2 = x.c * x.c, xa = x.c * a.c;
+          nX[k] = (x.c + swp(x.c)) + x.o;
+          nXX[k] = fma2(x.o, x.o, xx2 + swp(xx2));
+          nXA[k] = fma2(x.o, a.o, xa + swp(xa));
+          dn[k] = x.c - a.c;
         }
         if (rr >= 2) {
           // window sums (not divided by 9): every SSIM factor below is the reference's times 81,
-          // which cancels in the ratio and avoids a rounded 1/9 constant
+          // which cancels in the ratio and avoids a rounded 1/9 constant.  Numerator and
+          // denominator use mirrored operation orders so that X == A gives ssim == 1 exactly.
           const int o = rr - 2;
-          const f2 sA = hA[0] + hA[1] + nA;
-          const f2 sAA = hAA[0] + hAA[1] + nAA;
+          const f2 sA = (hA[0] + hA[1]) + nA;
+          const f2 sAA = (hAA[0] + hAA[1]) + nAA;
           const f2 aa2 = sA * sA;
-          const f2 vA = fma2(bc2(9.0f), sAA, neg2(aa2));     // 81 sigma_y
+          const f2 vA = fma2(aa2, bc2(-1.0f), sAA * bc2(9.0f));    // 81 sigma_y
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            if (k < ncand) {
-              f2 a = acc[k][o];
-              if (use_ssim) {
-                const f2 sX = hX[k][0] + hX[k][1] + nX[k];
-                const f2 sXX = hXX[k][0] + hXX[k][1] + nXX[k];
-                const f2 sXA = hXA[k][0] + hXA[k][1] + nXA[k];
-                // numerator and denominator are formed with mirrored operation orders so that
-                // X == A gives ssim == 1 exactly (identity candidate of identical frames is 0)
-                const f2 t = sX * sA, xx2 = sX * sX;
-                const f2 n1 = fma2(bc2(2.0f), t, C1);
-                const f2 n2 = fma2(bc2(2.0f), fma2(bc2(9.0f), sXA, neg2(t)), C2);
-                const f2 d1 = (xx2 + aa2) + C1;
-                const f2 d2 = (fma2(bc2(9.0f), sXX, neg2(xx2)) + vA) + C2;
-                const f2 ssim = div2(n1 * n2, d1 * d2);
-                a = fma2(sat2(fma2(ssim, bc2(-0.5f), bc2(0.5f))), wS, a);
-              }
-              acc[k][o] = fma2(l1p[k], wL, a);
+          for (int k = 0; k < NC; ++k) {
+            f2 a2 = acc[k][o];
+            if (use_ssim) {
+              const f2 sX = (hX[k][0] + hX[k][1]) + nX[k];
+              const f2 sXX = (hXX[k][0] + hXX[k][1]) + nXX[k];
+              const f2 sXA = (hXA[k][0] + hXA[k][1]) + nXA[k];
+              const f2 t = sX * sA, xs = sX * sX;
+              const f2 n1 = fma2(bc2(2.0f), t, C1);
+              const f2 n2 = fma2(bc2(2.0f), fma2(t, bc2(-1.0f), sXA * bc2(9.0f)), C2);
+              const f2 d1 = (xs + aa2) + C1;
+              const f2 d2 = (fma2(xs, bc2(-1.0f), sXX * bc2(9.0f)) + vA) + C2;
+              const f2 ssim = div2(n1 * n2, d1 * d2);
+              // clamp((1 - ssim) / 2, 0, 1), ssim_loss.py:53
+              const f2 l = mk2(__saturatef(fmaf(lo(ssim), -0.5f, 0.5f)), __saturatef(fmaf(hi(ssim), -0.5f, 0.5f)));
+              a2 = fma2(l, bc2(wS), a2);
             }
+            acc[k][o] = mk2(fmaf(fabsf(lo(dXA[k])), wL, lo(a2)), fmaf(fabsf(hi(dXA[k])), wL, hi(a2)));
           }
         }
         hA[0] = hA[1]; hA[1] = nA;
         hAA[0] = hAA[1]; hAA[1] = nAA;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (k < ncand) {
-            hX[k][0] = hX[k][1]; hX[k][1] = nX[k];
-            hXX[k][0] = hXX[k][1]; hXX[k][1] = nXX[k];
-            hXA[k][0] = hXA[k][1]; hXA[k][1] = nXA[k];
-            l1p[k] = l1n[k];
-          }
+        for (int k = 0; k < NC; ++k) {
+          hX[k][0] = hX[k][1]; hX[k][1] = nX[k];
+          hXX[k][0] = hXX[k][1]; hXX[k][1] = nXX[k];
+          hXA[k][0] = hXA[k][1]; hXA[k][1] = nXA[k];
+          dXA[k] = dn[k];
         }
       }
     }
     // candidates of this source: 2j (warp), 2j+1 (identity) with automask, else j
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k < ncand) {
-        const int idx = automask ? 2 * j + k : j;
+    for (int k = 0; k < NC; ++k) {
+      const int idx = AUTOMASK ? 2 * j + k : j;
 #pragma unroll
-        for (int o = 0; o < kRowsPerWarp; ++o) {
-          if (reduce_mean) {
-            best[o] = best[o] + acc[k][o];
-          } else {
-            // strict '<' keeps the first index on ties; a NaN candidate sticks (torch.min propagates NaN)
-            const f2 v = acc[k][o];
-            if (v.x < best[o].x || v.x != v.x) { best[o].x = v.x; arg[o][0] = idx; }
-            if (v.y < best[o].y || v.y != v.y) { best[o].y = v.y; arg[o][1] = idx; }
-          }
+      for (int o = 0; o < kRowsPerWarp; ++o) {
+        const float v0 = lo(acc[k][o]), v1 = hi(acc[k][o]);
+        if (reduce_mean) {
+          best[o][0] += v0;
+          best[o][1] += v1;
+        } else {
+          // strict '<' keeps the first index on ties; a NaN candidate sticks (torch.min propagates NaN)
+          if (v0 < best[o][0] || v0 != v0) { best[o][0] = v0; arg[o][0] = idx; }
+          if (v1 < best[o][1] || v1 != v1) { best[o][1] = v1; arg[o][1] = idx; }
         }
       }
     }
@@ -201,32 +215,29 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
   for (int o = 0; o < kRowsPerWarp; ++o) {
     const int gy = tc.y0 + r0 + o;
     if (gy < h) {
-      if (gx0 < w) { rec += best[o].x; if (amap) amap[gy * w + gx0] = (uint8_t)arg[o][0]; }
-      if (gx0 + 1 < w) { rec += best[o].y; if (amap) amap[gy * w + gx0 + 1] = (uint8_t)arg[o][1]; }
+      if (gx0 < w) { rec += best[o][0]; if (amap) amap[gy * w + gx0] = (uint8_t)arg[o][0]; }
+      if (gx0 + 1 < w) { rec += best[o][1]; if (amap) amap[gy * w + gx0 + 1] = (uint8_t)arg[o][1]; }
     }
   }
   if (p.smooth_scale[s] > 0.0f) {
-    // plane coordinates of pixel (row o, first column): (r0 + o + 1, c0 + 1)
-    const float* pinv = planes + kPlInv * kPlane + (r0 + 1) * kHW + c0;
+    // this lane's pair sits at halo'd position (r0 + o + 1, c0 + 1 .. c0 + 2); its right neighbour is
+    // column c0 + 3 and the pair below is one row down (smoothness_loss.py:62-80)
+    const float* pinv = planes + kPlInv * kPlane + plane_index(r0 + 1, c0 + 1);
 #pragma unroll
     for (int o = 0; o < kRowsPerWarp; ++o) {
       const int gy = tc.y0 + r0 + o;
-      // columns c0+1, c0+2 (own pair), c0+3 (right neighbour of the second pixel)
-      const f2 lo = ld2(pinv + o * kHW), hi = ld2(pinv + o * kHW + 2);
-      const f2 dn = ld2(pinv + (o + 1) * kHW + 2);
-      const float i0 = lo.y, i1 = hi.x, i2 = hi.y;
-      const float below0 = pinv[(o + 1) * kHW + 1], below1 = dn.x;
-      float ex0 = 0.0f, ex1 = 0.0f, ey0 = 0.0f, ey1 = 0.0f;  // mean_c |dI|
+      const f2 ic = ld2(pinv + o * kPitch), ib = ld2(pinv + (o + 1) * kPitch);
+      const float i0 = lo(ic), i1 = hi(ic), i2 = pinv[o * kPitch + 2];
+      float ex0 = 0.0f, ex1 = 0.0f, ey0 = 0.0f, ey1 = 0.0f;  // sum_c |dI|
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float* pa = planes + (kPlA + c) * kPlane + (r0 + 1 + o) * kHW + c0;
-        const f2 alo = ld2(pa), ahi = ld2(pa + 2);
-        const f2 adn = ld2(pa + kHW + 2);
-        const float a0 = alo.y, a1 = ahi.x, a2 = ahi.y;
+        const float* pa = planes + (kPlA + c) * kPlane + plane_index(r0 + 1 + o, c0 + 1);
+        const f2 ac = ld2(pa), ab = ld2(pa + kPitch);
+        const float a0 = lo(ac), a1 = hi(ac), a2 = pa[2];
         ex0 += fabsf(a0 - a1);
         ex1 += fabsf(a1 - a2);
-        ey0 += fabsf(a0 - pa[kHW + 1]);
-        ey1 += fabsf(a1 - adn.x);
+        ey0 += fabsf(a0 - lo(ab));
+        ey1 += fabsf(a1 - hi(ab));
       }
       if (gy < h) {
         const bool v0 = gx0 < w, v1 = gx0 + 1 < w, v2 = gx0 + 2 < w, vy = gy + 1 < h;
@@ -234,8 +245,8 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
         if (v1) sinv += i1;
         if (v1) smx += fabsf(i0 - i1) * expf(-ex0 * (1.0f / 3.0f));
         if (v2) smx += fabsf(i1 - i2) * expf(-ex1 * (1.0f / 3.0f));
-        if (v0 && vy) smy += fabsf(i0 - below0) * expf(-ey0 * (1.0f / 3.0f));
-        if (v1 && vy) smy += fabsf(i1 - below1) * expf(-ey1 * (1.0f / 3.0f));
+        if (v0 && vy) smy += fabsf(i0 - lo(ib)) * expf(-ey0 * (1.0f / 3.0f));
+        if (v1 && vy) smy += fabsf(i1 - hi(ib)) * expf(-ey1 * (1.0f / 3.0f));
       }
     }
   }
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
       for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
     if (lane == 0) {
       const double qh = p.h[qs], qw = p.w[qs], nB = p.B;
-      const int ncand = (automask ? 2 : 1) * p.S;
+      const int ncand = NC * p.S;
       double rec_q = a[0] / (nB * qh * qw) / p.n_scales;
       if (reduce_mean) rec_q /= ncand;
       const double mbar = fmax(a[3] / (qh * qw), 1e-6);
@@ -300,8 +311,12 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
 size_t mono_fwd_smem_bytes() { return (size_t)kFwdPlanes * kPlane * sizeof(float); }
 
 cudaError_t launch_mono_fwd(const MonoParams& p, cudaStream_t stream) {
-  // 47.5 KB of dynamic shared memory: below the 48 KB default limit, no opt-in attribute needed
-  mono_fwd_kernel<<<p.tile_start[p.n_scales], kThreads, mono_fwd_smem_bytes(), stream>>>(p);
+  const bool automask = (p.flags & SDE_MONO_AUTOMASK) != 0;
+  auto kernel = automask ? mono_fwd_kernel<true> : mono_fwd_kernel<false>;
+  // 48.9 KB of dynamic shared memory needs the opt-in attribute (per device; cheap and idempotent)
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mono_fwd_smem_bytes());
+  if (e != cudaSuccess) return e;
+  kernel<<<p.tile_start[p.n_scales], kThreads, mono_fwd_smem_bytes(), stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -12,60 +12,61 @@ namespace sde {
 // (PTX *.f32x2 -> SASS FADD2/FMUL2/FFMA2, with free LO/HI swizzles); every kernel here maps two
 // horizontally adjacent pixels onto one f2 so the SSIM arithmetic costs half the issue slots.
 // ---------------------------------------------------------------------------------------------
+// An f2 lives in one 64-bit register pair from load to store, so no repacking MOVs are needed.
 struct f2 {
-  float x, y;
+  unsigned long long v;
 };
 
-__device__ __forceinline__ unsigned long long f2_pack(f2 a) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a.x), "f"(a.y));
-  return r;
-}
-__device__ __forceinline__ f2 f2_unpack(unsigned long long r) {
-  f2 a;
-  asm("mov.b64 {%0,%1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
-  return a;
-}
 __device__ __forceinline__ f2 mk2(float x, float y) {
   f2 r;
-  r.x = x;
-  r.y = y;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r.v) : "f"(x), "f"(y));
   return r;
 }
+__device__ __forceinline__ float lo(f2 a) {
+  float x, y;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+  return x;
+}
+__device__ __forceinline__ float hi(f2 a) {
+  float x, y;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+  return y;
+}
 __device__ __forceinline__ f2 bc2(float v) { return mk2(v, v); }
-__device__ __forceinline__ f2 swp(f2 a) { return mk2(a.y, a.x); }
+__device__ __forceinline__ f2 swp(f2 a) { return mk2(hi(a), lo(a)); }   // folds into a LO_HI operand swizzle
 __device__ __forceinline__ f2 operator+(f2 a, f2 b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
-  return f2_unpack(r);
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
 }
 __device__ __forceinline__ f2 operator*(f2 a, f2 b) {
-  unsigned long long r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
-  return f2_unpack(r);
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
 }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-  unsigned long long r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
-  return f2_unpack(r);
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
 }
+// a - b as fma(b, -1, a): one FFMA2 with an immediate
 __device__ __forceinline__ f2 operator-(f2 a, f2 b) { return fma2(b, bc2(-1.0f), a); }
-__device__ __forceinline__ f2 neg2(f2 a) { return mk2(-a.x, -a.y); }
-__device__ __forceinline__ f2 abs2(f2 a) { return mk2(fabsf(a.x), fabsf(a.y)); }
-__device__ __forceinline__ f2 sat2(f2 a) { return mk2(__saturatef(a.x), __saturatef(a.y)); }
-// a / b with the fast reciprocal (2 ulp); operands here are O(1e-8 .. 10), far from the
-// 2^126 range where __fdividef degrades.
-__device__ __forceinline__ f2 fdiv2(f2 a, f2 b) { return mk2(__fdividef(a.x, b.x), __fdividef(a.y, b.y)); }
 // a / b: hardware reciprocal plus one Newton correction on the quotient (two packed FMAs).
 // Within 1 ulp of the IEEE quotient and exactly 1 when a == b.
-__device__ __forceinline__ f2 div2(f2 a, f2 b) {
-  const f2 r = mk2(__frcp_rn(b.x), __frcp_rn(b.y));
-  const f2 q = a * r;
-  return fma2(r, fma2(neg2(q), b, a), q);
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
-__device__ __forceinline__ f2 ld2(const float* p) {
-  float2 v = *reinterpret_cast<const float2*>(p);
-  return mk2(v.x, v.y);
+__device__ __forceinline__ f2 div2(f2 a, f2 b) {
+  const f2 r = mk2(rcp_approx(lo(b)), rcp_approx(hi(b)));
+  const f2 q = a * r;
+  return fma2(r, fma2(q * bc2(-1.0f), b, a), q);
+}
+__device__ __forceinline__ f2 ld2(const float* p) {   // 8-byte aligned
+  f2 r;
+  r.v = *reinterpret_cast<const unsigned long long*>(p);
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------------
