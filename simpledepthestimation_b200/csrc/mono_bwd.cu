@@ -25,8 +25,11 @@
 
 namespace sde {
 
-constexpr int kBwdPlanes = 13;  // A[3], S[3], 1/d, coef a/b/c, gS[3]
-constexpr int kBA = 0, kBS = 3, kBInv = 6, kBCoef = 7, kBG = 10;
+constexpr int kBwdPlanes = 13;  // A[3], S[3], depth, coef a/b/c, gS[3]
+constexpr int kBA = 0, kBS = 3, kBD = 6, kBCoef = 7, kBG = 10;
+#ifndef SDE_NB
+#define SDE_NB 2
+#endif
 constexpr int kPosPerThread = (kBwdW * kBwdH + kThreads - 1) / kThreads;  // 7
 
 struct BwdShared {
@@ -66,8 +69,6 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
 
   const float* __restrict__ depth = p.depth[s] + (size_t)b * hw;
   const float* __restrict__ tg0 = p.target[s] + (size_t)b * 3 * hw;
-  const float* __restrict__ tg1 = tg0 + hw;
-  const float* __restrict__ tg2 = tg1 + hw;
   const uint8_t* __restrict__ amap = reduce_mean ? nullptr : p.argmin[s] + (size_t)b * hw;
 
   const float g_rec = __ldg(p.grad_losses), g_smooth = __ldg(p.grad_losses + 1);
@@ -91,6 +92,15 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
 #pragma unroll
   for (int k = 0; k < kPosPerThread; ++k) gd[k] = 0.0f;
 
+  StageArgs sa;
+  sa.depth = depth; sa.src = nullptr; sa.tgt = tg0; sa.amap = amap;
+  sa.planes = planes; sa.arg = sh.arg; sa.oy = oy; sa.ox = ox; sa.h = h; sa.w = w; sa.hw = hw;
+  sa.plS = kBS; sa.plI = 0; sa.plA = kBA; sa.plD = kBD;
+  // ------------------------------------------------------------------ phase 0: depth + target + argmin
+  if (interior) stage_target<true, true>(sa, tid, reduce_mean);
+  else          stage_target<false, true>(sa, tid, reduce_mean);
+  __syncthreads();
+
   for (int j = 0; j < p.S; ++j) {
     const int cand = automask ? 2 * j : j;
     const Cam cam = sh.cam;
@@ -99,40 +109,9 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     const float* __restrict__ sc1 = sc0 + hw;
     const float* __restrict__ sc2 = sc1 + hw;
     // ---------------------------------------------------------------- phase 1
-    {
-      int yy = tid / kHW, xx = tid - yy * kHW;
-      for (int i = tid; i < kPositions; i += kThreads) {
-        const int ty = oy + yy, tx = ox + xx;
-        int gy = ty, gx = tx;
-        if (!interior) {
-          gy = reflect_clamp(ty, h);
-          gx = reflect_clamp(tx, w);
-        }
-        const int pix = gy * w + gx;
-        const float d = __ldg(depth + pix);
-        float P[3], den, X, Y;
-        project_full(cam, pj, (float)gx, (float)gy, d, P, den, X, Y);
-        const Cell cell = bilinear_cell(X, Y, w, h);
-        const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
-        const float w00 = bx * by, w01 = cell.ax * by, w10 = bx * cell.ay, w11 = cell.ax * cell.ay;
-        float* dst = planes + plane_index(yy, xx);
-        dst[(kBS + 0) * kPlane] = tap4(sc0, cell.off, w, w00, w01, w10, w11);
-        dst[(kBS + 1) * kPlane] = tap4(sc1, cell.off, w, w00, w01, w10, w11);
-        dst[(kBS + 2) * kPlane] = tap4(sc2, cell.off, w, w00, w01, w10, w11);
-        if (j == 0) {
-          dst[(kBA + 0) * kPlane] = __ldg(tg0 + pix);
-          dst[(kBA + 1) * kPlane] = __ldg(tg1 + pix);
-          dst[(kBA + 2) * kPlane] = __ldg(tg2 + pix);
-          dst[kBInv * kPlane] = 1.0f / (d < 1e-6f ? 1e-6f : d);  // clamp(min=1e-6) keeps NaN, as torch.clamp does
-          const bool inside = ty >= 0 && ty < h && tx >= 0 && tx < w;
-          // 255 never matches a candidate: windows centred outside the image do not exist
-          sh.arg[plane_index(yy, xx)] = inside ? (reduce_mean ? (uint8_t)254 : amap[pix]) : (uint8_t)255;
-        }
-        xx += kThreads - kHW;
-        yy += 1;
-        if (xx >= kHW) { xx -= kHW; yy += 1; }
-      }
-    }
+    sa.src = sc0;
+    if (interior) stage_source<true, false, SDE_NB>(sa, cam, pj, tid);
+    else          stage_source<false, false, SDE_NB>(sa, cam, pj, tid);
     __syncthreads();
 
 #pragma unroll 1
@@ -254,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
           const float g0 = planes[kBG * kPlane + pl], g1 = planes[(kBG + 1) * kPlane + pl],
                       g2 = planes[(kBG + 2) * kPlane + pl];
           if (g0 != 0.0f || g1 != 0.0f || g2 != 0.0f) {
-            const float d = __ldg(depth + gy * w + gx);
+            const float d = planes[kBD * kPlane + pl];
             const float fxp = (float)gx, fyp = (float)gy;
             float P[3], den, X, Y;
             project_full(cam, pj, fxp, fyp, d, P, den, X, Y);
@@ -334,8 +313,10 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
         float g = gd[it];
         if (sscale > 0.0f) {
           const int pl = plane_index(ly + 2, lx + 2);
-          const float* pi = planes + kBInv * kPlane + pl;
-          const float ic = pi[0];
+          const float* pd = planes + kBD * kPlane + pl;
+          auto inv = [](float d) { return 1.0f / (d < 1e-6f ? 1e-6f : d); };   // NaN-preserving clamp(min=1e-6)
+          const float d = pd[0];
+          const float ic = inv(d);
           float el = 0.0f, er = 0.0f, eu = 0.0f, edn = 0.0f;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -346,11 +327,10 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
           }
           float G = 0.0f;
           auto sgn = [](float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); };
-          if (gx + 1 < w) G += sgn(ic - pi[1]) * expf(-er * (1.0f / 3.0f)) * inx;
-          if (gx >= 1) G -= sgn(pi[-1] - ic) * expf(-el * (1.0f / 3.0f)) * inx;
-          if (gy + 1 < h) G += sgn(ic - pi[kPitch]) * expf(-edn * (1.0f / 3.0f)) * iny;
-          if (gy >= 1) G -= sgn(pi[-kPitch] - ic) * expf(-eu * (1.0f / 3.0f)) * iny;
-          const float d = __ldg(depth + gy * w + gx);
+          if (gx + 1 < w) G += sgn(ic - inv(pd[1])) * expf(-er * (1.0f / 3.0f)) * inx;
+          if (gx >= 1) G -= sgn(inv(pd[-1]) - ic) * expf(-el * (1.0f / 3.0f)) * inx;
+          if (gy + 1 < h) G += sgn(ic - inv(pd[kPitch])) * expf(-edn * (1.0f / 3.0f)) * iny;
+          if (gy >= 1) G -= sgn(inv(pd[-kPitch]) - ic) * expf(-eu * (1.0f / 3.0f)) * iny;
           const float g_inv = G / mbar - homog;
           if (d >= 1e-6f) g += -ic * ic * g_inv * (g_smooth * sscale);
         }

@@ -78,12 +78,143 @@ __device__ __forceinline__ Cell bilinear_cell(float X, float Y, int w, int h) {
   return c;
 }
 
-// one channel: sum of the four taps in ATen's order (nw, ne, sw, se)
-__device__ __forceinline__ float tap4(const float* __restrict__ pl, int off, int w, float w00, float w01, float w10,
-                                      float w11) {
-  const float* r0 = pl + off;
-  const float* r1 = r0 + w;
-  return __ldg(r0) * w00 + __ldg(r0 + 1) * w01 + __ldg(r1) * w10 + __ldg(r1 + 1) * w11;
+// Everything phase 1 needs about one (tile, source): where the halo'd tile sits, which planes
+// receive what.
+struct StageArgs {
+  const float* __restrict__ depth;   // [h*w] of this sample
+  const float* __restrict__ src;     // [3*h*w] source frame of this sample
+  const float* __restrict__ tgt;     // [3*h*w] target frame of this sample
+  const uint8_t* __restrict__ amap;  // [h*w] argmin bytes (backward) or nullptr
+  float* planes;                     // shared-memory plane array
+  uint8_t* arg;                      // shared-memory argmin plane (backward)
+  int oy, ox;                        // image coordinates of plane position (0, 0)
+  int h, w, hw;
+  int plS, plI, plA, plD;            // plane numbers: warped, identity, target, depth
+};
+
+// Pins a base pointer in a register pair so that every access is one IMAD.WIDE (index * 4 + base)
+// instead of a re-derived 64-bit sum of the sample / plane / pixel offsets.
+template <typename T>
+__device__ __forceinline__ const T* pinned(const T* p) {
+  unsigned long long v = reinterpret_cast<unsigned long long>(p);
+  asm volatile("" : "+l"(v));
+  return reinterpret_cast<const T*>(v);
+}
+
+__device__ __forceinline__ void position_of(int i, int& yy, int& xx) {
+  yy = (i * 993) >> 16;  // i / 66 for i < 1188
+  xx = i - yy * kHW;
+}
+
+template <bool INTERIOR>
+__device__ __forceinline__ int pixel_of(const StageArgs& a, int yy, int xx, int& gy, int& gx) {
+  gy = a.oy + yy;
+  gx = a.ox + xx;
+  if (!INTERIOR) {
+    gy = reflect_clamp(gy, a.h);
+    gx = reflect_clamp(gx, a.w);
+  }
+  return gy * a.w + gx;
+}
+
+// Phase 0 of both kernels: stage what does not depend on the source -- depth, target (and the
+// argmin bytes in the backward kernel) of the halo'd tile.  All loads are independent and issued
+// before the first store, so the tile pays one memory round trip here.
+template <bool INTERIOR, bool ARG>
+__device__ __forceinline__ void stage_target(const StageArgs& a0, int tid, bool reduce_mean) {
+  StageArgs a = a0;
+  a.depth = pinned(a0.depth);
+  a.tgt = pinned(a0.tgt);
+  constexpr int kIter = (kPositions + kThreads - 1) / kThreads;  // 10
+#pragma unroll 2
+  for (int k = 0; k < kIter; k += 2) {
+    float d[2], t[2][3];
+    uint8_t m[2];
+    int pl[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = tid + (k + u) * kThreads;
+      ok[u] = i < kPositions;
+      int yy, xx, gy, gx;
+      position_of(ok[u] ? i : tid, yy, xx);
+      const int pix = pixel_of<INTERIOR>(a, yy, xx, gy, gx);
+      pl[u] = plane_index(yy, xx);
+      d[u] = __ldg(a.depth + pix);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) t[u][c] = __ldg(a.tgt + (pix + c * a.hw));
+      if (ARG) {
+        const int ty = a.oy + yy, tx = a.ox + xx;
+        const bool inside = ty >= 0 && ty < a.h && tx >= 0 && tx < a.w;
+        // 255 never matches a candidate: windows centred outside the image do not exist
+        m[u] = inside ? (reduce_mean ? (uint8_t)254 : a.amap[pix]) : (uint8_t)255;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (ok[u]) {
+        a.planes[a.plD * kPlane + pl[u]] = d[u];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a.planes[(a.plA + c) * kPlane + pl[u]] = t[u][c];
+        if (ARG) a.arg[pl[u]] = m[u];
+      }
+    }
+  }
+}
+
+// Phase 1 of both kernels: project every staged position into one source (depth comes from shared
+// memory), gather its four bilinear taps per channel and store the warped value; NB positions per
+// thread are in flight at a time (12 NB independent gather loads).
+//   IDENT: also stage the unwarped source (identity / automask candidate)
+template <bool INTERIOR, bool IDENT, int NB>
+__device__ __forceinline__ void stage_source(const StageArgs& a0, const Cam& cam, const Proj& pj, int tid) {
+  StageArgs a = a0;
+  a.src = pinned(a0.src);
+  const int w = a.w, hw = a.hw;
+#pragma unroll 1
+  for (int base = tid; base < kPositions; base += NB * kThreads) {
+    int pl[NB], off[NB], pix[NB];
+    float w00[NB], w01[NB], w10[NB], w11[NB];
+    bool ok[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int i = base + u * kThreads;
+      ok[u] = i < kPositions;
+      int yy, xx, gy, gx;
+      position_of(ok[u] ? i : base, yy, xx);
+      pix[u] = pixel_of<INTERIOR>(a, yy, xx, gy, gx);
+      pl[u] = plane_index(yy, xx);
+      const float d = a.planes[a.plD * kPlane + pl[u]];
+      float P[3], den, X, Y;
+      project_full(cam, pj, (float)gx, (float)gy, d, P, den, X, Y);
+      const Cell cell = bilinear_cell(X, Y, w, a.h);
+      const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
+      off[u] = cell.off;
+      w00[u] = bx * by; w01[u] = cell.ax * by; w10[u] = bx * cell.ay; w11[u] = cell.ax * cell.ay;
+    }
+    float v[NB][3], id[NB][3];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* q = a.src + (off[u] + c * hw);
+        const float t00 = __ldg(q), t01 = __ldg(q + 1), t10 = __ldg(q + w), t11 = __ldg(q + w + 1);
+        if (IDENT) id[u][c] = __ldg(a.src + (pix[u] + c * hw));
+        // ATen's accumulation order: nw, ne, sw, se
+        v[u][c] = t00 * w00[u] + t01 * w01[u] + t10 * w10[u] + t11 * w11[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      if (ok[u]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          a.planes[(a.plS + c) * kPlane + pl[u]] = v[u][c];
+          if (IDENT) a.planes[(a.plI + c) * kPlane + pl[u]] = id[u][c];
+        }
+      }
+    }
+  }
 }
 
 }  // namespace sde

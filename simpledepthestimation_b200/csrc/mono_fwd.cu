@@ -19,10 +19,20 @@
 // (deterministic, no float atomics) and writes rec_loss / smooth_loss.
 #include "mono_device.cuh"
 
+#ifndef SDE_FWD_OCC
+#define SDE_FWD_OCC 4
+#endif
+#ifndef SDE_FWD_CARVEOUT
+#define SDE_FWD_CARVEOUT -1
+#endif
+
 namespace sde {
 
-constexpr int kFwdPlanes = 10;      // A[3], S[3], I[3], 1/d
-constexpr int kPlA = 0, kPlS = 3, kPlI = 6, kPlInv = 9;
+constexpr int kFwdPlanes = 10;      // A[3], S[3], I[3], depth
+constexpr int kPlA = 0, kPlS = 3, kPlI = 6, kPlD = 9;
+#ifndef SDE_NB
+#define SDE_NB 2
+#endif
 
 struct FwdShared {
   Cam cam;
@@ -32,7 +42,7 @@ struct FwdShared {
 };
 
 template <bool AUTOMASK>
-__global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_constant__ MonoParams p) {
+__global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const __grid_constant__ MonoParams p) {
   extern __shared__ __align__(16) float planes[];  // [kFwdPlanes][kPlane]
   __shared__ FwdShared sh;
   constexpr int NC = AUTOMASK ? 2 : 1;             // candidates per source: warp [+ identity]
@@ -53,8 +63,6 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
 
   const float* __restrict__ depth = p.depth[s] + (size_t)b * hw;
   const float* __restrict__ tg0 = p.target[s] + (size_t)b * 3 * hw;
-  const float* __restrict__ tg1 = tg0 + hw;
-  const float* __restrict__ tg2 = tg1 + hw;
   // tiles whose halo lies inside the image need no reflection / clamping of the staged positions
   const bool interior = tc.x0 >= 1 && tc.y0 >= 1 && tc.x0 + kTileW + 1 <= w && tc.y0 + kTileH + 1 <= h;
 
@@ -73,48 +81,23 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
     arg[o][0] = arg[o][1] = 0;
   }
 
+  StageArgs sa;
+  sa.depth = depth; sa.src = nullptr; sa.tgt = tg0; sa.amap = nullptr;
+  sa.planes = planes; sa.arg = nullptr; sa.oy = tc.y0 - 1; sa.ox = tc.x0 - 1; sa.h = h; sa.w = w; sa.hw = hw;
+  sa.plS = kPlS; sa.plI = kPlI; sa.plA = kPlA; sa.plD = kPlD;
+  // ------------------------------------------------------------------ phase 0: depth + target
+  if (interior) stage_target<true, false>(sa, tid, false);
+  else          stage_target<false, false>(sa, tid, false);
+  __syncthreads();
+
   for (int j = 0; j < p.S; ++j) {
     // ---------------------------------------------------------------- phase 1
     {
       const Cam cam = sh.cam;
       const Proj pj = sh.proj[j];
-      const float* __restrict__ sc0 = p.source[s][j] + (size_t)b * 3 * hw;
-      const float* __restrict__ sc1 = sc0 + hw;
-      const float* __restrict__ sc2 = sc1 + hw;
-      int yy = tid / kHW, xx = tid - yy * kHW;
-      for (int i = tid; i < kPositions; i += kThreads) {
-        int gy = tc.y0 - 1 + yy, gx = tc.x0 - 1 + xx;
-        if (!interior) {
-          gy = reflect_clamp(gy, h);
-          gx = reflect_clamp(gx, w);
-        }
-        const int pix = gy * w + gx;
-        const float d = __ldg(depth + pix);
-        float P[3], den, X, Y;
-        project_full(cam, pj, (float)gx, (float)gy, d, P, den, X, Y);
-        const Cell cell = bilinear_cell(X, Y, w, h);
-        const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
-        const float w00 = bx * by, w01 = cell.ax * by, w10 = bx * cell.ay, w11 = cell.ax * cell.ay;
-        float* dst = planes + plane_index(yy, xx);
-        dst[(kPlS + 0) * kPlane] = tap4(sc0, cell.off, w, w00, w01, w10, w11);
-        dst[(kPlS + 1) * kPlane] = tap4(sc1, cell.off, w, w00, w01, w10, w11);
-        dst[(kPlS + 2) * kPlane] = tap4(sc2, cell.off, w, w00, w01, w10, w11);
-        if (AUTOMASK) {
-          dst[(kPlI + 0) * kPlane] = __ldg(sc0 + pix);
-          dst[(kPlI + 1) * kPlane] = __ldg(sc1 + pix);
-          dst[(kPlI + 2) * kPlane] = __ldg(sc2 + pix);
-        }
-        if (j == 0) {
-          dst[(kPlA + 0) * kPlane] = __ldg(tg0 + pix);
-          dst[(kPlA + 1) * kPlane] = __ldg(tg1 + pix);
-          dst[(kPlA + 2) * kPlane] = __ldg(tg2 + pix);
-          dst[kPlInv * kPlane] = 1.0f / (d < 1e-6f ? 1e-6f : d);  // clamp(min=1e-6) keeps NaN, as torch.clamp does
-        }
-        // next position: i + 128 = one row down and 62 columns right (mod 66)
-        xx += kThreads - kHW;
-        yy += 1;
-        if (xx >= kHW) { xx -= kHW; yy += 1; }
-      }
+      sa.src = p.source[s][j] + (size_t)b * 3 * hw;
+      if (interior) stage_source<true, AUTOMASK, SDE_NB>(sa, cam, pj, tid);
+      else          stage_source<false, AUTOMASK, SDE_NB>(sa, cam, pj, tid);
     }
     __syncthreads();
 
@@ -222,12 +205,15 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
   if (p.smooth_scale[s] > 0.0f) {
     // this lane's pair sits at halo'd position (r0 + o + 1, c0 + 1 .. c0 + 2); its right neighbour is
     // column c0 + 3 and the pair below is one row down (smoothness_loss.py:62-80)
-    const float* pinv = planes + kPlInv * kPlane + plane_index(r0 + 1, c0 + 1);
+    const float* pd = planes + kPlD * kPlane + plane_index(r0 + 1, c0 + 1);
+    // 1 / clamp(d, min=1e-6); the comparison form keeps a NaN depth NaN, as torch.clamp does
+    auto inv = [](float d) { return 1.0f / (d < 1e-6f ? 1e-6f : d); };
 #pragma unroll
     for (int o = 0; o < kRowsPerWarp; ++o) {
       const int gy = tc.y0 + r0 + o;
-      const f2 ic = ld2(pinv + o * kPitch), ib = ld2(pinv + (o + 1) * kPitch);
-      const float i0 = lo(ic), i1 = hi(ic), i2 = pinv[o * kPitch + 2];
+      const f2 dc = ld2(pd + o * kPitch), db = ld2(pd + (o + 1) * kPitch);
+      const float i0 = inv(lo(dc)), i1 = inv(hi(dc)), i2 = inv(pd[o * kPitch + 2]);
+      const float ib0 = inv(lo(db)), ib1 = inv(hi(db));
       float ex0 = 0.0f, ex1 = 0.0f, ey0 = 0.0f, ey1 = 0.0f;  // sum_c |dI|
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -245,8 +231,8 @@ __global__ void __launch_bounds__(kThreads, 4) mono_fwd_kernel(const __grid_cons
         if (v1) sinv += i1;
         if (v1) smx += fabsf(i0 - i1) * expf(-ex0 * (1.0f / 3.0f));
         if (v2) smx += fabsf(i1 - i2) * expf(-ex1 * (1.0f / 3.0f));
-        if (v0 && vy) smy += fabsf(i0 - lo(ib)) * expf(-ey0 * (1.0f / 3.0f));
-        if (v1 && vy) smy += fabsf(i1 - hi(ib)) * expf(-ey1 * (1.0f / 3.0f));
+        if (v0 && vy) smy += fabsf(i0 - ib0) * expf(-ey0 * (1.0f / 3.0f));
+        if (v1 && vy) smy += fabsf(i1 - ib1) * expf(-ey1 * (1.0f / 3.0f));
       }
     }
   }
@@ -316,6 +302,7 @@ cudaError_t launch_mono_fwd(const MonoParams& p, cudaStream_t stream) {
   // 48.9 KB of dynamic shared memory needs the opt-in attribute (per device; cheap and idempotent)
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mono_fwd_smem_bytes());
   if (e != cudaSuccess) return e;
+  if (SDE_FWD_CARVEOUT >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, SDE_FWD_CARVEOUT);
   kernel<<<p.tile_start[p.n_scales], kThreads, mono_fwd_smem_bytes(), stream>>>(p);
   return cudaGetLastError();
 }
