@@ -189,14 +189,15 @@ def run_ours(args):
     losses = [torch.empty(2, device=dev) for _ in range(nsets)]
     gd = [[torch.empty_like(d) for d in s[2]] for s in sets]
     gp = [[torch.empty_like(p) for p in s[4]] for s in sets]
-    argm = [plan.forward(*s, out=losses[k])[1] for k, s in enumerate(sets)]
+    warped = [plan.new_warped() for _ in sets]
+    argm = [plan.forward(*s, out=losses[k], warped=warped[k])[1] for k, s in enumerate(sets)]
     loss_sum = torch.zeros(2, device=dev)
     side = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def step(i):
         k = i % nsets
-        plan.forward(*sets[k], out=losses[k], argmin_out=argm[k])
-        plan.backward(*sets[k], argm[k], ones, gd[k], gp[k])
+        plan.forward(*sets[k], out=losses[k], argmin_out=argm[k], warped=warped[k])
+        plan.backward(*sets[k], argm[k], ones, gd[k], gp[k], warped=warped[k])
         if world > 1:
             # the loss scalars are logging-only in the reference (comm.reduce_dict, train.py:95): reduce them
             # asynchronously on a side stream so the 8-byte collective never stalls the compute stream
@@ -243,10 +244,10 @@ def run_ours(args):
     value = world * warped_px / (ms_step * 1e-3) / 1e6
 
     # per-kernel durations (CUDA events on the launching stream) for the roofline of the dominant kernel
-    ms_fwd = timed(lambda i: plan.forward(*sets[i % nsets], out=losses[i % nsets], argmin_out=argm[i % nsets]),
-                   args.steps, 3)
-    ms_bwd = timed(lambda i: plan.backward(*sets[i % nsets], argm[i % nsets], ones, gd[i % nsets], gp[i % nsets]),
-                   args.steps, 3)
+    ms_fwd = timed(lambda i: plan.forward(*sets[i % nsets], out=losses[i % nsets], argmin_out=argm[i % nsets],
+                                          warped=warped[i % nsets]), args.steps, 3)
+    ms_bwd = timed(lambda i: plan.backward(*sets[i % nsets], argm[i % nsets], ones, gd[i % nsets], gp[i % nsets],
+                                           warped=warped[i % nsets]), args.steps, 3)
     peak, peak_src = peaks()
     dom = "mono_bwd_kernel" if ms_bwd >= ms_fwd else "mono_fwd_kernel"
     dom_bytes = target_px * (BYTES_BWD_PER_TARGET_PX if dom == "mono_bwd_kernel" else BYTES_FWD_PER_TARGET_PX)

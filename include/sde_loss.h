@@ -83,6 +83,10 @@ typedef struct sde_mono_buffers {
   float* losses;                      /* [2]: rec_loss, smooth_loss */
   uint8_t* argmin[SDE_MAX_SCALES];    /* [B,h_i,w_i] winning candidate index (warp0,ident0,warp1,ident1..) */
   float* saved_stats;                 /* [n_scales*B*2] per-image (mean inverse depth, smoothness) for backward */
+  /* optional, forward output / backward input: the warped sources [B,3,h_i,w_i].  When given, the
+   * backward kernel reads them instead of re-gathering (trades 24 B/pixel/source of HBM traffic,
+   * which this path has to spare, for the dominant gather cost).  NULL = recompute the warp. */
+  float* warped[SDE_MAX_SCALES][SDE_MAX_SOURCES];
   /* backward inputs / outputs */
   const float* grad_losses;           /* [2] upstream d/d rec_loss, d/d smooth_loss (device) */
   float* grad_depth[SDE_MAX_SCALES];  /* [B,1,h_i,w_i] */

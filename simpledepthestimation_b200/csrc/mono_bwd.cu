@@ -110,8 +110,14 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     const float* __restrict__ sc2 = sc1 + hw;
     // ---------------------------------------------------------------- phase 1
     sa.src = sc0;
-    if (interior) stage_source<true, false, SDE_NB>(sa, cam, pj, tid);
-    else          stage_source<false, false, SDE_NB>(sa, cam, pj, tid);
+    if (p.warped[s][j] != nullptr) {
+      const float* wsrc = p.warped[s][j] + (size_t)b * 3 * hw;
+      if (interior) stage_saved<true>(sa, wsrc, tid);
+      else          stage_saved<false>(sa, wsrc, tid);
+    } else {
+      if (interior) stage_source<true, false, SDE_NB>(sa, cam, pj, tid);
+      else          stage_source<false, false, SDE_NB>(sa, cam, pj, tid);
+    }
     __syncthreads();
 
 #pragma unroll 1

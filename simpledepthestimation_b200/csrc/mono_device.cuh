@@ -217,4 +217,37 @@ __device__ __forceinline__ void stage_source(const StageArgs& a0, const Cam& cam
   }
 }
 
+// Phase 1 of the backward kernel when the forward pass kept the warped source: plain coalesced
+// loads of the halo'd tile (a reflected halo position takes the warp of the reflected pixel,
+// which is what re-projecting it would give).
+template <bool INTERIOR>
+__device__ __forceinline__ void stage_saved(const StageArgs& a0, const float* __restrict__ warped, int tid) {
+  StageArgs a = a0;
+  const float* wp = pinned(warped);
+  constexpr int kIter = (kPositions + kThreads - 1) / kThreads;  // 10
+#pragma unroll 2
+  for (int k = 0; k < kIter; k += 2) {
+    float v[2][3];
+    int pl[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = tid + (k + u) * kThreads;
+      ok[u] = i < kPositions;
+      int yy, xx, gy, gx;
+      position_of(ok[u] ? i : tid, yy, xx);
+      const int pix = pixel_of<INTERIOR>(a, yy, xx, gy, gx);
+      pl[u] = plane_index(yy, xx);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[u][c] = __ldg(wp + (pix + c * a.hw));
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (ok[u]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a.planes[(a.plS + c) * kPlane + pl[u]] = v[u][c];
+      }
+  }
+}
+
 }  // namespace sde

@@ -101,6 +101,28 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
     }
     __syncthreads();
 
+    // optional: keep the warped source for the backward pass (tile interior, coalesced pair stores)
+    if (p.warped[s][j] != nullptr) {
+      float* __restrict__ wout = p.warped[s][j] + (size_t)b * 3 * hw;
+      const int gxw = tc.x0 + c0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int o = 0; o < kRowsPerWarp; ++o) {
+          const int gy = tc.y0 + r0 + o;
+          if (gy < h && gxw < w) {
+            const float* ps = planes + (kPlS + c) * kPlane + plane_index(r0 + o + 1, c0 + 1);
+            float* po = wout + c * hw + gy * w + gxw;
+            if (gxw + 1 < w && (w & 1) == 0) {
+              *reinterpret_cast<float2*>(po) = *reinterpret_cast<const float2*>(ps);
+            } else {
+              po[0] = ps[0];
+              if (gxw + 1 < w) po[1] = ps[1];
+            }
+          }
+        }
+    }
+
     // ---------------------------------------------------------------- phase 2
     f2 acc[NC][kRowsPerWarp];
 #pragma unroll

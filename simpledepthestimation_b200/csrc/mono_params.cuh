@@ -25,6 +25,7 @@ struct MonoParams {
   const float* K;
   const float* pose[SDE_MAX_SOURCES];
   uint8_t* argmin[SDE_MAX_SCALES];
+  float* warped[SDE_MAX_SCALES][SDE_MAX_SOURCES];   // optional saved warps (nullptr = recompute)
   float* losses;
   float* stats;           // [n_scales*B][2] = (mean inverse depth, per-image smoothness)
   float ssim_w, l1_w, c1, c2;

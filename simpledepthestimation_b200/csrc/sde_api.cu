@@ -80,6 +80,7 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
     for (int j = 0; j < d->n_sources; ++j) {
       if (!b->source[i][j]) return SDE_ERR_INVALID_ARG;
       p.source[i][j] = b->source[i][j];
+      p.warped[i][j] = b->warped[i][j];
     }
     const double scale_w = 1.0 / (double)(1 << (d->n_scales - i - 1));
     p.smooth_scale[i] = d->smooth_weight > 0.0f ? (float)(scale_w * (double)d->smooth_weight / d->n_scales) : 0.0f;
@@ -107,6 +108,13 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
   p.partials = reinterpret_cast<float*>(ws + L.off_partials);
   p.pose_partials = reinterpret_cast<float*>(ws + L.off_pose);
   p.grad_losses = b->grad_losses;
+  // saved warps are all-or-nothing
+  {
+    int have = 0, total = 0;
+    for (int i = 0; i < d->n_scales; ++i)
+      for (int j = 0; j < d->n_sources; ++j) { ++total; have += b->warped[i][j] != nullptr; }
+    if (have != 0 && have != total) return SDE_ERR_INVALID_ARG;
+  }
   if (!backward) {
     if (!b->losses) return SDE_ERR_INVALID_ARG;
   } else {

@@ -37,7 +37,8 @@ class MonoLossPlan:
     """
 
     def __init__(self, batch: int, sizes: Sequence[Sequence[int]], n_sources: int, full_size: Sequence[int],
-                 device, ssim_weight=0.85, c1=1e-4, c2=9e-4, smooth_weight=1e-3, automask=True, reduce="min"):
+                 device, ssim_weight=0.85, c1=1e-4, c2=9e-4, smooth_weight=1e-3, automask=True, reduce="min",
+                 save_warped=False):
         if reduce not in ("min", "mean"):
             raise NotImplementedError(reduce)  # same as MonoDepth2.py:120-121
         if len(sizes) > _lib.MAX_SCALES or n_sources > _lib.MAX_SOURCES:
@@ -46,6 +47,8 @@ class MonoLossPlan:
         self.device = torch.device(device)
         self.batch, self.sizes, self.n_sources = batch, [tuple(s) for s in sizes], n_sources
         self.full_size = tuple(full_size)
+        # keep the warped sources from forward to backward (faster) or recompute them (leaner)
+        self.save_warped = bool(save_warped)
         d = _lib.MonoDesc()
         d.batch, d.n_scales, d.n_sources = batch, len(sizes), n_sources
         for i, (h, w) in enumerate(self.sizes):
@@ -93,10 +96,25 @@ class MonoLossPlan:
             if tuple(pose[j].shape) != (B, 4, 4):
                 raise _lib.SdeError("pose must be [B,4,4]")
 
-    def forward(self, target, source, depth, K, pose, want_argmin=True, out=None, argmin_out=None):
-        """Runs the forward kernel.  Returns (losses[2], argmin list).  All inputs contiguous fp32 CUDA."""
+    def new_warped(self):
+        """Buffers for the warped sources of one step ([scale][source] -> [B,3,h,w]), or None."""
+        if not self.save_warped:
+            return None
+        return [[torch.empty(self.batch, 3, h, w, dtype=torch.float32, device=self.device)
+                 for _ in range(self.n_sources)] for h, w in self.sizes]
+
+    def _set_warped(self, b, warped):
+        if warped is not None:
+            for i in range(len(self.sizes)):
+                for j in range(self.n_sources):
+                    b.warped[i][j] = warped[i][j].data_ptr()
+
+    def forward(self, target, source, depth, K, pose, want_argmin=True, out=None, argmin_out=None, warped=None):
+        """Runs the forward kernel.  Returns (losses[2], argmin list).  All inputs contiguous fp32 CUDA.
+        `warped` (from new_warped()) receives the warped sources for the backward pass."""
         self._check(target, source, depth, K, pose)
         b = self._buffers(target, source, depth, K, pose)
+        self._set_warped(b, warped)
         losses = out if out is not None else torch.empty(2, dtype=torch.float32, device=self.device)
         b.losses = losses.data_ptr()
         argmin = []
@@ -113,9 +131,12 @@ class MonoLossPlan:
         _lib.check(st, "sde_mono_loss_forward")
         return losses, argmin
 
-    def backward(self, target, source, depth, K, pose, argmin, grad_losses, grad_depth=None, grad_pose=None):
-        """Runs the backward kernel (recomputes the warp).  Returns (grad_depth list, grad_pose list)."""
+    def backward(self, target, source, depth, K, pose, argmin, grad_losses, grad_depth=None, grad_pose=None,
+                 warped=None):
+        """Runs the backward kernel (reads `warped` if given, else recomputes the warp).
+        Returns (grad_depth list, grad_pose list)."""
         b = self._buffers(target, source, depth, K, pose)
+        self._set_warped(b, warped)
         b.grad_losses = grad_losses.data_ptr()
         if grad_depth is None:
             grad_depth = [torch.empty_like(d) for d in depth]
@@ -141,8 +162,10 @@ class _MonoLossFn(torch.autograd.Function):
         target = [_contig(t) for t in rest[:n_scales]]
         source = [[_contig(rest[n_scales + i * n_sources + j]) for j in range(n_sources)] for i in range(n_scales)]
         K = _contig(K)
-        losses, argmin = plan.forward(target, source, depth, K, pose)
+        warped = plan.new_warped()
+        losses, argmin = plan.forward(target, source, depth, K, pose, warped=warped)
         ctx.plan, ctx.n_scales, ctx.n_sources = plan, n_scales, n_sources
+        ctx.warped = warped
         ctx.save_for_backward(K, *depth, *pose, *target, *[s for row in source for s in row], *argmin)
         ctx.stats = plan.stats.clone()  # the plan may be reused before backward runs
         for a in argmin:
@@ -163,7 +186,8 @@ class _MonoLossFn(torch.autograd.Function):
         zero = torch.zeros((), dtype=torch.float32, device=K.device)
         g = torch.stack([g_rec if g_rec is not None else zero, g_smooth if g_smooth is not None else zero]).float()
         plan.stats.copy_(ctx.stats)
-        grad_depth, grad_pose = plan.backward(target, source, depth, K, pose, argmin, g.contiguous())
+        grad_depth, grad_pose = plan.backward(target, source, depth, K, pose, argmin, g.contiguous(),
+                                              warped=ctx.warped)
         return (None, None, None, None, *grad_depth, *grad_pose, *([None] * (n + n * S)))
 
 
@@ -201,6 +225,7 @@ class HostLossRunner:
         self.grad_depth = [torch.empty_like(d) for d in self.depth]
         self.grad_pose = [torch.empty_like(p) for p in self.pose]
         self.ones = torch.ones(2, device=self.device)
+        self.warped = plan.new_warped()
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
         self.h_losses = pin(self.losses)
         self.h_grad_depth = [pin(t) for t in self.grad_depth]
@@ -231,9 +256,9 @@ class HostLossRunner:
         for d, h in zip(self.pose, pose):
             d.copy_(h, non_blocking=True)
         self.plan.forward(self.target, self.source, self.depth, self.K, self.pose, out=self.losses,
-                          argmin_out=self.argmin)
+                          argmin_out=self.argmin, warped=self.warped)
         self.plan.backward(self.target, self.source, self.depth, self.K, self.pose, self.argmin, self.ones,
-                           self.grad_depth, self.grad_pose)
+                           self.grad_depth, self.grad_pose, warped=self.warped)
         self.h_losses.copy_(self.losses, non_blocking=True)
         for h, d in zip(self.h_grad_depth, self.grad_depth):
             h.copy_(d, non_blocking=True)

@@ -146,6 +146,7 @@ def test_cfg2_batch_linearity_at_full_size(dev):
 # ------------------------------------------------------------------------------------------- edge cases
 def _against_oracle(inp, dev, loss_tol=LOSS_TOL, **kw):
     plan_kw = {k: v for k, v in kw.items()}
+    kw = {k: v for k, v in kw.items() if k != "save_warped"}
     port_kw = dict(automask=kw.get("automask", True), reduce=kw.get("reduce", "min"),
                    ssim_w=kw.get("ssim_weight", 0.85), smooth_w=kw.get("smooth_weight", 1e-3))
     out = gpu_mono_from_vec(inp, dev, **plan_kw)
@@ -238,6 +239,19 @@ def test_odd_sizes_single_scale(dev, shape):
     g, r = out["grad_depth"][0], ref["grad_depth"][0]
     err = (g.double() - r).abs() / r.abs().max()
     assert float(torch.quantile(err.flatten(), 0.99)) < GRAD_TOL
+
+
+def test_recompute_and_saved_warp_backward_agree(dev):
+    """The backward kernel either reads the warped sources kept by the forward pass (default) or
+    recomputes the warp (`save_warped=False`, nothing but argmin bytes and O(B) scalars kept):
+    both must give the same bits."""
+    inp = mono_inputs(2, 48, 160, seed=21)
+    a = gpu_mono_from_vec(inp, dev, save_warped=True)
+    b = gpu_mono_from_vec(inp, dev, save_warped=False)
+    assert torch.equal(a["rec_loss"], b["rec_loss"]) and torch.equal(a["smooth_loss"], b["smooth_loss"])
+    for x, y in zip(a["grad_depth"] + a["grad_pose_vec"] + a["argmin"], b["grad_depth"] + b["grad_pose_vec"] + b["argmin"]):
+        assert torch.equal(x, y)
+    _against_oracle(inp, dev, save_warped=False)
 
 
 def test_single_source_single_sample(dev):
