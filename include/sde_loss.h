@@ -101,6 +101,59 @@ int sde_mono_loss_forward(const sde_mono_desc* desc, const sde_mono_buffers* buf
 /* reads argmin, saved_stats, grad_losses; recomputes the warp; writes grad_depth, grad_pose */
 int sde_mono_loss_backward(const sde_mono_desc* desc, const sde_mono_buffers* buf, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MotionLearning two-frame loss (fused).  One call covers n_dirs directions (1->2 and 2->1) of
+ * one scale.  Replaces, per direction, MotionLearningModel.rgbd_consistency_loss
+ * (detectron2/modeling/meta_arch/MotionLearning.py:248-291): view_synthesis of cat[frame_B,
+ * depth_B] (geometry/camera.py:166-202) with the per-pixel translation t = pose[:3,3] + field,
+ * occlusion mask, rgb L1, depth-proximity weight, WeightedSSIM
+ * (modeling/losses/ssim_loss.py:84-111); plus smoothness_loss(depth_A, frame_A)
+ * (modeling/losses/smoothness_loss.py:42-80; MotionLearning.py:231-235).
+ * Direction d uses frame_a[d] as the target (A) and frame_b[d] / depth_b[d] as the source (B).
+ * ------------------------------------------------------------------------------------------ */
+#define SDE_MAX_DIRS 2
+#define SDE_MOTION_FIELD 1u        /* field[d] given: residual translation [B,3,h,w] (motion_pred) */
+#define SDE_MOTION_N_LOSSES 4      /* per direction: rgb_l1_loss, ssim_loss, smooth_loss, reserved */
+
+typedef struct sde_motion_desc {
+  int32_t batch;                 /* B */
+  int32_t n_dirs;                /* 1 or 2 */
+  int32_t height, width;         /* size of this scale */
+  float scale_x, scale_y;        /* scale_intrinsics factors (MotionLearning.py:131-132); 1 at full size */
+  float ssim_weight;             /* LOSS.SSIM_WEIGHT (3.0): ssim_loss = mean(ssim * avg_w) * ssim_weight * 0.5 */
+  float c1, c2;                  /* LOSS.C1 / LOSS.C2; INFINITY selects the reference's one-factor forms */
+  uint32_t flags;                /* SDE_MOTION_* */
+} sde_motion_desc;
+
+typedef struct sde_motion_buffers {
+  /* inputs, per direction */
+  const float* frame_a[SDE_MAX_DIRS];   /* [B,3,h,w] target frame A */
+  const float* frame_b[SDE_MAX_DIRS];   /* [B,3,h,w] source frame B */
+  const float* depth_a[SDE_MAX_DIRS];   /* [B,1,h,w] */
+  const float* depth_b[SDE_MAX_DIRS];   /* [B,1,h,w] */
+  const float* pose[SDE_MAX_DIRS];      /* [B,4,4] A->B */
+  const float* field[SDE_MAX_DIRS];     /* [B,3,h,w] residual translation or NULL */
+  const float* intrinsics;              /* [B,3,3] at full size; scaled by (scale_x, scale_y) in-kernel */
+  /* forward outputs */
+  float* losses;                        /* [n_dirs][SDE_MOTION_N_LOSSES] */
+  float* saved_stats;                   /* [n_dirs][B][4]: depth_err_2nd_mom, sum(occ), mean 1/depth, smoothness */
+  float* occlusion[SDE_MAX_DIRS];       /* optional [B,1,h,w] occlusion_mask (MotionLearning.py:257-259) */
+  float* weight[SDE_MAX_DIRS];          /* optional [B,1,h,w] depth_proximity_weight (MotionLearning.py:279-282) */
+  float* coords[SDE_MAX_DIRS];          /* optional [B,h,w,2] coords_A_in_B, normalised (camera.py:190-193) */
+  /* backward */
+  const float* grad_losses;             /* [n_dirs][SDE_MOTION_N_LOSSES] upstream gradients (device) */
+  float* grad_depth_a[SDE_MAX_DIRS];    /* [B,1,h,w] */
+  float* grad_pose[SDE_MAX_DIRS];       /* [B,4,4] (rows 0..2 = [dR | dt]; dt = sum over pixels) */
+  float* grad_field[SDE_MAX_DIRS];      /* [B,3,h,w], required iff SDE_MOTION_FIELD */
+  void* workspace;                      /* sde_motion_workspace_bytes(), zero-filled once */
+} sde_motion_buffers;
+
+size_t sde_motion_workspace_bytes(const sde_motion_desc* desc);
+/* writes losses, saved_stats and the optional maps (two launches: statistics pre-pass + fused loss) */
+int sde_motion_loss_forward(const sde_motion_desc* desc, const sde_motion_buffers* buf, void* stream);
+/* reads saved_stats, grad_losses; recomputes the warp; writes grad_depth_a, grad_pose, grad_field */
+int sde_motion_loss_backward(const sde_motion_desc* desc, const sde_motion_buffers* buf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,9 @@ MAX_SCALES = 6
 MAX_SOURCES = 4
 FLAG_AUTOMASK = 1
 FLAG_REDUCE_MEAN = 2
+MAX_DIRS = 2
+MOTION_FLAG_FIELD = 1
+MOTION_N_LOSSES = 4
 
 _f32p = C.c_void_p  # device pointers travel as integers
 
@@ -37,6 +40,28 @@ class MonoBuffers(C.Structure):
         ("grad_losses", _f32p),
         ("grad_depth", _f32p * MAX_SCALES),
         ("grad_pose", _f32p * MAX_SOURCES),
+        ("workspace", _f32p),
+    ]
+
+
+class MotionDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("n_dirs", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("scale_x", C.c_float), ("scale_y", C.c_float), ("ssim_weight", C.c_float),
+        ("c1", C.c_float), ("c2", C.c_float), ("flags", C.c_uint32),
+    ]
+
+
+class MotionBuffers(C.Structure):
+    _fields_ = [
+        ("frame_a", _f32p * MAX_DIRS), ("frame_b", _f32p * MAX_DIRS),
+        ("depth_a", _f32p * MAX_DIRS), ("depth_b", _f32p * MAX_DIRS),
+        ("pose", _f32p * MAX_DIRS), ("field", _f32p * MAX_DIRS),
+        ("intrinsics", _f32p),
+        ("losses", _f32p), ("saved_stats", _f32p),
+        ("occlusion", _f32p * MAX_DIRS), ("weight", _f32p * MAX_DIRS), ("coords", _f32p * MAX_DIRS),
+        ("grad_losses", _f32p),
+        ("grad_depth_a", _f32p * MAX_DIRS), ("grad_pose", _f32p * MAX_DIRS), ("grad_field", _f32p * MAX_DIRS),
         ("workspace", _f32p),
     ]
 
@@ -73,6 +98,12 @@ def load():
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(MonoDesc), C.POINTER(MonoBuffers), C.c_void_p]
+    lib.sde_motion_workspace_bytes.restype = C.c_size_t
+    lib.sde_motion_workspace_bytes.argtypes = [C.POINTER(MotionDesc)]
+    for name in ("sde_motion_loss_forward", "sde_motion_loss_backward"):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(MotionDesc), C.POINTER(MotionBuffers), C.c_void_p]
     _lib = lib
     return lib
 

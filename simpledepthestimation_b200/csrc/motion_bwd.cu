@@ -1,0 +1,380 @@
+// Backward of the MotionLearning two-frame loss (sm_100a).
+//
+// Gradients flow through the warped rgb only: the occlusion mask is a comparison, the proximity
+// weight is detached and DEPTH_L1_WEIGHT is 0 in every shipped config (MotionLearning.py:259,
+// 264-267,283).  One CTA owns a 64x16 block Q of WeightedSSIM window centres of one
+// (direction, sample) and emits gradients for Q's 62x14 interior P:
+//   phase 1  as the forward kernel: project + gather on Q + 1-pixel halo -> planes S, A, U, WZ, depth
+//   per channel:
+//     phase 2  window sums -> coefficients of  d ssim_q / d S_p = U_p (a_q + S_p b_q + A_p c_q)
+//              scaled by the upstream gradient and avg_w_q, to shared planes
+//     phase 3  adjoint of reflect-pad + 3x3 box, times U_p, plus the occlusion-masked L1 term
+//   phase 4  warp backward per pixel of P: d/d depth_A, d/d pose (12 sums) and the per-pixel
+//            d/d translation field  K^T g_p.
+// Smoothness gradient from the saved per-image mean and loss.  Deterministic reductions.
+#include "motion_device.cuh"
+
+namespace sde {
+
+// WZ (zero-padded weight) is only read before the first phase 3 (avg_w), so it shares gS plane 0
+constexpr int kNA = 0, kNS = 3, kNU = 6, kND = 7, kNCoef = 8, kNG = 11, kNW = kNG;
+constexpr int kMotionBwdPlanes = 14;
+constexpr int kMPosPerThread = (kBwdW * kBwdH + kThreads - 1) / kThreads;  // 7
+
+struct MotionBwdShared {
+  MCam cam;
+  float red[12][kThreads / 32];
+  unsigned ticket;
+  __align__(8) uint8_t occ[kPlane];      // occlusion mask of the staged positions (0 / 1)
+  __align__(8) uint8_t inside[kPlane];   // window centre lies in the image
+};
+
+__global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_constant__ MotionParams p) {
+  extern __shared__ __align__(16) float planes[];  // [kMotionBwdPlanes][kPlane]
+  __shared__ MotionBwdShared sh;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int dir, b, tx0, ty0;
+  decode_motion_tile(blockIdx.x, p.btiles_per_dir, p.btiles_x, p.btiles_y, kBwdW, kBwdH, dir, b, tx0, ty0);
+  const int h = p.h, w = p.w, hw = h * w;
+  const int ox = tx0 - 2, oy = ty0 - 2;
+  const bool lr_border = ox + 2 <= 1 || ox + kHW - 3 >= w - 2;
+
+  if (tid == 0) load_mcam(sh.cam, p.K, p.pose[dir], b, p.sx, p.sy);
+  for (int i = tid; i < 3 * kPlane; i += kThreads) planes[kNCoef * kPlane + i] = 0.0f;
+  __syncthreads();
+
+  MotionStage st;
+  st.depth_a = pinned(p.depth_a[dir] + (size_t)b * hw);
+  st.depth_b = pinned(p.depth_b[dir] + (size_t)b * hw);
+  st.frame_a = pinned(p.frame_a[dir] + (size_t)b * 3 * hw);
+  st.frame_b = pinned(p.frame_b[dir] + (size_t)b * 3 * hw);
+  st.field = p.field[dir] ? pinned(p.field[dir] + (size_t)b * 3 * hw) : nullptr;
+  st.planes = planes; st.oy = oy; st.ox = ox; st.h = h; st.w = w; st.hw = hw;
+  st.m2 = __ldg(p.stats + (dir * p.B + b) * 4);
+
+  const float* gl = p.grad_losses + dir * 4;
+  const float g_l1v = __ldg(gl), g_ssv = __ldg(gl + 1), g_smooth = __ldg(gl + 2);
+  const float inv_n = 1.0f / ((float)p.B * 3.0f * (float)h * (float)w);
+  const float g_l1 = g_l1v * inv_n;
+  const float g_ss = p.ssim_w > 0.0f ? g_ssv * inv_n * p.ssim_w * 0.5f * -0.5f : 0.0f;   // d loss / d ssim_q / avg_w_q
+  const bool use_ssim = p.ssim_w > 0.0f;
+
+  // ------------------------------------------------------------------ phase 1
+  {
+    const MCam mc = sh.cam;
+#pragma unroll 1
+    for (int i = tid; i < kPositions; i += kThreads) {
+      int yy, xx;
+      position_of(i, yy, xx);
+      const int ty = oy + yy, tx = ox + xx;
+      const bool inside = ty >= 0 && ty < h && tx >= 0 && tx < w;
+      const int gy = reflect_clamp(ty, h), gx = reflect_clamp(tx, w);
+      const int pix = gy * w + gx;
+      MotionSample sm;
+      motion_sample(st, mc, gy, gx, pix, true, sm);
+      const int pl = plane_index(yy, xx);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        planes[(kNS + c) * kPlane + pl] = sm.S[c];
+        planes[(kNA + c) * kPlane + pl] = sm.A[c];
+      }
+      planes[kNU * kPlane + pl] = sm.wgt + 1e-2f;
+      planes[kNW * kPlane + pl] = inside ? sm.wgt : 0.0f;
+      planes[kND * kPlane + pl] = sm.d;
+      sh.occ[pl] = sm.occ != 0.0f ? 1 : 0;
+      sh.inside[pl] = inside ? 1 : 0;
+    }
+  }
+  __syncthreads();
+
+  const int r0 = wid * kRowsPerWarp;
+  const int c0 = 2 * lane;
+  const int px0 = ox + c0 + 1, px1 = px0 + 1;
+  const float eL0 = px0 == 1 ? 1.0f : 0.0f, eL1 = px1 == 1 ? 1.0f : 0.0f;
+  const float eR0 = px0 == w - 2 ? 1.0f : 0.0f, eR1 = px1 == w - 2 ? 1.0f : 0.0f;
+  const f2 C1 = bc2(p.c1), C2 = bc2(p.c2);
+  const f2 ninth = bc2(1.0f / 9.0f);
+
+  // avg_w and (1/9) inverse_avg_w of this lane's window centres (rows r0+1 .. r0+4 of the plane)
+  f2 avgw[kRowsPerWarp], q9[kRowsPerWarp];
+  if (use_ssim) {
+    const float* pw = planes + kNW * kPlane + plane_index(r0, c0);
+    f2 hW[2];
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
+      const Row4 wz = ld_row(pw + rr * kPitch);
+      const f2 nW = (wz.c + swp(wz.c)) + wz.o;
+      if (rr >= 2) {
+        const int o = rr - 2;
+        avgw[o] = ((hW[0] + hW[1]) + nW) * ninth;
+        q9[o] = div2(ninth, avgw[o] + bc2(1e-2f));
+      }
+      hW[0] = hW[1]; hW[1] = nW;
+    }
+  }
+
+#pragma unroll 1
+  for (int c = 0; c < 3; ++c) {
+    // ---------------------------------------------------------------- phase 2: coefficients on Q
+    if (use_ssim) {
+      const float* pa = planes + (kNA + c) * kPlane + plane_index(r0, c0);
+      const float* px = planes + (kNS + c) * kPlane + plane_index(r0, c0);
+      const float* pu = planes + kNU * kPlane + plane_index(r0, c0);
+      f2 hX[2], hA[2], hXX[2], hAA[2], hXA[2];
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
+        const Row4 u = ld_row(pu + rr * kPitch), x = ld_row(px + rr * kPitch), a = ld_row(pa + rr * kPitch);
+        const f2 uxc = u.c * x.c, uxo = u.o * x.o, uac = u.c * a.c, uao = u.o * a.o;
+        const f2 xxc = uxc * x.c, aac = uac * a.c, xac = uxc * a.c;
+        const f2 nX = (uxc + swp(uxc)) + uxo;
+        const f2 nA = (uac + swp(uac)) + uao;
+        const f2 nXX = fma2(uxo, x.o, xxc + swp(xxc));
+        const f2 nAA = fma2(uao, a.o, aac + swp(aac));
+        const f2 nXA = fma2(uxo, a.o, xac + swp(xac));
+        if (rr >= 2) {
+          const int o = rr - 2;
+          const int row = r0 + rr - 1;   // plane row of the window centre
+          const f2 k = q9[o];
+          const f2 mx = ((hX[0] + hX[1]) + nX) * k, my = ((hA[0] + hA[1]) + nA) * k;
+          const f2 exx = ((hXX[0] + hXX[1]) + nXX) * k, eaa = ((hAA[0] + hAA[1]) + nAA) * k;
+          const f2 exa = ((hXA[0] + hXA[1]) + nXA) * k;
+          const f2 sx = fma2(mx * bc2(-1.0f), mx, exx), sy = fma2(my * bc2(-1.0f), my, eaa);
+          const f2 sxy = fma2(mx * bc2(-1.0f), my, exa);
+          const f2 n2 = fma2(bc2(2.0f), sxy, C2), d2 = (sx + sy) + C2;
+          const f2 n1 = fma2(bc2(2.0f), mx * my, C1), d1 = fma2(mx, mx, my * my) + C1;
+          f2 N, D;
+          if (p.mode == 1) { N = n2; D = d2; }
+          else if (p.mode == 2) { N = n1; D = d1; }
+          else { N = n1 * n2; D = d1 * d2; }
+          const f2 ssim = div2(N, D);
+          const uchar2 in = *reinterpret_cast<const uchar2*>(sh.inside + plane_index(row, c0 + 1));
+          const float h0 = fmaf(lo(ssim), -0.5f, 0.5f), h1 = fmaf(hi(ssim), -0.5f, 0.5f);
+          // torch.clamp passes the gradient on the closed interval; windows centred outside the image do not exist
+          const f2 g = mk2((in.x && h0 >= 0.0f && h0 <= 1.0f) ? g_ss : 0.0f, (in.y && h1 >= 0.0f && h1 <= 1.0f) ? g_ss : 0.0f);
+          // d ssim / d x_p = U_p * base * [ ... ]  with  base = 2 g avg_w (inverse_avg_w / 9) / D
+          const f2 base = div2((g * avgw[o]) * (k * bc2(2.0f)), D);
+          f2 ca, cb, cc;
+          if (p.mode == 1) {
+            cc = base;
+            cb = (base * ssim) * bc2(-1.0f);
+            ca = (cb * mx + cc * my) * bc2(-1.0f);
+          } else if (p.mode == 2) {
+            cc = bc2(0.0f); cb = bc2(0.0f);
+            ca = base * (my - ssim * mx);
+          } else {
+            cc = base * n1;
+            cb = ((base * ssim) * d1) * bc2(-1.0f);
+            ca = (base * my) * n2 - ((base * ssim) * mx) * d2 - (cb * mx + cc * my);
+          }
+          float* pc = planes + kNCoef * kPlane + plane_index(row, c0 + 1);
+          *reinterpret_cast<unsigned long long*>(pc) = ca.v;
+          *reinterpret_cast<unsigned long long*>(pc + kPlane) = cb.v;
+          *reinterpret_cast<unsigned long long*>(pc + 2 * kPlane) = cc.v;
+        }
+        hX[0] = hX[1]; hX[1] = nX; hA[0] = hA[1]; hA[1] = nA;
+        hXX[0] = hXX[1]; hXX[1] = nXX; hAA[0] = hAA[1]; hAA[1] = nAA; hXA[0] = hXA[1]; hXA[1] = nXA;
+      }
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- phase 3: adjoint -> gS_c on P
+    {
+      f2 hq[3][2];
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
+        f2 nq[3];
+        if (use_ssim) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const Row4 q = ld_row(planes + (kNCoef + k) * kPlane + plane_index(r0 + rr, c0));
+            f2 hsum = (q.c + swp(q.c)) + q.o;
+            if (lr_border) hsum = hsum + mk2(eL0 * lo(q.o) + eR0 * hi(q.c), eL1 * lo(q.c) + eR1 * hi(q.o));
+            nq[k] = hsum;
+          }
+        }
+        if (rr >= 2) {
+          const int row = r0 + rr - 1;
+          const int py = oy + row;
+          const f2 wu = bc2(py == 1 ? 2.0f : 1.0f), wd = bc2(py == h - 2 ? 2.0f : 1.0f);
+          const int pl = plane_index(row, c0 + 1);
+          const f2 Sp = ld2(planes + (kNS + c) * kPlane + pl);
+          const f2 Ap = ld2(planes + (kNA + c) * kPlane + pl);
+          f2 gS = bc2(0.0f);
+          if (use_ssim) {
+            const f2 va = fma2(wu, hq[0][0], fma2(wd, nq[0], hq[0][1]));
+            const f2 vb = fma2(wu, hq[1][0], fma2(wd, nq[1], hq[1][1]));
+            const f2 vc = fma2(wu, hq[2][0], fma2(wd, nq[2], hq[2][1]));
+            const f2 Up = ld2(planes + kNU * kPlane + pl);
+            gS = Up * fma2(Sp, vb, fma2(Ap, vc, va));
+          }
+          // rgb L1 on the pixel itself: occlusion * sign(S - A)
+          const uchar2 m = *reinterpret_cast<const uchar2*>(sh.occ + pl);
+          const f2 df = Sp - Ap;
+          const float d0 = lo(df), d1v = hi(df);
+          const float l0 = m.x ? (d0 > 0.0f ? g_l1 : (d0 < 0.0f ? -g_l1 : 0.0f)) : 0.0f;
+          const float l1 = m.y ? (d1v > 0.0f ? g_l1 : (d1v < 0.0f ? -g_l1 : 0.0f)) : 0.0f;
+          gS = gS + mk2(l0, l1);
+          *reinterpret_cast<unsigned long long*>(planes + (kNG + c) * kPlane + pl) = gS.v;
+        }
+        if (use_ssim) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { hq[k][0] = hq[k][1]; hq[k][1] = nq[k]; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ phase 4: warp backward on P + smoothness
+  {
+    const MCam mc = sh.cam;
+    const float* __restrict__ sc0 = st.frame_b;
+    float* __restrict__ gout = p.grad_depth[dir] + (size_t)b * hw;
+    float* __restrict__ gfield = p.grad_field[dir] ? p.grad_field[dir] + (size_t)b * 3 * hw : nullptr;
+    const float mbar = p.stats[(dir * p.B + b) * 4 + 2], Lb = p.stats[(dir * p.B + b) * 4 + 3];
+    const float inx = 1.0f / ((float)p.B * (float)h * (float)(w - 1));
+    const float iny = 1.0f / ((float)p.B * (float)(h - 1) * (float)w);
+    const float homog = mbar > 1e-6f ? Lb / ((float)h * (float)w * mbar) : 0.0f;
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
+#pragma unroll 1
+    for (int it = 0; it < kMPosPerThread; ++it) {
+      const int i = tid + it * kThreads;
+      const int ly = i / kBwdW, lx = i - ly * kBwdW;
+      const int gy = ty0 + ly, gx = tx0 + lx;
+      if (i < kBwdW * kBwdH && gy < h && gx < w) {
+        const int pl = plane_index(ly + 2, lx + 2);
+        const int pix = gy * w + gx;
+        const float g0 = planes[kNG * kPlane + pl], g1 = planes[(kNG + 1) * kPlane + pl], g2 = planes[(kNG + 2) * kPlane + pl];
+        const float d = planes[kND * kPlane + pl];
+        float gd = 0.0f, gt0 = 0.0f, gt1 = 0.0f, gt2 = 0.0f;
+        if (g0 != 0.0f || g1 != 0.0f || g2 != 0.0f) {
+          float f0 = 0.0f, f1 = 0.0f, f2v = 0.0f;
+          if (st.field) { f0 = __ldg(st.field + pix); f1 = __ldg(st.field + pix + hw); f2v = __ldg(st.field + pix + 2 * hw); }
+          const float fxp = (float)gx, fyp = (float)gy;
+          float P[3], den, X, Y, Z;
+          mproject(mc, fxp, fyp, d, f0, f1, f2v, P, den, X, Y, Z);
+          const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
+          const bool gate_x = (X >= 0.0f) && (X <= wm1);   // nan_to_num + clamp gates (camera.py:184-188)
+          const bool gate_y = (Y >= 0.0f) && (Y <= hm1);
+          if (gate_x || gate_y) {
+            const Cell cell = bilinear_cell(X, Y, w, h);
+            const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
+            float gX = 0.0f, gY = 0.0f;
+            const float gs[3] = {g0, g1, g2};
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+              const float* q0 = sc0 + cc * hw + cell.off;
+              const float* q1 = q0 + w;
+              const float v00 = __ldg(q0), v01 = __ldg(q0 + 1), v10 = __ldg(q1), v11 = __ldg(q1 + 1);
+              gX += gs[cc] * ((v01 - v00) * by + (v11 - v10) * cell.ay);
+              gY += gs[cc] * ((v10 - v00) * bx + (v11 - v01) * cell.ax);
+            }
+            if (!gate_x) gX = 0.0f;
+            if (!gate_y) gY = 0.0f;
+            const float q = 1.0f / den;
+            const float u0 = gX * q, u1 = gY * q;
+            const float dx = gate_x ? X - mc.cam.cx : 0.0f, dy = gate_y ? Y - mc.cam.cy : 0.0f;
+            // K^T g_p = d loss / d (t_pose + field) of this pixel
+            gt0 = mc.cam.fx * u0;
+            gt1 = mc.cam.sk * u0 + mc.cam.fy * u1;
+            gt2 = -(gX * dx + gY * dy) * q;
+            acc[0] += gt0 * P[0]; acc[1] += gt0 * P[1]; acc[2] += gt0 * P[2]; acc[3] += gt0;
+            acc[4] += gt1 * P[0]; acc[5] += gt1 * P[1]; acc[6] += gt1 * P[2]; acc[7] += gt1;
+            acc[8] += gt2 * P[0]; acc[9] += gt2 * P[1]; acc[10] += gt2 * P[2]; acc[11] += gt2;
+            const float gP0 = mc.r[0] * gt0 + mc.r[3] * gt1 + mc.r[6] * gt2;
+            const float gP1 = mc.r[1] * gt0 + mc.r[4] * gt1 + mc.r[7] * gt2;
+            const float gP2 = mc.r[2] * gt0 + mc.r[5] * gt1 + mc.r[8] * gt2;
+            const float rx = mc.cam.ki[0] * fxp + mc.cam.ki[1] * fyp + mc.cam.ki[2];
+            const float ry = mc.cam.ki[3] * fxp + mc.cam.ki[4] * fyp + mc.cam.ki[5];
+            const float rz = mc.cam.ki[6] * fxp + mc.cam.ki[7] * fyp + mc.cam.ki[8];
+            gd = gP0 * rx + gP1 * ry + gP2 * rz;
+          }
+        }
+        if (g_smooth != 0.0f) {
+          const float* pd = planes + kND * kPlane + pl;
+          auto inv = [](float v) { return 1.0f / (v < 1e-6f ? 1e-6f : v); };
+          const float ic = inv(d);
+          float el = 0.0f, er = 0.0f, eu = 0.0f, edn = 0.0f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float* pa = planes + (kNA + c) * kPlane + pl;
+            const float a = pa[0];
+            el += fabsf(pa[-1] - a); er += fabsf(a - pa[1]);
+            eu += fabsf(pa[-kPitch] - a); edn += fabsf(a - pa[kPitch]);
+          }
+          float G = 0.0f;
+          auto sgn = [](float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); };
+          if (gx + 1 < w) G += sgn(ic - inv(pd[1])) * expf(-er * (1.0f / 3.0f)) * inx;
+          if (gx >= 1) G -= sgn(inv(pd[-1]) - ic) * expf(-el * (1.0f / 3.0f)) * inx;
+          if (gy + 1 < h) G += sgn(ic - inv(pd[kPitch])) * expf(-edn * (1.0f / 3.0f)) * iny;
+          if (gy >= 1) G -= sgn(inv(pd[-kPitch]) - ic) * expf(-eu * (1.0f / 3.0f)) * iny;
+          const float g_inv = G / mbar - homog;
+          if (d >= 1e-6f) gd += -ic * ic * g_inv * g_smooth;
+        }
+        gout[pix] = gd;
+        if (gfield) { gfield[pix] = gt0; gfield[pix + hw] = gt1; gfield[pix + 2 * hw] = gt2; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const float v = warp_sum(acc[k]);
+      if (lane == 0) sh.red[k][wid] = v;
+    }
+    __syncthreads();
+    if (tid < 12) {
+      float v = 0.0f;
+#pragma unroll
+      for (int k = 0; k < kThreads / 32; ++k) v += sh.red[tid][k];
+      p.pose_partials[(size_t)blockIdx.x * 12 + tid] = v;
+    }
+  }
+
+  // ------------------------------------------------------------------ last CTA: pose gradients
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sh.ticket = atomicAdd(p.counters + 2, 1u);
+  __syncthreads();
+  if (sh.ticket != gridDim.x - 1) return;
+  __threadfence();
+  const int per_img = p.btiles_x * p.btiles_y;
+  for (int task = wid; task < p.n_dirs * p.B; task += kThreads / 32) {   // one warp per (direction, sample)
+    const int td = task / p.B, tb = task - td * p.B;
+    double a[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) a[k] = 0.0;
+    const size_t first = (size_t)td * p.btiles_per_dir + (size_t)tb * per_img;
+    for (int t = lane; t < per_img; t += 32) {
+      const float4* part = reinterpret_cast<const float4*>(p.pose_partials + (first + t) * 12);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float4 v = __ldcg(part + k);
+        a[4 * k] += (double)v.x; a[4 * k + 1] += (double)v.y; a[4 * k + 2] += (double)v.z; a[4 * k + 3] += (double)v.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+    if (lane == 0) {
+      float* gp = p.grad_pose[td] + tb * 16;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) gp[k] = (float)a[k];
+      gp[12] = gp[13] = gp[14] = gp[15] = 0.0f;
+    }
+  }
+  if (tid == 0) p.counters[2] = 0u;
+}
+
+size_t motion_bwd_smem_bytes() { return (size_t)kMotionBwdPlanes * kPlane * sizeof(float); }
+
+cudaError_t launch_motion_bwd(const MotionParams& p, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(motion_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)motion_bwd_smem_bytes());
+  if (e != cudaSuccess) return e;
+  motion_bwd_kernel<<<p.n_dirs * p.btiles_per_dir, kThreads, motion_bwd_smem_bytes(), stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace sde

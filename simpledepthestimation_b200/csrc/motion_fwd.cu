@@ -1,0 +1,346 @@
+// Forward of the MotionLearning two-frame loss (sm_100a): statistics pre-pass + fused loss kernel.
+//
+// motion_stats_kernel   per (direction, sample): sum(occlusion) and sum(depth_error * occlusion)
+//                       -> depth_err_2nd_mom (MotionLearning.py:262,276).  The proximity weight of
+//                       every pixel depends on this per-sample scalar, so it needs its own pass:
+//                       project + 1-channel gather of depth_B, nothing else.
+// motion_fwd_kernel     one CTA = one 64x16 tile of one (direction, sample):
+//   phase 1  project every pixel of the tile + 1-pixel halo with its own translation, gather
+//            rgb + depth of frame B (camera.py:166-202), occlusion, proximity weight; planes
+//            S (warped rgb), A, U = weight + 0.01, WZ = weight with zero padding, depth_A.
+//            rgb L1 (MotionLearning.py:269-271) and the optional maps are produced here.
+//   phase 2  WeightedSSIM (ssim_loss.py:84-111): window sums of U*x, U*y, U*x^2, U*y^2, U*x*y on
+//            the reflect-padded products, avg_w with zero padding; two pixels per lane (packed
+//            f2), sums carried down the rows in registers; accumulates ssim * avg_w.
+// plus smoothness_loss(depth_A, frame_A) from the same planes (1-homogeneity).
+// Deterministic: per-CTA partial slots, last CTA adds them in a fixed order in fp64.
+#include "motion_device.cuh"
+
+namespace sde {
+
+constexpr int kMA = 0, kMS = 3, kMU = 6, kMW = 7, kMD = 8;
+constexpr int kMotionFwdPlanes = 9;
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStatThreads) motion_stats_kernel(const __grid_constant__ MotionParams p) {
+  __shared__ MCam s_cam;
+  __shared__ float red[2][kStatThreads / 32];
+  __shared__ unsigned ticket;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int img = blockIdx.x / p.stat_blocks, chunk = blockIdx.x - img * p.stat_blocks;
+  const int dir = img / p.B, b = img - dir * p.B;
+  const int hw = p.h * p.w;
+  if (tid == 0) load_mcam(s_cam, p.K, p.pose[dir], b, p.sx, p.sy);
+  __syncthreads();
+  const MCam mc = s_cam;
+  MotionStage st;
+  st.depth_a = p.depth_a[dir] + (size_t)b * hw;
+  st.depth_b = p.depth_b[dir] + (size_t)b * hw;
+  st.frame_a = nullptr; st.frame_b = nullptr;
+  st.field = p.field[dir] ? p.field[dir] + (size_t)b * 3 * hw : nullptr;
+  st.planes = nullptr; st.oy = 0; st.ox = 0; st.h = p.h; st.w = p.w; st.hw = hw; st.m2 = 1.0f;
+  float socc = 0.0f, serr = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kStatPixPerThread; ++k) {
+    const int pix = chunk * kStatPix + k * kStatThreads + tid;
+    if (pix < hw) {
+      const int gy = pix / p.w, gx = pix - gy * p.w;
+      MotionSample sm;
+      motion_sample(st, mc, gy, gx, pix, false, sm);
+      const float e = sm.Zc - sm.Sd;
+      socc += sm.occ;
+      serr += (e * e) * sm.occ;
+    }
+  }
+  socc = warp_sum(socc); serr = warp_sum(serr);
+  if (lane == 0) { red[0][wid] = socc; red[1][wid] = serr; }
+  __syncthreads();
+  if (tid < 2) {
+    float v = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kStatThreads / 32; ++k) v += red[tid][k];
+    p.stat_partials[(size_t)blockIdx.x * 2 + tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket = atomicAdd(p.counters, 1u);
+  __syncthreads();
+  if (ticket != gridDim.x - 1) return;
+  __threadfence();
+  for (int q = wid; q < p.n_dirs * p.B; q += kStatThreads / 32) {   // one warp per (direction, sample)
+    double a0 = 0.0, a1 = 0.0;
+    for (int t = lane; t < p.stat_blocks; t += 32) {
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(p.stat_partials) + (size_t)q * p.stat_blocks + t);
+      a0 += (double)v.x; a1 += (double)v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (lane == 0) {
+      // depth_err_2nd_mom = sum(err * occ) / (sum(occ) + 1) + 1e-4   (MotionLearning.py:262,276)
+      p.stats[q * 4 + 0] = (float)(a1 / (a0 + 1.0) + 1e-4);
+      p.stats[q * 4 + 1] = (float)a0;
+    }
+  }
+  if (tid == 0) p.counters[0] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct MotionFwdShared {
+  MCam cam;
+  float red[5][kThreads / 32];
+  unsigned ticket;
+};
+
+__global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_constant__ MotionParams p) {
+  extern __shared__ __align__(16) float planes[];  // [kMotionFwdPlanes][kPlane]
+  __shared__ MotionFwdShared sh;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int dir, b, tx0, ty0;
+  decode_motion_tile(blockIdx.x, p.tiles_per_dir, p.tiles_x, p.tiles_y, kTileW, kTileH, dir, b, tx0, ty0);
+  const int h = p.h, w = p.w, hw = h * w;
+  if (tid == 0) load_mcam(sh.cam, p.K, p.pose[dir], b, p.sx, p.sy);
+  __syncthreads();
+
+  MotionStage st;
+  st.depth_a = pinned(p.depth_a[dir] + (size_t)b * hw);
+  st.depth_b = pinned(p.depth_b[dir] + (size_t)b * hw);
+  st.frame_a = pinned(p.frame_a[dir] + (size_t)b * 3 * hw);
+  st.frame_b = pinned(p.frame_b[dir] + (size_t)b * 3 * hw);
+  st.field = p.field[dir] ? pinned(p.field[dir] + (size_t)b * 3 * hw) : nullptr;
+  st.planes = planes; st.oy = ty0 - 1; st.ox = tx0 - 1; st.h = h; st.w = w; st.hw = hw;
+  st.m2 = __ldg(p.stats + (dir * p.B + b) * 4);
+
+  float* __restrict__ occ_out = p.occ[dir] ? p.occ[dir] + (size_t)b * hw : nullptr;
+  float* __restrict__ wgt_out = p.weight[dir] ? p.weight[dir] + (size_t)b * hw : nullptr;
+  float* __restrict__ crd_out = p.coords[dir] ? p.coords[dir] + (size_t)b * hw * 2 : nullptr;
+
+  // ------------------------------------------------------------------ phase 1
+  float l1 = 0.0f;
+  {
+    const MCam mc = sh.cam;
+#pragma unroll 1
+    for (int i = tid; i < kPositions; i += kThreads) {
+      int yy, xx;
+      position_of(i, yy, xx);
+      const int ty = st.oy + yy, tx = st.ox + xx;
+      const bool inside = ty >= 0 && ty < h && tx >= 0 && tx < w;
+      const int gy = reflect_clamp(ty, h), gx = reflect_clamp(tx, w);
+      const int pix = gy * w + gx;
+      MotionSample sm;
+      motion_sample(st, mc, gy, gx, pix, true, sm);
+      const int pl = plane_index(yy, xx);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        planes[(kMS + c) * kPlane + pl] = sm.S[c];
+        planes[(kMA + c) * kPlane + pl] = sm.A[c];
+      }
+      planes[kMU * kPlane + pl] = sm.wgt + 1e-2f;            // w = w + 1e-2 (ssim_loss.py:89)
+      planes[kMW * kPlane + pl] = inside ? sm.wgt : 0.0f;    // avg_pool2d(w, padding=1) pads with zeros
+      planes[kMD * kPlane + pl] = sm.d;
+      const bool owned = inside && yy >= 1 && yy <= kTileH && xx >= 1 && xx <= kTileW;
+      if (owned) {
+        // rgb_l1_loss = mean(|S - A| * occlusion)   (MotionLearning.py:269-271)
+        l1 += (fabsf(sm.S[0] - sm.A[0]) + fabsf(sm.S[1] - sm.A[1]) + fabsf(sm.S[2] - sm.A[2])) * sm.occ;
+        if (occ_out) occ_out[pix] = sm.occ;
+        if (wgt_out) wgt_out[pix] = sm.wgt;
+        if (crd_out) {
+          // coords = 2 * clamp(X) / (w - 1) - 1   (camera.py:190-193)
+          float2 cn;
+          cn.x = __fdiv_rn(2.0f * sm.Xs, (float)(w - 1)) - 1.0f;
+          cn.y = __fdiv_rn(2.0f * sm.Ys, (float)(h - 1)) - 1.0f;
+          *reinterpret_cast<float2*>(crd_out + (size_t)pix * 2) = cn;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase 2: WeightedSSIM
+  const int r0 = wid * kRowsPerWarp;
+  const int c0 = 2 * lane;
+  float ssim_sum = 0.0f;
+  if (p.ssim_w > 0.0f) {
+    const f2 C1 = bc2(p.c1), C2 = bc2(p.c2);
+    const f2 ninth = bc2(1.0f / 9.0f);
+    f2 avgw[kRowsPerWarp], q9[kRowsPerWarp], acc[kRowsPerWarp];
+#pragma unroll
+    for (int o = 0; o < kRowsPerWarp; ++o) acc[o] = bc2(0.0f);
+    {
+      // avg_w = avg_pool2d(w, 3, 1, padding=1); inverse_avg_w = 1 / (avg_w + 1e-2)   (ssim_loss.py:88-90)
+      const float* pw = planes + kMW * kPlane + plane_index(r0, c0);
+      f2 hW[2];
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
+        const Row4 wz = ld_row(pw + rr * kPitch);
+        const f2 nW = (wz.c + swp(wz.c)) + wz.o;
+        if (rr >= 2) {
+          const int o = rr - 2;
+          avgw[o] = ((hW[0] + hW[1]) + nW) * ninth;
+          const f2 den = avgw[o] + bc2(1e-2f);
+          q9[o] = div2(ninth, den);   // (1/9) * inverse_avg_w: turns window sums into weighted means
+        }
+        hW[0] = hW[1]; hW[1] = nW;
+      }
+    }
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      const float* pa = planes + (kMA + c) * kPlane + plane_index(r0, c0);
+      const float* px = planes + (kMS + c) * kPlane + plane_index(r0, c0);
+      const float* pu = planes + kMU * kPlane + plane_index(r0, c0);
+      f2 hX[2], hA[2], hXX[2], hAA[2], hXA[2];
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
+        const Row4 u = ld_row(pu + rr * kPitch), x = ld_row(px + rr * kPitch), a = ld_row(pa + rr * kPitch);
+        const f2 uxc = u.c * x.c, uxo = u.o * x.o, uac = u.c * a.c, uao = u.o * a.o;
+        const f2 xxc = uxc * x.c, aac = uac * a.c, xac = uxc * a.c;
+        const f2 nX = (uxc + swp(uxc)) + uxo;
+        const f2 nA = (uac + swp(uac)) + uao;
+        const f2 nXX = fma2(uxo, x.o, xxc + swp(xxc));
+        const f2 nAA = fma2(uao, a.o, aac + swp(aac));
+        const f2 nXA = fma2(uxo, a.o, xac + swp(xac));
+        if (rr >= 2) {
+          const int o = rr - 2;
+          const f2 k = q9[o];
+          const f2 mx = ((hX[0] + hX[1]) + nX) * k, my = ((hA[0] + hA[1]) + nA) * k;
+          const f2 exx = ((hXX[0] + hXX[1]) + nXX) * k, eaa = ((hAA[0] + hAA[1]) + nAA) * k;
+          const f2 exa = ((hXA[0] + hXA[1]) + nXA) * k;
+          const f2 sx = fma2(mx * bc2(-1.0f), mx, exx), sy = fma2(my * bc2(-1.0f), my, eaa);
+          const f2 sxy = fma2(mx * bc2(-1.0f), my, exa);
+          f2 n, d;
+          if (p.mode == 1) {            // C1 == inf
+            n = fma2(bc2(2.0f), sxy, C2);
+            d = (sx + sy) + C2;
+          } else if (p.mode == 2) {     // C2 == inf
+            n = fma2(bc2(2.0f), mx * my, C1);
+            d = fma2(mx, mx, my * my) + C1;
+          } else {
+            n = fma2(bc2(2.0f), sxy, C2) * fma2(bc2(2.0f), mx * my, C1);
+            d = ((sx + sy) + C2) * (fma2(mx, mx, my * my) + C1);
+          }
+          const f2 ssim = div2(n, d);
+          const f2 l = mk2(__saturatef(fmaf(lo(ssim), -0.5f, 0.5f)), __saturatef(fmaf(hi(ssim), -0.5f, 0.5f)));
+          acc[o] = fma2(l, avgw[o], acc[o]);
+        }
+        hX[0] = hX[1]; hX[1] = nX; hA[0] = hA[1]; hA[1] = nA;
+        hXX[0] = hXX[1]; hXX[1] = nXX; hAA[0] = hAA[1]; hAA[1] = nAA; hXA[0] = hXA[1]; hXA[1] = nXA;
+      }
+    }
+    const int gx0 = tx0 + c0;
+#pragma unroll
+    for (int o = 0; o < kRowsPerWarp; ++o) {
+      const int gy = ty0 + r0 + o;
+      if (gy < h) {
+        if (gx0 < w) ssim_sum += lo(acc[o]);
+        if (gx0 + 1 < w) ssim_sum += hi(acc[o]);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ smoothness(depth_A, frame_A)
+  float smx = 0.0f, smy = 0.0f, sinv = 0.0f;
+  {
+    const int gx0 = tx0 + c0;
+    const float* pd = planes + kMD * kPlane + plane_index(r0 + 1, c0 + 1);
+    auto inv = [](float d) { return 1.0f / (d < 1e-6f ? 1e-6f : d); };   // NaN-preserving clamp(min=1e-6)
+#pragma unroll
+    for (int o = 0; o < kRowsPerWarp; ++o) {
+      const int gy = ty0 + r0 + o;
+      const f2 dc = ld2(pd + o * kPitch), db = ld2(pd + (o + 1) * kPitch);
+      const float i0 = inv(lo(dc)), i1 = inv(hi(dc)), i2 = inv(pd[o * kPitch + 2]);
+      const float ib0 = inv(lo(db)), ib1 = inv(hi(db));
+      float ex0 = 0.0f, ex1 = 0.0f, ey0 = 0.0f, ey1 = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* pa = planes + (kMA + c) * kPlane + plane_index(r0 + 1 + o, c0 + 1);
+        const f2 ac = ld2(pa), ab = ld2(pa + kPitch);
+        const float a0 = lo(ac), a1 = hi(ac), a2 = pa[2];
+        ex0 += fabsf(a0 - a1);
+        ex1 += fabsf(a1 - a2);
+        ey0 += fabsf(a0 - lo(ab));
+        ey1 += fabsf(a1 - hi(ab));
+      }
+      if (gy < h) {
+        const bool v0 = gx0 < w, v1 = gx0 + 1 < w, v2 = gx0 + 2 < w, vy = gy + 1 < h;
+        if (v0) sinv += i0;
+        if (v1) sinv += i1;
+        if (v1) smx += fabsf(i0 - i1) * expf(-ex0 * (1.0f / 3.0f));
+        if (v2) smx += fabsf(i1 - i2) * expf(-ex1 * (1.0f / 3.0f));
+        if (v0 && vy) smy += fabsf(i0 - ib0) * expf(-ey0 * (1.0f / 3.0f));
+        if (v1 && vy) smy += fabsf(i1 - ib1) * expf(-ey1 * (1.0f / 3.0f));
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ CTA reduction -> partial slot
+  l1 = warp_sum(l1); ssim_sum = warp_sum(ssim_sum); smx = warp_sum(smx); smy = warp_sum(smy); sinv = warp_sum(sinv);
+  if (lane == 0) {
+    sh.red[0][wid] = l1; sh.red[1][wid] = ssim_sum; sh.red[2][wid] = smx; sh.red[3][wid] = smy; sh.red[4][wid] = sinv;
+  }
+  __syncthreads();
+  if (tid < 5) {
+    float v = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) v += sh.red[tid][k];
+    p.partials[(size_t)blockIdx.x * 8 + tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sh.ticket = atomicAdd(p.counters + 1, 1u);
+  __syncthreads();
+  if (sh.ticket != gridDim.x - 1) return;
+
+  // ------------------------------------------------------------------ last CTA: fixed-order final reduction
+  __threadfence();
+  const int per_img = p.tiles_x * p.tiles_y;
+  if (wid < p.n_dirs) {   // one warp per direction; samples in order
+    const int qd = wid;
+    double L1 = 0.0, LS = 0.0, LSm = 0.0;
+    for (int qb = 0; qb < p.B; ++qb) {
+      const float* part = p.partials + ((size_t)qd * p.tiles_per_dir + (size_t)qb * per_img) * 8;
+      double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int t = lane; t < per_img; t += 32) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (size_t)t * 8));
+        const float v4 = __ldcg(part + (size_t)t * 8 + 4);
+        a[0] += (double)v.x; a[1] += (double)v.y; a[2] += (double)v.z; a[3] += (double)v.w; a[4] += (double)v4;
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+      const double qh = h, qw = w, nB = p.B;
+      const double mbar = fmax(a[4] / (qh * qw), 1e-6);
+      const double Lb = (a[2] / (nB * qh * (qw - 1.0)) + a[3] / (nB * (qh - 1.0) * qw)) / mbar;
+      L1 += a[0]; LS += a[1]; LSm += Lb;
+      if (lane == 0) {
+        p.stats[(qd * p.B + qb) * 4 + 2] = (float)mbar;
+        p.stats[(qd * p.B + qb) * 4 + 3] = (float)Lb;
+      }
+    }
+    if (lane == 0) {
+      const double n = (double)p.B * 3.0 * h * w;
+      p.losses[qd * 4 + 0] = (float)(L1 / n);
+      p.losses[qd * 4 + 1] = (float)(LS / n * (double)p.ssim_w * 0.5);   // MotionLearning.py:286-289
+      p.losses[qd * 4 + 2] = (float)LSm;
+      p.losses[qd * 4 + 3] = 0.0f;
+    }
+  }
+  if (tid == 0) p.counters[1] = 0u;
+}
+
+size_t motion_fwd_smem_bytes() { return (size_t)kMotionFwdPlanes * kPlane * sizeof(float); }
+
+cudaError_t launch_motion_fwd(const MotionParams& p, cudaStream_t stream) {
+  motion_stats_kernel<<<p.n_dirs * p.B * p.stat_blocks, kStatThreads, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(motion_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)motion_fwd_smem_bytes());
+  if (e != cudaSuccess) return e;
+  motion_fwd_kernel<<<p.n_dirs * p.tiles_per_dir, kThreads, motion_fwd_smem_bytes(), stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace sde

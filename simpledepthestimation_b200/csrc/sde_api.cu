@@ -2,11 +2,15 @@
 // construction and kernel launches.  No torch types, no allocation, no synchronisation.
 #include <string.h>
 
-#include "mono_params.cuh"
+#include <math.h>
+
+#include "motion_device.cuh"
 
 namespace sde {
 cudaError_t launch_mono_fwd(const MonoParams& p, cudaStream_t stream);
 cudaError_t launch_mono_bwd(const MonoParams& p, cudaStream_t stream);
+cudaError_t launch_motion_fwd(const MotionParams& p, cudaStream_t stream);
+cudaError_t launch_motion_bwd(const MotionParams& p, cudaStream_t stream);
 
 static thread_local char g_cuda_err[256] = "";
 
@@ -126,6 +130,79 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
   }
   return SDE_OK;
 }
+// ------------------------------------------------------------------------------------------------
+struct MotionLayout {
+  int tiles_x, tiles_y, btiles_x, btiles_y, stat_blocks, grid, bgrid;
+  size_t off_stat, off_partials, off_pose, total;
+};
+
+static int motion_check(const sde_motion_desc* d) {
+  if (!d) return SDE_ERR_INVALID_ARG;
+  if (d->batch < 1 || d->n_dirs < 1 || d->n_dirs > SDE_MAX_DIRS) return SDE_ERR_INVALID_ARG;
+  if (d->height < 2 || d->width < 2) return SDE_ERR_INVALID_ARG;
+  if (!(d->ssim_weight >= 0.0f) || !(d->scale_x > 0.0f) || !(d->scale_y > 0.0f)) return SDE_ERR_INVALID_ARG;
+  if (isinf(d->c1) && isinf(d->c2)) return SDE_ERR_INVALID_ARG;
+  return SDE_OK;
+}
+
+static MotionLayout motion_layout(const sde_motion_desc* d) {
+  MotionLayout L;
+  L.tiles_x = (d->width + kTileW - 1) / kTileW;
+  L.tiles_y = (d->height + kTileH - 1) / kTileH;
+  L.btiles_x = (d->width + kBwdW - 1) / kBwdW;
+  L.btiles_y = (d->height + kBwdH - 1) / kBwdH;
+  L.stat_blocks = (d->height * d->width + kStatPix - 1) / kStatPix;
+  L.grid = d->n_dirs * d->batch * L.tiles_x * L.tiles_y;
+  L.bgrid = d->n_dirs * d->batch * L.btiles_x * L.btiles_y;
+  size_t off = 16;  // three counters
+  L.off_stat = off;
+  off = align16(off + (size_t)d->n_dirs * d->batch * L.stat_blocks * 2 * sizeof(float));
+  L.off_partials = off;
+  off = align16(off + (size_t)L.grid * 8 * sizeof(float));
+  L.off_pose = off;
+  off = align16(off + (size_t)L.bgrid * 12 * sizeof(float));
+  L.total = off;
+  return L;
+}
+
+static int motion_params(const sde_motion_desc* d, const sde_motion_buffers* b, bool backward, MotionParams& p) {
+  int st = motion_check(d);
+  if (st != SDE_OK) return st;
+  if (!b || !b->intrinsics || !b->workspace || !b->saved_stats) return SDE_ERR_INVALID_ARG;
+  memset(&p, 0, sizeof(p));
+  const MotionLayout L = motion_layout(d);
+  p.B = d->batch; p.n_dirs = d->n_dirs; p.h = d->height; p.w = d->width;
+  p.tiles_x = L.tiles_x; p.tiles_y = L.tiles_y; p.tiles_per_dir = d->batch * L.tiles_x * L.tiles_y;
+  p.btiles_x = L.btiles_x; p.btiles_y = L.btiles_y; p.btiles_per_dir = d->batch * L.btiles_x * L.btiles_y;
+  p.stat_blocks = L.stat_blocks;
+  p.sx = d->scale_x; p.sy = d->scale_y;
+  const bool field = (d->flags & SDE_MOTION_FIELD) != 0;
+  for (int k = 0; k < d->n_dirs; ++k) {
+    if (!b->frame_a[k] || !b->frame_b[k] || !b->depth_a[k] || !b->depth_b[k] || !b->pose[k]) return SDE_ERR_INVALID_ARG;
+    if (field && !b->field[k]) return SDE_ERR_INVALID_ARG;
+    p.frame_a[k] = b->frame_a[k]; p.frame_b[k] = b->frame_b[k];
+    p.depth_a[k] = b->depth_a[k]; p.depth_b[k] = b->depth_b[k];
+    p.pose[k] = b->pose[k];
+    p.field[k] = field ? b->field[k] : nullptr;
+    p.occ[k] = b->occlusion[k]; p.weight[k] = b->weight[k]; p.coords[k] = b->coords[k];
+    p.grad_depth[k] = b->grad_depth_a[k]; p.grad_pose[k] = b->grad_pose[k];
+    p.grad_field[k] = field ? b->grad_field[k] : nullptr;
+    if (backward && (!b->grad_depth_a[k] || !b->grad_pose[k] || (field && !b->grad_field[k]))) return SDE_ERR_INVALID_ARG;
+  }
+  p.K = b->intrinsics;
+  p.ssim_w = d->ssim_weight; p.c1 = d->c1; p.c2 = d->c2;
+  p.mode = isinf(d->c1) ? 1 : (isinf(d->c2) ? 2 : 0);   // ssim_loss.py:97-105
+  p.losses = b->losses; p.stats = b->saved_stats;
+  char* ws = static_cast<char*>(b->workspace);
+  p.counters = reinterpret_cast<unsigned*>(ws);
+  p.stat_partials = reinterpret_cast<float*>(ws + L.off_stat);
+  p.partials = reinterpret_cast<float*>(ws + L.off_partials);
+  p.pose_partials = reinterpret_cast<float*>(ws + L.off_pose);
+  p.grad_losses = b->grad_losses;
+  if (!backward && !b->losses) return SDE_ERR_INVALID_ARG;
+  if (backward && !b->grad_losses) return SDE_ERR_INVALID_ARG;
+  return SDE_OK;
+}
 }  // namespace sde
 
 using namespace sde;
@@ -165,6 +242,27 @@ int sde_mono_loss_backward(const sde_mono_desc* desc, const sde_mono_buffers* bu
   int st = mono_params(desc, buf, true, p);
   if (st != SDE_OK) return st;
   cudaError_t e = launch_mono_bwd(p, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SDE_OK : cuda_fail(e);
+}
+
+size_t sde_motion_workspace_bytes(const sde_motion_desc* desc) {
+  if (motion_check(desc) != SDE_OK) return 0;
+  return motion_layout(desc).total;
+}
+
+int sde_motion_loss_forward(const sde_motion_desc* desc, const sde_motion_buffers* buf, void* stream) {
+  MotionParams p;
+  int st = motion_params(desc, buf, false, p);
+  if (st != SDE_OK) return st;
+  cudaError_t e = launch_motion_fwd(p, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SDE_OK : cuda_fail(e);
+}
+
+int sde_motion_loss_backward(const sde_motion_desc* desc, const sde_motion_buffers* buf, void* stream) {
+  MotionParams p;
+  int st = motion_params(desc, buf, true, p);
+  if (st != SDE_OK) return st;
+  cudaError_t e = launch_motion_bwd(p, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SDE_OK : cuda_fail(e);
 }
 

@@ -13,7 +13,8 @@ import torch
 
 from . import _lib
 
-__all__ = ["MonoLossPlan", "HostLossRunner", "mono_photometric_smoothness_loss"]
+__all__ = ["MonoLossPlan", "HostLossRunner", "mono_photometric_smoothness_loss", "MotionLossPlan",
+           "motion_rgbd_smoothness_loss"]
 
 
 def _require_cuda(t: torch.Tensor, name: str):
@@ -266,3 +267,169 @@ class HostLossRunner:
             h.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.h_losses, self.h_grad_depth, self.h_grad_pose
+
+
+# =================================================================================================
+# MotionLearning two-frame loss
+# =================================================================================================
+class MotionLossPlan:
+    """Shape-specialised launcher of the fused MotionLearning loss of one scale (both directions).
+
+    Mirrors the options MotionLearningModel.__init__ reads for this path
+    (detectron2/modeling/meta_arch/MotionLearning.py:36-42): LOSS.SSIM_WEIGHT, LOSS.C1 ('inf'
+    allowed), LOSS.C2.  `scale` is the scale_intrinsics factor of the scale (MotionLearning.py:131-132).
+    """
+
+    def __init__(self, batch: int, size: Sequence[int], device, n_dirs=2, ssim_weight=3.0, c1=float("inf"), c2=9e-6,
+                 scale=(1.0, 1.0), with_field=True):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.batch, self.size, self.n_dirs, self.with_field = batch, tuple(size), n_dirs, bool(with_field)
+        d = _lib.MotionDesc()
+        d.batch, d.n_dirs, d.height, d.width = batch, n_dirs, self.size[0], self.size[1]
+        d.scale_x, d.scale_y = float(scale[0]), float(scale[1])
+        d.ssim_weight, d.c1, d.c2 = float(ssim_weight), float(c1), float(c2)
+        d.flags = _lib.MOTION_FLAG_FIELD if with_field else 0
+        self.desc = d
+        nbytes = self.lib.sde_motion_workspace_bytes(C.byref(d))
+        if nbytes == 0:
+            raise _lib.SdeError("invalid motion-loss descriptor (size >= 2, 1..2 directions, C1 and C2 not both inf)")
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self.stats = torch.empty(n_dirs * batch * 4, dtype=torch.float32, device=self.device)
+
+    def _check(self, frame_a, frame_b, depth_a, depth_b, K, pose, field):
+        B, (h, w) = self.batch, self.size
+        for k in range(self.n_dirs):
+            for t, name, c in ((frame_a[k], "frame_a", 3), (frame_b[k], "frame_b", 3), (depth_a[k], "depth_a", 1),
+                               (depth_b[k], "depth_b", 1)):
+                _require_cuda(t, name)
+                if tuple(t.shape) != (B, c, h, w) or not t.is_contiguous():
+                    raise _lib.SdeError(f"{name}[{k}] must be contiguous [B,{c},{h},{w}]")
+            _require_cuda(pose[k], "pose")
+            if tuple(pose[k].shape) != (B, 4, 4) or not pose[k].is_contiguous():
+                raise _lib.SdeError("pose must be contiguous [B,4,4]")
+            if self.with_field:
+                _require_cuda(field[k], "field")
+                if tuple(field[k].shape) != (B, 3, h, w) or not field[k].is_contiguous():
+                    raise _lib.SdeError(f"field[{k}] must be contiguous [B,3,{h},{w}]")
+        _require_cuda(K, "intrinsics")
+        if tuple(K.shape) != (B, 3, 3) or not K.is_contiguous():
+            raise _lib.SdeError("intrinsics must be contiguous [B,3,3]")
+
+    def _buffers(self, frame_a, frame_b, depth_a, depth_b, K, pose, field):
+        b = _lib.MotionBuffers()
+        for k in range(self.n_dirs):
+            b.frame_a[k], b.frame_b[k] = frame_a[k].data_ptr(), frame_b[k].data_ptr()
+            b.depth_a[k], b.depth_b[k] = depth_a[k].data_ptr(), depth_b[k].data_ptr()
+            b.pose[k] = pose[k].data_ptr()
+            if self.with_field:
+                b.field[k] = field[k].data_ptr()
+        b.intrinsics = K.data_ptr()
+        b.saved_stats = self.stats.data_ptr()
+        b.workspace = self.workspace.data_ptr()
+        return b
+
+    def forward(self, frame_a, frame_b, depth_a, depth_b, K, pose, field=None, want_maps=True, out=None):
+        """Statistics pre-pass + fused loss.  Returns (losses [n_dirs,4], maps) where maps is a list per
+        direction of dict(occlusion_mask [B,1,h,w], depth_proximity_weight [B,1,h,w], coords_A_in_B [B,h,w,2])."""
+        self._check(frame_a, frame_b, depth_a, depth_b, K, pose, field)
+        b = self._buffers(frame_a, frame_b, depth_a, depth_b, K, pose, field)
+        losses = out if out is not None else torch.empty(self.n_dirs, _lib.MOTION_N_LOSSES, dtype=torch.float32,
+                                                         device=self.device)
+        b.losses = losses.data_ptr()
+        maps = []
+        if want_maps:
+            B, (h, w) = self.batch, self.size
+            for k in range(self.n_dirs):
+                m = dict(occlusion_mask=torch.empty(B, 1, h, w, dtype=torch.float32, device=self.device),
+                         depth_proximity_weight=torch.empty(B, 1, h, w, dtype=torch.float32, device=self.device),
+                         coords_A_in_B=torch.empty(B, h, w, 2, dtype=torch.float32, device=self.device))
+                b.occlusion[k] = m["occlusion_mask"].data_ptr()
+                b.weight[k] = m["depth_proximity_weight"].data_ptr()
+                b.coords[k] = m["coords_A_in_B"].data_ptr()
+                maps.append(m)
+        st = self.lib.sde_motion_loss_forward(C.byref(self.desc), C.byref(b), torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "sde_motion_loss_forward")
+        return losses, maps
+
+    def backward(self, frame_a, frame_b, depth_a, depth_b, K, pose, field, grad_losses, grad_depth=None,
+                 grad_pose=None, grad_field=None):
+        b = self._buffers(frame_a, frame_b, depth_a, depth_b, K, pose, field)
+        b.grad_losses = grad_losses.data_ptr()
+        if grad_depth is None:
+            grad_depth = [torch.empty_like(d) for d in depth_a]
+        if grad_pose is None:
+            grad_pose = [torch.empty_like(p) for p in pose]
+        if grad_field is None and self.with_field:
+            grad_field = [torch.empty_like(f) for f in field]
+        for k in range(self.n_dirs):
+            b.grad_depth_a[k] = grad_depth[k].data_ptr()
+            b.grad_pose[k] = grad_pose[k].data_ptr()
+            if self.with_field:
+                b.grad_field[k] = grad_field[k].data_ptr()
+        st = self.lib.sde_motion_loss_backward(C.byref(self.desc), C.byref(b), torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "sde_motion_loss_backward")
+        return grad_depth, grad_pose, grad_field
+
+
+class _MotionLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: MotionLossPlan, K, want_maps, *tensors):
+        n = plan.n_dirs
+        depth_a = [_contig(t) for t in tensors[0:n]]
+        pose = [_contig(t) for t in tensors[n:2 * n]]
+        field = [_contig(t) for t in tensors[2 * n:3 * n]] if plan.with_field else None
+        rest = tensors[3 * n:] if plan.with_field else tensors[2 * n:]
+        frame_a = [_contig(t) for t in rest[0:n]]
+        frame_b = [_contig(t) for t in rest[n:2 * n]]
+        depth_b = [_contig(t) for t in rest[2 * n:3 * n]]
+        K = _contig(K)
+        losses, maps = plan.forward(frame_a, frame_b, depth_a, depth_b, K, pose, field, want_maps=want_maps)
+        ctx.plan = plan
+        ctx.save_for_backward(K, *depth_a, *pose, *(field or []), *frame_a, *frame_b, *depth_b)
+        ctx.stats = plan.stats.clone()
+        flat = []
+        for m in maps:
+            flat += [m["occlusion_mask"], m["depth_proximity_weight"], m["coords_A_in_B"]]
+        for t in flat:
+            ctx.mark_non_differentiable(t)
+        return (losses, *flat)
+
+    @staticmethod
+    def backward(ctx, g_losses, *_):
+        plan = ctx.plan
+        n = plan.n_dirs
+        sv = ctx.saved_tensors
+        K = sv[0]
+        i = 1
+        depth_a = list(sv[i:i + n]); i += n
+        pose = list(sv[i:i + n]); i += n
+        field = None
+        if plan.with_field:
+            field = list(sv[i:i + n]); i += n
+        frame_a = list(sv[i:i + n]); i += n
+        frame_b = list(sv[i:i + n]); i += n
+        depth_b = list(sv[i:i + n]); i += n
+        plan.stats.copy_(ctx.stats)
+        gd, gp, gf = plan.backward(frame_a, frame_b, depth_a, depth_b, K, pose, field, g_losses.contiguous().float())
+        grads = [*gd, *gp] + (list(gf) if plan.with_field else [])
+        return (None, None, None, *grads, *([None] * (3 * n)))
+
+
+def motion_rgbd_smoothness_loss(plan: MotionLossPlan, frame_a, frame_b, depth_a, depth_b, K, pose, field=None,
+                                want_maps=True):
+    """Differentiable fused MotionLearning loss of one scale.
+
+    Per direction k: rgbd_consistency_loss(frame_a[k], frame_b[k], depth_a[k], depth_b[k], K, R_k, t_k + field[k])
+    (MotionLearning.py:248-291) and smoothness_loss(depth_a[k], frame_a[k]).  Returns
+    (losses [n_dirs,4] = rgb_l1_loss, ssim_loss, smooth_loss, 0; maps per direction).  Gradients reach
+    depth_a, pose and field; depth_b receives none (occlusion is a comparison, the proximity weight is
+    detached and DEPTH_L1_WEIGHT is 0 in the reference's configs)."""
+    if plan.with_field and field is None:
+        raise _lib.SdeError("plan was built with_field=True but no field was given")
+    ts = [*depth_a, *pose] + (list(field) if plan.with_field else []) + [*frame_a, *frame_b, *depth_b]
+    out = _MotionLossFn.apply(plan, K, want_maps, *ts)
+    losses, flat = out[0], out[1:]
+    maps = [dict(occlusion_mask=flat[3 * k], depth_proximity_weight=flat[3 * k + 1], coords_A_in_B=flat[3 * k + 2])
+            for k in range(len(flat) // 3)]
+    return losses, maps

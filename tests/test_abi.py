@@ -17,7 +17,8 @@ def declared_symbols():
 def test_header_declares_entry_points():
     syms = declared_symbols()
     for s in ("sde_version", "sde_strerror", "sde_mono_workspace_bytes", "sde_mono_loss_forward",
-              "sde_mono_loss_backward"):
+              "sde_mono_loss_backward", "sde_motion_workspace_bytes", "sde_motion_loss_forward",
+              "sde_motion_loss_backward"):
         assert s in syms
 
 
@@ -61,6 +62,22 @@ def test_null_buffers_are_rejected_without_touching_the_gpu(sde_lib):
     assert sde_lib.sde_mono_loss_forward(ctypes.byref(d), ctypes.byref(b), None) == -1
     assert sde_lib.sde_mono_loss_backward(ctypes.byref(d), ctypes.byref(b), None) == -1
     assert sde_lib.sde_mono_loss_forward(None, None, None) == -1
+
+
+def test_motion_descriptor_and_null_buffers(sde_lib):
+    from simpledepthestimation_b200 import _lib
+
+    d = _lib.MotionDesc(batch=4, n_dirs=2, height=1280, width=1920, scale_x=1.0, scale_y=1.0, ssim_weight=3.0,
+                        c1=float("inf"), c2=9e-6, flags=1)
+    assert sde_lib.sde_motion_workspace_bytes(ctypes.byref(d)) > 0
+    b = _lib.MotionBuffers()
+    assert sde_lib.sde_motion_loss_forward(ctypes.byref(d), ctypes.byref(b), None) == -1
+    assert sde_lib.sde_motion_loss_backward(ctypes.byref(d), ctypes.byref(b), None) == -1
+    d.n_dirs = 3
+    assert sde_lib.sde_motion_workspace_bytes(ctypes.byref(d)) == 0
+    d.n_dirs, d.c2 = 2, float("inf")   # C1 and C2 both infinite leaves no SSIM factor
+    assert sde_lib.sde_motion_workspace_bytes(ctypes.byref(d)) == 0
+    assert sde_lib.sde_motion_workspace_bytes(None) == 0
 
 
 def test_python_api_refuses_cpu_tensors(sde_lib):
