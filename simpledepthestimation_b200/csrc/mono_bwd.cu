@@ -36,6 +36,7 @@ struct BwdShared {
   Cam cam;
   Proj proj[SDE_MAX_SOURCES];
   float red[12][kThreads / 32];
+  double dred[12][kThreads / 32];
   unsigned ticket;
   __align__(8) uint8_t arg[kPlane];
 };
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     const float inx = 1.0f / ((float)p.B * (float)h * (float)(w - 1));
     const float iny = 1.0f / ((float)p.B * (float)(h - 1) * (float)w);
     const float homog = mbar > 1e-6f ? Lb / ((float)h * (float)w * mbar) : 0.0f;
+    const float rmbar = 1.0f / mbar;
     float* __restrict__ gout = p.grad_depth[s] + (size_t)b * hw;
 #pragma unroll
     for (int it = 0; it < kPosPerThread; ++it) {
@@ -320,24 +322,10 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
         if (sscale > 0.0f) {
           const int pl = plane_index(ly + 2, lx + 2);
           const float* pd = planes + kBD * kPlane + pl;
-          auto inv = [](float d) { return 1.0f / (d < 1e-6f ? 1e-6f : d); };   // NaN-preserving clamp(min=1e-6)
           const float d = pd[0];
-          const float ic = inv(d);
-          float el = 0.0f, er = 0.0f, eu = 0.0f, edn = 0.0f;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float* pa = planes + (kBA + c) * kPlane + pl;
-            const float a = pa[0];
-            el += fabsf(pa[-1] - a); er += fabsf(a - pa[1]);
-            eu += fabsf(pa[-kPitch] - a); edn += fabsf(a - pa[kPitch]);
-          }
-          float G = 0.0f;
-          auto sgn = [](float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); };
-          if (gx + 1 < w) G += sgn(ic - inv(pd[1])) * expf(-er * (1.0f / 3.0f)) * inx;
-          if (gx >= 1) G -= sgn(inv(pd[-1]) - ic) * expf(-el * (1.0f / 3.0f)) * inx;
-          if (gy + 1 < h) G += sgn(ic - inv(pd[kPitch])) * expf(-edn * (1.0f / 3.0f)) * iny;
-          if (gy >= 1) G -= sgn(inv(pd[-kPitch]) - ic) * expf(-eu * (1.0f / 3.0f)) * iny;
-          const float g_inv = G / mbar - homog;
+          const float ic = inv_depth(d);
+          const float G = smooth_grad_local(pd, planes + kBA * kPlane + pl, ic, gx, gy, w, h, inx, iny);
+          const float g_inv = G * rmbar - homog;
           if (d >= 1e-6f) g += -ic * ic * g_inv * (g_smooth * sscale);
         }
         gout[gy * w + gx] = g;
@@ -345,22 +333,25 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     }
   }
 
-  // ------------------------------------------------------------------ last CTA: pose gradients
+  // ------------------------------------------------------------------ last tile of a sample: pose gradients
+  // The tile that finishes a sample last (over all scales) adds that sample's per-CTA slots in a fixed
+  // order in fp64, while other samples are still being computed.
   __threadfence();
   __syncthreads();
-  if (tid == 0) sh.ticket = atomicAdd(p.counter_bwd, 1u);
+  int total_b = 0;
+  for (int ss = 0; ss < p.n_scales; ++ss) total_b += p.btiles_x[ss] * p.btiles_y[ss];
+  if (tid == 0) sh.ticket = atomicAdd(p.smp_counter + b, 1u);
   __syncthreads();
-  if (sh.ticket != gridDim.x - 1) return;
+  if (sh.ticket != (unsigned)(total_b - 1)) return;
   __threadfence();
-  for (int task = wid; task < p.B * p.S; task += kThreads / 32) {  // one warp per (sample, source)
-    const int tb = task / p.S, tj = task - tb * p.S;
+  for (int tj = 0; tj < p.S; ++tj) {
     double a[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) a[k] = 0.0;
     for (int ss = 0; ss < p.n_scales; ++ss) {
       const int per = p.btiles_x[ss] * p.btiles_y[ss];
-      const size_t first = (size_t)p.btile_start[ss] + (size_t)tb * per;
-      for (int t = lane; t < per; t += 32) {
+      const size_t first = (size_t)p.btile_start[ss] + (size_t)b * per;
+      for (int t = tid; t < per; t += kThreads) {
         const float4* part = reinterpret_cast<const float4*>(p.pose_partials + ((first + t) * p.S + tj) * 12);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -370,17 +361,23 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       }
     }
 #pragma unroll
-    for (int k = 0; k < 12; ++k)
+    for (int k = 0; k < 12; ++k) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+    }
+    __syncthreads();
     if (lane == 0) {
-      float* gp = p.grad_pose[tj] + tb * 16;
 #pragma unroll
-      for (int k = 0; k < 12; ++k) gp[k] = (float)a[k];   // rows 0..2 = [dR | dt]
-      gp[12] = gp[13] = gp[14] = gp[15] = 0.0f;
+      for (int k = 0; k < 12; ++k) sh.dred[k][wid] = a[k];
+    }
+    __syncthreads();
+    if (tid < 12) {
+      float* gp = p.grad_pose[tj] + b * 16;
+      gp[tid] = (float)(((sh.dred[tid][0] + sh.dred[tid][1]) + sh.dred[tid][2]) + sh.dred[tid][3]);   // rows 0..2 = [dR | dt]
+      if (tid < 4) gp[12 + tid] = 0.0f;
     }
   }
-  if (tid == 0) *p.counter_bwd = 0u;
+  if (tid == 0) p.smp_counter[b] = 0u;   // leave the workspace zeroed for the next call
 }
 
 size_t mono_bwd_smem_bytes() { return (size_t)kBwdPlanes * kPlane * sizeof(float); }

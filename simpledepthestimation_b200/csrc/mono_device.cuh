@@ -117,6 +117,36 @@ __device__ __forceinline__ int pixel_of(const StageArgs& a, int yy, int xx, int&
   return gy * a.w + gx;
 }
 
+// 1 / clamp(d, min=1e-6) (smoothness_loss.py:62) with a refined hardware reciprocal (<= 1 ulp);
+// the comparison form keeps a NaN depth NaN, as torch.clamp does.
+__device__ __forceinline__ float inv_depth(float d) {
+  const float c = d < 1e-6f ? 1e-6f : d;
+  float r = rcp_approx(c);
+  return fmaf(fmaf(-c, r, 1.0f), r, r);
+}
+
+// d smoothness / d (1/depth) of one pixel, before the division by the per-image mean
+// (smoothness_loss.py:62-80): +-exp(-mean_c |dI|) / N over the four edges of the pixel.
+// pd / pa0 point at the pixel in the depth plane / first image plane (planes kPlane apart).
+__device__ __forceinline__ float smooth_grad_local(const float* pd, const float* pa0, float ic, int gx, int gy, int w, int h,
+                                                   float inx, float iny) {
+  float el = 0.0f, er = 0.0f, eu = 0.0f, edn = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* pa = pa0 + c * kPlane;
+    const float a = pa[0];
+    el += fabsf(pa[-1] - a); er += fabsf(a - pa[1]);
+    eu += fabsf(pa[-kPitch] - a); edn += fabsf(a - pa[kPitch]);
+  }
+  auto sgn = [](float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); };
+  float G = 0.0f;
+  if (gx + 1 < w) G += sgn(ic - inv_depth(pd[1])) * __expf(-er * (1.0f / 3.0f)) * inx;
+  if (gx >= 1) G -= sgn(inv_depth(pd[-1]) - ic) * __expf(-el * (1.0f / 3.0f)) * inx;
+  if (gy + 1 < h) G += sgn(ic - inv_depth(pd[kPitch])) * __expf(-edn * (1.0f / 3.0f)) * iny;
+  if (gy >= 1) G -= sgn(inv_depth(pd[-kPitch]) - ic) * __expf(-eu * (1.0f / 3.0f)) * iny;
+  return G;
+}
+
 // Phase 0 of both kernels: stage what does not depend on the source -- depth, target (and the
 // argmin bytes in the backward kernel) of the halo'd tile.  All loads are independent and issued
 // before the first store, so the tile pays one memory round trip here.

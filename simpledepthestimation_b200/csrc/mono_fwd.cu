@@ -38,6 +38,7 @@ struct FwdShared {
   Cam cam;
   Proj proj[SDE_MAX_SOURCES];
   float red[4][kThreads / 32];
+  double dred[4][kThreads / 32];
   unsigned ticket;
 };
 
@@ -271,48 +272,65 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   }
   __threadfence();
   __syncthreads();
-  if (tid == 0) sh.ticket = atomicAdd(p.counter, 1u);
+  // ------------------------------------------------------------------ two-level fixed-order reduction
+  // The last tile of a (scale, image) pair adds that image's partial slots (while other images are still
+  // being computed); the last pair to finish adds the per-image results.  Same order every run.
+  const int q = s * p.B + b, per = p.tiles_x[s] * p.tiles_y[s];
+  if (tid == 0) sh.ticket = atomicAdd(p.img_counter + q, 1u);
   __syncthreads();
-  if (sh.ticket != gridDim.x - 1) return;
-
-  // ------------------------------------------------------------------ last CTA: fixed-order final reduction
+  if (sh.ticket != (unsigned)(per - 1)) return;
   __threadfence();
-  double* fin = p.fin;  // [n_scales*B][2] staging
-  const int pairs = p.n_scales * p.B;
-  for (int q = wid; q < pairs; q += kThreads / 32) {   // one warp per (scale, image)
-    const int qs = q / p.B, qb = q - qs * p.B;
-    const int per = p.tiles_x[qs] * p.tiles_y[qs];
-    const float* part = p.partials + ((size_t)p.tile_start[qs] + (size_t)qb * per) * 4;
+  {
+    const float* part = p.partials + ((size_t)p.tile_start[s] + (size_t)b * per) * 4;
     double a[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int t = lane; t < per; t += 32) {
+    for (int t = tid; t < per; t += kThreads) {
       const float4 v = __ldcg(reinterpret_cast<const float4*>(part) + t);
       a[0] += (double)v.x; a[1] += (double)v.y; a[2] += (double)v.z; a[3] += (double)v.w;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 4; ++k) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+    }
+    __syncthreads();   // sh.red is reused below
     if (lane == 0) {
-      const double qh = p.h[qs], qw = p.w[qs], nB = p.B;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sh.dred[k][wid] = a[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double t4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t4[k] = ((sh.dred[k][0] + sh.dred[k][1]) + sh.dred[k][2]) + sh.dred[k][3];
+      const double qh = h, qw = w, nB = p.B;
       const int ncand = NC * p.S;
-      double rec_q = a[0] / (nB * qh * qw) / p.n_scales;
+      double rec_q = t4[0] / (nB * qh * qw) / p.n_scales;
       if (reduce_mean) rec_q /= ncand;
-      const double mbar = fmax(a[3] / (qh * qw), 1e-6);
-      const double Lb = (a[1] / (nB * qh * (qw - 1.0)) + a[2] / (nB * (qh - 1.0) * qw)) / mbar;
+      const double mbar = fmax(t4[3] / (qh * qw), 1e-6);
+      const double Lb = (t4[1] / (nB * qh * (qw - 1.0)) + t4[2] / (nB * (qh - 1.0) * qw)) / mbar;
       p.stats[q * 2 + 0] = (float)mbar;
       p.stats[q * 2 + 1] = (float)Lb;
-      fin[q * 2 + 0] = rec_q;
-      fin[q * 2 + 1] = Lb * (double)p.smooth_scale[qs];
+      p.fin[q * 2 + 0] = rec_q;
+      p.fin[q * 2 + 1] = Lb * (double)p.smooth_scale[s];
+      p.img_counter[q] = 0u;   // leave the workspace zeroed for the next call
+      __threadfence();
+      sh.ticket = atomicAdd(p.counter, 1u);
     }
   }
-  __threadfence();
   __syncthreads();
-  if (tid == 0) {
+  const int pairs = p.n_scales * p.B;
+  if (sh.ticket != (unsigned)(pairs - 1)) return;
+  __threadfence();
+  if (wid == 0) {
     double r = 0.0, sm = 0.0;
-    for (int q = 0; q < pairs; ++q) { r += __ldcg(fin + q * 2); sm += __ldcg(fin + q * 2 + 1); }
-    p.losses[0] = (float)r;
-    p.losses[1] = (float)sm;
-    *p.counter = 0u;  // leave the workspace zeroed for the next call
+    for (int k = lane; k < pairs; k += 32) { r += __ldcg(p.fin + k * 2); sm += __ldcg(p.fin + k * 2 + 1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { r += __shfl_xor_sync(0xffffffffu, r, o); sm += __shfl_xor_sync(0xffffffffu, sm, o); }
+    if (lane == 0) {
+      p.losses[0] = (float)r;
+      p.losses[1] = (float)sm;
+      *p.counter = 0u;
+    }
   }
 }
 

@@ -34,13 +34,14 @@ struct MonoParams {
   // forward workspace
   float* partials;        // [grid][4]
   double* fin;            // [n_scales*B][2]
-  unsigned* counter;
+  unsigned* counter;       // global ticket: (scale, image) pairs finished
+  unsigned* img_counter;   // [n_scales*B] tiles finished per (scale, image)
   // backward
   const float* grad_losses;
   float* grad_depth[SDE_MAX_SCALES];
   float* grad_pose[SDE_MAX_SOURCES];
   float* pose_partials;   // [bwd grid][S][12]
-  unsigned* counter_bwd;
+  unsigned* smp_counter;   // [B] backward tiles finished per sample (all scales)
   int btiles_x[SDE_MAX_SCALES], btiles_y[SDE_MAX_SCALES];
   int btile_start[SDE_MAX_SCALES + 1];
 };

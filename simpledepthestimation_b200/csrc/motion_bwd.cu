@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
     const float inx = 1.0f / ((float)p.B * (float)h * (float)(w - 1));
     const float iny = 1.0f / ((float)p.B * (float)(h - 1) * (float)w);
     const float homog = mbar > 1e-6f ? Lb / ((float)h * (float)w * mbar) : 0.0f;
+    const float rmbar = 1.0f / mbar;
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
@@ -294,23 +295,9 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
         }
         if (g_smooth != 0.0f) {
           const float* pd = planes + kND * kPlane + pl;
-          auto inv = [](float v) { return 1.0f / (v < 1e-6f ? 1e-6f : v); };
-          const float ic = inv(d);
-          float el = 0.0f, er = 0.0f, eu = 0.0f, edn = 0.0f;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float* pa = planes + (kNA + c) * kPlane + pl;
-            const float a = pa[0];
-            el += fabsf(pa[-1] - a); er += fabsf(a - pa[1]);
-            eu += fabsf(pa[-kPitch] - a); edn += fabsf(a - pa[kPitch]);
-          }
-          float G = 0.0f;
-          auto sgn = [](float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); };
-          if (gx + 1 < w) G += sgn(ic - inv(pd[1])) * expf(-er * (1.0f / 3.0f)) * inx;
-          if (gx >= 1) G -= sgn(inv(pd[-1]) - ic) * expf(-el * (1.0f / 3.0f)) * inx;
-          if (gy + 1 < h) G += sgn(ic - inv(pd[kPitch])) * expf(-edn * (1.0f / 3.0f)) * iny;
-          if (gy >= 1) G -= sgn(inv(pd[-kPitch]) - ic) * expf(-eu * (1.0f / 3.0f)) * iny;
-          const float g_inv = G / mbar - homog;
+          const float ic = inv_depth(d);
+          const float G = smooth_grad_local(pd, planes + kNA * kPlane + pl, ic, gx, gy, w, h, inx, iny);
+          const float g_inv = G * rmbar - homog;
           if (d >= 1e-6f) gd += -ic * ic * g_inv * g_smooth;
         }
         gout[pix] = gd;

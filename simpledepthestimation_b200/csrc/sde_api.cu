@@ -24,7 +24,7 @@ static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 struct MonoLayout {
   int grid, bgrid;
-  size_t off_fin, off_partials, off_pose, total;
+  size_t off_imgc, off_smpc, off_fin, off_partials, off_pose, total;
 };
 
 static int mono_check(const sde_mono_desc* d) {
@@ -46,7 +46,11 @@ static MonoLayout mono_layout(const sde_mono_desc* d) {
     L.grid += d->batch * ((d->width[i] + kTileW - 1) / kTileW) * ((d->height[i] + kTileH - 1) / kTileH);
     L.bgrid += d->batch * ((d->width[i] + kBwdW - 1) / kBwdW) * ((d->height[i] + kBwdH - 1) / kBwdH);
   }
-  size_t off = 16;  // two counters
+  size_t off = 16;  // global ticket
+  L.off_imgc = off;
+  off = align16(off + (size_t)d->n_scales * d->batch * sizeof(unsigned));
+  L.off_smpc = off;
+  off = align16(off + (size_t)d->batch * sizeof(unsigned));
   L.off_fin = off;
   off = align16(off + (size_t)d->n_scales * d->batch * 2 * sizeof(double));
   L.off_partials = off;
@@ -107,7 +111,8 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
   const MonoLayout L = mono_layout(d);
   char* ws = static_cast<char*>(b->workspace);
   p.counter = reinterpret_cast<unsigned*>(ws);
-  p.counter_bwd = reinterpret_cast<unsigned*>(ws) + 1;
+  p.img_counter = reinterpret_cast<unsigned*>(ws + L.off_imgc);
+  p.smp_counter = reinterpret_cast<unsigned*>(ws + L.off_smpc);
   p.fin = reinterpret_cast<double*>(ws + L.off_fin);
   p.partials = reinterpret_cast<float*>(ws + L.off_partials);
   p.pose_partials = reinterpret_cast<float*>(ws + L.off_pose);
