@@ -154,6 +154,96 @@ int sde_motion_loss_forward(const sde_motion_desc* desc, const sde_motion_buffer
 /* reads saved_stats, grad_losses; recomputes the warp; writes grad_depth_a, grad_pose, grad_field */
 int sde_motion_loss_backward(const sde_motion_desc* desc, const sde_motion_buffers* buf, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone operators: one entry point per reference function, for callers that use the pieces
+ * outside the fused losses.  Same conventions as above.
+ * ------------------------------------------------------------------------------------------ */
+
+/* view_synthesis(image_B, depth_A, intrinsics, R_A_to_B, t_A_to_B), detectron2/geometry/camera.py:166-202
+ * (inv_intrinsics :25-37, img_to_points :125-138, points_to_img :141-163, nan_to_num + clamp + normalise
+ * :184-193, F.grid_sample bilinear / align_corners=True :196).  `intrinsics` is used as given (already
+ * scaled to this size). */
+#define SDE_VS_T_PER_PIXEL 1u      /* translation is [B,3,h,w]; otherwise [B,3] */
+typedef struct sde_vs_desc {
+  int32_t batch, channels, height, width;
+  uint32_t flags;
+} sde_vs_desc;
+
+typedef struct sde_vs_buffers {
+  const float* image_b;        /* [B,C,h,w] */
+  const float* depth_a;        /* [B,1,h,w] */
+  const float* intrinsics;     /* [B,3,3] */
+  const float* rotation;       /* [B,3,3] */
+  const float* translation;    /* [B,3,h,w] or [B,3] */
+  /* forward outputs */
+  float* sampled;              /* [B,C,h,w] */
+  float* depth_in_b;           /* [B,1,h,w], optional */
+  float* coords;               /* [B,h,w,2] normalised (x,y), optional */
+  uint8_t* valid;              /* [B,1,h,w] 0/1, optional */
+  /* backward inputs (upstream gradients; the last two optional) and outputs */
+  const float* grad_sampled;
+  const float* grad_depth_in_b;
+  const float* grad_coords;
+  float* grad_depth_a;         /* [B,1,h,w] */
+  float* grad_rotation;        /* [B,3,3] */
+  float* grad_translation;     /* same shape as translation */
+  float* grad_image_b;         /* [B,C,h,w], optional: bilinear scatter, accumulated in 64-bit fixed point
+                                  (integer atomics: order-independent, hence deterministic; |sum| < 5e5) */
+  void* workspace;             /* sde_view_synthesis_workspace_bytes(), zero-filled once */
+} sde_vs_buffers;
+
+size_t sde_view_synthesis_workspace_bytes(const sde_vs_desc* desc);
+int sde_view_synthesis_forward(const sde_vs_desc* desc, const sde_vs_buffers* buf, void* stream);
+int sde_view_synthesis_backward(const sde_vs_desc* desc, const sde_vs_buffers* buf, void* stream);
+
+/* SSIM(C1,C2)(x,y) -> clamp((1-ssim)/2,0,1), detectron2/modeling/losses/ssim_loss.py:34-53, and
+ * WeightedSSIM(C1,C2)(x,y,w) -> (map, avg_w), ssim_loss.py:84-111 (weight != NULL).  Backward w.r.t. x
+ * and y (the weight is detached at the reference's only call site, MotionLearning.py:279-285). */
+typedef struct sde_ssim_desc {
+  int32_t batch, channels, height, width;
+  float c1, c2;                /* INFINITY selects the one-factor forms of WeightedSSIM */
+} sde_ssim_desc;
+
+typedef struct sde_ssim_buffers {
+  const float* x;              /* [B,C,h,w] */
+  const float* y;              /* [B,C,h,w] */
+  const float* weight;         /* [B,1,h,w] or NULL (plain SSIM) */
+  float* out;                  /* [B,C,h,w] */
+  float* avg_w;                /* [B,1,h,w], optional (WeightedSSIM) */
+  const float* grad_out;       /* [B,C,h,w] */
+  float* grad_x;               /* optional */
+  float* grad_y;               /* optional */
+  void* workspace;             /* sde_ssim_workspace_bytes(): six coefficient planes; no initialisation needed */
+} sde_ssim_buffers;
+
+size_t sde_ssim_workspace_bytes(const sde_ssim_desc* desc);
+int sde_ssim_forward(const sde_ssim_desc* desc, const sde_ssim_buffers* buf, void* stream);
+int sde_ssim_backward(const sde_ssim_desc* desc, const sde_ssim_buffers* buf, void* stream);
+
+/* smoothness_loss(depth, image), detectron2/modeling/losses/smoothness_loss.py:42-80. */
+typedef struct sde_smooth_desc {
+  int32_t batch, channels, height, width;   /* channels of `image` */
+} sde_smooth_desc;
+
+typedef struct sde_smooth_buffers {
+  const float* depth;          /* [B,1,h,w] */
+  const float* image;          /* [B,C,h,w] */
+  float* loss;                 /* [1] */
+  float* saved_stats;          /* [B*2] per-image (mean inverse depth, loss) for backward */
+  const float* grad_loss;      /* [1] (device) */
+  float* grad_depth;           /* [B,1,h,w] */
+  void* workspace;             /* sde_smoothness_workspace_bytes(), zero-filled once */
+} sde_smooth_buffers;
+
+size_t sde_smoothness_workspace_bytes(const sde_smooth_desc* desc);
+int sde_smoothness_forward(const sde_smooth_desc* desc, const sde_smooth_buffers* buf, void* stream);
+int sde_smoothness_backward(const sde_smooth_desc* desc, const sde_smooth_buffers* buf, void* stream);
+
+/* resize_img(image, dst_size) = F.interpolate(mode='bilinear', align_corners=True),
+ * detectron2/geometry/camera.py:40-46: src [planes,sh,sw] -> dst [planes,dh,dw]. */
+int sde_resize_bilinear(const float* src, float* dst, int32_t planes, int32_t src_h, int32_t src_w, int32_t dst_h,
+                        int32_t dst_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,35 @@ class MotionBuffers(C.Structure):
     ]
 
 
+class VsDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+                ("flags", C.c_uint32)]
+
+
+class VsBuffers(C.Structure):
+    _fields_ = [(n, _f32p) for n in (
+        "image_b", "depth_a", "intrinsics", "rotation", "translation", "sampled", "depth_in_b", "coords", "valid",
+        "grad_sampled", "grad_depth_in_b", "grad_coords", "grad_depth_a", "grad_rotation", "grad_translation",
+        "grad_image_b", "workspace")]
+
+
+class SsimDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+                ("c1", C.c_float), ("c2", C.c_float)]
+
+
+class SsimBuffers(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("x", "y", "weight", "out", "avg_w", "grad_out", "grad_x", "grad_y", "workspace")]
+
+
+class SmoothDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32)]
+
+
+class SmoothBuffers(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("depth", "image", "loss", "saved_stats", "grad_loss", "grad_depth", "workspace")]
+
+
 class SdeError(RuntimeError):
     pass
 
@@ -104,6 +133,16 @@ def load():
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(MotionDesc), C.POINTER(MotionBuffers), C.c_void_p]
+    for prefix, D, B in (("sde_view_synthesis", VsDesc, VsBuffers), ("sde_ssim", SsimDesc, SsimBuffers),
+                         ("sde_smoothness", SmoothDesc, SmoothBuffers)):
+        ws = getattr(lib, prefix + "_workspace_bytes")
+        ws.restype, ws.argtypes = C.c_size_t, [C.POINTER(D)]
+        for suffix in ("_forward", "_backward"):
+            fn = getattr(lib, prefix + suffix)
+            fn.restype, fn.argtypes = C.c_int, [C.POINTER(D), C.POINTER(B), C.c_void_p]
+    lib.sde_resize_bilinear.restype = C.c_int
+    lib.sde_resize_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p]
     _lib = lib
     return lib
 

@@ -1,0 +1,60 @@
+// Parameter blocks of the stand-alone operators (ops.cu).
+#pragma once
+#include <stdint.h>
+
+namespace sde {
+
+struct VsParams {
+  int B, C, h, w;
+  int t_per_pixel;              // t is [B,3,h,w] (1) or [B,3] (0)
+  const float* image;           // [B,C,h,w]
+  const float* depth;           // [B,1,h,w]
+  const float* K;               // [B,3,3] at this size
+  const float* R;               // [B,3,3]
+  const float* t;
+  // forward outputs
+  float* sampled;               // [B,C,h,w]
+  float* depth_in_b;            // [B,1,h,w] or null
+  float* coords;                // [B,h,w,2] or null
+  uint8_t* valid;               // [B,1,h,w] or null
+  // backward
+  const float* g_sampled;       // [B,C,h,w]
+  const float* g_depth_in_b;    // or null
+  const float* g_coords;        // or null
+  float* g_depth;               // [B,1,h,w]
+  float* g_R;                   // [B,3,3]
+  float* g_t;                   // [B,3,h,w] or [B,3]
+  long long* g_image_fix;       // [B,C,h,w] 64-bit fixed-point accumulator (zero on entry and on exit) or null
+  float* partials;              // [B][blocks][12]
+  unsigned* counters;           // [B]
+};
+
+struct SsimParams {
+  int B, C, h, w;
+  float c1, c2;
+  int mode;                     // 0 both factors, 1 C1 = inf, 2 C2 = inf
+  const float* x;
+  const float* y;
+  const float* weight;          // [B,1,h,w] or null (plain SSIM)
+  float* out;                   // [B,C,h,w]
+  float* avg_w;                 // [B,1,h,w] or null
+  const float* g_out;
+  float* g_x;                   // or null
+  float* g_y;                   // or null
+  float* coef;                  // [6][B*C][h*w]
+};
+
+struct SmoothParams {
+  int B, C, h, w;
+  const float* depth;           // [B,1,h,w]
+  const float* image;           // [B,C,h,w]
+  float* loss;                  // [1]
+  float* stats;                 // [B][2] mean inverse depth, per-image loss
+  float* partials;              // [B][blocks][4]
+  double* fin;                  // [B]
+  unsigned* counters;           // [1 + B]
+  const float* g_loss;          // [1]
+  float* g_depth;
+};
+
+}  // namespace sde

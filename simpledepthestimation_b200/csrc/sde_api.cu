@@ -5,12 +5,21 @@
 #include <math.h>
 
 #include "motion_device.cuh"
+#include "ops_params.cuh"
 
 namespace sde {
 cudaError_t launch_mono_fwd(const MonoParams& p, cudaStream_t stream);
 cudaError_t launch_mono_bwd(const MonoParams& p, cudaStream_t stream);
 cudaError_t launch_motion_fwd(const MotionParams& p, cudaStream_t stream);
 cudaError_t launch_motion_bwd(const MotionParams& p, cudaStream_t stream);
+cudaError_t launch_vs_fwd(const VsParams& p, cudaStream_t stream);
+cudaError_t launch_vs_bwd(const VsParams& p, float* g_image, cudaStream_t stream);
+cudaError_t launch_ssim_fwd(const SsimParams& p, cudaStream_t stream);
+cudaError_t launch_ssim_bwd(const SsimParams& p, cudaStream_t stream);
+cudaError_t launch_smooth_fwd(const SmoothParams& p, cudaStream_t stream);
+cudaError_t launch_smooth_bwd(const SmoothParams& p, cudaStream_t stream);
+cudaError_t launch_resize_bilinear(const float* src, float* dst, int planes, int sh, int sw, int dh, int dw, cudaStream_t stream);
+constexpr int kOpBlock = 256;
 
 static thread_local char g_cuda_err[256] = "";
 
@@ -208,6 +217,94 @@ static int motion_params(const sde_motion_desc* d, const sde_motion_buffers* b, 
   if (backward && !b->grad_losses) return SDE_ERR_INVALID_ARG;
   return SDE_OK;
 }
+// ------------------------------------------------------------------------------------------------ ops
+static bool vs_ok(const sde_vs_desc* d) {
+  return d && d->batch >= 1 && d->channels >= 1 && d->height >= 2 && d->width >= 2;
+}
+struct VsLayout { int blocks; size_t off_partials, off_fix, total; };
+static VsLayout vs_layout(const sde_vs_desc* d) {
+  VsLayout L;
+  L.blocks = (d->height * d->width + kOpBlock - 1) / kOpBlock;
+  size_t off = align16((size_t)d->batch * sizeof(unsigned));
+  L.off_partials = off;
+  off = align16(off + (size_t)d->batch * L.blocks * 12 * sizeof(float));
+  L.off_fix = off;
+  off = align16(off + (size_t)d->batch * d->channels * d->height * d->width * sizeof(long long));
+  L.total = off;
+  return L;
+}
+static int vs_params(const sde_vs_desc* d, const sde_vs_buffers* b, bool backward, VsParams& p) {
+  if (!vs_ok(d) || !b) return SDE_ERR_INVALID_ARG;
+  if (!b->image_b || !b->depth_a || !b->intrinsics || !b->rotation || !b->translation) return SDE_ERR_INVALID_ARG;
+  memset(&p, 0, sizeof(p));
+  p.B = d->batch; p.C = d->channels; p.h = d->height; p.w = d->width;
+  p.t_per_pixel = (d->flags & SDE_VS_T_PER_PIXEL) ? 1 : 0;
+  p.image = b->image_b; p.depth = b->depth_a; p.K = b->intrinsics; p.R = b->rotation; p.t = b->translation;
+  p.sampled = b->sampled; p.depth_in_b = b->depth_in_b; p.coords = b->coords; p.valid = b->valid;
+  if (!backward) return b->sampled ? SDE_OK : SDE_ERR_INVALID_ARG;
+  if (!b->grad_sampled || !b->grad_depth_a || !b->grad_rotation || !b->grad_translation || !b->workspace)
+    return SDE_ERR_INVALID_ARG;
+  const VsLayout L = vs_layout(d);
+  char* ws = static_cast<char*>(b->workspace);
+  p.g_sampled = b->grad_sampled; p.g_depth_in_b = b->grad_depth_in_b; p.g_coords = b->grad_coords;
+  p.g_depth = b->grad_depth_a; p.g_R = b->grad_rotation; p.g_t = b->grad_translation;
+  p.g_image_fix = b->grad_image_b ? reinterpret_cast<long long*>(ws + L.off_fix) : nullptr;
+  p.counters = reinterpret_cast<unsigned*>(ws);
+  p.partials = reinterpret_cast<float*>(ws + L.off_partials);
+  return SDE_OK;
+}
+
+static bool ssim_ok(const sde_ssim_desc* d) {
+  return d && d->batch >= 1 && d->channels >= 1 && d->height >= 2 && d->width >= 2 && !(isinf(d->c1) && isinf(d->c2));
+}
+static int ssim_params(const sde_ssim_desc* d, const sde_ssim_buffers* b, bool backward, SsimParams& p) {
+  if (!ssim_ok(d) || !b || !b->x || !b->y) return SDE_ERR_INVALID_ARG;
+  memset(&p, 0, sizeof(p));
+  p.B = d->batch; p.C = d->channels; p.h = d->height; p.w = d->width;
+  p.c1 = d->c1; p.c2 = d->c2;
+  p.mode = isinf(d->c1) ? 1 : (isinf(d->c2) ? 2 : 0);
+  p.x = b->x; p.y = b->y; p.weight = b->weight; p.out = b->out; p.avg_w = b->avg_w;
+  if (!backward) return b->out ? SDE_OK : SDE_ERR_INVALID_ARG;
+  if (!b->grad_out || !b->workspace || (!b->grad_x && !b->grad_y)) return SDE_ERR_INVALID_ARG;
+  p.g_out = b->grad_out; p.g_x = b->grad_x; p.g_y = b->grad_y;
+  p.coef = static_cast<float*>(b->workspace);
+  return SDE_OK;
+}
+
+static bool smooth_ok(const sde_smooth_desc* d) {
+  return d && d->batch >= 1 && d->channels >= 1 && d->height >= 2 && d->width >= 2;
+}
+struct SmoothLayout { int blocks; size_t off_fin, off_partials, total; };
+static SmoothLayout smooth_layout(const sde_smooth_desc* d) {
+  SmoothLayout L;
+  L.blocks = (d->height * d->width + kOpBlock - 1) / kOpBlock;
+  size_t off = align16((size_t)(1 + d->batch) * sizeof(unsigned));
+  L.off_fin = off;
+  off = align16(off + (size_t)d->batch * sizeof(double));
+  L.off_partials = off;
+  off = align16(off + (size_t)d->batch * L.blocks * 4 * sizeof(float));
+  L.total = off;
+  return L;
+}
+static int smooth_params(const sde_smooth_desc* d, const sde_smooth_buffers* b, bool backward, SmoothParams& p) {
+  if (!smooth_ok(d) || !b || !b->depth || !b->image || !b->saved_stats) return SDE_ERR_INVALID_ARG;
+  memset(&p, 0, sizeof(p));
+  p.B = d->batch; p.C = d->channels; p.h = d->height; p.w = d->width;
+  p.depth = b->depth; p.image = b->image; p.stats = b->saved_stats;
+  if (!backward) {
+    if (!b->loss || !b->workspace) return SDE_ERR_INVALID_ARG;
+    const SmoothLayout L = smooth_layout(d);
+    char* ws = static_cast<char*>(b->workspace);
+    p.loss = b->loss;
+    p.counters = reinterpret_cast<unsigned*>(ws);
+    p.fin = reinterpret_cast<double*>(ws + L.off_fin);
+    p.partials = reinterpret_cast<float*>(ws + L.off_partials);
+  } else {
+    if (!b->grad_loss || !b->grad_depth) return SDE_ERR_INVALID_ARG;
+    p.g_loss = b->grad_loss; p.g_depth = b->grad_depth;
+  }
+  return SDE_OK;
+}
 }  // namespace sde
 
 using namespace sde;
@@ -269,6 +366,64 @@ int sde_motion_loss_backward(const sde_motion_desc* desc, const sde_motion_buffe
   if (st != SDE_OK) return st;
   cudaError_t e = launch_motion_bwd(p, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SDE_OK : cuda_fail(e);
+}
+
+#define SDE_LAUNCH(expr) do { cudaError_t e_ = (expr); return e_ == cudaSuccess ? SDE_OK : cuda_fail(e_); } while (0)
+
+size_t sde_view_synthesis_workspace_bytes(const sde_vs_desc* desc) { return vs_ok(desc) ? vs_layout(desc).total : 0; }
+
+int sde_view_synthesis_forward(const sde_vs_desc* desc, const sde_vs_buffers* buf, void* stream) {
+  VsParams p;
+  int st = vs_params(desc, buf, false, p);
+  if (st != SDE_OK) return st;
+  SDE_LAUNCH(launch_vs_fwd(p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_view_synthesis_backward(const sde_vs_desc* desc, const sde_vs_buffers* buf, void* stream) {
+  VsParams p;
+  int st = vs_params(desc, buf, true, p);
+  if (st != SDE_OK) return st;
+  SDE_LAUNCH(launch_vs_bwd(p, buf->grad_image_b, static_cast<cudaStream_t>(stream)));
+}
+
+size_t sde_ssim_workspace_bytes(const sde_ssim_desc* desc) {
+  return ssim_ok(desc) ? (size_t)6 * desc->batch * desc->channels * desc->height * desc->width * sizeof(float) : 0;
+}
+
+int sde_ssim_forward(const sde_ssim_desc* desc, const sde_ssim_buffers* buf, void* stream) {
+  SsimParams p;
+  int st = ssim_params(desc, buf, false, p);
+  if (st != SDE_OK) return st;
+  SDE_LAUNCH(launch_ssim_fwd(p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_ssim_backward(const sde_ssim_desc* desc, const sde_ssim_buffers* buf, void* stream) {
+  SsimParams p;
+  int st = ssim_params(desc, buf, true, p);
+  if (st != SDE_OK) return st;
+  SDE_LAUNCH(launch_ssim_bwd(p, static_cast<cudaStream_t>(stream)));
+}
+
+size_t sde_smoothness_workspace_bytes(const sde_smooth_desc* desc) { return smooth_ok(desc) ? smooth_layout(desc).total : 0; }
+
+int sde_smoothness_forward(const sde_smooth_desc* desc, const sde_smooth_buffers* buf, void* stream) {
+  SmoothParams p;
+  int st = smooth_params(desc, buf, false, p);
+  if (st != SDE_OK) return st;
+  SDE_LAUNCH(launch_smooth_fwd(p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_smoothness_backward(const sde_smooth_desc* desc, const sde_smooth_buffers* buf, void* stream) {
+  SmoothParams p;
+  int st = smooth_params(desc, buf, true, p);
+  if (st != SDE_OK) return st;
+  SDE_LAUNCH(launch_smooth_bwd(p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_resize_bilinear(const float* src, float* dst, int32_t planes, int32_t src_h, int32_t src_w, int32_t dst_h,
+                        int32_t dst_w, void* stream) {
+  if (!src || !dst || planes < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return SDE_ERR_INVALID_ARG;
+  SDE_LAUNCH(launch_resize_bilinear(src, dst, planes, src_h, src_w, dst_h, dst_w, static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

@@ -28,9 +28,16 @@ def inv_intrinsics(K):
 
 
 def resize_img(image, dst_size, mode="bilinear"):
-    """align_corners bilinear resize, identity when the size already matches (camera.py:40-46)."""
+    """align_corners bilinear resize, identity when the size already matches (camera.py:40-46).
+
+    CUDA fp32 data tensors (the image pyramid of the loss path, MonoDepth2.py:82,88) go through the
+    sde_resize_bilinear kernel; tensors that need a gradient, other modes and host tensors (data
+    loading) use F.interpolate, which is what the reference calls."""
     if image.shape[-2] == dst_size[-2] and image.shape[-1] == dst_size[-1]:
         return image
+    if mode == "bilinear" and image.is_cuda and image.dtype == torch.float32 and not image.requires_grad:
+        from ..ops import resize_bilinear
+        return resize_bilinear(image, dst_size)
     return F.interpolate(image, size=tuple(dst_size), mode=mode,
                          align_corners=True if mode != "nearest" else None)
 
@@ -40,3 +47,13 @@ def resize_img_avgpool(image, dst_size):
     if image.shape[-2] == dst_size[-2] and image.shape[-1] == dst_size[-1]:
         return image
     return F.adaptive_avg_pool2d(image, tuple(dst_size))
+
+
+def view_synthesis(image_B, depth_A, intrinsics, R_A_to_B, t_A_to_B):
+    """Warps image_B into frame A (camera.py:166-202): back-project depth_A with K^-1, move by (R, t),
+    project with K, clamp, bilinear sample.  image_B [B,C,H,W], depth_A [B,1,H,W], intrinsics [B,3,3] (at
+    this size), R_A_to_B [B,3,3], t_A_to_B [B,3,1,1] or [B,3,H,W].  Returns (sampled [B,C,H,W],
+    depth_in_B [B,1,H,W], coords [B,H,W,2] normalised (x,y), valid [B,1,H,W] bool).  Differentiable
+    w.r.t. depth_A, R, t and image_B (deterministic scatter).  One CUDA launch forward, one backward."""
+    from ..ops import view_synthesis as _vs
+    return _vs(image_B, depth_A, intrinsics, R_A_to_B, t_A_to_B)

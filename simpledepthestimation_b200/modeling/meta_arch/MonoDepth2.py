@@ -8,8 +8,9 @@ import torch
 import torch.nn as nn
 
 from ...functional import MonoLossPlan, mono_photometric_smoothness_loss
-from ...geometry.camera import resize_img
+from ...geometry.camera import resize_img, view_synthesis
 from ...utils.memory import to_cuda
+from ..losses.ssim_loss import SSIM
 from ..nets import build_depth_net, build_pose_net
 from .build import META_ARCH_REGISTRY
 
@@ -39,6 +40,7 @@ class MonoDepth2Model(nn.Module):
         self.register_buffer("pixel_mean", torch.Tensor(cfg.MODEL.PIXEL_MEAN).view(1, -1, 1, 1))
         self.register_buffer("pixel_std", torch.Tensor(cfg.MODEL.PIXEL_STD).view(1, -1, 1, 1))
         self._plans = {}
+        self.ssim = SSIM(self.c1, self.c2)
 
     @property
     def device(self):
@@ -84,3 +86,18 @@ class MonoDepth2Model(nn.Module):
         else:
             output["depth_pred"] = batch["depth_pred"][0]
         return output
+
+    def rgb_consistency_loss(self, frame_A, frame_B, depth_A, intrinsics, R_A2B=None, t_A2B=None):
+        """Photometric error of one (scale, source) pair, [B,1,H,W] (MonoDepth2.py:130-151): the un-fused
+        form of what forward() computes inside the fused kernels -- view_synthesis + SSIM as two CUDA
+        operators.  With R_A2B / t_A2B omitted frame_B is compared unwarped (identity / automask term)."""
+        if R_A2B is not None and t_A2B is not None:
+            if t_A2B.dim() == 2:
+                t_A2B = t_A2B[:, :, None, None]
+            sampled, _, _, _ = view_synthesis(frame_B, depth_A, intrinsics, R_A2B, t_A2B)
+        else:
+            sampled = frame_B
+        loss = (sampled - frame_A).abs().mean(1, True)
+        if self.ssim_loss_weight > 0.0:
+            loss = self.ssim(sampled, frame_A).mean(1, True) * self.ssim_loss_weight + loss * (1 - self.ssim_loss_weight)
+        return loss

@@ -13,9 +13,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ...functional import MotionLossPlan, motion_rgbd_smoothness_loss
-from ...geometry.camera import resize_img_avgpool
+from ...geometry.camera import resize_img_avgpool, view_synthesis
 from ...utils.memory import to_cuda
 from ..losses.motion_loss import motion_consistency_loss, motion_smoothness_loss_fn, motion_sparsity_loss_fn
+from ..losses.ssim_loss import WeightedSSIM
 from ..nets import build_depth_net, build_pose_net
 from .build import META_ARCH_REGISTRY
 
@@ -58,6 +59,7 @@ class MotionLearningModel(nn.Module):
         self.register_buffer("pixel_mean", torch.Tensor(cfg.MODEL.PIXEL_MEAN).view(1, -1, 1, 1))
         self.register_buffer("pixel_std", torch.Tensor(cfg.MODEL.PIXEL_STD).view(1, -1, 1, 1))
         self._plans = {}
+        self.ssim = WeightedSSIM(self.c1, self.c2)
 
     @property
     def device(self):
@@ -159,3 +161,25 @@ class MotionLearningModel(nn.Module):
 
         batch.update(losses)
         return batch
+
+    def rgbd_consistency_loss(self, frame_A, frame_B, depth_A, depth_B, intrinsics, R_A2B, t_A2B):
+        """One direction of the rgb-d consistency loss as a dict (MotionLearning.py:248-291): the un-fused form
+        of what forward() computes in the fused kernel -- view_synthesis + WeightedSSIM as CUDA operators, the
+        per-sample statistics in torch."""
+        out = {}
+        sampled, depth_in_B, coords, valid = view_synthesis(torch.cat([frame_B, depth_B], 1), depth_A, intrinsics,
+                                                            R_A2B, t_A2B)
+        out["coords_A_in_B"] = coords
+        sampled_frame_B, sampled_depth_B = torch.split(sampled, [3, 1], dim=1)
+        occ = (depth_in_B < sampled_depth_B).float() * valid.float()
+        out["occlusion_mask"] = occ
+        normalizer = occ.sum([1, 2, 3]) + 1
+        out["rgb_l1_loss"] = ((sampled_frame_B - frame_A).abs() * occ).mean()
+        if self.ssim_loss_w > 0.0:
+            err = (depth_in_B - sampled_depth_B) ** 2
+            m2 = ((err * occ).sum([1, 2, 3]) / normalizer + 1e-4).view(-1, 1, 1, 1)
+            weight = ((m2 / (err + m2)) * valid.float()).detach()
+            ssim_map, avg_w = self.ssim(sampled_frame_B, frame_A, weight)
+            out["depth_proximity_weight"] = weight
+            out["ssim_loss"] = (ssim_map * avg_w).mean() * self.ssim_loss_w * 0.5
+        return out

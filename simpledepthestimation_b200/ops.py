@@ -1,0 +1,224 @@
+"""torch.autograd.Function wrappers of the stand-alone CUDA operators (csrc/ops.cu): view_synthesis,
+SSIM / WeightedSSIM, smoothness_loss, resize_img.  The reference-named entry points live in
+geometry/camera.py and modeling/losses/*.py; this module is the plumbing (device memory, stream,
+workspaces).  No CPU path: CPU tensors raise."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.SdeError(f"{name} must be a CUDA tensor: the view-synthesis loss path has no CPU implementation")
+    if t.dtype != torch.float32:
+        raise _lib.SdeError(f"{name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_WS = {}
+
+
+def _zero_workspace(kind, key, nbytes, device):
+    """Zero-initialised workspaces are re-zeroed by the kernels, so they are cached per shape and stream."""
+    k = (kind, key, str(device), _stream())
+    ws = _WS.get(k)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=device)
+        _WS[k] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------------ view_synthesis
+class _ViewSynthesisFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image_B, depth_A, K, R, t):
+        lib = _lib.load()
+        image_B, depth_A = _cuda_f32(image_B, "image_B"), _cuda_f32(depth_A, "depth_A")
+        K, R, t = _cuda_f32(K, "intrinsics"), _cuda_f32(R, "R_A_to_B"), _cuda_f32(t, "t_A_to_B")
+        B, Cc, h, w = image_B.shape
+        if tuple(depth_A.shape) != (B, 1, h, w) or tuple(K.shape) != (B, 3, 3) or tuple(R.shape) != (B, 3, 3):
+            raise _lib.SdeError("view_synthesis: expected image_B [B,C,H,W], depth_A [B,1,H,W], intrinsics / R [B,3,3]")
+        per_pixel = tuple(t.shape) == (B, 3, h, w) and (h, w) != (1, 1)
+        if not per_pixel and t.numel() != B * 3:
+            raise _lib.SdeError("view_synthesis: t_A_to_B must be [B,3,1,1] or [B,3,H,W]")
+        d = _lib.VsDesc(B, Cc, h, w, _lib_flag(per_pixel))
+        b = _lib.VsBuffers()
+        dev = image_B.device
+        sampled = torch.empty_like(image_B)
+        z = torch.empty(B, 1, h, w, device=dev)
+        coords = torch.empty(B, h, w, 2, device=dev)
+        valid = torch.empty(B, 1, h, w, dtype=torch.uint8, device=dev)
+        b.image_b, b.depth_a, b.intrinsics, b.rotation, b.translation = (x.data_ptr() for x in (image_B, depth_A, K, R, t))
+        b.sampled, b.depth_in_b, b.coords, b.valid = sampled.data_ptr(), z.data_ptr(), coords.data_ptr(), valid.data_ptr()
+        _lib.check(lib.sde_view_synthesis_forward(C.byref(d), C.byref(b), _stream()), "sde_view_synthesis_forward")
+        ctx.save_for_backward(image_B, depth_A, K, R, t)
+        ctx.per_pixel, ctx.t_shape = per_pixel, tuple(t.shape)
+        valid = valid.bool()
+        ctx.mark_non_differentiable(valid)
+        return sampled, z, coords, valid
+
+    @staticmethod
+    def backward(ctx, g_sampled, g_z, g_coords, _g_valid):
+        lib = _lib.load()
+        image_B, depth_A, K, R, t = ctx.saved_tensors
+        B, Cc, h, w = image_B.shape
+        dev = image_B.device
+        d = _lib.VsDesc(B, Cc, h, w, _lib_flag(ctx.per_pixel))
+        nbytes = lib.sde_view_synthesis_workspace_bytes(C.byref(d))
+        ws = _zero_workspace("vs", (B, Cc, h, w), nbytes, dev)
+        b = _lib.VsBuffers()
+        b.image_b, b.depth_a, b.intrinsics, b.rotation, b.translation = (x.data_ptr() for x in (image_B, depth_A, K, R, t))
+        keep = []
+        gs = g_sampled.contiguous().float() if g_sampled is not None else torch.zeros_like(image_B)
+        keep.append(gs)
+        b.grad_sampled = gs.data_ptr()
+        if g_z is not None:
+            g_z = g_z.contiguous().float(); keep.append(g_z); b.grad_depth_in_b = g_z.data_ptr()
+        if g_coords is not None:
+            g_coords = g_coords.contiguous().float(); keep.append(g_coords); b.grad_coords = g_coords.data_ptr()
+        g_depth = torch.empty_like(depth_A)
+        g_R = torch.empty_like(R)
+        g_t = torch.empty(B, 3, h, w, device=dev) if ctx.per_pixel else torch.empty(B, 3, device=dev)
+        b.grad_depth_a, b.grad_rotation, b.grad_translation = g_depth.data_ptr(), g_R.data_ptr(), g_t.data_ptr()
+        g_img = None
+        if ctx.needs_input_grad[0]:
+            g_img = torch.empty_like(image_B)
+            b.grad_image_b = g_img.data_ptr()
+        b.workspace = ws.data_ptr()
+        _lib.check(lib.sde_view_synthesis_backward(C.byref(d), C.byref(b), _stream()), "sde_view_synthesis_backward")
+        return g_img, g_depth, None, g_R, g_t.view(ctx.t_shape)
+
+
+def _lib_flag(per_pixel):
+    return 1 if per_pixel else 0
+
+
+def view_synthesis(image_B, depth_A, intrinsics, R_A_to_B, t_A_to_B):
+    return _ViewSynthesisFn.apply(image_B, depth_A, intrinsics, R_A_to_B, t_A_to_B)
+
+
+# ------------------------------------------------------------------------------------------------ SSIM
+class _SsimFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, w, c1, c2):
+        lib = _lib.load()
+        x, y = _cuda_f32(x, "x"), _cuda_f32(y, "y")
+        if x.shape != y.shape or x.dim() != 4:
+            raise _lib.SdeError("SSIM: x and y must be [B,C,H,W] of the same shape")
+        B, Cc, h, w_ = x.shape
+        d = _lib.SsimDesc(B, Cc, h, w_, float(c1), float(c2))
+        b = _lib.SsimBuffers()
+        out = torch.empty_like(x)
+        b.x, b.y, b.out = x.data_ptr(), y.data_ptr(), out.data_ptr()
+        avg_w = None
+        if w is not None:
+            w = _cuda_f32(w, "w")
+            if tuple(w.shape) != (B, 1, h, w_):
+                raise _lib.SdeError("WeightedSSIM: w must be [B,1,H,W]")
+            avg_w = torch.empty_like(w)
+            b.weight, b.avg_w = w.data_ptr(), avg_w.data_ptr()
+        if lib.sde_ssim_workspace_bytes(C.byref(d)) == 0:
+            raise _lib.SdeError("SSIM: invalid sizes (H, W >= 2) or C1 and C2 both infinite")
+        _lib.check(lib.sde_ssim_forward(C.byref(d), C.byref(b), _stream()), "sde_ssim_forward")
+        ctx.save_for_backward(x, y, w if w is not None else x.new_empty(0))
+        ctx.consts = (float(c1), float(c2), w is not None)
+        if avg_w is None:
+            return out
+        ctx.mark_non_differentiable(avg_w)
+        return out, avg_w
+
+    @staticmethod
+    def backward(ctx, g_out, *_):
+        lib = _lib.load()
+        x, y, w = ctx.saved_tensors
+        c1, c2, weighted = ctx.consts
+        B, Cc, h, w_ = x.shape
+        d = _lib.SsimDesc(B, Cc, h, w_, c1, c2)
+        b = _lib.SsimBuffers()
+        g_out = g_out.contiguous().float()
+        ws = torch.empty(lib.sde_ssim_workspace_bytes(C.byref(d)), dtype=torch.uint8, device=x.device)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        if gx is None and gy is None:
+            return None, None, None, None, None
+        b.x, b.y, b.grad_out, b.workspace = x.data_ptr(), y.data_ptr(), g_out.data_ptr(), ws.data_ptr()
+        if weighted:
+            b.weight = w.data_ptr()
+        if gx is not None:
+            b.grad_x = gx.data_ptr()
+        if gy is not None:
+            b.grad_y = gy.data_ptr()
+        _lib.check(lib.sde_ssim_backward(C.byref(d), C.byref(b), _stream()), "sde_ssim_backward")
+        return gx, gy, None, None, None
+
+
+def ssim(x, y, c1, c2):
+    return _SsimFn.apply(x, y, None, c1, c2)
+
+
+def weighted_ssim(x, y, w, c1, c2):
+    return _SsimFn.apply(x, y, w.detach(), c1, c2)
+
+
+# ------------------------------------------------------------------------------------------------ smoothness
+class _SmoothnessFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, image):
+        lib = _lib.load()
+        depth, image = _cuda_f32(depth, "depth"), _cuda_f32(image, "image")
+        B, Cc, h, w = image.shape
+        if tuple(depth.shape) != (B, 1, h, w):
+            raise _lib.SdeError("smoothness_loss: expected depth [B,1,H,W] and image [B,C,H,W]")
+        d = _lib.SmoothDesc(B, Cc, h, w)
+        nbytes = lib.sde_smoothness_workspace_bytes(C.byref(d))
+        if nbytes == 0:
+            raise _lib.SdeError("smoothness_loss: H and W must be >= 2")
+        ws = _zero_workspace("smooth", (B, Cc, h, w), nbytes, depth.device)
+        loss = torch.empty(1, device=depth.device)
+        stats = torch.empty(B * 2, device=depth.device)
+        b = _lib.SmoothBuffers()
+        b.depth, b.image, b.loss, b.saved_stats, b.workspace = (depth.data_ptr(), image.data_ptr(), loss.data_ptr(),
+                                                               stats.data_ptr(), ws.data_ptr())
+        _lib.check(lib.sde_smoothness_forward(C.byref(d), C.byref(b), _stream()), "sde_smoothness_forward")
+        ctx.save_for_backward(depth, image, stats)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        depth, image, stats = ctx.saved_tensors
+        B, Cc, h, w = image.shape
+        d = _lib.SmoothDesc(B, Cc, h, w)
+        g = g.reshape(1).contiguous().float()
+        gd = torch.empty_like(depth)
+        b = _lib.SmoothBuffers()
+        b.depth, b.image, b.saved_stats, b.grad_loss, b.grad_depth = (depth.data_ptr(), image.data_ptr(), stats.data_ptr(),
+                                                                      g.data_ptr(), gd.data_ptr())
+        _lib.check(lib.sde_smoothness_backward(C.byref(d), C.byref(b), _stream()), "sde_smoothness_backward")
+        return gd, None
+
+
+def smoothness(depth, image):
+    return _SmoothnessFn.apply(depth, image.detach())
+
+
+# ------------------------------------------------------------------------------------------------ resize
+def resize_bilinear(image: torch.Tensor, dst_size) -> torch.Tensor:
+    """F.interpolate(image, dst_size, mode='bilinear', align_corners=True) for a CUDA fp32 [..., H, W] tensor."""
+    lib = _lib.load()
+    image = _cuda_f32(image, "image")
+    sh, sw = image.shape[-2:]
+    dh, dw = int(dst_size[-2]), int(dst_size[-1])
+    planes = image.numel() // (sh * sw)
+    out = torch.empty(*image.shape[:-2], dh, dw, device=image.device)
+    _lib.check(lib.sde_resize_bilinear(image.data_ptr(), out.data_ptr(), planes, sh, sw, dh, dw, _stream()),
+               "sde_resize_bilinear")
+    return out
