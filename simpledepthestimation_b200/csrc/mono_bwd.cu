@@ -38,6 +38,8 @@ struct BwdShared {
   float red[12][kThreads / 32];
   double dred[12][kThreads / 32];
   unsigned ticket;
+  int cnt[kPosPerThread][kThreads / 32];         // selected pixels per (pass, warp)
+  unsigned short list[kBwdW * kBwdH];            // dense list of the selected pixels of P
   __align__(8) uint8_t arg[kPlane];
 };
 
@@ -226,65 +228,97 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     }
 
     // ---------------------------------------------------------------- phase 4: warp backward on P
+    // Only pixels whose argmin is this source's warped candidate carry a gradient (with automasking
+    // that is often a minority), so they are first compacted into a dense list -- in a fixed order, so
+    // the pose sums stay deterministic -- and the expensive part runs on full warps.
     {
-      float acc[12];
-#pragma unroll
-      for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
+      unsigned selbits = 0;
+      int rank[kPosPerThread];
 #pragma unroll
       for (int it = 0; it < kPosPerThread; ++it) {
         const int i = tid + it * kThreads;
         const int ly = i / kBwdW, lx = i - ly * kBwdW;
         const int gy = tc.y0 + ly, gx = tc.x0 + lx;
+        bool sel = false;
         if (i < kBwdW * kBwdH && gy < h && gx < w) {
           const int pl = plane_index(ly + 2, lx + 2);
-          const float g0 = planes[kBG * kPlane + pl], g1 = planes[(kBG + 1) * kPlane + pl],
-                      g2 = planes[(kBG + 2) * kPlane + pl];
-          if (g0 != 0.0f || g1 != 0.0f || g2 != 0.0f) {
-            const float d = planes[kBD * kPlane + pl];
-            const float fxp = (float)gx, fyp = (float)gy;
-            float P[3], den, X, Y;
-            project_full(cam, pj, fxp, fyp, d, P, den, X, Y);
-            const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
-            // gradient gates of nan_to_num and clamp (closed interval), camera.py:184-188
-            const bool gate_x = (X >= 0.0f) && (X <= wm1);   // false for NaN / +-inf
-            const bool gate_y = (Y >= 0.0f) && (Y <= hm1);
-            if (gate_x || gate_y) {
-              const Cell cell = bilinear_cell(X, Y, w, h);
-              const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
-              float gX = 0.0f, gY = 0.0f;
-              const float gs[3] = {g0, g1, g2};
-              const float* pls[3] = {sc0, sc1, sc2};
-#pragma unroll
-              for (int cc = 0; cc < 3; ++cc) {
-                const float* q0 = pls[cc] + cell.off;
-                const float* q1 = q0 + w;
-                const float v00 = __ldg(q0), v01 = __ldg(q0 + 1), v10 = __ldg(q1), v11 = __ldg(q1 + 1);
-                gX += gs[cc] * ((v01 - v00) * by + (v11 - v10) * cell.ay);
-                gY += gs[cc] * ((v10 - v00) * bx + (v11 - v01) * cell.ax);
-              }
-              if (!gate_x) gX = 0.0f;
-              if (!gate_y) gY = 0.0f;
-              const float q = 1.0f / den;
-              const float u0 = gX * q, u1 = gY * q;
-              // K^T g_p, with the third row formed per pixel in camera-centred coordinates
-              const float dx = gate_x ? X - cam.cx : 0.0f, dy = gate_y ? Y - cam.cy : 0.0f;
-              const float gc0 = cam.fx * u0;
-              const float gc1 = cam.sk * u0 + cam.fy * u1;
-              const float gc2 = -(gX * dx + gY * dy) * q;
-              acc[0] += gc0 * P[0]; acc[1] += gc0 * P[1]; acc[2] += gc0 * P[2]; acc[3] += gc0;
-              acc[4] += gc1 * P[0]; acc[5] += gc1 * P[1]; acc[6] += gc1 * P[2]; acc[7] += gc1;
-              acc[8] += gc2 * P[0]; acc[9] += gc2 * P[1]; acc[10] += gc2 * P[2]; acc[11] += gc2;
-              // d/d depth: (R^T K^T g_p) . K^-1 [x,y,1]
-              const float gP0 = pj.r[0] * gc0 + pj.r[3] * gc1 + pj.r[6] * gc2;
-              const float gP1 = pj.r[1] * gc0 + pj.r[4] * gc1 + pj.r[7] * gc2;
-              const float gP2 = pj.r[2] * gc0 + pj.r[5] * gc1 + pj.r[8] * gc2;
-              const float rx = cam.ki[0] * fxp + cam.ki[1] * fyp + cam.ki[2];
-              const float ry = cam.ki[3] * fxp + cam.ki[4] * fyp + cam.ki[5];
-              const float rz = cam.ki[6] * fxp + cam.ki[7] * fyp + cam.ki[8];
-              gd[it] += gP0 * rx + gP1 * ry + gP2 * rz;
-            }
-          }
+          sel = planes[kBG * kPlane + pl] != 0.0f || planes[(kBG + 1) * kPlane + pl] != 0.0f ||
+                planes[(kBG + 2) * kPlane + pl] != 0.0f;
         }
+        const unsigned bal = __ballot_sync(0xffffffffu, sel);
+        rank[it] = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) sh.cnt[it][wid] = __popc(bal);
+        selbits |= (sel ? 1u : 0u) << it;
+      }
+      __syncthreads();
+      int run = 0;
+#pragma unroll
+      for (int it = 0; it < kPosPerThread; ++it) {
+#pragma unroll
+        for (int w2 = 0; w2 < kThreads / 32; ++w2) {
+          if (w2 == wid && ((selbits >> it) & 1u)) sh.list[run + rank[it]] = (unsigned short)(tid + it * kThreads);
+          run += sh.cnt[it][w2];
+        }
+      }
+      const int total = run;
+      __syncthreads();
+
+      float acc[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
+      float* const scratch = planes + kBCoef * kPlane;   // coefficient plane 0 is free until the next phase 2
+#pragma unroll 1
+      for (int k = tid; k < total; k += kThreads) {
+        const int i = sh.list[k];
+        const int ly = i / kBwdW, lx = i - ly * kBwdW;
+        const int gy = tc.y0 + ly, gx = tc.x0 + lx;
+        const int pl = plane_index(ly + 2, lx + 2);
+        const float g0 = planes[kBG * kPlane + pl], g1 = planes[(kBG + 1) * kPlane + pl], g2 = planes[(kBG + 2) * kPlane + pl];
+        const float d = planes[kBD * kPlane + pl];
+        const float fxp = (float)gx, fyp = (float)gy;
+        float P[3], den, X, Y;
+        project_full(cam, pj, fxp, fyp, d, P, den, X, Y);
+        const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
+        // gradient gates of nan_to_num and clamp (closed interval), camera.py:184-188
+        const bool gate_x = (X >= 0.0f) && (X <= wm1);   // false for NaN / +-inf
+        const bool gate_y = (Y >= 0.0f) && (Y <= hm1);
+        float gdep = 0.0f;
+        if (gate_x || gate_y) {
+          const Cell cell = bilinear_cell(X, Y, w, h);
+          const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
+          float gX = 0.0f, gY = 0.0f;
+          const float gs[3] = {g0, g1, g2};
+          const float* pls[3] = {sc0, sc1, sc2};
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            const float* q0 = pls[cc] + cell.off;
+            const float* q1 = q0 + w;
+            const float v00 = __ldg(q0), v01 = __ldg(q0 + 1), v10 = __ldg(q1), v11 = __ldg(q1 + 1);
+            gX += gs[cc] * ((v01 - v00) * by + (v11 - v10) * cell.ay);
+            gY += gs[cc] * ((v10 - v00) * bx + (v11 - v01) * cell.ax);
+          }
+          if (!gate_x) gX = 0.0f;
+          if (!gate_y) gY = 0.0f;
+          const float q = 1.0f / den;
+          const float u0 = gX * q, u1 = gY * q;
+          // K^T g_p, with the third row formed per pixel in camera-centred coordinates
+          const float dx = gate_x ? X - cam.cx : 0.0f, dy = gate_y ? Y - cam.cy : 0.0f;
+          const float gc0 = cam.fx * u0;
+          const float gc1 = cam.sk * u0 + cam.fy * u1;
+          const float gc2 = -(gX * dx + gY * dy) * q;
+          acc[0] += gc0 * P[0]; acc[1] += gc0 * P[1]; acc[2] += gc0 * P[2]; acc[3] += gc0;
+          acc[4] += gc1 * P[0]; acc[5] += gc1 * P[1]; acc[6] += gc1 * P[2]; acc[7] += gc1;
+          acc[8] += gc2 * P[0]; acc[9] += gc2 * P[1]; acc[10] += gc2 * P[2]; acc[11] += gc2;
+          // d/d depth: (R^T K^T g_p) . K^-1 [x,y,1]
+          const float gP0 = pj.r[0] * gc0 + pj.r[3] * gc1 + pj.r[6] * gc2;
+          const float gP1 = pj.r[1] * gc0 + pj.r[4] * gc1 + pj.r[7] * gc2;
+          const float gP2 = pj.r[2] * gc0 + pj.r[5] * gc1 + pj.r[8] * gc2;
+          const float rx = cam.ki[0] * fxp + cam.ki[1] * fyp + cam.ki[2];
+          const float ry = cam.ki[3] * fxp + cam.ki[4] * fyp + cam.ki[5];
+          const float rz = cam.ki[6] * fxp + cam.ki[7] * fyp + cam.ki[8];
+          gdep = gP0 * rx + gP1 * ry + gP2 * rz;
+        }
+        scratch[pl] = gdep;
       }
       // CTA reduction of the 12 pose sums of this source -> per-CTA slot
 #pragma unroll
@@ -299,7 +333,16 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
         for (int k = 0; k < kThreads / 32; ++k) v += sh.red[tid][k];
         p.pose_partials[((size_t)blockIdx.x * p.S + j) * 12 + tid] = v;
       }
-      // the __syncthreads above also orders phase 4's plane reads before the next phase 1 / 3
+      // the __syncthreads above makes the depth gradients of the dense pass visible; pick up this thread's pixels
+      // (the next phase 2, which overwrites the scratch plane, is behind another barrier)
+#pragma unroll
+      for (int it = 0; it < kPosPerThread; ++it) {
+        if ((selbits >> it) & 1u) {
+          const int i = tid + it * kThreads;
+          const int ly = i / kBwdW, lx = i - ly * kBwdW;
+          gd[it] += scratch[plane_index(ly + 2, lx + 2)];
+        }
+      }
     }
   }
 

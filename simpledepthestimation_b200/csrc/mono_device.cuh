@@ -147,6 +147,12 @@ __device__ __forceinline__ float smooth_grad_local(const float* pd, const float*
   return G;
 }
 
+// positions a thread keeps in flight in the plain (coalesced) staging loops: 5 x 4 loads, two round trips per tile
+#ifndef SDE_STAGE_BATCH
+#define SDE_STAGE_BATCH 5
+#endif
+constexpr int kStageBatch = SDE_STAGE_BATCH;
+
 // Phase 0 of both kernels: stage what does not depend on the source -- depth, target (and the
 // argmin bytes in the backward kernel) of the halo'd tile.  All loads are independent and issued
 // before the first store, so the tile pays one memory round trip here.
@@ -156,14 +162,14 @@ __device__ __forceinline__ void stage_target(const StageArgs& a0, int tid, bool 
   a.depth = pinned(a0.depth);
   a.tgt = pinned(a0.tgt);
   constexpr int kIter = (kPositions + kThreads - 1) / kThreads;  // 10
-#pragma unroll 2
-  for (int k = 0; k < kIter; k += 2) {
-    float d[2], t[2][3];
-    uint8_t m[2];
-    int pl[2];
-    bool ok[2];
+#pragma unroll 1
+  for (int k = 0; k < kIter; k += kStageBatch) {
+    float d[kStageBatch], t[kStageBatch][3];
+    uint8_t m[kStageBatch];
+    int pl[kStageBatch];
+    bool ok[kStageBatch];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < kStageBatch; ++u) {
       const int i = tid + (k + u) * kThreads;
       ok[u] = i < kPositions;
       int yy, xx, gy, gx;
@@ -181,7 +187,7 @@ __device__ __forceinline__ void stage_target(const StageArgs& a0, int tid, bool 
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < kStageBatch; ++u) {
       if (ok[u]) {
         a.planes[a.plD * kPlane + pl[u]] = d[u];
 #pragma unroll
@@ -255,13 +261,13 @@ __device__ __forceinline__ void stage_saved(const StageArgs& a0, const float* __
   StageArgs a = a0;
   const float* wp = pinned(warped);
   constexpr int kIter = (kPositions + kThreads - 1) / kThreads;  // 10
-#pragma unroll 2
-  for (int k = 0; k < kIter; k += 2) {
-    float v[2][3];
-    int pl[2];
-    bool ok[2];
+#pragma unroll 1
+  for (int k = 0; k < kIter; k += kStageBatch) {
+    float v[kStageBatch][3];
+    int pl[kStageBatch];
+    bool ok[kStageBatch];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < kStageBatch; ++u) {
       const int i = tid + (k + u) * kThreads;
       ok[u] = i < kPositions;
       int yy, xx, gy, gx;
@@ -272,7 +278,7 @@ __device__ __forceinline__ void stage_saved(const StageArgs& a0, const float* __
       for (int c = 0; c < 3; ++c) v[u][c] = __ldg(wp + (pix + c * a.hw));
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < kStageBatch; ++u)
       if (ok[u]) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) a.planes[(a.plS + c) * kPlane + pl[u]] = v[u][c];

