@@ -2,7 +2,7 @@
 //
 // Nothing but the uint8 argmin maps and O(B) per-image statistics is kept from the forward pass:
 // the warp is recomputed.  One CTA owns a 64x16 block Q of SSIM window centres of one
-// (scale, sample) and emits gradients for Q's 62x14 interior P (a pixel's gradient collects the
+// (scale, sample) and emits gradients for Q's 60x14 interior P (a pixel's gradient collects the
 // 3x3 windows around it).  Per source frame j:
 //   phase 1  as in the forward kernel: project + bilinear gather on Q + 1-pixel halo -> planes S;
 //            target A, 1/depth and the argmin bytes are staged on the first source.
@@ -30,6 +30,9 @@ constexpr int kBA = 0, kBS = 3, kBD = 6, kBCoef = 7, kBG = 10;
 #ifndef SDE_NB
 #define SDE_NB 2
 #endif
+// the gradient block P starts at plane column 3 (not 2): with 60-wide tiles that puts plane index 0 at image
+// column tile_x0 - 4, a multiple of 4, which the TMA box start needs
+constexpr int kBwdColOff = 3;
 constexpr int kPosPerThread = (kBwdW * kBwdH + kThreads - 1) / kThreads;  // 7
 
 struct BwdShared {
@@ -38,13 +41,15 @@ struct BwdShared {
   float red[12][kThreads / 32];
   double dred[12][kThreads / 32];
   unsigned ticket;
+  __align__(8) uint64_t bar;                     // TMA completion barrier
   int cnt[kPosPerThread][kThreads / 32];         // selected pixels per (pass, warp)
   unsigned short list[kBwdW * kBwdH];            // dense list of the selected pixels of P
   __align__(8) uint8_t arg[kPlane];
 };
 
-__global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_constant__ MonoParams p) {
-  extern __shared__ __align__(16) float planes[];  // [kBwdPlanes][kPlane]
+__global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_constant__ MonoParams p,
+                                                               const __grid_constant__ MonoTma maps) {
+  extern __shared__ __align__(128) float planes[];  // [kBwdPlanes][kPlane]
   __shared__ BwdShared sh;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -53,8 +58,8 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
   const bool automask = (p.flags & SDE_MONO_AUTOMASK) != 0;
   const bool reduce_mean = (p.flags & SDE_MONO_REDUCE_MEAN) != 0;
   const bool use_ssim = p.ssim_w > 0.0f;
-  // plane (yy, xx) <-> image (oy + yy, ox + xx); Q = plane [1..16]x[1..64]; P = plane [2..15]x[2..63]
-  const int ox = tc.x0 - 2, oy = tc.y0 - 2;
+  // plane (yy, xx) <-> image (oy + yy, ox + xx); Q = plane [1..16]x[1..64]; P = plane [2..15]x[3..62]
+  const int ox = tc.x0 - kBwdColOff, oy = tc.y0 - 2;
   const bool interior = ox >= 0 && oy >= 0 && ox + kHW <= w && oy + kHH <= h;
   // reflect-pad adjoint: pixels next to the image border also receive the mirrored pad position
   const bool lr_border = ox + 2 <= 1 || ox + kHW - 3 >= w - 2;
@@ -65,6 +70,20 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     load_cam(cam, k, p.K, b, p.sx[s], p.sy[s]);
     if (tid == 0) sh.cam = cam;
     load_proj(sh.proj[tid], k, p.pose[tid], b);
+  }
+  // TMA path (saved warps, row pitch a multiple of 16 bytes): one thread hands the tile planes -- target,
+  // depth and the first source's warp -- to the copy engine before anything else happens in the CTA
+  const bool tma = p.tma[s] != 0;
+  if (tma && tid == 0) {
+    mbar_init(&sh.bar, 1);
+    mbar_init_fence();
+    mbar_arrive_expect_tx(&sh.bar, 7 * kPlaneBytesTma);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      tma_load_plane(planes + (kBA + c) * kPlane, &maps.target[s], &sh.bar, ox - kColOff, oy, b * 3 + c);
+      tma_load_plane(planes + (kBS + c) * kPlane, &maps.warped[s][0], &sh.bar, ox - kColOff, oy, b * 3 + c);
+    }
+    tma_load_plane(planes + kBD * kPlane, &maps.depth[s], &sh.bar, ox - kColOff, oy, b);
   }
   // coefficient planes: the 1-pixel border is never written and must read as zero
   for (int i = tid; i < 3 * kPlane; i += kThreads) planes[kBCoef * kPlane + i] = 0.0f;
@@ -100,8 +119,13 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
   sa.planes = planes; sa.arg = sh.arg; sa.oy = oy; sa.ox = ox; sa.h = h; sa.w = w; sa.hw = hw;
   sa.plS = kBS; sa.plI = 0; sa.plA = kBA; sa.plD = kBD;
   // ------------------------------------------------------------------ phase 0: depth + target + argmin
-  if (interior) stage_target<true, true>(sa, tid, reduce_mean);
-  else          stage_target<false, true>(sa, tid, reduce_mean);
+  unsigned tma_phase = 0;
+  if (tma) {
+    stage_arg(sh.arg, amap, oy, ox, h, w, reduce_mean, tid);   // argmin bytes: plain loads while the copy engine works
+  } else {
+    if (interior) stage_target<true, true>(sa, tid, reduce_mean);
+    else          stage_target<false, true>(sa, tid, reduce_mean);
+  }
   __syncthreads();
 
   for (int j = 0; j < p.S; ++j) {
@@ -113,7 +137,14 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     const float* __restrict__ sc2 = sc1 + hw;
     // ---------------------------------------------------------------- phase 1
     sa.src = sc0;
-    if (p.warped[s][j] != nullptr) {
+    if (tma) {
+      mbar_wait(&sh.bar, tma_phase);
+      tma_phase ^= 1u;
+      if (!interior) {
+        if (j == 0) reflect_fixup(planes, kBA, 3, oy, ox, h, w, tid), reflect_fixup(planes, kBD, 1, oy, ox, h, w, tid);
+        reflect_fixup(planes, kBS, 3, oy, ox, h, w, tid);
+      }
+    } else if (p.warped[s][j] != nullptr) {
       const float* wsrc = p.warped[s][j] + (size_t)b * 3 * hw;
       if (interior) stage_saved<true>(sa, wsrc, tid);
       else          stage_saved<false>(sa, wsrc, tid);
@@ -227,6 +258,14 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       __syncthreads();
     }
 
+    // the S planes are dead from here on: let the copy engine fetch the next source's warp during phase 4
+    if (tma && j + 1 < p.S && tid == 0) {
+      proxy_fence();
+      mbar_arrive_expect_tx(&sh.bar, 3 * kPlaneBytesTma);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        tma_load_plane(planes + (kBS + c) * kPlane, &maps.warped[s][j + 1], &sh.bar, ox - kColOff, oy, b * 3 + c);
+    }
     // ---------------------------------------------------------------- phase 4: warp backward on P
     // Only pixels whose argmin is this source's warped candidate carry a gradient (with automasking
     // that is often a minority), so they are first compacted into a dense list -- in a fixed order, so
@@ -241,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
         const int gy = tc.y0 + ly, gx = tc.x0 + lx;
         bool sel = false;
         if (i < kBwdW * kBwdH && gy < h && gx < w) {
-          const int pl = plane_index(ly + 2, lx + 2);
+          const int pl = plane_index(ly + 2, lx + kBwdColOff);
           sel = planes[kBG * kPlane + pl] != 0.0f || planes[(kBG + 1) * kPlane + pl] != 0.0f ||
                 planes[(kBG + 2) * kPlane + pl] != 0.0f;
         }
@@ -272,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
         const int i = sh.list[k];
         const int ly = i / kBwdW, lx = i - ly * kBwdW;
         const int gy = tc.y0 + ly, gx = tc.x0 + lx;
-        const int pl = plane_index(ly + 2, lx + 2);
+        const int pl = plane_index(ly + 2, lx + kBwdColOff);
         const float g0 = planes[kBG * kPlane + pl], g1 = planes[(kBG + 1) * kPlane + pl], g2 = planes[(kBG + 2) * kPlane + pl];
         const float d = planes[kBD * kPlane + pl];
         const float fxp = (float)gx, fyp = (float)gy;
@@ -340,7 +379,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
         if ((selbits >> it) & 1u) {
           const int i = tid + it * kThreads;
           const int ly = i / kBwdW, lx = i - ly * kBwdW;
-          gd[it] += scratch[plane_index(ly + 2, lx + 2)];
+          gd[it] += scratch[plane_index(ly + 2, lx + kBwdColOff)];
         }
       }
     }
@@ -363,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       if (i < kBwdW * kBwdH && gy < h && gx < w) {
         float g = gd[it];
         if (sscale > 0.0f) {
-          const int pl = plane_index(ly + 2, lx + 2);
+          const int pl = plane_index(ly + 2, lx + kBwdColOff);
           const float* pd = planes + kBD * kPlane + pl;
           const float d = pd[0];
           const float ic = inv_depth(d);
@@ -425,12 +464,12 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
 
 size_t mono_bwd_smem_bytes() { return (size_t)kBwdPlanes * kPlane * sizeof(float); }
 
-cudaError_t launch_mono_bwd(const MonoParams& p, cudaStream_t stream) {
+cudaError_t launch_mono_bwd(const MonoParams& p, const MonoTma& t, cudaStream_t stream) {
   // 61.8 KB of dynamic shared memory needs the opt-in attribute (per device; cheap and idempotent)
   cudaError_t e = cudaFuncSetAttribute(mono_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)mono_bwd_smem_bytes());
   if (e != cudaSuccess) return e;
-  mono_bwd_kernel<<<p.btile_start[p.n_scales], kThreads, mono_bwd_smem_bytes(), stream>>>(p);
+  mono_bwd_kernel<<<p.btile_start[p.n_scales], kThreads, mono_bwd_smem_bytes(), stream>>>(p, t);
   return cudaGetLastError();
 }
 

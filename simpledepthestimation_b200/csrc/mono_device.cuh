@@ -1,19 +1,33 @@
 // Device functions shared by the forward and backward MonoDepth2 loss kernels.
 #pragma once
 #include "mono_params.cuh"
+#include "tma.cuh"
 
 namespace sde {
 
-// Shared-memory plane of a tile + 1-pixel halo: 18 rows x 66 columns.  Column xx is stored at
-// index xx + 1 of a 68-float row so that the pixel pair owned by a lane (columns 2*lane+1, 2*lane+2)
-// is 8-byte aligned and lands in one register pair with a single LDS.64.
+// Shared-memory plane of a tile + 1-pixel halo: 18 rows x 66 columns.  Column xx is stored at index
+// xx + kColOff of a kPitch-float row; kColOff is odd so that the pixel pair owned by a lane (columns
+// 2*lane+1, 2*lane+2) is 8-byte aligned and lands in one register pair with a single LDS.64.
+// A translation unit may pick its own (pitch, offset) before including this header: the TMA path needs
+// the image column of index 0 to be a multiple of 4 (16-byte aligned box start), which is column
+// tile_x0 - 4 with (72, 3) in the forward kernel (tile at columns 1..64) and with (68, 1) in the
+// backward kernel (gradient block at columns 3..62).
+#ifndef SDE_PITCH
+#define SDE_PITCH 68
+#endif
+#ifndef SDE_COL_OFF
+#define SDE_COL_OFF 1
+#endif
 constexpr int kHW = kTileW + 2;       // 66 columns
 constexpr int kHH = kTileH + 2;       // 18 rows
-constexpr int kPitch = 68;
-constexpr int kPlane = kHH * kPitch;  // 1224 floats
+constexpr int kPitch = SDE_PITCH;
+constexpr int kColOff = SDE_COL_OFF;
+constexpr int kPlane = ((kHH * kPitch * 4 + 127) / 128) * 32;   // floats; every plane starts 128-byte aligned (TMA)
+static_assert(kPlane >= kHH * kPitch && (kPlane * 4) % 128 == 0 && (kColOff & 1) == 1 && kHW + kColOff <= kPitch, "plane layout");
+constexpr unsigned kPlaneBytesTma = kHH * kPitch * 4;   // bytes one {kPitch, 18, 1} box delivers
 constexpr int kPositions = kHH * kHW; // 1188 staged positions
 
-__device__ __forceinline__ int plane_index(int yy, int xx) { return yy * kPitch + xx + 1; }
+__device__ __forceinline__ int plane_index(int yy, int xx) { return yy * kPitch + xx + kColOff; }
 
 // Row access of phase 2: centre pair (columns c0+1, c0+2) and outer pair (c0, c0+3).
 struct Row4 {
@@ -283,6 +297,37 @@ __device__ __forceinline__ void stage_saved(const StageArgs& a0, const float* __
 #pragma unroll
         for (int c = 0; c < 3; ++c) a.planes[(a.plS + c) * kPlane + pl[u]] = v[u][c];
       }
+  }
+}
+
+// After a TMA box load of a tile that touches the image border: out-of-image elements arrived as zeros.
+// Positions exactly one pixel outside are nn.ReflectionPad2d(1) positions (ssim_loss.py:32,35) and take the
+// mirrored pixel, which always lies inside the same staged tile; positions further out are never read by a
+// valid output and stay zero.  n_planes consecutive planes starting at plane0.
+__device__ __forceinline__ void reflect_fixup(float* planes, int plane0, int n_planes, int oy, int ox, int h, int w, int tid) {
+  for (int i = tid; i < kPositions; i += kThreads) {
+    int yy, xx;
+    position_of(i, yy, xx);
+    const int ty = oy + yy, tx = ox + xx;
+    const bool oy1 = ty == -1 || ty == h, ox1 = tx == -1 || tx == w;
+    const bool iny = ty >= 0 && ty < h, inx = tx >= 0 && tx < w;
+    if ((oy1 && (inx || ox1)) || (ox1 && iny)) {
+      const int ry = ty == -1 ? 1 : (ty == h ? h - 2 : ty), rx = tx == -1 ? 1 : (tx == w ? w - 2 : tx);
+      const int dst = plane_index(yy, xx), src = plane_index(ry - oy, rx - ox);
+      for (int k = 0; k < n_planes; ++k) planes[(plane0 + k) * kPlane + dst] = planes[(plane0 + k) * kPlane + src];
+    }
+  }
+}
+
+// argmin bytes of the halo'd tile (backward): 255 where no window centre exists, 254 = every candidate ('mean')
+__device__ __forceinline__ void stage_arg(uint8_t* arg, const uint8_t* __restrict__ amap, int oy, int ox, int h, int w,
+                                          bool reduce_mean, int tid) {
+  for (int i = tid; i < kPositions; i += kThreads) {
+    int yy, xx;
+    position_of(i, yy, xx);
+    const int ty = oy + yy, tx = ox + xx;
+    const bool inside = ty >= 0 && ty < h && tx >= 0 && tx < w;
+    arg[plane_index(yy, xx)] = inside ? (reduce_mean ? (uint8_t)254 : amap[ty * w + tx]) : (uint8_t)255;
   }
 }
 

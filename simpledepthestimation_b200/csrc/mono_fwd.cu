@@ -17,6 +17,10 @@
 // un-normalised |d(1/d)|*exp(-|dI|) sums, the division by the per-image mean happens in the final
 // reduction.  Partial sums go to a per-CTA slot; the last CTA to finish adds them in a fixed order
 // (deterministic, no float atomics) and writes rec_loss / smooth_loss.
+// plane layout of this kernel: 72-float rows, column xx at index xx + 3, so that index 0 is image column
+// tile_x0 - 4 (TMA boxes must start 16-byte aligned)
+#define SDE_PITCH 72
+#define SDE_COL_OFF 3
 #include "mono_device.cuh"
 
 #ifndef SDE_FWD_OCC
@@ -40,11 +44,13 @@ struct FwdShared {
   float red[4][kThreads / 32];
   double dred[4][kThreads / 32];
   unsigned ticket;
+  __align__(8) uint64_t bar;   // TMA completion barrier
 };
 
 template <bool AUTOMASK>
-__global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const __grid_constant__ MonoParams p) {
-  extern __shared__ __align__(16) float planes[];  // [kFwdPlanes][kPlane]
+__global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const __grid_constant__ MonoParams p,
+                                                                       const __grid_constant__ MonoTma maps) {
+  extern __shared__ __align__(128) float planes[];  // [kFwdPlanes][kPlane]
   __shared__ FwdShared sh;
   constexpr int NC = AUTOMASK ? 2 : 1;             // candidates per source: warp [+ identity]
 
@@ -52,6 +58,21 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   const TileCoord tc = decode_tile(p, blockIdx.x);
   const int s = tc.s, b = tc.b, h = p.h[s], w = p.w[s], hw = h * w;
   const bool reduce_mean = (p.flags & SDE_MONO_REDUCE_MEAN) != 0;
+  // TMA path (row pitch a multiple of 16 bytes): target, depth and the first source's unwarped frame (the
+  // identity candidate) are handed to the copy engine before anything else happens in the CTA
+  const bool tma = p.tma[s] != 0;
+  const int ox = tc.x0 - 1, oy = tc.y0 - 1;
+  if (tma && tid == 0) {
+    mbar_init(&sh.bar, 1);
+    mbar_init_fence();
+    mbar_arrive_expect_tx(&sh.bar, (AUTOMASK ? 7 : 4) * kPlaneBytesTma);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      tma_load_plane(planes + (kPlA + c) * kPlane, &maps.target[s], &sh.bar, ox - kColOff, oy, b * 3 + c);
+      if (AUTOMASK) tma_load_plane(planes + (kPlI + c) * kPlane, &maps.source[s][0], &sh.bar, ox - kColOff, oy, b * 3 + c);
+    }
+    tma_load_plane(planes + kPlD * kPlane, &maps.depth[s], &sh.bar, ox - kColOff, oy, b);
+  }
   if (tid < p.S) {
     Cam cam;
     float k[9];
@@ -86,8 +107,19 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   sa.planes = planes; sa.arg = nullptr; sa.oy = tc.y0 - 1; sa.ox = tc.x0 - 1; sa.h = h; sa.w = w; sa.hw = hw;
   sa.plS = kPlS; sa.plI = kPlI; sa.plA = kPlA; sa.plD = kPlD;
   // ------------------------------------------------------------------ phase 0: depth + target
-  if (interior) stage_target<true, false>(sa, tid, false);
-  else          stage_target<false, false>(sa, tid, false);
+  unsigned tma_phase = 0;
+  if (tma) {
+    mbar_wait(&sh.bar, tma_phase);
+    tma_phase ^= 1u;
+    if (!interior) {
+      reflect_fixup(planes, kPlA, 3, oy, ox, h, w, tid);
+      reflect_fixup(planes, kPlD, 1, oy, ox, h, w, tid);
+      if (AUTOMASK) reflect_fixup(planes, kPlI, 3, oy, ox, h, w, tid);
+    }
+  } else {
+    if (interior) stage_target<true, false>(sa, tid, false);
+    else          stage_target<false, false>(sa, tid, false);
+  }
   __syncthreads();
 
   for (int j = 0; j < p.S; ++j) {
@@ -96,8 +128,19 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
       const Cam cam = sh.cam;
       const Proj pj = sh.proj[j];
       sa.src = p.source[s][j] + (size_t)b * 3 * hw;
-      if (interior) stage_source<true, AUTOMASK, SDE_NB>(sa, cam, pj, tid);
-      else          stage_source<false, AUTOMASK, SDE_NB>(sa, cam, pj, tid);
+      if (tma) {
+        // the identity planes come from the copy engine: gather only
+        if (interior) stage_source<true, false, SDE_NB>(sa, cam, pj, tid);
+        else          stage_source<false, false, SDE_NB>(sa, cam, pj, tid);
+        if (AUTOMASK && j > 0) {
+          mbar_wait(&sh.bar, tma_phase);
+          tma_phase ^= 1u;
+          if (!interior) reflect_fixup(planes, kPlI, 3, oy, ox, h, w, tid);
+        }
+      } else {
+        if (interior) stage_source<true, AUTOMASK, SDE_NB>(sa, cam, pj, tid);
+        else          stage_source<false, AUTOMASK, SDE_NB>(sa, cam, pj, tid);
+      }
     }
     __syncthreads();
 
@@ -209,7 +252,16 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
         }
       }
     }
-    if (j + 1 < p.S) __syncthreads();  // S/I planes are overwritten by the next source
+    if (j + 1 < p.S) {
+      __syncthreads();  // S/I planes are overwritten by the next source
+      if (tma && AUTOMASK && tid == 0) {   // next identity planes: fetched while the next gather runs
+        proxy_fence();
+        mbar_arrive_expect_tx(&sh.bar, 3 * kPlaneBytesTma);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          tma_load_plane(planes + (kPlI + c) * kPlane, &maps.source[s][j + 1], &sh.bar, ox - kColOff, oy, b * 3 + c);
+      }
+    }
   }
 
   // ------------------------------------------------------------------ per-thread sums, argmin, smoothness
@@ -335,14 +387,14 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
 
 size_t mono_fwd_smem_bytes() { return (size_t)kFwdPlanes * kPlane * sizeof(float); }
 
-cudaError_t launch_mono_fwd(const MonoParams& p, cudaStream_t stream) {
+cudaError_t launch_mono_fwd(const MonoParams& p, const MonoTma& t, cudaStream_t stream) {
   const bool automask = (p.flags & SDE_MONO_AUTOMASK) != 0;
   auto kernel = automask ? mono_fwd_kernel<true> : mono_fwd_kernel<false>;
   // 48.9 KB of dynamic shared memory needs the opt-in attribute (per device; cheap and idempotent)
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mono_fwd_smem_bytes());
   if (e != cudaSuccess) return e;
   if (SDE_FWD_CARVEOUT >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, SDE_FWD_CARVEOUT);
-  kernel<<<p.tile_start[p.n_scales], kThreads, mono_fwd_smem_bytes(), stream>>>(p);
+  kernel<<<p.tile_start[p.n_scales], kThreads, mono_fwd_smem_bytes(), stream>>>(p, t);
   return cudaGetLastError();
 }
 

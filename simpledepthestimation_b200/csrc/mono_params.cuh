@@ -1,5 +1,7 @@
 // Kernel-side parameter block of the fused MonoDepth2 loss (one launch covers every scale).
 #pragma once
+#include <cuda.h>
+
 #include "sde_common.cuh"
 
 namespace sde {
@@ -10,7 +12,7 @@ constexpr int kThreads = 128;
 constexpr int kRowsPerWarp = 4;
 // backward: a CTA recomputes SSIM on a kTileW x kTileH block of window centres and emits
 // gradients for its interior (the 3x3 adjoint needs one ring of neighbours)
-constexpr int kBwdW = kTileW - 2;   // 62
+constexpr int kBwdW = kTileW - 4;   // 60: a multiple of 4, so that TMA boxes of the backward tiles start 16-byte aligned
 constexpr int kBwdH = kTileH - 2;   // 14
 
 struct MonoParams {
@@ -44,6 +46,16 @@ struct MonoParams {
   unsigned* smp_counter;   // [B] backward tiles finished per sample (all scales)
   int btiles_x[SDE_MAX_SCALES], btiles_y[SDE_MAX_SCALES];
   int btile_start[SDE_MAX_SCALES + 1];
+  int tma[SDE_MAX_SCALES];   // tile planes of this scale are staged by TMA (tensor maps in MonoTma are valid)
+};
+
+// Tensor maps over the [planes, h, w] inputs of every scale, box {68, 18, 1} (tma.cuh).  Second kernel
+// parameter: the copy engine reads the descriptors straight from the parameter space.
+struct alignas(64) MonoTma {
+  CUtensorMap target[SDE_MAX_SCALES];
+  CUtensorMap depth[SDE_MAX_SCALES];
+  CUtensorMap source[SDE_MAX_SCALES][SDE_MAX_SOURCES];
+  CUtensorMap warped[SDE_MAX_SCALES][SDE_MAX_SOURCES];
 };
 
 struct TileCoord {

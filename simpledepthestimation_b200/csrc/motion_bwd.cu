@@ -3,7 +3,7 @@
 // Gradients flow through the warped rgb only: the occlusion mask is a comparison, the proximity
 // weight is detached and DEPTH_L1_WEIGHT is 0 in every shipped config (MotionLearning.py:259,
 // 264-267,283).  One CTA owns a 64x16 block Q of WeightedSSIM window centres of one
-// (direction, sample) and emits gradients for Q's 62x14 interior P:
+// (direction, sample) and emits gradients for Q's 60x14 interior P:
 //   phase 1  as the forward kernel: project + gather on Q + 1-pixel halo -> planes S, A, U, WZ, depth
 //   per channel:
 //     phase 2  window sums -> coefficients of  d ssim_q / d S_p = U_p (a_q + S_p b_q + A_p c_q)

@@ -1,5 +1,6 @@
 // C ABI of libsde_loss.so (see include/sde_loss.h): argument validation, parameter-block
 // construction and kernel launches.  No torch types, no allocation, no synchronisation.
+#include <stdlib.h>
 #include <string.h>
 
 #include <math.h>
@@ -8,8 +9,8 @@
 #include "ops_params.cuh"
 
 namespace sde {
-cudaError_t launch_mono_fwd(const MonoParams& p, cudaStream_t stream);
-cudaError_t launch_mono_bwd(const MonoParams& p, cudaStream_t stream);
+cudaError_t launch_mono_fwd(const MonoParams& p, const MonoTma& t, cudaStream_t stream);
+cudaError_t launch_mono_bwd(const MonoParams& p, const MonoTma& t, cudaStream_t stream);
 cudaError_t launch_motion_fwd(const MotionParams& p, cudaStream_t stream);
 cudaError_t launch_motion_bwd(const MotionParams& p, cudaStream_t stream);
 cudaError_t launch_vs_fwd(const VsParams& p, cudaStream_t stream);
@@ -144,6 +145,61 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
   }
   return SDE_OK;
 }
+// ------------------------------------------------------------------------------------------------ TMA
+// cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime once, so the library
+// keeps no link-time dependency on libcuda and still loads on a machine without a driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// tensor map over a contiguous [planes, h, w] fp32 tensor with the tile-plane box {68, 18, 1}; zero fill outside
+static bool encode_planes(CUtensorMap* m, const float* base, int planes, int h, int w, int box_w) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || (w & 3) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
+  const cuuint64_t gstride[2] = {(cuuint64_t)w * 4, (cuuint64_t)h * w * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)kHH, 1};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estride,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Decides per scale whether the tile planes are staged by TMA (row pitch a multiple of 16 bytes, encoder
+// available; the backward pass also needs the saved warps) and builds the descriptors.
+static void mono_tma(const sde_mono_desc* d, const sde_mono_buffers* b, bool backward, MonoParams& p, MonoTma& t) {
+  memset(&t, 0, sizeof(t));
+  // SDE_DISABLE_TMA=1 forces the thread-staged path on every shape (used by the parity tests to cover it)
+  const char* off = getenv("SDE_DISABLE_TMA");
+  const bool disabled = off && off[0] == '1';
+  for (int i = 0; i < d->n_scales; ++i) {
+    p.tma[i] = 0;
+    if (disabled) continue;
+    if (backward && !b->warped[i][0]) continue;
+    const int h = d->height[i], w = d->width[i];
+    const int bw = backward ? 68 : 72;   // row pitch of the kernel's shared-memory planes (mono_bwd.cu / mono_fwd.cu)
+    bool ok = encode_planes(&t.target[i], b->target[i], d->batch * 3, h, w, bw) &&
+              encode_planes(&t.depth[i], b->depth[i], d->batch, h, w, bw);
+    for (int j = 0; ok && j < d->n_sources; ++j) {
+      if (backward) ok = encode_planes(&t.warped[i][j], b->warped[i][j], d->batch * 3, h, w, bw);
+      else ok = encode_planes(&t.source[i][j], b->source[i][j], d->batch * 3, h, w, bw);
+    }
+    p.tma[i] = ok ? 1 : 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 struct MotionLayout {
   int tiles_x, tiles_y, btiles_x, btiles_y, stat_blocks, grid, bgrid;
@@ -335,7 +391,9 @@ int sde_mono_loss_forward(const sde_mono_desc* desc, const sde_mono_buffers* buf
   MonoParams p;
   int st = mono_params(desc, buf, false, p);
   if (st != SDE_OK) return st;
-  cudaError_t e = launch_mono_fwd(p, static_cast<cudaStream_t>(stream));
+  MonoTma t;
+  mono_tma(desc, buf, false, p, t);
+  cudaError_t e = launch_mono_fwd(p, t, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SDE_OK : cuda_fail(e);
 }
 
@@ -343,7 +401,9 @@ int sde_mono_loss_backward(const sde_mono_desc* desc, const sde_mono_buffers* bu
   MonoParams p;
   int st = mono_params(desc, buf, true, p);
   if (st != SDE_OK) return st;
-  cudaError_t e = launch_mono_bwd(p, static_cast<cudaStream_t>(stream));
+  MonoTma t;
+  mono_tma(desc, buf, true, p, t);
+  cudaError_t e = launch_mono_bwd(p, t, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SDE_OK : cuda_fail(e);
 }
 
