@@ -61,15 +61,17 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   // TMA path (row pitch a multiple of 16 bytes): target, depth and the first source's unwarped frame (the
   // identity candidate) are handed to the copy engine before anything else happens in the CTA
   const bool tma = p.tma[s] != 0;
+  const bool prewarp = p.prewarp[s] != 0;   // the warped sources come from the warp kernel (mono_warp.cu)
   const int ox = tc.x0 - 1, oy = tc.y0 - 1;
   if (tma && tid == 0) {
     mbar_init(&sh.bar, 1);
     mbar_init_fence();
-    mbar_arrive_expect_tx(&sh.bar, (AUTOMASK ? 7 : 4) * kPlaneBytesTma);
+    mbar_arrive_expect_tx(&sh.bar, (4 + (AUTOMASK ? 3 : 0) + (p.prewarp[s] ? 3 : 0)) * kPlaneBytesTma);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       tma_load_plane(planes + (kPlA + c) * kPlane, &maps.target[s], &sh.bar, ox - kColOff, oy, b * 3 + c);
       if (AUTOMASK) tma_load_plane(planes + (kPlI + c) * kPlane, &maps.source[s][0], &sh.bar, ox - kColOff, oy, b * 3 + c);
+      if (p.prewarp[s]) tma_load_plane(planes + (kPlS + c) * kPlane, &maps.warped[s][0], &sh.bar, ox - kColOff, oy, b * 3 + c);
     }
     tma_load_plane(planes + kPlD * kPlane, &maps.depth[s], &sh.bar, ox - kColOff, oy, b);
   }
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
       reflect_fixup(planes, kPlA, 3, oy, ox, h, w, tid);
       reflect_fixup(planes, kPlD, 1, oy, ox, h, w, tid);
       if (AUTOMASK) reflect_fixup(planes, kPlI, 3, oy, ox, h, w, tid);
+      if (prewarp) reflect_fixup(planes, kPlS, 3, oy, ox, h, w, tid);
     }
   } else {
     if (interior) stage_target<true, false>(sa, tid, false);
@@ -129,13 +132,19 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
       const Proj pj = sh.proj[j];
       sa.src = p.source[s][j] + (size_t)b * 3 * hw;
       if (tma) {
-        // the identity planes come from the copy engine: gather only
-        if (interior) stage_source<true, false, SDE_NB>(sa, cam, pj, tid);
-        else          stage_source<false, false, SDE_NB>(sa, cam, pj, tid);
-        if (AUTOMASK && j > 0) {
+        // the identity planes come from the copy engine; so do the warped ones when the warp kernel ran,
+        // otherwise gather here
+        if (!prewarp) {
+          if (interior) stage_source<true, false, SDE_NB>(sa, cam, pj, tid);
+          else          stage_source<false, false, SDE_NB>(sa, cam, pj, tid);
+        }
+        if ((AUTOMASK || prewarp) && j > 0) {
           mbar_wait(&sh.bar, tma_phase);
           tma_phase ^= 1u;
-          if (!interior) reflect_fixup(planes, kPlI, 3, oy, ox, h, w, tid);
+          if (!interior) {
+            if (AUTOMASK) reflect_fixup(planes, kPlI, 3, oy, ox, h, w, tid);
+            if (prewarp) reflect_fixup(planes, kPlS, 3, oy, ox, h, w, tid);
+          }
         }
       } else {
         if (interior) stage_source<true, AUTOMASK, SDE_NB>(sa, cam, pj, tid);
@@ -145,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
     __syncthreads();
 
     // optional: keep the warped source for the backward pass (tile interior, coalesced pair stores)
-    if (p.warped[s][j] != nullptr) {
+    if (p.warped[s][j] != nullptr && !prewarp) {
       float* __restrict__ wout = p.warped[s][j] + (size_t)b * 3 * hw;
       const int gxw = tc.x0 + c0;
 #pragma unroll
@@ -254,12 +263,14 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
     }
     if (j + 1 < p.S) {
       __syncthreads();  // S/I planes are overwritten by the next source
-      if (tma && AUTOMASK && tid == 0) {   // next identity planes: fetched while the next gather runs
+      if (tma && (AUTOMASK || prewarp) && tid == 0) {   // next source's planes (fetched while a gather, if any, runs)
         proxy_fence();
-        mbar_arrive_expect_tx(&sh.bar, 3 * kPlaneBytesTma);
+        mbar_arrive_expect_tx(&sh.bar, ((AUTOMASK ? 3 : 0) + (prewarp ? 3 : 0)) * kPlaneBytesTma);
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          tma_load_plane(planes + (kPlI + c) * kPlane, &maps.source[s][j + 1], &sh.bar, ox - kColOff, oy, b * 3 + c);
+        for (int c = 0; c < 3; ++c) {
+          if (AUTOMASK) tma_load_plane(planes + (kPlI + c) * kPlane, &maps.source[s][j + 1], &sh.bar, ox - kColOff, oy, b * 3 + c);
+          if (prewarp) tma_load_plane(planes + (kPlS + c) * kPlane, &maps.warped[s][j + 1], &sh.bar, ox - kColOff, oy, b * 3 + c);
+        }
       }
     }
   }

@@ -47,6 +47,8 @@ struct MonoParams {
   int btiles_x[SDE_MAX_SCALES], btiles_y[SDE_MAX_SCALES];
   int btile_start[SDE_MAX_SCALES + 1];
   int tma[SDE_MAX_SCALES];   // tile planes of this scale are staged by TMA (tensor maps in MonoTma are valid)
+  int prewarp[SDE_MAX_SCALES];            // forward: the warp kernel has filled warped[s][*]; the loss kernel only reads them
+  int warp_start[SDE_MAX_SCALES + 1];     // warp kernel: first block of scale s (blocks of 256 pixels per sample)
 };
 
 // Tensor maps over the [planes, h, w] inputs of every scale, box {68, 18, 1} (tma.cuh).  Second kernel

@@ -1,0 +1,80 @@
+// Warp kernel of the MonoDepth2 loss (sm_100a): project + bilinear gather of every source at every scale,
+// one thread per target pixel, written as [B,3,h,w] planes (the `warped` buffers of sde_mono_buffers).
+//
+// The fused loss kernels are stencil kernels with fat threads (128-160 registers, 12-16 warps per SM),
+// which is the wrong shape for the gather: it is latency-bound and wants many thin threads.  Run on its own
+// with 64-register threads the gather gets 4x the warps per SM and no halo redundancy (the fused forward
+// kernel re-gathers 16 % halo positions, the backward kernel 37 %); the loss kernels then receive the warped
+// planes through TMA like every other input.  Same device functions, same operation order as the in-kernel
+// gather (mono_device.cuh: project_full, bilinear_cell), hence bit-identical planes.
+#include "mono_device.cuh"
+
+namespace sde {
+
+constexpr int kWarpThreads = 256;
+constexpr int kWarpPixPerThread = 4;
+constexpr int kWarpChunk = kWarpThreads * kWarpPixPerThread;   // pixels per block
+
+struct WarpShared {
+  Cam cam;
+  Proj proj[SDE_MAX_SOURCES];
+};
+
+__global__ void __launch_bounds__(kWarpThreads, 4) mono_warp_kernel(const __grid_constant__ MonoParams p) {
+  __shared__ WarpShared sh;
+  // blockIdx.x -> (scale, sample, chunk of 1024 pixels); scales that do not take the TMA path are skipped
+  int s = 0, bid = blockIdx.x;
+  while (s + 1 < p.n_scales && bid >= p.warp_start[s + 1]) ++s;
+  bid -= p.warp_start[s];
+  const int h = p.h[s], w = p.w[s], hw = h * w;
+  const int chunks = (hw + kWarpChunk - 1) / kWarpChunk;
+  const int b = bid / chunks, chunk = bid - b * chunks;
+  const int tid = threadIdx.x;
+  if (tid < p.S) {
+    Cam cam;
+    float k[9];
+    load_cam(cam, k, p.K, b, p.sx[s], p.sy[s]);
+    if (tid == 0) sh.cam = cam;
+    load_proj(sh.proj[tid], k, p.pose[tid], b);
+  }
+  __syncthreads();
+  const Cam& cam = sh.cam;
+#pragma unroll 1
+  for (int it = 0; it < kWarpPixPerThread; ++it) {
+    const int pix = chunk * kWarpChunk + it * kWarpThreads + tid;
+    if (pix >= hw) return;
+    const int gy = pix / w, gx = pix - gy * w;
+    const float d = __ldg(p.depth[s] + (size_t)b * hw + pix);
+#pragma unroll 1
+    for (int j = 0; j < p.S; ++j) {
+      const Proj& pj = sh.proj[j];
+      float P[3], den, X, Y;
+      project_full(cam, pj, (float)gx, (float)gy, d, P, den, X, Y);
+      const Cell cell = bilinear_cell(X, Y, w, h);
+      const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
+      const float w00 = bx * by, w01 = cell.ax * by, w10 = bx * cell.ay, w11 = cell.ax * cell.ay;
+      const float* src = p.source[s][j] + (size_t)b * 3 * hw + cell.off;
+      float* dst = p.warped[s][j] + (size_t)b * 3 * hw + pix;
+      float t[3][4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        // scalar taps: a 16-byte load per lane is served quarter-warp by quarter-warp and touched MORE L1
+        // sectors on the scattered addresses of this gather (measured: 100 us against 62 us)
+        const float* q = src + c * hw;
+        t[c][0] = __ldg(q); t[c][1] = __ldg(q + 1); t[c][2] = __ldg(q + w); t[c][3] = __ldg(q + w + 1);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)   // ATen's accumulation order: nw, ne, sw, se
+        dst[c * hw] = t[c][0] * w00 + t[c][1] * w01 + t[c][2] * w10 + t[c][3] * w11;
+    }
+  }
+}
+
+cudaError_t launch_mono_warp(const MonoParams& p, cudaStream_t stream) {
+  const int grid = p.warp_start[p.n_scales];
+  if (grid == 0) return cudaSuccess;
+  mono_warp_kernel<<<grid, kWarpThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace sde

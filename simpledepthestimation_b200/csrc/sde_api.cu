@@ -11,6 +11,7 @@
 namespace sde {
 cudaError_t launch_mono_fwd(const MonoParams& p, const MonoTma& t, cudaStream_t stream);
 cudaError_t launch_mono_bwd(const MonoParams& p, const MonoTma& t, cudaStream_t stream);
+cudaError_t launch_mono_warp(const MonoParams& p, cudaStream_t stream);
 cudaError_t launch_motion_fwd(const MotionParams& p, cudaStream_t stream);
 cudaError_t launch_motion_bwd(const MotionParams& p, cudaStream_t stream);
 cudaError_t launch_vs_fwd(const VsParams& p, cudaStream_t stream);
@@ -192,11 +193,19 @@ static void mono_tma(const sde_mono_desc* d, const sde_mono_buffers* b, bool bac
     const int bw = backward ? 68 : 72;   // row pitch of the kernel's shared-memory planes (mono_bwd.cu / mono_fwd.cu)
     bool ok = encode_planes(&t.target[i], b->target[i], d->batch * 3, h, w, bw) &&
               encode_planes(&t.depth[i], b->depth[i], d->batch, h, w, bw);
+    // forward with `warped` buffers: the warp kernel fills them and the loss kernel takes them through TMA
+    const bool prewarp = !backward && b->warped[i][0] != nullptr;
     for (int j = 0; ok && j < d->n_sources; ++j) {
-      if (backward) ok = encode_planes(&t.warped[i][j], b->warped[i][j], d->batch * 3, h, w, bw);
-      else ok = encode_planes(&t.source[i][j], b->source[i][j], d->batch * 3, h, w, bw);
+      if (backward || prewarp) ok = encode_planes(&t.warped[i][j], b->warped[i][j], d->batch * 3, h, w, bw);
+      if (!backward && ok) ok = encode_planes(&t.source[i][j], b->source[i][j], d->batch * 3, h, w, bw);
     }
     p.tma[i] = ok ? 1 : 0;
+    p.prewarp[i] = (ok && prewarp) ? 1 : 0;
+  }
+  int start = 0;
+  for (int i = 0; i <= SDE_MAX_SCALES; ++i) {
+    p.warp_start[i] = start;
+    if (i < d->n_scales && p.prewarp[i]) start += d->batch * ((d->height[i] * d->width[i] + 1023) / 1024);   // kWarpChunk pixels per block
   }
 }
 
@@ -393,7 +402,9 @@ int sde_mono_loss_forward(const sde_mono_desc* desc, const sde_mono_buffers* buf
   if (st != SDE_OK) return st;
   MonoTma t;
   mono_tma(desc, buf, false, p, t);
-  cudaError_t e = launch_mono_fwd(p, t, static_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_mono_warp(p, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  e = launch_mono_fwd(p, t, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SDE_OK : cuda_fail(e);
 }
 
