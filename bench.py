@@ -3,12 +3,14 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-ours:       a "step" is one forward + one backward launch of the fused MonoDepth2 loss over one
-            batch of synthetic KITTI-shaped input (BASELINE.json configs[1]: 640x192, batch 12 per
-            GPU, 4 scales, 2 sources, automask + smoothness).  `value` = warped Mpix/s with inputs
-            resident in HBM (three input sets are rotated so that every step reads from HBM, not
-            L2); `e2e` = the same through host buffers (pinned H2D of every input, D2H of losses
-            and gradients inside the timed region).  N>1: one process per GPU (torchrun), each rank
+ours:       a "step" is one forward + one backward pass of the fused MonoDepth2 loss (three launches:
+            warp kernel, loss forward, loss backward) over one batch of synthetic KITTI-shaped input
+            (BASELINE.json configs[1]: 640x192, batch 12 per GPU, 4 scales, 2 sources, automask +
+            smoothness).  `value` = warped Mpix/s with inputs resident in HBM (three input sets are
+            rotated so that every step reads from HBM, not L2); `e2e` = the same through host buffers:
+            the full-resolution frames, depth pyramid, intrinsics and poses are copied from pinned host
+            memory every step, the image pyramid is built on the device, losses and gradients are
+            copied back -- all inside the timed region, copies pipelined against the kernels.  N>1: one process per GPU (torchrun), each rank
             its own batch of 12 (weak scaling; at N=8 the global batch is configs[4]'s 96); the only
             cross-GPU traffic is one all-reduce of the two loss scalars per step.
 reference:  the reference's CPU implementation of the same path (oracle/port.py, the same ATen op
@@ -156,12 +158,75 @@ def make_sets(dev, rank, nsets):
         tgt = [resize_img(inp["img"], s).contiguous() for s in sizes]
         src = [[resize_img(c, s).contiguous() for c in inp["ctx"]] for s in sizes]
         pose = [euler_pose(v).contiguous() for v in inp["pose_vec"]]
-        h = (tgt, src, [d.contiguous() for d in inp["depth"]], inp["K"].contiguous(), pose)
-        host.append(h)
+        depth = [d.contiguous() for d in inp["depth"]]
+        # host side of the e2e leg: what the data loader and the networks hand over (full-resolution frames)
+        host.append((inp["img"].contiguous(), [c.contiguous() for c in inp["ctx"]], depth, inp["K"].contiguous(), pose))
         mv = lambda t: t.to(dev)  # noqa: E731
-        sets.append(([mv(t) for t in tgt], [[mv(x) for x in row] for row in src], [mv(d) for d in h[2]], mv(h[3]),
+        sets.append(([mv(t) for t in tgt], [[mv(x) for x in row] for row in src], [mv(d) for d in depth], mv(inp["K"]),
                      [mv(p) for p in pose]))
     return sets, host
+
+
+def other_configs(dev):
+    """Secondary measurements (not the bench line): BASELINE.json configs[2] (MonoDepth2 1024x320, batch 8) and
+    configs[3] (MotionLearning 1920x1280, batch 4, both directions, translation field), fwd+bwd, HBM-resident."""
+    from simpledepthestimation_b200.functional import MonoLossPlan, MotionLossPlan
+    from simpledepthestimation_b200.geometry.camera import resize_img
+    from simpledepthestimation_b200.synthetic import euler_pose, mono_inputs, motion_inputs
+
+    def timeit(fn, iters=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = {}
+    B3, H3, W3 = 8, 320, 1024
+    inp = mono_inputs(B3, H3, W3, SCALES, S, seed=3)
+    sizes = [tuple(d.shape[-2:]) for d in inp["depth"]]
+    mv = lambda t: t.to(dev).contiguous()  # noqa: E731
+    tgt = [mv(resize_img(inp["img"], s)) for s in sizes]
+    src = [[mv(resize_img(c, s)) for c in inp["ctx"]] for s in sizes]
+    depth, K, pose = [mv(d) for d in inp["depth"]], mv(inp["K"]), [mv(euler_pose(v)) for v in inp["pose_vec"]]
+    plan = MonoLossPlan(B3, sizes, S, (H3, W3), dev)
+    losses, ones, warped = torch.empty(2, device=dev), torch.ones(2, device=dev), plan.new_warped()
+    _, argm = plan.forward(tgt, src, depth, K, pose, out=losses, warped=warped)
+    gd, gp = [torch.empty_like(d) for d in depth], [torch.empty_like(p) for p in pose]
+
+    def mono_step():
+        plan.forward(tgt, src, depth, K, pose, out=losses, argmin_out=argm, warped=warped)
+        plan.backward(tgt, src, depth, K, pose, argm, ones, gd, gp, warped=warped)
+    ms = timeit(mono_step)
+    px = S * sum(B3 * h * w for h, w in sizes)
+    out["cfg3_mono_1024x320_b8"] = {"ms_per_step": ms, "warped_mpix_s": px / (ms * 1e-3) / 1e6,
+                                    "frac_of_hbm_roofline": (px / S * 84.0 / (ms * 1e-3) / 1e9) / peaks()[0]}
+    del tgt, src, depth, warped, gd, argm, plan
+
+    B4, H4, W4 = 4, 1280, 1920
+    mi = motion_inputs(B4, H4, W4, seed=0)
+    f1, f2, d1, d2, K4 = mv(mi["img1"]), mv(mi["img2"]), mv(mi["depth1"]), mv(mi["depth2"]), mv(mi["K"])
+    pose4, mo = mv(euler_pose(mi["pose_vec"])), mv(mi["motion"])
+    mplan = MotionLossPlan(B4, (H4, W4), dev, 2, with_field=True)
+    args4 = ([f1, f2], [f2, f1], [d1, d2], [d2, d1], K4, [pose4[:B4].contiguous(), pose4[B4:].contiguous()],
+             [mo[:B4].contiguous(), mo[B4:].contiguous()])
+    ml, gl = torch.empty(2, 4, device=dev), torch.ones(2, 4, device=dev)
+    mgd, mgp = [torch.empty_like(d1), torch.empty_like(d2)], [torch.empty(B4, 4, 4, device=dev) for _ in range(2)]
+    mgf = [torch.empty_like(args4[6][0]) for _ in range(2)]
+
+    def motion_step():
+        mplan.forward(*args4, want_maps=False, out=ml)
+        mplan.backward(*args4, gl, mgd, mgp, mgf)
+    ms = timeit(motion_step, iters=3)
+    px = 2 * B4 * H4 * W4
+    out["cfg4_motion_1920x1280_b4"] = {"ms_per_step": ms, "warped_mpix_s": px / (ms * 1e-3) / 1e6,
+                                       "frac_of_hbm_roofline": (px * 104.0 / (ms * 1e-3) / 1e9) / peaks()[0]}
+    return out
 
 
 def run_ours(args):
@@ -269,8 +334,18 @@ def run_ours(args):
     runner = HostLossRunner(plan, dev)
     pinned = [runner.pin(h) for h in host]
     e2e_ms = timed(lambda i: runner.step(pinned[i % nsets]), max(3, min(args.steps, 20)), 3)
+    runner.finish()
     e2e = {"value": world * warped_px / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
-           "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_ms}
+           "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_ms,
+           "gpu_launches_per_step": runner.launches_per_step,
+           "path": "pinned host frames/depth/K/pose -> H2D -> device pyramid -> warp + loss fwd + loss bwd -> D2H losses+grads"}
+
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            extra = other_configs(dev)
+        except Exception as exc:  # secondary numbers must never break the bench line
+            extra = {"error": repr(exc)[:200]}
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -285,7 +360,8 @@ def run_ours(args):
                                    "automask + smoothness, fwd+bwd (BASELINE.json configs[1]; global batch 96 at 8 GPUs = configs[4])",
                        "global_batch": B_PER_GPU * world, "parallelism": f"dp{world}",
                        "l2": f"{nsets} input sets rotated ({nsets * 86} MB > 126 MB L2)"},
-            "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
+            "gpu_launches": (3 if plan.save_warped else 2) * args.steps, "clocks": clocks, "other_configs": extra,
         }
         print(json.dumps(line))
     if world > 1:
@@ -299,6 +375,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs (cfg3, cfg4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -210,64 +210,89 @@ def mono_photometric_smoothness_loss(plan: MonoLossPlan, target: List[torch.Tens
 
 
 class HostLossRunner:
-    """End-to-end step through HOST buffers: pinned host inputs -> device (H2D on the compute
-    stream), fused forward + backward, losses and gradients -> pinned host (D2H), then one
-    stream synchronise.  This is the call a host-side integration (data on the CPU side of the
-    C ABI) makes; `h2d_bytes` / `d2h_bytes` count exactly the tensors copied per step."""
+    """End-to-end step through HOST buffers, the call a host-side integration makes: the full-resolution
+    frames, the predicted depth pyramid, intrinsics and poses start in pinned host memory; every step copies
+    them to the device, builds the image pyramid there (resize_img, MonoDepth2.py:82,88), runs the fused
+    forward + backward and copies the losses and gradients back to pinned host memory.
 
-    def __init__(self, plan: MonoLossPlan, device):
+    Copies and compute are software-pipelined over two input slots: the H2D copy of step i+1 (copy stream)
+    overlaps the kernels and the D2H copy of step i (compute stream).  Every step still performs its own H2D
+    and D2H; `h2d_bytes` / `d2h_bytes` count exactly the tensors copied per step.  step() is asynchronous;
+    finish() waits for the last step and returns its host results."""
+
+    def __init__(self, plan: MonoLossPlan, device, slots=2):
+        from .ops import resize_bilinear
+        self._resize = resize_bilinear
         self.plan, self.device = plan, torch.device(device)
         B, S = plan.batch, plan.n_sources
+        H, W = plan.full_size
         new = lambda *shape, dt=torch.float32: torch.empty(*shape, dtype=dt, device=self.device)  # noqa: E731
-        self.target = [new(B, 3, h, w) for h, w in plan.sizes]
-        self.source = [[new(B, 3, h, w) for _ in range(S)] for h, w in plan.sizes]
-        self.depth = [new(B, 1, h, w) for h, w in plan.sizes]
-        self.K = new(B, 3, 3)
-        self.pose = [new(B, 4, 4) for _ in range(S)]
+        self.slots = []
+        for _ in range(slots):
+            sl = dict(img=new(B, 3, H, W), ctx=[new(B, 3, H, W) for _ in range(S)],
+                      depth=[new(B, 1, h, w) for h, w in plan.sizes], K=new(B, 3, 3), pose=[new(B, 4, 4) for _ in range(S)],
+                      ready=torch.cuda.Event(), free=torch.cuda.Event())
+            sl["free"].record()
+            self.slots.append(sl)
         self.losses = new(2)
         self.argmin = [new(B, h, w, dt=torch.uint8) for h, w in plan.sizes]
-        self.grad_depth = [torch.empty_like(d) for d in self.depth]
-        self.grad_pose = [torch.empty_like(p) for p in self.pose]
+        self.grad_depth = [new(B, 1, h, w) for h, w in plan.sizes]
+        self.grad_pose = [new(B, 4, 4) for _ in range(S)]
         self.ones = torch.ones(2, device=self.device)
         self.warped = plan.new_warped()
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
         self.h_losses = pin(self.losses)
         self.h_grad_depth = [pin(t) for t in self.grad_depth]
         self.h_grad_pose = [pin(t) for t in self.grad_pose]
-        dev_in = self.target + [s for row in self.source for s in row] + self.depth + [self.K] + self.pose
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        sl = self.slots[0]
+        dev_in = [sl["img"]] + sl["ctx"] + sl["depth"] + [sl["K"]] + sl["pose"]
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in dev_in)
         outs = [self.losses] + self.grad_depth + self.grad_pose
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in outs)
+        self._i = 0
+        # kernels per step: pyramid (3 frames x coarse scales), warp + loss forward, backward
+        self.launches_per_step = (1 + S) * (len(plan.sizes) - 1) + (2 if plan.save_warped else 1) + 1
 
     @staticmethod
     def pin(host_set):
-        """Pins a (target, source, depth, K, pose) tuple of CPU tensors."""
-        tgt, src, depth, K, pose = host_set
+        """Pins an (img, ctx list, depth list, K, pose list) tuple of CPU tensors."""
+        img, ctx, depth, K, pose = host_set
         p = lambda t: t.contiguous().pin_memory()  # noqa: E731
-        return ([p(t) for t in tgt], [[p(x) for x in row] for row in src], [p(d) for d in depth], p(K),
-                [p(x) for x in pose])
+        return (p(img), [p(c) for c in ctx], [p(d) for d in depth], p(K), [p(x) for x in pose])
 
     def step(self, host_set):
-        tgt, src, depth, K, pose = host_set
-        for d, h in zip(self.target, tgt):
-            d.copy_(h, non_blocking=True)
-        for drow, hrow in zip(self.source, src):
-            for d, h in zip(drow, hrow):
+        img, ctx, depth, K, pose = host_set
+        sl = self.slots[self._i % len(self.slots)]
+        self._i += 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(sl["free"])       # the kernels that last read this slot are done
+            sl["img"].copy_(img, non_blocking=True)
+            for d, h in zip(sl["ctx"], ctx):
                 d.copy_(h, non_blocking=True)
-        for d, h in zip(self.depth, depth):
-            d.copy_(h, non_blocking=True)
-        self.K.copy_(K, non_blocking=True)
-        for d, h in zip(self.pose, pose):
-            d.copy_(h, non_blocking=True)
-        self.plan.forward(self.target, self.source, self.depth, self.K, self.pose, out=self.losses,
-                          argmin_out=self.argmin, warped=self.warped)
-        self.plan.backward(self.target, self.source, self.depth, self.K, self.pose, self.argmin, self.ones,
-                           self.grad_depth, self.grad_pose, warped=self.warped)
+            for d, h in zip(sl["depth"], depth):
+                d.copy_(h, non_blocking=True)
+            sl["K"].copy_(K, non_blocking=True)
+            for d, h in zip(sl["pose"], pose):
+                d.copy_(h, non_blocking=True)
+            sl["ready"].record()
+        main.wait_event(sl["ready"])
+        sizes = self.plan.sizes
+        target = [sl["img"] if tuple(s) == tuple(sl["img"].shape[-2:]) else self._resize(sl["img"], s) for s in sizes]
+        source = [[c if tuple(s) == tuple(c.shape[-2:]) else self._resize(c, s) for c in sl["ctx"]] for s in sizes]
+        self.plan.forward(target, source, sl["depth"], sl["K"], sl["pose"], out=self.losses, argmin_out=self.argmin,
+                          warped=self.warped)
+        self.plan.backward(target, source, sl["depth"], sl["K"], sl["pose"], self.argmin, self.ones, self.grad_depth,
+                           self.grad_pose, warped=self.warped)
+        sl["free"].record()
         self.h_losses.copy_(self.losses, non_blocking=True)
         for h, d in zip(self.h_grad_depth, self.grad_depth):
             h.copy_(d, non_blocking=True)
         for h, d in zip(self.h_grad_pose, self.grad_pose):
             h.copy_(d, non_blocking=True)
+
+    def finish(self):
         torch.cuda.current_stream().synchronize()
         return self.h_losses, self.h_grad_depth, self.h_grad_pose
 
