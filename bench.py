@@ -106,7 +106,7 @@ def cpu_loss_step(inp, pyr, threads):
     pose = [euler_pose(v).requires_grad_() for v in inp["pose_vec"]]
     out = port.mono_loss(inp["img"], None, inp["K"], depth, pose, pyramid=pyr)
     (out["rec_loss"] + out["smooth_loss"]).backward()
-    return float(out["rec_loss"])
+    return float(out["rec_loss"].detach())
 
 
 def cpu_baseline(steps, warmup, batch=1):

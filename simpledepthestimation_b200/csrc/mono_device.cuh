@@ -319,16 +319,26 @@ __device__ __forceinline__ void reflect_fixup(float* planes, int plane0, int n_p
   }
 }
 
-// argmin bytes of the halo'd tile (backward): 255 where no window centre exists, 254 = every candidate ('mean')
+// argmin bytes of the halo'd tile (backward): 255 where no window centre exists, 254 = every candidate ('mean').
+// All of a thread's loads are issued before the first store (one memory round trip per tile).
 __device__ __forceinline__ void stage_arg(uint8_t* arg, const uint8_t* __restrict__ amap, int oy, int ox, int h, int w,
                                           bool reduce_mean, int tid) {
-  for (int i = tid; i < kPositions; i += kThreads) {
+  constexpr int kIter = (kPositions + kThreads - 1) / kThreads;  // 10
+  uint8_t m[kIter];
+  int pl[kIter];
+#pragma unroll
+  for (int k = 0; k < kIter; ++k) {
+    const int i = tid + k * kThreads;
     int yy, xx;
-    position_of(i, yy, xx);
+    position_of(i < kPositions ? i : tid, yy, xx);
     const int ty = oy + yy, tx = ox + xx;
     const bool inside = ty >= 0 && ty < h && tx >= 0 && tx < w;
-    arg[plane_index(yy, xx)] = inside ? (reduce_mean ? (uint8_t)254 : amap[ty * w + tx]) : (uint8_t)255;
+    pl[k] = i < kPositions ? plane_index(yy, xx) : -1;
+    m[k] = inside ? (reduce_mean ? (uint8_t)254 : __ldg(amap + ty * w + tx)) : (uint8_t)255;
   }
+#pragma unroll
+  for (int k = 0; k < kIter; ++k)
+    if (pl[k] >= 0) arg[pl[k]] = m[k];
 }
 
 }  // namespace sde

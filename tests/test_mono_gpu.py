@@ -120,22 +120,22 @@ def test_bit_identical_across_runs(dev):
             assert torch.equal(a, b)
 
 
-def test_cfg2_batch_linearity_at_full_size(dev):
-    """BASELINE.json configs[1] (640x192, batch 12): the batch loss is the mean of the per-sample
-    losses and a sample's gradients are 1/B of its stand-alone gradients (size-independent check
-    that needs no CPU oracle at this size)."""
-    B = 12
-    inp = mono_inputs(B, 192, 640, seed=2)
+@pytest.mark.parametrize("B,H,W", [(12, 192, 640), (8, 320, 1024)])
+def test_batch_linearity_at_full_size(dev, B, H, W):
+    """BASELINE.json configs[1] (640x192, batch 12) and configs[2] (1024x320, batch 8): the batch loss is the
+    mean of the per-sample losses and a sample's gradients are 1/B of its stand-alone gradients
+    (size-independent check that needs no CPU oracle at this size)."""
+    inp = mono_inputs(B, H, W, seed=2)
     # pyramid and pose matrices are built once on the CPU and sliced, so the batched and the
     # per-sample runs see identical input bits (library resize / bmm kernels vary with batch size)
     tgt, src = build_pyramid(inp)
     pose = [euler_pose(v) for v in inp["pose_vec"]]
-    full = gpu_mono_from_pose(inp["depth"], inp["K"], pose, tgt, src, (192, 640), dev)
+    full = gpu_mono_from_pose(inp["depth"], inp["K"], pose, tgt, src, (H, W), dev)
     rec, sm = [], []
     for b in range(B):
         sl = slice(b, b + 1)
         o = gpu_mono_from_pose([d[sl] for d in inp["depth"]], inp["K"][sl], [p[sl] for p in pose],
-                               [t[sl] for t in tgt], [[x[sl] for x in row] for row in src], (192, 640), dev)
+                               [t[sl] for t in tgt], [[x[sl] for x in row] for row in src], (H, W), dev)
         rec.append(float(o["rec_loss"]))
         sm.append(float(o["smooth_loss"]))
         for i in range(4):

@@ -127,6 +127,45 @@ def test_motion_deterministic_and_workspace_reuse(sde_lib):
         assert torch.equal(a[k], b[k]), k
 
 
+def test_cfg4_full_size_sample_linearity_and_determinism(sde_lib):
+    """BASELINE.json configs[3] shape (1920x1280, translation field, both directions; batch 2 here): size-independent
+    properties that need no CPU oracle at this size -- the batch losses are the means of the per-sample losses,
+    a sample's gradients are 1/B of its stand-alone gradients, and a second run gives the same bits."""
+    from simpledepthestimation_b200.functional import MotionLossPlan, motion_rgbd_smoothness_loss
+
+    B, H, W = 2, 1280, 1920
+    inp = motion_inputs(B, H, W, seed=5)
+    dev = "cuda:0"
+    pose_all = euler_pose(inp["pose_vec"].float())
+
+    def run(sl):
+        g = lambda t: t.to(dev).contiguous()  # noqa: E731
+        n = sl.stop - sl.start
+        d1, d2 = g(inp["depth1"][sl]).requires_grad_(), g(inp["depth2"][sl]).requires_grad_()
+        p12 = g(pose_all[:B][sl]).requires_grad_()
+        p21 = g(pose_all[B:][sl]).requires_grad_()
+        m12, m21 = g(inp["motion"][:B][sl]).requires_grad_(), g(inp["motion"][B:][sl]).requires_grad_()
+        f1, f2, K = g(inp["img1"][sl]), g(inp["img2"][sl]), g(inp["K"][sl])
+        plan = MotionLossPlan(n, (H, W), dev, 2, with_field=True)
+        losses, _ = motion_rgbd_smoothness_loss(plan, [f1, f2], [f2, f1], [d1, d2], [d2, d1], K, [p12, p21], [m12, m21],
+                                                want_maps=False)
+        (losses[:, :3] * torch.tensor(WTS, device=dev)).sum().backward()
+        torch.cuda.synchronize()
+        return dict(losses=losses.detach().cpu()[:, :3], gd1=d1.grad.cpu(), gd2=d2.grad.cpu(), gp12=p12.grad.cpu(),
+                    gm12=m12.grad.cpu())
+
+    full = run(slice(0, B))
+    again = run(slice(0, B))
+    for k in full:
+        assert torch.equal(full[k], again[k]), k
+    singles = [run(slice(b, b + 1)) for b in range(B)]
+    mean = sum(s["losses"] for s in singles) / B
+    assert rel_err(full["losses"], mean) < 2e-6
+    for b in range(B):
+        for k in ("gd1", "gd2", "gp12", "gm12"):
+            assert rel_err(full[k][b] * B, singles[b][k][0]) < 1e-4, k
+
+
 def test_motion_identical_frames_and_identity_pose(sde_lib):
     """frame_B == frame_A, depth_B == depth_A, R = I, t = 0: the warp is the identity up to the 1e-6 in the
     divide (camera.py:150-151), so rgb_l1 is tiny and the result must still match the oracle."""
