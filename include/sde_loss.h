@@ -244,6 +244,57 @@ int sde_smoothness_backward(const sde_smooth_desc* desc, const sde_smooth_buffer
 int sde_resize_bilinear(const float* src, float* dst, int32_t planes, int32_t src_h, int32_t src_w, int32_t dst_h,
                         int32_t dst_w, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MotionLearning regularisers, detectron2/modeling/losses/motion_loss.py (callers
+ * MotionLearning.py:188-220).
+ * ------------------------------------------------------------------------------------------ */
+
+/* motion_consistency_loss(coords_A_in_B, mask, R_A2B, R_B2A, t_A2B, t_B2A), motion_loss.py:7-48: the
+ * translation term  mean(mask * |R_A2B t_hat + t_A2B|^2 / (|t_A2B|^2 + |t_hat|^2 + 1e-24))  with
+ * t_hat = grid_sample(t_B2A, coords) (bilinear, zeros, align_corners=True; coords carry no gradient, :11).
+ * The rotation term (:24,35-38) is [B,3,3] arithmetic and stays on the host side. */
+typedef struct sde_mcons_desc {
+  int32_t batch, height, width;
+} sde_mcons_desc;
+
+typedef struct sde_mcons_buffers {
+  const float* coords;        /* [B,h,w,2] normalised (x,y) */
+  const float* mask;          /* [B,1,h,w] */
+  const float* rotation;      /* [B,3,3] R_A2B */
+  const float* t_ab;          /* [B,3,h,w] */
+  const float* t_ba;          /* [B,3,h,w] */
+  float* loss;                /* [1] trans_error */
+  const float* grad_loss;     /* [1] (device) */
+  float* grad_t_ab;           /* [B,3,h,w] */
+  float* grad_t_ba;           /* [B,3,h,w]: bilinear scatter, 64-bit fixed point + integer atomics (deterministic) */
+  float* grad_rotation;       /* [B,3,3] */
+  void* workspace;            /* sde_motion_consistency_workspace_bytes(), zero-filled once */
+} sde_mcons_buffers;
+
+size_t sde_motion_consistency_workspace_bytes(const sde_mcons_desc* desc);
+int sde_motion_consistency_forward(const sde_mcons_desc* desc, const sde_mcons_buffers* buf, void* stream);
+int sde_motion_consistency_backward(const sde_mcons_desc* desc, const sde_mcons_buffers* buf, void* stream);
+
+/* motion_smoothness_loss_fn(m), motion_loss.py:51-55, and motion_sparsity_loss_fn(m), motion_loss.py:58-64. */
+typedef struct sde_mreg_desc {
+  int32_t batch, channels, height, width;
+} sde_mreg_desc;
+
+typedef struct sde_mreg_buffers {
+  const float* field;         /* [B,C,h,w] */
+  float* loss;                /* [1] */
+  float* saved_stats;         /* sparsity: [B*C] mean |m| per plane (detached in the reference, :60) */
+  const float* grad_loss;     /* [1] (device) */
+  float* grad_field;          /* [B,C,h,w] */
+  void* workspace;            /* sde_motion_reg_workspace_bytes(), zero-filled once */
+} sde_mreg_buffers;
+
+size_t sde_motion_reg_workspace_bytes(const sde_mreg_desc* desc);
+int sde_motion_smoothness_forward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream);
+int sde_motion_smoothness_backward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream);
+int sde_motion_sparsity_forward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream);
+int sde_motion_sparsity_backward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,23 @@ class SmoothBuffers(C.Structure):
     _fields_ = [(n, _f32p) for n in ("depth", "image", "loss", "saved_stats", "grad_loss", "grad_depth", "workspace")]
 
 
+class McDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32)]
+
+
+class McBuffers(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("coords", "mask", "rotation", "t_ab", "t_ba", "loss", "grad_loss", "grad_t_ab",
+                                     "grad_t_ba", "grad_rotation", "workspace")]
+
+
+class MregDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32)]
+
+
+class MregBuffers(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("field", "loss", "saved_stats", "grad_loss", "grad_field", "workspace")]
+
+
 class SdeError(RuntimeError):
     pass
 
@@ -140,6 +157,17 @@ def load():
         for suffix in ("_forward", "_backward"):
             fn = getattr(lib, prefix + suffix)
             fn.restype, fn.argtypes = C.c_int, [C.POINTER(D), C.POINTER(B), C.c_void_p]
+    lib.sde_motion_consistency_workspace_bytes.restype = C.c_size_t
+    lib.sde_motion_consistency_workspace_bytes.argtypes = [C.POINTER(McDesc)]
+    for suffix in ("_forward", "_backward"):
+        fn = getattr(lib, "sde_motion_consistency" + suffix)
+        fn.restype, fn.argtypes = C.c_int, [C.POINTER(McDesc), C.POINTER(McBuffers), C.c_void_p]
+    lib.sde_motion_reg_workspace_bytes.restype = C.c_size_t
+    lib.sde_motion_reg_workspace_bytes.argtypes = [C.POINTER(MregDesc)]
+    for name in ("smoothness", "sparsity"):
+        for suffix in ("_forward", "_backward"):
+            fn = getattr(lib, f"sde_motion_{name}{suffix}")
+            fn.restype, fn.argtypes = C.c_int, [C.POINTER(MregDesc), C.POINTER(MregBuffers), C.c_void_p]
     lib.sde_resize_bilinear.restype = C.c_int
     lib.sde_resize_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p]

@@ -58,3 +58,34 @@ struct SmoothParams {
 };
 
 }  // namespace sde
+
+namespace sde {
+
+struct McParams {   // motion_consistency_loss, translation term
+  int B, h, w;
+  const float* coords;      // [B,h,w,2]
+  const float* mask;        // [B,1,h,w]
+  const float* R;           // [B,3,3] A->B
+  const float* t_ab;        // [B,3,h,w]
+  const float* t_ba;        // [B,3,h,w]
+  float* loss;              // [1]
+  const float* g_loss;
+  float* g_t_ab;
+  long long* g_t_ba_fix;    // [B,3,h,w] fixed-point accumulator (zero on entry and exit)
+  float* g_R;               // [B,3,3]
+  float* slots;             // forward: [B*blocks]; backward: [B*blocks][12]
+  unsigned* counters;       // [1 + B]
+};
+
+struct MregParams {   // motion_smoothness_loss_fn / motion_sparsity_loss_fn
+  int B, C, h, w;
+  const float* field;       // [B,C,h,w]
+  float* loss;              // [1]
+  float* stats;             // sparsity: [B*C] mean |m|
+  const float* g_loss;
+  float* g_field;
+  float* slots;             // [B*C*blocks]
+  unsigned* counters;       // [1 + B*C]
+};
+
+}  // namespace sde

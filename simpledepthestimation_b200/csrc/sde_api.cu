@@ -21,6 +21,9 @@ cudaError_t launch_ssim_bwd(const SsimParams& p, cudaStream_t stream);
 cudaError_t launch_smooth_fwd(const SmoothParams& p, cudaStream_t stream);
 cudaError_t launch_smooth_bwd(const SmoothParams& p, cudaStream_t stream);
 cudaError_t launch_resize_bilinear(const float* src, float* dst, int planes, int sh, int sw, int dh, int dw, cudaStream_t stream);
+cudaError_t launch_mcons_fwd(const McParams& p, cudaStream_t stream);
+cudaError_t launch_mcons_bwd(const McParams& p, float* g_t_ba, cudaStream_t stream);
+cudaError_t launch_mreg(int which, const MregParams& p, cudaStream_t stream);
 constexpr int kOpBlock = 256;
 
 static thread_local char g_cuda_err[256] = "";
@@ -370,6 +373,69 @@ static int smooth_params(const sde_smooth_desc* d, const sde_smooth_buffers* b, 
   }
   return SDE_OK;
 }
+// ------------------------------------------------------------------------------------------------ motion regularisers
+static bool mcons_ok(const sde_mcons_desc* d) { return d && d->batch >= 1 && d->height >= 2 && d->width >= 2; }
+struct McLayout { int blocks; size_t off_slots, off_fix, total; };
+static McLayout mcons_layout(const sde_mcons_desc* d) {
+  McLayout L;
+  L.blocks = (d->height * d->width + kOpBlock - 1) / kOpBlock;
+  size_t off = align16((size_t)(1 + d->batch) * sizeof(unsigned));
+  L.off_slots = off;
+  off = align16(off + (size_t)d->batch * L.blocks * 12 * sizeof(float));
+  L.off_fix = off;
+  off = align16(off + (size_t)d->batch * 3 * d->height * d->width * sizeof(long long));
+  L.total = off;
+  return L;
+}
+static int mcons_params(const sde_mcons_desc* d, const sde_mcons_buffers* b, bool backward, McParams& p) {
+  if (!mcons_ok(d) || !b || !b->coords || !b->mask || !b->rotation || !b->t_ab || !b->t_ba || !b->workspace)
+    return SDE_ERR_INVALID_ARG;
+  memset(&p, 0, sizeof(p));
+  const McLayout L = mcons_layout(d);
+  char* ws = static_cast<char*>(b->workspace);
+  p.B = d->batch; p.h = d->height; p.w = d->width;
+  p.coords = b->coords; p.mask = b->mask; p.R = b->rotation; p.t_ab = b->t_ab; p.t_ba = b->t_ba;
+  p.loss = b->loss;
+  p.counters = reinterpret_cast<unsigned*>(ws);
+  p.slots = reinterpret_cast<float*>(ws + L.off_slots);
+  p.g_t_ba_fix = reinterpret_cast<long long*>(ws + L.off_fix);
+  if (!backward) return b->loss ? SDE_OK : SDE_ERR_INVALID_ARG;
+  if (!b->grad_loss || !b->grad_t_ab || !b->grad_t_ba || !b->grad_rotation) return SDE_ERR_INVALID_ARG;
+  p.g_loss = b->grad_loss; p.g_t_ab = b->grad_t_ab; p.g_R = b->grad_rotation;
+  return SDE_OK;
+}
+
+static bool mreg_ok(const sde_mreg_desc* d) {
+  return d && d->batch >= 1 && d->channels >= 1 && d->height >= 2 && d->width >= 2;
+}
+struct MregLayout { int blocks; size_t off_slots, total; };
+static MregLayout mreg_layout(const sde_mreg_desc* d) {
+  MregLayout L;
+  L.blocks = (d->height * d->width + kOpBlock - 1) / kOpBlock;
+  size_t off = align16((size_t)(1 + d->batch * d->channels) * sizeof(unsigned));
+  L.off_slots = off;
+  off = align16(off + (size_t)d->batch * d->channels * L.blocks * sizeof(float));
+  L.total = off;
+  return L;
+}
+static int mreg_params(const sde_mreg_desc* d, const sde_mreg_buffers* b, bool backward, bool sparsity, MregParams& p) {
+  if (!mreg_ok(d) || !b || !b->field || (sparsity && !b->saved_stats)) return SDE_ERR_INVALID_ARG;
+  memset(&p, 0, sizeof(p));
+  p.B = d->batch; p.C = d->channels; p.h = d->height; p.w = d->width;
+  p.field = b->field; p.stats = b->saved_stats;
+  if (!backward) {
+    if (!b->loss || !b->workspace) return SDE_ERR_INVALID_ARG;
+    const MregLayout L = mreg_layout(d);
+    char* ws = static_cast<char*>(b->workspace);
+    p.loss = b->loss;
+    p.counters = reinterpret_cast<unsigned*>(ws);
+    p.slots = reinterpret_cast<float*>(ws + L.off_slots);
+  } else {
+    if (!b->grad_loss || !b->grad_field) return SDE_ERR_INVALID_ARG;
+    p.g_loss = b->grad_loss; p.g_field = b->grad_field;
+  }
+  return SDE_OK;
+}
 }  // namespace sde
 
 using namespace sde;
@@ -495,6 +561,44 @@ int sde_resize_bilinear(const float* src, float* dst, int32_t planes, int32_t sr
                         int32_t dst_w, void* stream) {
   if (!src || !dst || planes < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return SDE_ERR_INVALID_ARG;
   SDE_LAUNCH(launch_resize_bilinear(src, dst, planes, src_h, src_w, dst_h, dst_w, static_cast<cudaStream_t>(stream)));
+}
+
+size_t sde_motion_consistency_workspace_bytes(const sde_mcons_desc* desc) { return mcons_ok(desc) ? mcons_layout(desc).total : 0; }
+
+int sde_motion_consistency_forward(const sde_mcons_desc* desc, const sde_mcons_buffers* buf, void* stream) {
+  McParams p;
+  int st = mcons_params(desc, buf, false, p);
+  if (st != SDE_OK) return st;
+  SDE_LAUNCH(launch_mcons_fwd(p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_motion_consistency_backward(const sde_mcons_desc* desc, const sde_mcons_buffers* buf, void* stream) {
+  McParams p;
+  int st = mcons_params(desc, buf, true, p);
+  if (st != SDE_OK) return st;
+  SDE_LAUNCH(launch_mcons_bwd(p, buf->grad_t_ba, static_cast<cudaStream_t>(stream)));
+}
+
+size_t sde_motion_reg_workspace_bytes(const sde_mreg_desc* desc) { return mreg_ok(desc) ? mreg_layout(desc).total : 0; }
+
+static int mreg_call(int which, bool backward, bool sparsity, const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream) {
+  MregParams p;
+  int st = mreg_params(desc, buf, backward, sparsity, p);
+  if (st != SDE_OK) return st;
+  SDE_LAUNCH(launch_mreg(which, p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_motion_smoothness_forward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream) {
+  return mreg_call(0, false, false, desc, buf, stream);
+}
+int sde_motion_smoothness_backward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream) {
+  return mreg_call(1, true, false, desc, buf, stream);
+}
+int sde_motion_sparsity_forward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream) {
+  return mreg_call(2, false, true, desc, buf, stream);
+}
+int sde_motion_sparsity_backward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream) {
+  return mreg_call(3, true, true, desc, buf, stream);
 }
 
 }  // extern "C"

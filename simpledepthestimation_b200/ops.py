@@ -222,3 +222,94 @@ def resize_bilinear(image: torch.Tensor, dst_size) -> torch.Tensor:
     _lib.check(lib.sde_resize_bilinear(image.data_ptr(), out.data_ptr(), planes, sh, sw, dh, dw, _stream()),
                "sde_resize_bilinear")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ motion regularisers
+class _MotionConsistencyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords, mask, R, t_ab, t_ba):
+        lib = _lib.load()
+        coords, mask, R = _cuda_f32(coords.detach(), "coords_A_in_B"), _cuda_f32(mask.detach(), "mask"), _cuda_f32(R, "R_A2B")
+        t_ab, t_ba = _cuda_f32(t_ab, "t_A2B"), _cuda_f32(t_ba, "t_B2A")
+        B, _, h, w = t_ab.shape
+        if tuple(coords.shape) != (B, h, w, 2) or tuple(mask.shape) != (B, 1, h, w) or tuple(R.shape) != (B, 3, 3) \
+                or tuple(t_ab.shape) != (B, 3, h, w) or tuple(t_ba.shape) != (B, 3, h, w):
+            raise _lib.SdeError("motion_consistency_loss: expected coords [B,H,W,2], mask [B,1,H,W], R [B,3,3], t [B,3,H,W]")
+        d = _lib.McDesc(B, h, w)
+        nbytes = lib.sde_motion_consistency_workspace_bytes(C.byref(d))
+        if nbytes == 0:
+            raise _lib.SdeError("motion_consistency_loss: H and W must be >= 2")
+        ws = _zero_workspace("mcons", (B, h, w), nbytes, t_ab.device)
+        loss = torch.empty(1, device=t_ab.device)
+        b = _lib.McBuffers()
+        b.coords, b.mask, b.rotation, b.t_ab, b.t_ba = (x.data_ptr() for x in (coords, mask, R, t_ab, t_ba))
+        b.loss, b.workspace = loss.data_ptr(), ws.data_ptr()
+        _lib.check(lib.sde_motion_consistency_forward(C.byref(d), C.byref(b), _stream()), "sde_motion_consistency_forward")
+        ctx.save_for_backward(coords, mask, R, t_ab, t_ba)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        coords, mask, R, t_ab, t_ba = ctx.saved_tensors
+        B, _, h, w = t_ab.shape
+        d = _lib.McDesc(B, h, w)
+        ws = _zero_workspace("mcons", (B, h, w), lib.sde_motion_consistency_workspace_bytes(C.byref(d)), t_ab.device)
+        g = g.reshape(1).contiguous().float()
+        g_ab, g_ba, g_R = torch.empty_like(t_ab), torch.empty_like(t_ba), torch.empty_like(R)
+        b = _lib.McBuffers()
+        b.coords, b.mask, b.rotation, b.t_ab, b.t_ba = (x.data_ptr() for x in (coords, mask, R, t_ab, t_ba))
+        b.grad_loss, b.grad_t_ab, b.grad_t_ba, b.grad_rotation = g.data_ptr(), g_ab.data_ptr(), g_ba.data_ptr(), g_R.data_ptr()
+        b.workspace = ws.data_ptr()
+        _lib.check(lib.sde_motion_consistency_backward(C.byref(d), C.byref(b), _stream()), "sde_motion_consistency_backward")
+        return None, None, g_R, g_ab, g_ba
+
+
+def motion_translation_consistency(coords, mask, R_A2B, t_A2B, t_B2A):
+    return _MotionConsistencyFn.apply(coords, mask, R_A2B, t_A2B, t_B2A)
+
+
+class _MotionRegFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, field, kind):
+        lib = _lib.load()
+        field = _cuda_f32(field, "motion_field")
+        if field.dim() != 4:
+            raise _lib.SdeError("motion regulariser: expected a [B,C,H,W] field")
+        B, Cc, h, w = field.shape
+        d = _lib.MregDesc(B, Cc, h, w)
+        nbytes = lib.sde_motion_reg_workspace_bytes(C.byref(d))
+        if nbytes == 0:
+            raise _lib.SdeError("motion regulariser: H and W must be >= 2")
+        ws = _zero_workspace("mreg", (B, Cc, h, w), nbytes, field.device)
+        loss = torch.empty(1, device=field.device)
+        stats = torch.empty(B * Cc, device=field.device)
+        b = _lib.MregBuffers()
+        b.field, b.loss, b.saved_stats, b.workspace = field.data_ptr(), loss.data_ptr(), stats.data_ptr(), ws.data_ptr()
+        fn = lib.sde_motion_smoothness_forward if kind == "smoothness" else lib.sde_motion_sparsity_forward
+        _lib.check(fn(C.byref(d), C.byref(b), _stream()), f"sde_motion_{kind}_forward")
+        ctx.save_for_backward(field, stats)
+        ctx.kind = kind
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        field, stats = ctx.saved_tensors
+        B, Cc, h, w = field.shape
+        d = _lib.MregDesc(B, Cc, h, w)
+        g = g.reshape(1).contiguous().float()
+        gf = torch.empty_like(field)
+        b = _lib.MregBuffers()
+        b.field, b.saved_stats, b.grad_loss, b.grad_field = field.data_ptr(), stats.data_ptr(), g.data_ptr(), gf.data_ptr()
+        fn = lib.sde_motion_smoothness_backward if ctx.kind == "smoothness" else lib.sde_motion_sparsity_backward
+        _lib.check(fn(C.byref(d), C.byref(b), _stream()), f"sde_motion_{ctx.kind}_backward")
+        return gf, None
+
+
+def motion_smoothness(field):
+    return _MotionRegFn.apply(field, "smoothness")
+
+
+def motion_sparsity(field):
+    return _MotionRegFn.apply(field, "sparsity")

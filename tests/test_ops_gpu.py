@@ -217,3 +217,62 @@ def test_model_methods_match_fused_path(sde_lib):
     assert float((pe.cpu().double() - ref_pe).abs().max()) < 5e-4
     ident = mono.rgb_consistency_loss(g(inp["img1"]), g(inp["img2"]), g(inp["depth1"]), g(inp["K"]))
     assert float((ident.cpu().double() - port.photometric_error(inp["img2"].to(dt), inp["img1"].to(dt))).abs().max()) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ motion regularisers (N1)
+def test_motion_consistency_loss(sde_lib):
+    from simpledepthestimation_b200.modeling.losses import motion_consistency_loss
+
+    B, H, W = 2, 40, 72
+    inp = motion_inputs(B, H, W, seed=6)
+    T = euler_pose(inp["pose_vec"].float())
+    R_ab, R_ba = T[:B, :3, :3].contiguous(), T[B:, :3, :3].contiguous()
+    t_ab = (T[:B, :3, 3][:, :, None, None] + inp["motion"][:B]).contiguous()
+    t_ba = (T[B:, :3, 3][:, :, None, None] + inp["motion"][B:]).contiguous()
+    gen = torch.Generator().manual_seed(3)
+    coords = (torch.rand(B, H, W, 2, generator=gen) * 2.2 - 1.1)      # some samples fall outside: zeros padding
+    mask = (torch.rand(B, 1, H, W, generator=gen) > 0.3).float()
+
+    def run_oracle(dt):
+        a = [x.to(dt).clone().requires_grad_() for x in (R_ab, R_ba, t_ab, t_ba)]
+        rot, tr = port.motion_consistency(coords.to(dt), mask.to(dt), *a)
+        (rot * 0.3 + tr * 1.7).backward()
+        return rot.detach(), tr.detach(), [x.grad for x in a]
+
+    rot64, tr64, g64 = run_oracle(torch.float64)
+    _, _, g32 = run_oracle(torch.float32)
+    a = [x.to(DEV).clone().requires_grad_() for x in (R_ab, R_ba, t_ab, t_ba)]
+    rot, tr = motion_consistency_loss(coords.to(DEV), mask.to(DEV), *a)
+    (rot * 0.3 + tr * 1.7).backward()
+    torch.cuda.synchronize()
+    assert rel_err(rot.detach(), rot64) < 1e-4 and rel_err(tr.detach(), tr64) < 1e-5
+    for k, name in enumerate(("R_A2B", "R_B2A", "t_A2B", "t_B2A")):
+        _quantile_ok(a[k].grad, g64[k], g32[k], name)
+    # deterministic scatter
+    b = [x.to(DEV).clone().requires_grad_() for x in (R_ab, R_ba, t_ab, t_ba)]
+    rot2, tr2 = motion_consistency_loss(coords.to(DEV), mask.to(DEV), *b)
+    (rot2 * 0.3 + tr2 * 1.7).backward()
+    assert torch.equal(a[3].grad, b[3].grad) and torch.equal(tr.detach(), tr2.detach())
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 32, 64), (1, 3, 50, 70), (2, 3, 192, 320)])
+def test_motion_smoothness_and_sparsity(sde_lib, shape):
+    from simpledepthestimation_b200.modeling.losses import motion_smoothness_loss_fn, motion_sparsity_loss_fn
+
+    gen = torch.Generator().manual_seed(shape[3])
+    m = 0.05 * torch.randn(*shape, generator=gen)
+    m[:, :, :4] = 0.0        # exact zeros: sqrt(1e-24) / sign(0) corner cases
+    for fn, ofn in ((motion_smoothness_loss_fn, port.motion_smoothness), (motion_sparsity_loss_fn, port.motion_sparsity)):
+        def run_oracle(dt):
+            x = m.to(dt).clone().requires_grad_()
+            L = ofn(x)
+            (L * 0.8).backward()
+            return L.detach(), x.grad
+        L64, g64 = run_oracle(torch.float64)
+        _, g32 = run_oracle(torch.float32)
+        x = m.to(DEV).requires_grad_()
+        L = fn(x)
+        (L * 0.8).backward()
+        torch.cuda.synchronize()
+        assert rel_err(L.detach(), L64) < 1e-5, fn.__name__
+        _quantile_ok(x.grad, g64, g32, fn.__name__)
