@@ -60,6 +60,7 @@ class MotionBuffers(C.Structure):
         ("intrinsics", _f32p),
         ("losses", _f32p), ("saved_stats", _f32p),
         ("occlusion", _f32p * MAX_DIRS), ("weight", _f32p * MAX_DIRS), ("coords", _f32p * MAX_DIRS),
+        ("warped", _f32p * MAX_DIRS),
         ("grad_losses", _f32p),
         ("grad_depth_a", _f32p * MAX_DIRS), ("grad_pose", _f32p * MAX_DIRS), ("grad_field", _f32p * MAX_DIRS),
         ("workspace", _f32p),

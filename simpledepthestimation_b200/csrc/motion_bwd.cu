@@ -19,27 +19,47 @@ namespace sde {
 // WZ (zero-padded weight) is only read before the first phase 3 (avg_w), so it shares gS plane 0
 constexpr int kNA = 0, kNS = 3, kNU = 6, kND = 7, kNCoef = 8, kNG = 11, kNW = kNG;
 constexpr int kMotionBwdPlanes = 14;
+// the gradient block P starts at plane column 3: with 60-wide tiles plane index 0 is image column tile_x0 - 4 (TMA)
+constexpr int kMBwdColOff = 3;
 constexpr int kMPosPerThread = (kBwdW * kBwdH + kThreads - 1) / kThreads;  // 7
 
 struct MotionBwdShared {
   MCam cam;
   float red[12][kThreads / 32];
   unsigned ticket;
+  __align__(8) uint64_t bar;             // TMA completion barrier
   __align__(8) uint8_t occ[kPlane];      // occlusion mask of the staged positions (0 / 1)
   __align__(8) uint8_t inside[kPlane];   // window centre lies in the image
 };
 
-__global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_constant__ MotionParams p) {
-  extern __shared__ __align__(16) float planes[];  // [kMotionBwdPlanes][kPlane]
+__global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_constant__ MotionParams p,
+                                                                 const __grid_constant__ MotionTma maps) {
+  extern __shared__ __align__(128) float planes[];  // [kMotionBwdPlanes][kPlane]
   __shared__ MotionBwdShared sh;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int dir, b, tx0, ty0;
   decode_motion_tile(blockIdx.x, p.btiles_per_dir, p.btiles_x, p.btiles_y, kBwdW, kBwdH, dir, b, tx0, ty0);
   const int h = p.h, w = p.w, hw = h * w;
-  const int ox = tx0 - 2, oy = ty0 - 2;
+  const int ox = tx0 - kMBwdColOff, oy = ty0 - 2;
   const bool lr_border = ox + 2 <= 1 || ox + kHW - 3 >= w - 2;
 
+  const bool tma = p.tma != 0;
+  if (tma && tid == 0) {
+    // warp mode: warped rgb, depth error, valid/occlusion from the forward pass, frame A and depth A by TMA
+    mbar_init(&sh.bar, 1);
+    mbar_init_fence();
+    mbar_arrive_expect_tx(&sh.bar, 9 * kPlaneBytesTma);
+    const int bx = ox - kColOff;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      tma_load_plane(planes + (kNA + c) * kPlane, &maps.frame_a[dir], &sh.bar, bx, oy, b * 3 + c);
+      tma_load_plane(planes + (kNS + c) * kPlane, &maps.warped[dir], &sh.bar, bx, oy, b * 5 + c);
+    }
+    tma_load_plane(planes + kNU * kPlane, &maps.warped[dir], &sh.bar, bx, oy, b * 5 + 3);
+    tma_load_plane(planes + kNW * kPlane, &maps.warped[dir], &sh.bar, bx, oy, b * 5 + 4);
+    tma_load_plane(planes + kND * kPlane, &maps.depth_a[dir], &sh.bar, bx, oy, b);
+  }
   if (tid == 0) load_mcam(sh.cam, p.K, p.pose[dir], b, p.sx, p.sy);
   for (int i = tid; i < 3 * kPlane; i += kThreads) planes[kNCoef * kPlane + i] = 0.0f;
   __syncthreads();
@@ -61,7 +81,31 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
   const bool use_ssim = p.ssim_w > 0.0f;
 
   // ------------------------------------------------------------------ phase 1
-  {
+  if (tma) {
+    mbar_wait(&sh.bar, 0);
+    const bool interior = ox >= 0 && oy >= 0 && ox + kHW <= w && oy + kHH <= h;
+    if (!interior) {
+      reflect_fixup(planes, kNA, 6, oy, ox, h, w, tid);   // A and S
+      reflect_fixup(planes, kND, 1, oy, ox, h, w, tid);
+      __syncthreads();
+    }
+    for (int i = tid; i < kPositions; i += kThreads) {
+      int yy, xx;
+      position_of(i, yy, xx);
+      const int pl = plane_index(yy, xx);
+      const float derr = planes[kNU * kPlane + pl], vo = planes[kNW * kPlane + pl];
+      const float wgt = proximity_weight(derr, vo, st.m2);
+      planes[kNU * kPlane + pl] = wgt + 1e-2f;
+      planes[kNW * kPlane + pl] = wgt;
+      const int ty = oy + yy, tx = ox + xx;
+      sh.occ[pl] = vo >= 2.0f ? 1 : 0;
+      sh.inside[pl] = (ty >= 0 && ty < h && tx >= 0 && tx < w) ? 1 : 0;
+    }
+    if (!interior) {
+      __syncthreads();
+      reflect_fixup(planes, kNU, 1, oy, ox, h, w, tid);
+    }
+  } else {
     const MCam mc = sh.cam;
 #pragma unroll 1
     for (int i = tid; i < kPositions; i += kThreads) {
@@ -245,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
       const int ly = i / kBwdW, lx = i - ly * kBwdW;
       const int gy = ty0 + ly, gx = tx0 + lx;
       if (i < kBwdW * kBwdH && gy < h && gx < w) {
-        const int pl = plane_index(ly + 2, lx + 2);
+        const int pl = plane_index(ly + 2, lx + kMBwdColOff);
         const int pix = gy * w + gx;
         const float g0 = planes[kNG * kPlane + pl], g1 = planes[(kNG + 1) * kPlane + pl], g2 = planes[(kNG + 2) * kPlane + pl];
         const float d = planes[kND * kPlane + pl];
@@ -356,11 +400,11 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
 
 size_t motion_bwd_smem_bytes() { return (size_t)kMotionBwdPlanes * kPlane * sizeof(float); }
 
-cudaError_t launch_motion_bwd(const MotionParams& p, cudaStream_t stream) {
+cudaError_t launch_motion_bwd(const MotionParams& p, const MotionTma& t, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(motion_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)motion_bwd_smem_bytes());
   if (e != cudaSuccess) return e;
-  motion_bwd_kernel<<<p.n_dirs * p.btiles_per_dir, kThreads, motion_bwd_smem_bytes(), stream>>>(p);
+  motion_bwd_kernel<<<p.n_dirs * p.btiles_per_dir, kThreads, motion_bwd_smem_bytes(), stream>>>(p, t);
   return cudaGetLastError();
 }
 

@@ -32,6 +32,8 @@ struct MotionParams {
   float* occ[SDE_MAX_DIRS];
   float* weight[SDE_MAX_DIRS];
   float* coords[SDE_MAX_DIRS];
+  float* warped[SDE_MAX_DIRS];               // [B,5,h,w]: warped rgb, depth error, valid + 2 occlusion (or null)
+  int tma;                                   // loss kernels stage their planes through TMA from `warped`
   // workspace
   unsigned* counters;                        // [0] statistics, [1] forward, [2] backward
   float* stat_partials;                      // [n_dirs*B*stat_blocks][2]
@@ -137,7 +139,7 @@ struct MotionSample {
 
 // Projects pixel `pix` = (gy, gx), gathers rgb + depth of B, loads A; no shared memory involved.
 __device__ __forceinline__ void motion_sample(const MotionStage& a, const MCam& mc, int gy, int gx, int pix, bool rgb,
-                                              MotionSample& o) {
+                                              MotionSample& o, bool load_a = true) {
   o.d = __ldg(a.depth_a + pix);
   float f0 = 0.0f, f1 = 0.0f, f2v = 0.0f;
   if (a.field) { f0 = __ldg(a.field + pix); f1 = __ldg(a.field + pix + a.hw); f2v = __ldg(a.field + pix + 2 * a.hw); }
@@ -151,7 +153,7 @@ __device__ __forceinline__ void motion_sample(const MotionStage& a, const MCam& 
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       o.S[c] = bilinear4(a.frame_b + cell.off + c * a.hw, a.w, w00, w01, w10, w11);
-      o.A[c] = __ldg(a.frame_a + pix + c * a.hw);
+      if (load_a) o.A[c] = __ldg(a.frame_a + pix + c * a.hw);
     }
   }
   o.valid = valid_mask(X, Y, Z, a.w, a.h);
@@ -174,6 +176,19 @@ __device__ __forceinline__ void decode_motion_tile(int bid, int per_dir, int tx_
   b = t / ty_n;
   x0 = tx * tw;
   y0 = ty * th;
+}
+
+// Tensor maps of the TMA path (second kernel parameter), box {pitch, 18, 1}
+struct alignas(64) MotionTma {
+  CUtensorMap frame_a[SDE_MAX_DIRS];   // [B*3, h, w]
+  CUtensorMap depth_a[SDE_MAX_DIRS];   // [B, h, w]
+  CUtensorMap warped[SDE_MAX_DIRS];    // [B*5, h, w]
+};
+
+// proximity weight (MotionLearning.py:279-282) from the planes the warp kernel left: depth error and
+// vo = valid + 2 * occlusion
+__device__ __forceinline__ float proximity_weight(float derr, float vo, float m2) {
+  return fdiv(m2, derr + m2) * (vo != 0.0f ? 1.0f : 0.0f);
 }
 
 // Weighted-SSIM terms of one pixel pair from the window sums (ssim_loss.py:84-111).

@@ -14,6 +14,10 @@
 //            f2), sums carried down the rows in registers; accumulates ssim * avg_w.
 // plus smoothness_loss(depth_A, frame_A) from the same planes (1-homogeneity).
 // Deterministic: per-CTA partial slots, last CTA adds them in a fixed order in fp64.
+// plane layout of the tile kernel in this file: 72-float rows, column xx at index xx + 3, so that index 0 is
+// image column tile_x0 - 4 (TMA boxes must start 16-byte aligned)
+#define SDE_PITCH 72
+#define SDE_COL_OFF 3
 #include "motion_device.cuh"
 
 namespace sde {
@@ -39,17 +43,35 @@ __global__ void __launch_bounds__(kStatThreads) motion_stats_kernel(const __grid
   st.frame_a = nullptr; st.frame_b = nullptr;
   st.field = p.field[dir] ? p.field[dir] + (size_t)b * 3 * hw : nullptr;
   st.planes = nullptr; st.oy = 0; st.ox = 0; st.h = p.h; st.w = p.w; st.hw = hw; st.m2 = 1.0f;
+  st.frame_b = p.frame_b[dir] + (size_t)b * 3 * hw;
+  // warp mode: this pass also gathers the rgb channels and leaves the planes the loss kernels stage by TMA
+  float* __restrict__ wout = p.warped[dir] ? p.warped[dir] + (size_t)b * 5 * hw : nullptr;
+  float* __restrict__ occ_out = (wout && p.occ[dir]) ? p.occ[dir] + (size_t)b * hw : nullptr;
+  float* __restrict__ crd_out = (wout && p.coords[dir]) ? p.coords[dir] + (size_t)b * hw * 2 : nullptr;
   float socc = 0.0f, serr = 0.0f;
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < kStatPixPerThread; ++k) {
     const int pix = chunk * kStatPix + k * kStatThreads + tid;
     if (pix < hw) {
       const int gy = pix / p.w, gx = pix - gy * p.w;
       MotionSample sm;
-      motion_sample(st, mc, gy, gx, pix, false, sm);
+      motion_sample(st, mc, gy, gx, pix, wout != nullptr, sm, false);
       const float e = sm.Zc - sm.Sd;
+      const float derr = e * e;
       socc += sm.occ;
-      serr += (e * e) * sm.occ;
+      serr += derr * sm.occ;
+      if (wout) {
+        wout[pix] = sm.S[0]; wout[hw + pix] = sm.S[1]; wout[2 * hw + pix] = sm.S[2];
+        wout[3 * hw + pix] = derr;
+        wout[4 * hw + pix] = sm.valid + 2.0f * sm.occ;
+        if (occ_out) occ_out[pix] = sm.occ;
+        if (crd_out) {
+          float2 cn;
+          cn.x = __fdiv_rn(2.0f * sm.Xs, (float)(p.w - 1)) - 1.0f;
+          cn.y = __fdiv_rn(2.0f * sm.Ys, (float)(p.h - 1)) - 1.0f;
+          *reinterpret_cast<float2*>(crd_out + (size_t)pix * 2) = cn;
+        }
+      }
     }
   }
   socc = warp_sum(socc); serr = warp_sum(serr);
@@ -92,16 +114,35 @@ struct MotionFwdShared {
   MCam cam;
   float red[5][kThreads / 32];
   unsigned ticket;
+  __align__(8) uint64_t bar;   // TMA completion barrier
 };
 
-__global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_constant__ MotionParams p) {
-  extern __shared__ __align__(16) float planes[];  // [kMotionFwdPlanes][kPlane]
+__global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_constant__ MotionParams p,
+                                                                 const __grid_constant__ MotionTma maps) {
+  extern __shared__ __align__(128) float planes[];  // [kMotionFwdPlanes][kPlane]
   __shared__ MotionFwdShared sh;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int dir, b, tx0, ty0;
   decode_motion_tile(blockIdx.x, p.tiles_per_dir, p.tiles_x, p.tiles_y, kTileW, kTileH, dir, b, tx0, ty0);
   const int h = p.h, w = p.w, hw = h * w;
+  const bool tma = p.tma != 0;
+  if (tma && tid == 0) {
+    // warp mode: the statistics pass left warped rgb, depth error and valid/occlusion planes; the copy engine
+    // brings them in together with frame A and depth A (U and WZ are computed in place of the last two)
+    mbar_init(&sh.bar, 1);
+    mbar_init_fence();
+    mbar_arrive_expect_tx(&sh.bar, 9 * kPlaneBytesTma);
+    const int bx = tx0 - 1 - kColOff, by = ty0 - 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      tma_load_plane(planes + (kMA + c) * kPlane, &maps.frame_a[dir], &sh.bar, bx, by, b * 3 + c);
+      tma_load_plane(planes + (kMS + c) * kPlane, &maps.warped[dir], &sh.bar, bx, by, b * 5 + c);
+    }
+    tma_load_plane(planes + kMU * kPlane, &maps.warped[dir], &sh.bar, bx, by, b * 5 + 3);
+    tma_load_plane(planes + kMW * kPlane, &maps.warped[dir], &sh.bar, bx, by, b * 5 + 4);
+    tma_load_plane(planes + kMD * kPlane, &maps.depth_a[dir], &sh.bar, bx, by, b);
+  }
   if (tid == 0) load_mcam(sh.cam, p.K, p.pose[dir], b, p.sx, p.sy);
   __syncthreads();
 
@@ -120,7 +161,38 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
 
   // ------------------------------------------------------------------ phase 1
   float l1 = 0.0f;
-  {
+  if (tma) {
+    mbar_wait(&sh.bar, 0);
+    const bool interior = tx0 >= 1 && ty0 >= 1 && tx0 + kTileW + 1 <= w && ty0 + kTileH + 1 <= h;
+    if (!interior) {
+      reflect_fixup(planes, kMA, 6, st.oy, st.ox, h, w, tid);   // A and S (in-image sources only)
+      reflect_fixup(planes, kMD, 1, st.oy, st.ox, h, w, tid);
+      __syncthreads();
+    }
+    // depth error, valid/occlusion -> U = weight + 0.01 and WZ = weight (zero outside the image: valid = 0 there)
+    for (int i = tid; i < kPositions; i += kThreads) {
+      int yy, xx;
+      position_of(i, yy, xx);
+      const int pl = plane_index(yy, xx);
+      const float derr = planes[kMU * kPlane + pl], vo = planes[kMW * kPlane + pl];
+      const float wgt = proximity_weight(derr, vo, st.m2);
+      planes[kMU * kPlane + pl] = wgt + 1e-2f;
+      planes[kMW * kPlane + pl] = wgt;
+      const int ty = st.oy + yy, tx = st.ox + xx;
+      if (ty >= 0 && ty < h && tx >= 0 && tx < w && yy >= 1 && yy <= kTileH && xx >= 1 && xx <= kTileW) {
+        const float occ = vo >= 2.0f ? 1.0f : 0.0f;
+        float e = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) e += fabsf(planes[(kMS + c) * kPlane + pl] - planes[(kMA + c) * kPlane + pl]);
+        l1 += e * occ;
+        if (wgt_out) wgt_out[ty * w + tx] = wgt;
+      }
+    }
+    if (!interior) {
+      __syncthreads();
+      reflect_fixup(planes, kMU, 1, st.oy, st.ox, h, w, tid);   // the reflect-padded product x * (w + 0.01)
+    }
+  } else {
     const MCam mc = sh.cam;
 #pragma unroll 1
     for (int i = tid; i < kPositions; i += kThreads) {
@@ -333,13 +405,13 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
 
 size_t motion_fwd_smem_bytes() { return (size_t)kMotionFwdPlanes * kPlane * sizeof(float); }
 
-cudaError_t launch_motion_fwd(const MotionParams& p, cudaStream_t stream) {
+cudaError_t launch_motion_fwd(const MotionParams& p, const MotionTma& t, cudaStream_t stream) {
   motion_stats_kernel<<<p.n_dirs * p.B * p.stat_blocks, kStatThreads, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(motion_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)motion_fwd_smem_bytes());
   if (e != cudaSuccess) return e;
-  motion_fwd_kernel<<<p.n_dirs * p.tiles_per_dir, kThreads, motion_fwd_smem_bytes(), stream>>>(p);
+  motion_fwd_kernel<<<p.n_dirs * p.tiles_per_dir, kThreads, motion_fwd_smem_bytes(), stream>>>(p, t);
   return cudaGetLastError();
 }
 

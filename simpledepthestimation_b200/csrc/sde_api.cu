@@ -12,8 +12,8 @@ namespace sde {
 cudaError_t launch_mono_fwd(const MonoParams& p, const MonoTma& t, cudaStream_t stream);
 cudaError_t launch_mono_bwd(const MonoParams& p, const MonoTma& t, cudaStream_t stream);
 cudaError_t launch_mono_warp(const MonoParams& p, cudaStream_t stream);
-cudaError_t launch_motion_fwd(const MotionParams& p, cudaStream_t stream);
-cudaError_t launch_motion_bwd(const MotionParams& p, cudaStream_t stream);
+cudaError_t launch_motion_fwd(const MotionParams& p, const MotionTma& t, cudaStream_t stream);
+cudaError_t launch_motion_bwd(const MotionParams& p, const MotionTma& t, cudaStream_t stream);
 cudaError_t launch_vs_fwd(const VsParams& p, cudaStream_t stream);
 cudaError_t launch_vs_bwd(const VsParams& p, float* g_image, cudaStream_t stream);
 cudaError_t launch_ssim_fwd(const SsimParams& p, cudaStream_t stream);
@@ -212,6 +212,24 @@ static void mono_tma(const sde_mono_desc* d, const sde_mono_buffers* b, bool bac
   }
 }
 
+// Warp mode of the MotionLearning kernels: every direction has a `warped` buffer and the planes can be boxed.
+static void motion_tma(const sde_motion_desc* d, const sde_motion_buffers* b, bool backward, MotionParams& p, MotionTma& t) {
+  memset(&t, 0, sizeof(t));
+  p.tma = 0;
+  const char* off = getenv("SDE_DISABLE_TMA");
+  bool ok = !(off && off[0] == '1');
+  const int bw = backward ? 68 : 72;
+  for (int k = 0; ok && k < d->n_dirs; ++k) {
+    ok = b->warped[k] != nullptr &&
+         encode_planes(&t.frame_a[k], b->frame_a[k], d->batch * 3, d->height, d->width, bw) &&
+         encode_planes(&t.depth_a[k], b->depth_a[k], d->batch, d->height, d->width, bw) &&
+         encode_planes(&t.warped[k], b->warped[k], d->batch * 5, d->height, d->width, bw);
+  }
+  p.tma = ok ? 1 : 0;
+  if (!ok)
+    for (int k = 0; k < SDE_MAX_DIRS; ++k) p.warped[k] = nullptr;   // the statistics pass then only gathers depth
+}
+
 // ------------------------------------------------------------------------------------------------
 struct MotionLayout {
   int tiles_x, tiles_y, btiles_x, btiles_y, stat_blocks, grid, bgrid;
@@ -267,6 +285,7 @@ static int motion_params(const sde_motion_desc* d, const sde_motion_buffers* b, 
     p.pose[k] = b->pose[k];
     p.field[k] = field ? b->field[k] : nullptr;
     p.occ[k] = b->occlusion[k]; p.weight[k] = b->weight[k]; p.coords[k] = b->coords[k];
+    p.warped[k] = b->warped[k];
     p.grad_depth[k] = b->grad_depth_a[k]; p.grad_pose[k] = b->grad_pose[k];
     p.grad_field[k] = field ? b->grad_field[k] : nullptr;
     if (backward && (!b->grad_depth_a[k] || !b->grad_pose[k] || (field && !b->grad_field[k]))) return SDE_ERR_INVALID_ARG;
@@ -493,7 +512,9 @@ int sde_motion_loss_forward(const sde_motion_desc* desc, const sde_motion_buffer
   MotionParams p;
   int st = motion_params(desc, buf, false, p);
   if (st != SDE_OK) return st;
-  cudaError_t e = launch_motion_fwd(p, static_cast<cudaStream_t>(stream));
+  MotionTma t;
+  motion_tma(desc, buf, false, p, t);
+  cudaError_t e = launch_motion_fwd(p, t, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SDE_OK : cuda_fail(e);
 }
 
@@ -501,7 +522,9 @@ int sde_motion_loss_backward(const sde_motion_desc* desc, const sde_motion_buffe
   MotionParams p;
   int st = motion_params(desc, buf, true, p);
   if (st != SDE_OK) return st;
-  cudaError_t e = launch_motion_bwd(p, static_cast<cudaStream_t>(stream));
+  MotionTma t;
+  motion_tma(desc, buf, true, p, t);
+  cudaError_t e = launch_motion_bwd(p, t, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SDE_OK : cuda_fail(e);
 }
 

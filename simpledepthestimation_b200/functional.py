@@ -309,8 +309,11 @@ class MotionLossPlan:
     """
 
     def __init__(self, batch: int, size: Sequence[int], device, n_dirs=2, ssim_weight=3.0, c1=float("inf"), c2=9e-6,
-                 scale=(1.0, 1.0), with_field=True):
+                 scale=(1.0, 1.0), with_field=True, save_warped=True):
         self.lib = _lib.load()
+        # keep the warped planes (rgb, depth error, valid/occlusion: 20 B per pixel and direction) from the statistics
+        # pass for the forward and backward loss kernels (TMA-staged, no re-projection / re-gather), or recompute
+        self.save_warped = bool(save_warped)
         self.device = torch.device(device)
         self.batch, self.size, self.n_dirs, self.with_field = batch, tuple(size), n_dirs, bool(with_field)
         d = _lib.MotionDesc()
@@ -344,8 +347,18 @@ class MotionLossPlan:
         if tuple(K.shape) != (B, 3, 3) or not K.is_contiguous():
             raise _lib.SdeError("intrinsics must be contiguous [B,3,3]")
 
-    def _buffers(self, frame_a, frame_b, depth_a, depth_b, K, pose, field):
+    def new_warped(self):
+        """Buffers for the warped planes of one step (per direction [B,5,h,w]), or None."""
+        if not self.save_warped:
+            return None
+        h, w = self.size
+        return [torch.empty(self.batch, 5, h, w, dtype=torch.float32, device=self.device) for _ in range(self.n_dirs)]
+
+    def _buffers(self, frame_a, frame_b, depth_a, depth_b, K, pose, field, warped=None):
         b = _lib.MotionBuffers()
+        if warped is not None:
+            for k in range(self.n_dirs):
+                b.warped[k] = warped[k].data_ptr()
         for k in range(self.n_dirs):
             b.frame_a[k], b.frame_b[k] = frame_a[k].data_ptr(), frame_b[k].data_ptr()
             b.depth_a[k], b.depth_b[k] = depth_a[k].data_ptr(), depth_b[k].data_ptr()
@@ -357,11 +370,12 @@ class MotionLossPlan:
         b.workspace = self.workspace.data_ptr()
         return b
 
-    def forward(self, frame_a, frame_b, depth_a, depth_b, K, pose, field=None, want_maps=True, out=None):
-        """Statistics pre-pass + fused loss.  Returns (losses [n_dirs,4], maps) where maps is a list per
-        direction of dict(occlusion_mask [B,1,h,w], depth_proximity_weight [B,1,h,w], coords_A_in_B [B,h,w,2])."""
+    def forward(self, frame_a, frame_b, depth_a, depth_b, K, pose, field=None, want_maps=True, out=None, warped=None):
+        """Statistics / warp pass + fused loss.  Returns (losses [n_dirs,4], maps) where maps is a list per
+        direction of dict(occlusion_mask [B,1,h,w], depth_proximity_weight [B,1,h,w], coords_A_in_B [B,h,w,2]).
+        `warped` (from new_warped()) receives the warped planes for the loss kernels and the backward pass."""
         self._check(frame_a, frame_b, depth_a, depth_b, K, pose, field)
-        b = self._buffers(frame_a, frame_b, depth_a, depth_b, K, pose, field)
+        b = self._buffers(frame_a, frame_b, depth_a, depth_b, K, pose, field, warped)
         losses = out if out is not None else torch.empty(self.n_dirs, _lib.MOTION_N_LOSSES, dtype=torch.float32,
                                                          device=self.device)
         b.losses = losses.data_ptr()
@@ -381,8 +395,8 @@ class MotionLossPlan:
         return losses, maps
 
     def backward(self, frame_a, frame_b, depth_a, depth_b, K, pose, field, grad_losses, grad_depth=None,
-                 grad_pose=None, grad_field=None):
-        b = self._buffers(frame_a, frame_b, depth_a, depth_b, K, pose, field)
+                 grad_pose=None, grad_field=None, warped=None):
+        b = self._buffers(frame_a, frame_b, depth_a, depth_b, K, pose, field, warped)
         b.grad_losses = grad_losses.data_ptr()
         if grad_depth is None:
             grad_depth = [torch.empty_like(d) for d in depth_a]
@@ -412,8 +426,9 @@ class _MotionLossFn(torch.autograd.Function):
         frame_b = [_contig(t) for t in rest[n:2 * n]]
         depth_b = [_contig(t) for t in rest[2 * n:3 * n]]
         K = _contig(K)
-        losses, maps = plan.forward(frame_a, frame_b, depth_a, depth_b, K, pose, field, want_maps=want_maps)
-        ctx.plan = plan
+        warped = plan.new_warped()
+        losses, maps = plan.forward(frame_a, frame_b, depth_a, depth_b, K, pose, field, want_maps=want_maps, warped=warped)
+        ctx.plan, ctx.warped = plan, warped
         ctx.save_for_backward(K, *depth_a, *pose, *(field or []), *frame_a, *frame_b, *depth_b)
         ctx.stats = plan.stats.clone()
         flat = []
@@ -439,7 +454,8 @@ class _MotionLossFn(torch.autograd.Function):
         frame_b = list(sv[i:i + n]); i += n
         depth_b = list(sv[i:i + n]); i += n
         plan.stats.copy_(ctx.stats)
-        gd, gp, gf = plan.backward(frame_a, frame_b, depth_a, depth_b, K, pose, field, g_losses.contiguous().float())
+        gd, gp, gf = plan.backward(frame_a, frame_b, depth_a, depth_b, K, pose, field, g_losses.contiguous().float(),
+                                   warped=ctx.warped)
         grads = [*gd, *gp] + (list(gf) if plan.with_field else [])
         return (None, None, None, *grads, *([None] * (3 * n)))
 

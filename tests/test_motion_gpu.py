@@ -47,7 +47,7 @@ def oracle_motion(inp, dt, with_field, c1=INF, c2=9e-6, ssim_w=3.0):
                 gmo=mo.grad if with_field else None, maps=[o12, o21])
 
 
-def gpu_motion(inp, with_field, c1=INF, c2=9e-6, ssim_w=3.0, dev="cuda:0"):
+def gpu_motion(inp, with_field, c1=INF, c2=9e-6, ssim_w=3.0, dev="cuda:0", **plan_kw):
     from simpledepthestimation_b200.functional import MotionLossPlan, motion_rgbd_smoothness_loss
 
     B, _, H, W = inp["img1"].shape
@@ -56,7 +56,7 @@ def gpu_motion(inp, with_field, c1=INF, c2=9e-6, ssim_w=3.0, dev="cuda:0"):
     pose = g(euler_pose(inp["pose_vec"].float())).requires_grad_()
     mo = g(inp["motion"]).requires_grad_()
     f1, f2, K = g(inp["img1"]), g(inp["img2"]), g(inp["K"])
-    plan = MotionLossPlan(B, (H, W), dev, 2, ssim_w, c1, c2, with_field=with_field)
+    plan = MotionLossPlan(B, (H, W), dev, 2, ssim_w, c1, c2, with_field=with_field, **plan_kw)
     field = [mo[:B], mo[B:]] if with_field else None
     losses, maps = motion_rgbd_smoothness_loss(plan, [f1, f2], [f2, f1], [d1, d2], [d2, d1], K,
                                                [pose[:B], pose[B:]], field)
@@ -109,6 +109,22 @@ def test_motion_loss_matches_oracle(sde_lib, B, H, W, seed, field, c1, c2):
         ok = ~mism
         assert float((m["depth_proximity_weight"].double() - o["depth_proximity_weight"].detach()).abs()[ok].max()) < 1e-3
         assert float((m["coords_A_in_B"].double() - o["coords_A_in_B"]).abs().max()) < 1e-4
+
+
+def test_motion_warp_mode_and_recompute_agree(sde_lib):
+    """Warp mode (the statistics pass keeps warped rgb / depth error / valid+occlusion planes, the loss kernels take
+    them through TMA) against the recompute path (every kernel re-projects and re-gathers): same losses, maps and
+    gradients up to the rounding of the per-sample statistic."""
+    inp = motion_inputs(2, 64, 96, seed=8)
+    a = gpu_motion(inp, True)
+    b = gpu_motion(inp, True, save_warped=False)
+    assert rel_err(a["losses"], b["losses"]) < 1e-6
+    for k in ("gd1", "gd2", "gpose", "gmo"):   # a 1-ulp change of the statistic moves ill-conditioned SSIM gradients by ~3e-5
+        assert rel_err(a[k], b[k]) < 1e-4, k
+    for ma, mb in zip(a["maps"], b["maps"]):
+        assert torch.equal(ma["occlusion_mask"], mb["occlusion_mask"])
+        assert torch.equal(ma["coords_A_in_B"], mb["coords_A_in_B"])
+        assert rel_err(ma["depth_proximity_weight"], mb["depth_proximity_weight"]) < 1e-5
 
 
 def test_motion_deterministic_and_workspace_reuse(sde_lib):
