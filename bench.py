@@ -218,10 +218,11 @@ def other_configs(dev):
     ml, gl = torch.empty(2, 4, device=dev), torch.ones(2, 4, device=dev)
     mgd, mgp = [torch.empty_like(d1), torch.empty_like(d2)], [torch.empty(B4, 4, 4, device=dev) for _ in range(2)]
     mgf = [torch.empty_like(args4[6][0]) for _ in range(2)]
+    mwarped = mplan.new_warped()
 
     def motion_step():
-        mplan.forward(*args4, want_maps=False, out=ml)
-        mplan.backward(*args4, gl, mgd, mgp, mgf)
+        mplan.forward(*args4, want_maps=False, out=ml, warped=mwarped)
+        mplan.backward(*args4, gl, mgd, mgp, mgf, warped=mwarped)
     ms = timeit(motion_step, iters=3)
     px = 2 * B4 * H4 * W4
     out["cfg4_motion_1920x1280_b4"] = {"ms_per_step": ms, "warped_mpix_s": px / (ms * 1e-3) / 1e6,
