@@ -300,6 +300,22 @@ int sde_motion_smoothness_backward(const sde_mreg_desc* desc, const sde_mreg_buf
 int sde_motion_sparsity_forward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream);
 int sde_motion_sparsity_backward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream);
 
+/* variance_loss(depth) = 1 / mean((depth / mean(depth) - 1)^2), detectron2/modeling/losses/losses.py:16-18
+ * (PackNet config, projects/MonoDepth2/configs/packnet_1a.yaml:12; callers MonoDepth2.py:112-113,
+ * MotionLearning.py:237-239).  `count` = number of elements of the depth tensor. */
+typedef struct sde_var_buffers {
+  const float* depth;         /* [count] */
+  float* loss;                /* [1] */
+  float* saved_stats;         /* [2] mean and centred second moment, for backward */
+  const float* grad_loss;     /* [1] (device) */
+  float* grad_depth;          /* [count] */
+  void* workspace;            /* sde_variance_workspace_bytes(count), zero-filled once */
+} sde_var_buffers;
+
+size_t sde_variance_workspace_bytes(int64_t count);
+int sde_variance_loss_forward(int64_t count, const sde_var_buffers* buf, void* stream);
+int sde_variance_loss_backward(int64_t count, const sde_var_buffers* buf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

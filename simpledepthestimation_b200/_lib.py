@@ -113,6 +113,10 @@ class MregBuffers(C.Structure):
     _fields_ = [(n, _f32p) for n in ("field", "loss", "saved_stats", "grad_loss", "grad_field", "workspace")]
 
 
+class VarBuffers(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("depth", "loss", "saved_stats", "grad_loss", "grad_depth", "workspace")]
+
+
 class SdeError(RuntimeError):
     pass
 
@@ -169,6 +173,10 @@ def load():
         for suffix in ("_forward", "_backward"):
             fn = getattr(lib, f"sde_motion_{name}{suffix}")
             fn.restype, fn.argtypes = C.c_int, [C.POINTER(MregDesc), C.POINTER(MregBuffers), C.c_void_p]
+    lib.sde_variance_workspace_bytes.restype, lib.sde_variance_workspace_bytes.argtypes = C.c_size_t, [C.c_int64]
+    for suffix in ("_forward", "_backward"):
+        fn = getattr(lib, "sde_variance_loss" + suffix)
+        fn.restype, fn.argtypes = C.c_int, [C.c_int64, C.POINTER(VarBuffers), C.c_void_p]
     lib.sde_resize_bilinear.restype = C.c_int
     lib.sde_resize_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p]

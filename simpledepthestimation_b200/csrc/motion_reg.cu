@@ -305,6 +305,52 @@ __global__ void __launch_bounds__(kRegThreads) msparse_bwd_kernel(const __grid_c
   p.g_field[(size_t)blockIdx.y * hw + pix] = g * r * sg;
 }
 
+// ------------------------------------------------------------------------------------------------ variance_loss
+// variance_loss(depth) = 1 / mean((depth / mean(depth) - 1)^2) over the whole tensor (losses.py:16-18); two passes
+// (mean, then the centred second moment) so that a nearly constant depth map does not cancel catastrophically
+__global__ void __launch_bounds__(kRegThreads) var_mean_kernel(const __grid_constant__ VarParams p) {
+  const long long i = (long long)blockIdx.x * kRegThreads + threadIdx.x;
+  const float v = i < p.n ? __ldg(p.depth + i) : 0.0f;
+  double total;
+  if (group_sum(v, p.slots, blockIdx.x, gridDim.x, p.counters, total)) p.stats[0] = (float)(total / (double)p.n);
+}
+
+__global__ void __launch_bounds__(kRegThreads) var_sq_kernel(const __grid_constant__ VarParams p) {
+  const long long i = (long long)blockIdx.x * kRegThreads + threadIdx.x;
+  const float m = p.stats[0];
+  float v = 0.0f;
+  if (i < p.n) {
+    const float u = fdiv(__ldg(p.depth + i), m) - 1.0f;
+    v = u * u;
+  }
+  double total;
+  if (group_sum(v, p.slots, blockIdx.x, gridDim.x, p.counters, total)) {
+    const double V = total / (double)p.n;
+    p.stats[1] = (float)V;
+    p.loss[0] = (float)(1.0 / V);
+  }
+}
+
+__global__ void __launch_bounds__(kRegThreads) var_bwd_kernel(const __grid_constant__ VarParams p) {
+  const long long i = (long long)blockIdx.x * kRegThreads + threadIdx.x;
+  if (i >= p.n) return;
+  const float m = p.stats[0], V = p.stats[1];
+  const float u = fdiv(__ldg(p.depth + i), m) - 1.0f;
+  // d(1/V)/d depth_i = -(1/V^2) * 2 (u_i - V) / (N m)      (mean(u) = 0)
+  p.g_depth[i] = -__ldg(p.g_loss) * 2.0f * (u - V) / (V * V * (float)p.n * m);
+}
+
+cudaError_t launch_var(bool backward, const VarParams& p, cudaStream_t stream) {
+  const unsigned grid = (unsigned)((p.n + kRegThreads - 1) / kRegThreads);
+  if (backward) {
+    var_bwd_kernel<<<grid, kRegThreads, 0, stream>>>(p);
+  } else {
+    var_mean_kernel<<<grid, kRegThreads, 0, stream>>>(p);
+    var_sq_kernel<<<grid, kRegThreads, 0, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_mreg(int which, const MregParams& p, cudaStream_t stream) {
   const dim3 grid((p.h * p.w + kRegThreads - 1) / kRegThreads, p.B * p.C);
   switch (which) {

@@ -88,4 +88,15 @@ struct MregParams {   // motion_smoothness_loss_fn / motion_sparsity_loss_fn
   unsigned* counters;       // [1 + B*C]
 };
 
+struct VarParams {   // variance_loss
+  long long n;              // elements of the depth tensor
+  const float* depth;
+  float* loss;              // [1]
+  float* stats;             // [2] mean, centred second moment
+  const float* g_loss;
+  float* g_depth;
+  float* slots;             // [blocks]
+  unsigned* counters;       // [1]
+};
+
 }  // namespace sde

@@ -24,6 +24,7 @@ cudaError_t launch_resize_bilinear(const float* src, float* dst, int planes, int
 cudaError_t launch_mcons_fwd(const McParams& p, cudaStream_t stream);
 cudaError_t launch_mcons_bwd(const McParams& p, float* g_t_ba, cudaStream_t stream);
 cudaError_t launch_mreg(int which, const MregParams& p, cudaStream_t stream);
+cudaError_t launch_var(bool backward, const VarParams& p, cudaStream_t stream);
 constexpr int kOpBlock = 256;
 
 static thread_local char g_cuda_err[256] = "";
@@ -623,5 +624,30 @@ int sde_motion_sparsity_forward(const sde_mreg_desc* desc, const sde_mreg_buffer
 int sde_motion_sparsity_backward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream) {
   return mreg_call(3, true, true, desc, buf, stream);
 }
+
+size_t sde_variance_workspace_bytes(int64_t count) {
+  if (count < 1) return 0;
+  return align16(16 + (size_t)((count + kOpBlock - 1) / kOpBlock) * sizeof(float));
+}
+
+static int var_call(bool backward, int64_t count, const sde_var_buffers* b, void* stream) {
+  if (count < 1 || !b || !b->depth || !b->saved_stats) return SDE_ERR_INVALID_ARG;
+  VarParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = count; p.depth = b->depth; p.stats = b->saved_stats;
+  if (!backward) {
+    if (!b->loss || !b->workspace) return SDE_ERR_INVALID_ARG;
+    p.loss = b->loss;
+    p.counters = reinterpret_cast<unsigned*>(b->workspace);
+    p.slots = reinterpret_cast<float*>(static_cast<char*>(b->workspace) + 16);
+  } else {
+    if (!b->grad_loss || !b->grad_depth) return SDE_ERR_INVALID_ARG;
+    p.g_loss = b->grad_loss; p.g_depth = b->grad_depth;
+  }
+  SDE_LAUNCH(launch_var(backward, p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_variance_loss_forward(int64_t count, const sde_var_buffers* buf, void* stream) { return var_call(false, count, buf, stream); }
+int sde_variance_loss_backward(int64_t count, const sde_var_buffers* buf, void* stream) { return var_call(true, count, buf, stream); }
 
 }  // extern "C"

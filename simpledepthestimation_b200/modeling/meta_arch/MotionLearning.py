@@ -16,6 +16,7 @@ from ...functional import MotionLossPlan, motion_rgbd_smoothness_loss
 from ...geometry.camera import resize_img_avgpool, view_synthesis
 from ...utils.memory import to_cuda
 from ..losses.motion_loss import motion_consistency_loss, motion_smoothness_loss_fn, motion_sparsity_loss_fn
+from ..losses.losses import variance_loss
 from ..losses.ssim_loss import WeightedSSIM
 from ..nets import build_depth_net, build_pose_net
 from .build import META_ARCH_REGISTRY
@@ -51,9 +52,9 @@ class MotionLearningModel(nn.Module):
         self.with_mask = cfg.MODEL.get("WITH_MASK", False)
         self.mask_dilation = cfg.MODEL.get("MASK_DILATION", 8)
         self.return_loss = cfg.MODEL.get("RETURN_LOSS", False)
-        if self.depth_l1_loss_w > 0 or self.sup_loss_w > 0.0 or self.var_loss_w > 0.0:
+        if self.depth_l1_loss_w > 0 or self.sup_loss_w > 0.0:
             # 0 in every shipped config (projects/MotionLearning/configs/Base.yaml:11-26)
-            raise NotImplementedError("LOSS.DEPTH_L1_WEIGHT / SUPERVISED_WEIGHT / VAR_LOSS_WEIGHT > 0 are not "
+            raise NotImplementedError("LOSS.DEPTH_L1_WEIGHT / SUPERVISED_WEIGHT > 0 are not "
                                       "supported by the fused B200 loss path")
 
         self.register_buffer("pixel_mean", torch.Tensor(cfg.MODEL.PIXEL_MEAN).view(1, -1, 1, 1))
@@ -158,6 +159,10 @@ class MotionLearningModel(nn.Module):
                         losses["motion_smooth_loss"] += motion_smoothness_loss_fn(mn) * scale_w * self.motion_smooth_loss_w
                     if self.motion_sparsity_loss_w > 0.0:
                         losses["motion_sparsity_loss"] += motion_sparsity_loss_fn(mn) * scale_w * self.motion_sparsity_loss_w
+
+            if self.var_loss_w > 0.0:   # MotionLearning.py:237-239 (on the un-normalised resized depths)
+                r1, r2 = resize_img_avgpool(depth1[0], (H, W)), resize_img_avgpool(depth2[0], (H, W))
+                losses["var_loss"] += (variance_loss(r1) + variance_loss(r2)) * scale_w * self.var_loss_w
 
         batch.update(losses)
         return batch

@@ -313,3 +313,34 @@ def motion_smoothness(field):
 
 def motion_sparsity(field):
     return _MotionRegFn.apply(field, "sparsity")
+
+
+# ------------------------------------------------------------------------------------------------ variance_loss
+class _VarianceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth):
+        lib = _lib.load()
+        depth = _cuda_f32(depth, "depth")
+        n = depth.numel()
+        ws = _zero_workspace("var", n, lib.sde_variance_workspace_bytes(n), depth.device)
+        loss, stats = torch.empty(1, device=depth.device), torch.empty(2, device=depth.device)
+        b = _lib.VarBuffers()
+        b.depth, b.loss, b.saved_stats, b.workspace = depth.data_ptr(), loss.data_ptr(), stats.data_ptr(), ws.data_ptr()
+        _lib.check(lib.sde_variance_loss_forward(n, C.byref(b), _stream()), "sde_variance_loss_forward")
+        ctx.save_for_backward(depth, stats)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        depth, stats = ctx.saved_tensors
+        g = g.reshape(1).contiguous().float()
+        gd = torch.empty_like(depth)
+        b = _lib.VarBuffers()
+        b.depth, b.saved_stats, b.grad_loss, b.grad_depth = depth.data_ptr(), stats.data_ptr(), g.data_ptr(), gd.data_ptr()
+        _lib.check(lib.sde_variance_loss_backward(depth.numel(), C.byref(b), _stream()), "sde_variance_loss_backward")
+        return gd
+
+
+def variance(depth):
+    return _VarianceFn.apply(depth)

@@ -276,3 +276,45 @@ def test_motion_smoothness_and_sparsity(sde_lib, shape):
         torch.cuda.synchronize()
         assert rel_err(L.detach(), L64) < 1e-5, fn.__name__
         _quantile_ok(x.grad, g64, g32, fn.__name__)
+
+
+def test_variance_loss_and_packnet_config(sde_lib):
+    """variance_loss (losses.py:16-18) and the PackNet loss configuration (packnet_1a.yaml:12: VAR_LOSS_WEIGHT 1e-4)
+    through MonoDepth2Model against the oracle port."""
+    from simpledepthestimation_b200.modeling.losses import variance_loss
+    from simpledepthestimation_b200.synthetic import mono_inputs
+
+    inp = mono_inputs(2, 64, 96, seed=4)
+    for d in inp["depth"] + [torch.full((1, 1, 8, 8), 3.0) + 1e-3 * torch.rand(1, 1, 8, 8)]:   # nearly constant map too
+        ref = d.double().clone().requires_grad_()
+        L64 = port.variance_loss(ref)
+        (L64 * 0.5).backward()
+        r32 = d.clone().requires_grad_()
+        L32 = port.variance_loss(r32)
+        (L32 * 0.5).backward()
+        x = d.to(DEV).requires_grad_()
+        L = variance_loss(x)
+        (L * 0.5).backward()
+        torch.cuda.synchronize()
+        # a nearly constant map loses digits in depth / mean - 1 in ANY fp32 evaluation: bound by the reference's own
+        assert rel_err(L.detach(), L64.detach()) < max(1e-5, 3 * rel_err(L32.detach(), L64.detach()))
+        _quantile_ok(x.grad, ref.grad, r32.grad, "variance grad")
+
+    from test_model_gpu import make_cfg
+    from test_motion_gpu import _Inject
+    from simpledepthestimation_b200.modeling import DEPTH_NET_REGISTRY, POSE_NET_REGISTRY, build_model
+
+    if "InjectDepth" not in DEPTH_NET_REGISTRY:
+        DEPTH_NET_REGISTRY._do_register("InjectDepth", _Inject)
+        POSE_NET_REGISTRY._do_register("InjectPose", _Inject)
+    model = build_model(make_cfg(VAR_LOSS_WEIGHT=1e-4)).train()
+    depth = [d.to(DEV).requires_grad_() for d in inp["depth"]]
+    model.depth_net.payload = {"depth_pred": depth}
+    model.pose_net.payload = {"pose_pred": [euler_pose(v).to(DEV) for v in inp["pose_vec"]]}
+    out = model({"img": inp["img"], "ctx_img": list(inp["ctx"]), "img_orig": inp["img"], "ctx_img_orig": list(inp["ctx"]),
+                 "intrinsics": inp["K"]})
+    ref = port.mono_loss(inp["img"].double(), [c.double() for c in inp["ctx"]], inp["K"].double(),
+                         [d.double() for d in inp["depth"]], [euler_pose(v.double()) for v in inp["pose_vec"]], var_w=1e-4)
+    assert set(k for k in out if "loss" in k) == {"rec_loss", "smooth_loss", "var_loss"}
+    for k in ("rec_loss", "smooth_loss", "var_loss"):
+        assert rel_err(out[k].detach(), ref[k]) < 1e-5, k
