@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SDE_ABI_VERSION 1
+#define SDE_ABI_VERSION 2
 #define SDE_MAX_SCALES 6
 #define SDE_MAX_SOURCES 4
 
@@ -83,10 +83,17 @@ typedef struct sde_mono_buffers {
   float* losses;                      /* [2]: rec_loss, smooth_loss */
   uint8_t* argmin[SDE_MAX_SCALES];    /* [B,h_i,w_i] winning candidate index (warp0,ident0,warp1,ident1..) */
   float* saved_stats;                 /* [n_scales*B*2] per-image (mean inverse depth, smoothness) for backward */
-  /* optional, forward output / backward input: the warped sources [B,3,h_i,w_i].  When given, the
-   * backward kernel reads them instead of re-gathering (trades 24 B/pixel/source of HBM traffic,
-   * which this path has to spare, for the dominant gather cost).  NULL = recompute the warp. */
+  /* optional, forward output / backward input, all-or-nothing (every warped[i][j] and every smooth_g[i], or none):
+   * what the forward pass keeps for the backward pass.
+   *   warped[i][j]  [B,9,h_i,w_i]: planes 0..2 the warped source, planes 3..5 / 6..8 its derivatives
+   *                 d warped_c / dX and d warped_c / dY w.r.t. the sample coordinate (zero where nan_to_num /
+   *                 clamp gate the gradient, camera.py:184-188), written by the warp kernel;
+   *   smooth_g[i]   [B,1,h_i,w_i]: d smoothness / d (1/depth) before the division by the per-image mean.
+   * With them the loss kernels take the warped planes through TMA and the backward kernel neither re-projects
+   * the halo nor re-gathers (trades 72 B/pixel/source + 4 B/pixel of HBM traffic, which this issue-bound path
+   * has to spare, for the dominant gather cost).  NULL = the backward kernel recomputes everything. */
   float* warped[SDE_MAX_SCALES][SDE_MAX_SOURCES];
+  float* smooth_g[SDE_MAX_SCALES];
   /* backward inputs / outputs */
   const float* grad_losses;           /* [2] upstream d/d rec_loss, d/d smooth_loss (device) */
   float* grad_depth[SDE_MAX_SCALES];  /* [B,1,h_i,w_i] */

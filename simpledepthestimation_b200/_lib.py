@@ -37,6 +37,7 @@ class MonoBuffers(C.Structure):
         ("argmin", _f32p * MAX_SCALES),
         ("saved_stats", _f32p),
         ("warped", (_f32p * MAX_SOURCES) * MAX_SCALES),
+        ("smooth_g", _f32p * MAX_SCALES),
         ("grad_losses", _f32p),
         ("grad_depth", _f32p * MAX_SCALES),
         ("grad_pose", _f32p * MAX_SOURCES),

@@ -1,7 +1,11 @@
 // Fused backward of the MonoDepth2 self-supervised loss, all scales in one launch (sm_100a).
 //
-// Nothing but the uint8 argmin maps and O(B) per-image statistics is kept from the forward pass:
-// the warp is recomputed.  One CTA owns a 64x16 block Q of SSIM window centres of one
+// Two instantiations.  SAVED = false: nothing but the uint8 argmin maps and O(B) per-image statistics is kept
+// from the forward pass and the warp is recomputed (phase 1 and phase 4 gather from the source frames).
+// SAVED = true (default of the host side): the forward pass kept, per source, the warped planes and their
+// derivatives w.r.t. the sample coordinate (mono_warp.cu) and the local smoothness gradient (mono_fwd.cu); phase 1
+// is a TMA box load, phase 4 reads the derivative planes and the smoothness tail is a multiply-add.
+// One CTA owns a 64x16 block Q of SSIM window centres of one
 // (scale, sample) and emits gradients for Q's 60x14 interior P (a pixel's gradient collects the
 // 3x3 windows around it).  Per source frame j:
 //   phase 1  as in the forward kernel: project + bilinear gather on Q + 1-pixel halo -> planes S;
@@ -14,12 +18,13 @@
 //     phase 3  adjoint of reflect-pad + 3x3 box: each pixel of P gathers the coefficients of the
 //              windows that contain it (border multiplicities 2 where the pad mirrors onto it),
 //              adds the L1 term, and stores gS_c(p).
-//   phase 4  per pixel of P: re-project, re-read the four taps, gX = sum_c gS_c dS_c/dx (gated as
-//            nan_to_num/clamp gate the reference's autograd), then the camera-space gradient
-//            K^T g_p, accumulated into 12 pose sums per source (9 for R, 3 for t) and into
-//            d loss / d depth.
+//   phase 4  warp-autonomous (no CTA barrier): every warp compacts the pixels of ITS rows of P that carry a
+//            gradient into a dense fixed-order list, then per listed pixel: re-project, gX = sum_c gS_c dS_c/dX
+//            (derivative planes, or the four taps re-read; gated as nan_to_num/clamp gate the reference's
+//            autograd), then the camera-space gradient K^T g_p, accumulated into 12 pose sums per source (9 for
+//            R, 3 for t) and into d loss / d depth.
 // The smoothness gradient uses the saved per-image mean inverse depth and loss (1-homogeneity,
-// SURVEY.md A.5).  Pose sums: per-CTA slots, added by the last CTA in a fixed order in fp64
+// SURVEY.md A.5).  Pose sums: per-warp slots, added by the last CTA of a sample in a fixed order in fp64
 // (deterministic; no float atomics anywhere).
 #include "mono_device.cuh"
 
@@ -33,20 +38,20 @@ constexpr int kBA = 0, kBS = 3, kBD = 6, kBCoef = 7, kBG = 10;
 // the gradient block P starts at plane column 3 (not 2): with 60-wide tiles that puts plane index 0 at image
 // column tile_x0 - 4, a multiple of 4, which the TMA box start needs
 constexpr int kBwdColOff = 3;
-constexpr int kPosPerThread = (kBwdW * kBwdH + kThreads - 1) / kThreads;  // 7
+constexpr int kWarps = kThreads / 32;
+constexpr int kListPerWarp = kRowsPerWarp * kTileW;   // a warp lists pixels of its own four rows only
 
 struct BwdShared {
   Cam cam;
   Proj proj[SDE_MAX_SOURCES];
-  float red[12][kThreads / 32];
-  double dred[12][kThreads / 32];
+  double dred[12][kWarps];
   unsigned ticket;
   __align__(8) uint64_t bar;                     // TMA completion barrier
-  int cnt[kPosPerThread][kThreads / 32];         // selected pixels per (pass, warp)
-  unsigned short list[kBwdW * kBwdH];            // dense list of the selected pixels of P
+  unsigned short list[kWarps][kListPerWarp];     // per warp: dense list (plane indices) of its pixels of P that carry a gradient
   __align__(8) uint8_t arg[kPlane];
 };
 
+template <bool SAVED>
 __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_constant__ MonoParams p,
                                                                const __grid_constant__ MonoTma maps) {
   extern __shared__ __align__(128) float planes[];  // [kBwdPlanes][kPlane]
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
   }
   // TMA path (saved warps, row pitch a multiple of 16 bytes): one thread hands the tile planes -- target,
   // depth and the first source's warp -- to the copy engine before anything else happens in the CTA
-  const bool tma = p.tma[s] != 0;
+  const bool tma = SAVED && p.tma[s] != 0;
   if (tma && tid == 0) {
     mbar_init(&sh.bar, 1);
     mbar_init_fence();
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       tma_load_plane(planes + (kBA + c) * kPlane, &maps.target[s], &sh.bar, ox - kColOff, oy, b * 3 + c);
-      tma_load_plane(planes + (kBS + c) * kPlane, &maps.warped[s][0], &sh.bar, ox - kColOff, oy, b * 3 + c);
+      tma_load_plane(planes + (kBS + c) * kPlane, &maps.warped[s][0], &sh.bar, ox - kColOff, oy, b * kSavedPlanes + c);
     }
     tma_load_plane(planes + kBD * kPlane, &maps.depth[s], &sh.bar, ox - kColOff, oy, b);
   }
@@ -110,9 +115,14 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
   const float eL0 = px0 == 1 ? 1.0f : 0.0f, eL1 = px1 == 1 ? 1.0f : 0.0f;
   const float eR0 = px0 == w - 2 ? 1.0f : 0.0f, eR1 = px1 == w - 2 ? 1.0f : 0.0f;
 
-  float gd[kPosPerThread];
+  // d loss / d depth of this lane's pixel pairs (rows r0+1 .. r0+4, columns c0+1, c0+2 of the plane), summed over sources
+  f2 gd[kRowsPerWarp];
 #pragma unroll
-  for (int k = 0; k < kPosPerThread; ++k) gd[k] = 0.0f;
+  for (int k = 0; k < kRowsPerWarp; ++k) gd[k] = bc2(0.0f);
+  // this lane's pair belongs to the gradient block P (plane columns 3..62) and to the image
+  const int gxp = ox + c0 + 1;
+  const bool colP = lane >= 1 && lane <= 30;
+  const bool col_ok0 = colP && gxp < w, col_ok1 = colP && gxp + 1 < w;
 
   StageArgs sa;
   sa.depth = depth; sa.src = nullptr; sa.tgt = tg0; sa.amap = amap;
@@ -144,8 +154,8 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
         if (j == 0) reflect_fixup(planes, kBA, 3, oy, ox, h, w, tid), reflect_fixup(planes, kBD, 1, oy, ox, h, w, tid);
         reflect_fixup(planes, kBS, 3, oy, ox, h, w, tid);
       }
-    } else if (p.warped[s][j] != nullptr) {
-      const float* wsrc = p.warped[s][j] + (size_t)b * 3 * hw;
+    } else if (SAVED) {
+      const float* wsrc = p.warped[s][j] + (size_t)b * kSavedPlanes * hw;
       if (interior) stage_saved<true>(sa, wsrc, tid);
       else          stage_saved<false>(sa, wsrc, tid);
     } else {
@@ -264,80 +274,80 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       mbar_arrive_expect_tx(&sh.bar, 3 * kPlaneBytesTma);
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        tma_load_plane(planes + (kBS + c) * kPlane, &maps.warped[s][j + 1], &sh.bar, ox - kColOff, oy, b * 3 + c);
+        tma_load_plane(planes + (kBS + c) * kPlane, &maps.warped[s][j + 1], &sh.bar, ox - kColOff, oy, b * kSavedPlanes + c);
     }
     // ---------------------------------------------------------------- phase 4: warp backward on P
-    // Only pixels whose argmin is this source's warped candidate carry a gradient (with automasking
-    // that is often a minority), so they are first compacted into a dense list -- in a fixed order, so
-    // the pose sums stay deterministic -- and the expensive part runs on full warps.
+    // Only pixels whose 3x3 neighbourhood holds a window that selected this source's warped candidate carry a
+    // gradient, so each warp first compacts those of its own rows into a dense list -- in a fixed order, so the
+    // pose sums stay deterministic -- and the expensive part runs on full warps.  The gS planes of a warp's rows are
+    // read and written by that warp only: no CTA barrier until the next source's planes are needed.
     {
-      unsigned selbits = 0;
-      int rank[kPosPerThread];
+      unsigned short* const wlist = sh.list[wid];
+      const unsigned lt = (1u << lane) - 1u;
+      int total = 0;
 #pragma unroll
-      for (int it = 0; it < kPosPerThread; ++it) {
-        const int i = tid + it * kThreads;
-        const int ly = i / kBwdW, lx = i - ly * kBwdW;
-        const int gy = tc.y0 + ly, gx = tc.x0 + lx;
-        bool sel = false;
-        if (i < kBwdW * kBwdH && gy < h && gx < w) {
-          const int pl = plane_index(ly + 2, lx + kBwdColOff);
-          sel = planes[kBG * kPlane + pl] != 0.0f || planes[(kBG + 1) * kPlane + pl] != 0.0f ||
-                planes[(kBG + 2) * kPlane + pl] != 0.0f;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, sel);
-        rank[it] = __popc(bal & ((1u << lane) - 1u));
-        if (lane == 0) sh.cnt[it][wid] = __popc(bal);
-        selbits |= (sel ? 1u : 0u) << it;
+      for (int o = 0; o < kRowsPerWarp; ++o) {
+        const int row = r0 + 1 + o;
+        const int pl = plane_index(row, c0 + 1);
+        const bool row_ok = row >= 2 && row <= kBwdH + 1 && oy + row < h;
+        const f2 g0 = ld2(planes + kBG * kPlane + pl), g1 = ld2(planes + (kBG + 1) * kPlane + pl),
+                 g2 = ld2(planes + (kBG + 2) * kPlane + pl);
+        const bool s0 = row_ok && col_ok0 && (lo(g0) != 0.0f || lo(g1) != 0.0f || lo(g2) != 0.0f);
+        const bool s1 = row_ok && col_ok1 && (hi(g0) != 0.0f || hi(g1) != 0.0f || hi(g2) != 0.0f);
+        const unsigned b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1);
+        if (s0) wlist[total + __popc(b0 & lt)] = (unsigned short)pl;
+        total += __popc(b0);
+        if (s1) wlist[total + __popc(b1 & lt)] = (unsigned short)(pl + 1);
+        total += __popc(b1);
       }
-      __syncthreads();
-      int run = 0;
-#pragma unroll
-      for (int it = 0; it < kPosPerThread; ++it) {
-#pragma unroll
-        for (int w2 = 0; w2 < kThreads / 32; ++w2) {
-          if (w2 == wid && ((selbits >> it) & 1u)) sh.list[run + rank[it]] = (unsigned short)(tid + it * kThreads);
-          run += sh.cnt[it][w2];
-        }
-      }
-      const int total = run;
-      __syncthreads();
+      __syncwarp();
 
       float acc[12];
 #pragma unroll
       for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
-      float* const scratch = planes + kBCoef * kPlane;   // coefficient plane 0 is free until the next phase 2
+      const float* __restrict__ dw = SAVED ? p.warped[s][j] + ((size_t)b * kSavedPlanes + 3) * hw : nullptr;
+      const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
 #pragma unroll 1
-      for (int k = tid; k < total; k += kThreads) {
-        const int i = sh.list[k];
-        const int ly = i / kBwdW, lx = i - ly * kBwdW;
-        const int gy = tc.y0 + ly, gx = tc.x0 + lx;
-        const int pl = plane_index(ly + 2, lx + kBwdColOff);
-        const float g0 = planes[kBG * kPlane + pl], g1 = planes[(kBG + 1) * kPlane + pl], g2 = planes[(kBG + 2) * kPlane + pl];
+      for (int k = lane; k < total; k += 32) {
+        const int pl = wlist[k];
+        const int row = pl / kPitch, col = pl - row * kPitch - kColOff;
+        const int gy = oy + row, gx = ox + col;
+        float* const pg = planes + kBG * kPlane + pl;
+        const float g0 = pg[0], g1 = pg[kPlane], g2 = pg[2 * kPlane];
         const float d = planes[kBD * kPlane + pl];
         const float fxp = (float)gx, fyp = (float)gy;
         float P[3], den, X, Y;
         project_full(cam, pj, fxp, fyp, d, P, den, X, Y);
-        const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
         // gradient gates of nan_to_num and clamp (closed interval), camera.py:184-188
         const bool gate_x = (X >= 0.0f) && (X <= wm1);   // false for NaN / +-inf
         const bool gate_y = (Y >= 0.0f) && (Y <= hm1);
         float gdep = 0.0f;
         if (gate_x || gate_y) {
-          const Cell cell = bilinear_cell(X, Y, w, h);
-          const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
-          float gX = 0.0f, gY = 0.0f;
-          const float gs[3] = {g0, g1, g2};
-          const float* pls[3] = {sc0, sc1, sc2};
+          float gX, gY;
+          if (SAVED) {
+            // derivative planes of the warp kernel (already gated)
+            const float* q = dw + (gy * w + gx);
+            const float x0 = __ldg(q), x1 = __ldg(q + hw), x2 = __ldg(q + 2 * hw);
+            const float y0 = __ldg(q + 3 * hw), y1 = __ldg(q + 4 * hw), y2 = __ldg(q + 5 * hw);
+            gX = g0 * x0; gX += g1 * x1; gX += g2 * x2;
+            gY = g0 * y0; gY += g1 * y1; gY += g2 * y2;
+          } else {
+            const Cell cell = bilinear_cell(X, Y, w, h);
+            const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
+            gX = 0.0f; gY = 0.0f;
+            const float gs[3] = {g0, g1, g2};
+            const float* pls[3] = {sc0, sc1, sc2};
 #pragma unroll
-          for (int cc = 0; cc < 3; ++cc) {
-            const float* q0 = pls[cc] + cell.off;
-            const float* q1 = q0 + w;
-            const float v00 = __ldg(q0), v01 = __ldg(q0 + 1), v10 = __ldg(q1), v11 = __ldg(q1 + 1);
-            gX += gs[cc] * ((v01 - v00) * by + (v11 - v10) * cell.ay);
-            gY += gs[cc] * ((v10 - v00) * bx + (v11 - v01) * cell.ax);
+            for (int cc = 0; cc < 3; ++cc) {
+              const float* q0 = pls[cc] + cell.off;
+              const float* q1 = q0 + w;
+              const float v00 = __ldg(q0), v01 = __ldg(q0 + 1), v10 = __ldg(q1), v11 = __ldg(q1 + 1);
+              gX += gs[cc] * ((v01 - v00) * by + (v11 - v10) * cell.ay);
+              gY += gs[cc] * ((v10 - v00) * bx + (v11 - v01) * cell.ax);
+            }
+            if (!gate_x) gX = 0.0f;
+            if (!gate_y) gY = 0.0f;
           }
-          if (!gate_x) gX = 0.0f;
-          if (!gate_y) gY = 0.0f;
           const float q = 1.0f / den;
           const float u0 = gX * q, u1 = gY * q;
           // K^T g_p, with the third row formed per pixel in camera-centred coordinates
@@ -357,31 +367,20 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
           const float rz = cam.ki[6] * fxp + cam.ki[7] * fyp + cam.ki[8];
           gdep = gP0 * rx + gP1 * ry + gP2 * rz;
         }
-        scratch[pl] = gdep;
+        pg[0] = gdep;   // in place of gS_0: unlisted pixels of P hold gS_0 == 0 there
       }
-      // CTA reduction of the 12 pose sums of this source -> per-CTA slot
+      // the 12 pose sums of this (warp, source) -> per-warp slot
+      float mine = 0.0f;
 #pragma unroll
       for (int k = 0; k < 12; ++k) {
         const float v = warp_sum(acc[k]);
-        if (lane == 0) sh.red[k][wid] = v;
+        if (lane == k) mine = v;
       }
-      __syncthreads();
-      if (tid < 12) {
-        float v = 0.0f;
+      if (lane < 12) p.pose_partials[(((size_t)blockIdx.x * kWarps + wid) * p.S + j) * 12 + lane] = mine;
+      __syncwarp();
+      // pick up the depth gradients of this lane's own pixels (pairs outside P / the image hold garbage that is never stored)
 #pragma unroll
-        for (int k = 0; k < kThreads / 32; ++k) v += sh.red[tid][k];
-        p.pose_partials[((size_t)blockIdx.x * p.S + j) * 12 + tid] = v;
-      }
-      // the __syncthreads above makes the depth gradients of the dense pass visible; pick up this thread's pixels
-      // (the next phase 2, which overwrites the scratch plane, is behind another barrier)
-#pragma unroll
-      for (int it = 0; it < kPosPerThread; ++it) {
-        if ((selbits >> it) & 1u) {
-          const int i = tid + it * kThreads;
-          const int ly = i / kBwdW, lx = i - ly * kBwdW;
-          gd[it] += scratch[plane_index(ly + 2, lx + kBwdColOff)];
-        }
-      }
+      for (int o = 0; o < kRowsPerWarp; ++o) gd[o] = gd[o] + ld2(planes + kBG * kPlane + plane_index(r0 + 1 + o, c0 + 1));
     }
   }
 
@@ -393,24 +392,45 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     const float iny = 1.0f / ((float)p.B * (float)(h - 1) * (float)w);
     const float homog = mbar > 1e-6f ? Lb / ((float)h * (float)w * mbar) : 0.0f;
     const float rmbar = 1.0f / mbar;
+    const float gsm = g_smooth * sscale;
     float* __restrict__ gout = p.grad_depth[s] + (size_t)b * hw;
+    const float* __restrict__ sg = SAVED ? p.smooth_g[s] + (size_t)b * hw : nullptr;
+    // the pair (gxp, gxp + 1) is 8-byte aligned in global memory (gxp is even) if the rows and the buffers are
+    const bool even = (w & 1) == 0 && ((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(sg)) & 7) == 0;
 #pragma unroll
-    for (int it = 0; it < kPosPerThread; ++it) {
-      const int i = tid + it * kThreads;
-      const int ly = i / kBwdW, lx = i - ly * kBwdW;
-      const int gy = tc.y0 + ly, gx = tc.x0 + lx;
-      if (i < kBwdW * kBwdH && gy < h && gx < w) {
-        float g = gd[it];
+    for (int o = 0; o < kRowsPerWarp; ++o) {
+      const int row = r0 + 1 + o;
+      const int gy = oy + row;
+      if (row >= 2 && row <= kBwdH + 1 && gy < h && col_ok0) {
+        float g0 = lo(gd[o]), g1 = hi(gd[o]);
         if (sscale > 0.0f) {
-          const int pl = plane_index(ly + 2, lx + kBwdColOff);
+          const int pl = plane_index(row, c0 + 1);
           const float* pd = planes + kBD * kPlane + pl;
-          const float d = pd[0];
-          const float ic = inv_depth(d);
-          const float G = smooth_grad_local(pd, planes + kBA * kPlane + pl, ic, gx, gy, w, h, inx, iny);
-          const float g_inv = G * rmbar - homog;
-          if (d >= 1e-6f) g += -ic * ic * g_inv * (g_smooth * sscale);
+          const float d0 = pd[0], d1 = pd[1];
+          const float ic0 = inv_depth(d0), ic1 = inv_depth(d1);
+          float G0, G1;
+          if (SAVED) {
+            if (even) {
+              const float2 G = __ldg(reinterpret_cast<const float2*>(sg + gy * w + gxp));
+              G0 = G.x; G1 = G.y;
+            } else {
+              G0 = __ldg(sg + gy * w + gxp);
+              G1 = col_ok1 ? __ldg(sg + gy * w + gxp + 1) : 0.0f;
+            }
+          } else {
+            G0 = smooth_grad_local(pd, planes + kBA * kPlane + pl, ic0, gxp, gy, w, h, inx, iny);
+            G1 = smooth_grad_local(pd + 1, planes + kBA * kPlane + pl + 1, ic1, gxp + 1, gy, w, h, inx, iny);
+          }
+          if (d0 >= 1e-6f) g0 += -ic0 * ic0 * (G0 * rmbar - homog) * gsm;
+          if (d1 >= 1e-6f) g1 += -ic1 * ic1 * (G1 * rmbar - homog) * gsm;
         }
-        gout[gy * w + gx] = g;
+        float* po = gout + gy * w + gxp;
+        if (even && col_ok1) {
+          *reinterpret_cast<float2*>(po) = make_float2(g0, g1);
+        } else {
+          po[0] = g0;
+          if (col_ok1) po[1] = g1;
+        }
       }
     }
   }
@@ -431,8 +451,8 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
 #pragma unroll
     for (int k = 0; k < 12; ++k) a[k] = 0.0;
     for (int ss = 0; ss < p.n_scales; ++ss) {
-      const int per = p.btiles_x[ss] * p.btiles_y[ss];
-      const size_t first = (size_t)p.btile_start[ss] + (size_t)b * per;
+      const int per = p.btiles_x[ss] * p.btiles_y[ss] * kWarps;   // one slot per warp of every tile of the sample
+      const size_t first = ((size_t)p.btile_start[ss] + (size_t)b * p.btiles_x[ss] * p.btiles_y[ss]) * kWarps;
       for (int t = tid; t < per; t += kThreads) {
         const float4* part = reinterpret_cast<const float4*>(p.pose_partials + ((first + t) * p.S + tj) * 12);
 #pragma unroll
@@ -465,11 +485,12 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
 size_t mono_bwd_smem_bytes() { return (size_t)kBwdPlanes * kPlane * sizeof(float); }
 
 cudaError_t launch_mono_bwd(const MonoParams& p, const MonoTma& t, cudaStream_t stream) {
+  const bool saved = p.warped[0][0] != nullptr;   // all-or-nothing, checked by the caller
+  auto kernel = saved ? mono_bwd_kernel<true> : mono_bwd_kernel<false>;
   // 61.8 KB of dynamic shared memory needs the opt-in attribute (per device; cheap and idempotent)
-  cudaError_t e = cudaFuncSetAttribute(mono_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)mono_bwd_smem_bytes());
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mono_bwd_smem_bytes());
   if (e != cudaSuccess) return e;
-  mono_bwd_kernel<<<p.btile_start[p.n_scales], kThreads, mono_bwd_smem_bytes(), stream>>>(p, t);
+  kernel<<<p.btile_start[p.n_scales], kThreads, mono_bwd_smem_bytes(), stream>>>(p, t);
   return cudaGetLastError();
 }
 

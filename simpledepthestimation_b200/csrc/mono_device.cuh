@@ -305,13 +305,28 @@ __device__ __forceinline__ void stage_saved(const StageArgs& a0, const float* __
 // mirrored pixel, which always lies inside the same staged tile; positions further out are never read by a
 // valid output and stay zero.  n_planes consecutive planes starting at plane0.
 __device__ __forceinline__ void reflect_fixup(float* planes, int plane0, int n_planes, int oy, int ox, int h, int w, int tid) {
-  for (int i = tid; i < kPositions; i += kThreads) {
+  // Only the two plane rows / two plane columns that sit one pixel outside the image can hold such positions:
+  // walk those lines (2 * 66 + 2 * 18 candidates) instead of the whole tile.  Row lines take the corners (mirrored
+  // in both directions); every source position lies inside the image, so no fix-up reads another one's result.
+  for (int i = tid; i < 2 * kHW + 2 * kHH; i += kThreads) {
     int yy, xx;
-    position_of(i, yy, xx);
-    const int ty = oy + yy, tx = ox + xx;
-    const bool oy1 = ty == -1 || ty == h, ox1 = tx == -1 || tx == w;
-    const bool iny = ty >= 0 && ty < h, inx = tx >= 0 && tx < w;
-    if ((oy1 && (inx || ox1)) || (ox1 && iny)) {
+    bool ok;
+    if (i < 2 * kHW) {
+      const bool top = i < kHW;
+      xx = top ? i : i - kHW;
+      yy = (top ? -1 : h) - oy;
+      const int tx = ox + xx;
+      ok = yy >= 0 && yy < kHH && tx >= -1 && tx <= w;
+    } else {
+      const int k = i - 2 * kHW;
+      const bool left = k < kHH;
+      yy = left ? k : k - kHH;
+      xx = (left ? -1 : w) - ox;
+      const int ty = oy + yy;
+      ok = xx >= 0 && xx < kHW && ty >= 0 && ty < h;
+    }
+    if (ok) {
+      const int ty = oy + yy, tx = ox + xx;
       const int ry = ty == -1 ? 1 : (ty == h ? h - 2 : ty), rx = tx == -1 ? 1 : (tx == w ? w - 2 : tx);
       const int dst = plane_index(yy, xx), src = plane_index(ry - oy, rx - ox);
       for (int k = 0; k < n_planes; ++k) planes[(plane0 + k) * kPlane + dst] = planes[(plane0 + k) * kPlane + src];

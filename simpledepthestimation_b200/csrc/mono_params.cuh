@@ -10,6 +10,7 @@ constexpr int kTileW = 64;   // 32 lanes x 2 pixels (one f2 per lane)
 constexpr int kTileH = 16;   // 4 warps x 4 rows
 constexpr int kThreads = 128;
 constexpr int kRowsPerWarp = 4;
+constexpr int kSavedPlanes = 9;   // planes per sample of a `warped` buffer: warp[3], d/dX[3], d/dY[3]
 // backward: a CTA recomputes SSIM on a kTileW x kTileH block of window centres and emits
 // gradients for its interior (the 3x3 adjoint needs one ring of neighbours)
 constexpr int kBwdW = kTileW - 4;   // 60: a multiple of 4, so that TMA boxes of the backward tiles start 16-byte aligned
@@ -27,7 +28,8 @@ struct MonoParams {
   const float* K;
   const float* pose[SDE_MAX_SOURCES];
   uint8_t* argmin[SDE_MAX_SCALES];
-  float* warped[SDE_MAX_SCALES][SDE_MAX_SOURCES];   // optional saved warps (nullptr = recompute)
+  float* warped[SDE_MAX_SCALES][SDE_MAX_SOURCES];   // optional [B,9,h,w]: warp + d warp/dX + d warp/dY (nullptr = recompute)
+  float* smooth_g[SDE_MAX_SCALES];                  // optional [B,h,w]: local smoothness gradient kept by the forward pass
   float* losses;
   float* stats;           // [n_scales*B][2] = (mean inverse depth, per-image smoothness)
   float ssim_w, l1_w, c1, c2;
@@ -42,13 +44,13 @@ struct MonoParams {
   const float* grad_losses;
   float* grad_depth[SDE_MAX_SCALES];
   float* grad_pose[SDE_MAX_SOURCES];
-  float* pose_partials;   // [bwd grid][S][12]
+  float* pose_partials;   // [bwd grid][warps per CTA][S][12]
   unsigned* smp_counter;   // [B] backward tiles finished per sample (all scales)
   int btiles_x[SDE_MAX_SCALES], btiles_y[SDE_MAX_SCALES];
   int btile_start[SDE_MAX_SCALES + 1];
   int tma[SDE_MAX_SCALES];   // tile planes of this scale are staged by TMA (tensor maps in MonoTma are valid)
-  int prewarp[SDE_MAX_SCALES];            // forward: the warp kernel has filled warped[s][*]; the loss kernel only reads them
-  int warp_start[SDE_MAX_SCALES + 1];     // warp kernel: first block of scale s (blocks of 256 pixels per sample)
+  int prewarp[SDE_MAX_SCALES];            // forward: the loss kernel takes warped[s][*] (filled by the warp kernel) through TMA
+  int warp_start[SDE_MAX_SCALES + 1];     // warp kernel: first block of scale s (blocks of 1024 pixels per sample)
 };
 
 // Tensor maps over the [planes, h, w] inputs of every scale, box {68, 18, 1} (tma.cuh).  Second kernel

@@ -1,5 +1,8 @@
 // Warp kernel of the MonoDepth2 loss (sm_100a): project + bilinear gather of every source at every scale,
-// one thread per target pixel, written as [B,3,h,w] planes (the `warped` buffers of sde_mono_buffers).
+// one thread per target pixel, written as [B,9,h,w] planes (the `warped` buffers of sde_mono_buffers):
+// the warped source (planes 0..2) and, from the same four taps, its derivatives w.r.t. the sample coordinate
+// (planes 3..5: d/dX, 6..8: d/dY; zero where nan_to_num / clamp gate the reference's gradient,
+// camera.py:184-188), so that the backward kernel never touches the source frames again.
 //
 // The fused loss kernels are stencil kernels with fat threads (128-160 registers, 12-16 warps per SM),
 // which is the wrong shape for the gather: it is latency-bound and wants many thin threads.  Run on its own
@@ -22,7 +25,7 @@ struct WarpShared {
 
 __global__ void __launch_bounds__(kWarpThreads, 4) mono_warp_kernel(const __grid_constant__ MonoParams p) {
   __shared__ WarpShared sh;
-  // blockIdx.x -> (scale, sample, chunk of 1024 pixels); scales that do not take the TMA path are skipped
+  // blockIdx.x -> (scale, sample, chunk of 1024 pixels)
   int s = 0, bid = blockIdx.x;
   while (s + 1 < p.n_scales && bid >= p.warp_start[s + 1]) ++s;
   bid -= p.warp_start[s];
@@ -54,7 +57,10 @@ __global__ void __launch_bounds__(kWarpThreads, 4) mono_warp_kernel(const __grid
       const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
       const float w00 = bx * by, w01 = cell.ax * by, w10 = bx * cell.ay, w11 = cell.ax * cell.ay;
       const float* src = p.source[s][j] + (size_t)b * 3 * hw + cell.off;
-      float* dst = p.warped[s][j] + (size_t)b * 3 * hw + pix;
+      float* dst = p.warped[s][j] + (size_t)b * kSavedPlanes * hw + pix;
+      // gradient gates of nan_to_num and clamp (closed interval): false for NaN / +-inf
+      const float gate_x = (X >= 0.0f && X <= (float)(w - 1)) ? 1.0f : 0.0f;
+      const float gate_y = (Y >= 0.0f && Y <= (float)(h - 1)) ? 1.0f : 0.0f;
       float t[3][4];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -64,8 +70,11 @@ __global__ void __launch_bounds__(kWarpThreads, 4) mono_warp_kernel(const __grid
         t[c][0] = __ldg(q); t[c][1] = __ldg(q + 1); t[c][2] = __ldg(q + w); t[c][3] = __ldg(q + w + 1);
       }
 #pragma unroll
-      for (int c = 0; c < 3; ++c)   // ATen's accumulation order: nw, ne, sw, se
+      for (int c = 0; c < 3; ++c) {  // ATen's accumulation order: nw, ne, sw, se
         dst[c * hw] = t[c][0] * w00 + t[c][1] * w01 + t[c][2] * w10 + t[c][3] * w11;
+        dst[(3 + c) * hw] = gate_x * ((t[c][1] - t[c][0]) * by + (t[c][3] - t[c][2]) * cell.ay);
+        dst[(6 + c) * hw] = gate_y * ((t[c][2] - t[c][0]) * bx + (t[c][3] - t[c][1]) * cell.ax);
+      }
     }
   }
 }

@@ -71,7 +71,7 @@ static MonoLayout mono_layout(const sde_mono_desc* d) {
   L.off_partials = off;
   off = align16(off + (size_t)L.grid * 4 * sizeof(float));
   L.off_pose = off;
-  off = align16(off + (size_t)L.bgrid * d->n_sources * 12 * sizeof(float));
+  off = align16(off + (size_t)L.bgrid * (kThreads / 32) * d->n_sources * 12 * sizeof(float));
   L.total = off;
   return L;
 }
@@ -99,6 +99,7 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
     p.sy[i] = (float)((double)p.h[i] / (double)d->full_height);
     p.target[i] = b->target[i]; p.depth[i] = b->depth[i];
     p.argmin[i] = b->argmin[i];
+    p.smooth_g[i] = b->smooth_g[i];
     p.grad_depth[i] = b->grad_depth[i];
     for (int j = 0; j < d->n_sources; ++j) {
       if (!b->source[i][j]) return SDE_ERR_INVALID_ARG;
@@ -132,11 +133,13 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
   p.partials = reinterpret_cast<float*>(ws + L.off_partials);
   p.pose_partials = reinterpret_cast<float*>(ws + L.off_pose);
   p.grad_losses = b->grad_losses;
-  // saved warps are all-or-nothing
+  // what the forward pass keeps for the backward pass is all-or-nothing
   {
     int have = 0, total = 0;
-    for (int i = 0; i < d->n_scales; ++i)
+    for (int i = 0; i < d->n_scales; ++i) {
+      ++total; have += b->smooth_g[i] != nullptr;
       for (int j = 0; j < d->n_sources; ++j) { ++total; have += b->warped[i][j] != nullptr; }
+    }
     if (have != 0 && have != total) return SDE_ERR_INVALID_ARG;
   }
   if (!backward) {
@@ -200,7 +203,7 @@ static void mono_tma(const sde_mono_desc* d, const sde_mono_buffers* b, bool bac
     // forward with `warped` buffers: the warp kernel fills them and the loss kernel takes them through TMA
     const bool prewarp = !backward && b->warped[i][0] != nullptr;
     for (int j = 0; ok && j < d->n_sources; ++j) {
-      if (backward || prewarp) ok = encode_planes(&t.warped[i][j], b->warped[i][j], d->batch * 3, h, w, bw);
+      if (backward || prewarp) ok = encode_planes(&t.warped[i][j], b->warped[i][j], d->batch * kSavedPlanes, h, w, bw);
       if (!backward && ok) ok = encode_planes(&t.source[i][j], b->source[i][j], d->batch * 3, h, w, bw);
     }
     p.tma[i] = ok ? 1 : 0;
@@ -209,7 +212,9 @@ static void mono_tma(const sde_mono_desc* d, const sde_mono_buffers* b, bool bac
   int start = 0;
   for (int i = 0; i <= SDE_MAX_SCALES; ++i) {
     p.warp_start[i] = start;
-    if (i < d->n_scales && p.prewarp[i]) start += d->batch * ((d->height[i] * d->width[i] + 1023) / 1024);   // kWarpChunk pixels per block
+    // the warp kernel fills the `warped` buffers of every scale (the loss kernels of a scale that cannot take
+    // the TMA path stage them with plain loads / gather themselves)
+    if (i < d->n_scales && !backward && b->warped[i][0]) start += d->batch * ((d->height[i] * d->width[i] + 1023) / 1024);   // kWarpChunk pixels per block
   }
 }
 

@@ -28,6 +28,15 @@ def _contig(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+class MonoSaved:
+    """Device buffers a MonoDepth2 loss step keeps between its forward and backward pass (MonoLossPlan.new_warped)."""
+
+    __slots__ = ("warped", "smooth_g")
+
+    def __init__(self, warped, smooth_g):
+        self.warped, self.smooth_g = warped, smooth_g
+
+
 class MonoLossPlan:
     """Shape-specialised launcher of the fused MonoDepth2 loss (forward + backward).
 
@@ -101,17 +110,21 @@ class MonoLossPlan:
                 raise _lib.SdeError("pose must be [B,4,4]")
 
     def new_warped(self):
-        """Buffers for the warped sources of one step ([scale][source] -> [B,3,h,w]), or None."""
+        """What one step keeps from the forward to the backward pass (sde_mono_buffers.warped / .smooth_g), or None:
+        per (scale, source) a [B,9,h,w] buffer -- the warped source and its derivatives w.r.t. the sample coordinate
+        -- and per scale the [B,1,h,w] local smoothness gradient."""
         if not self.save_warped:
             return None
-        return [[torch.empty(self.batch, 3, h, w, dtype=torch.float32, device=self.device)
-                 for _ in range(self.n_sources)] for h, w in self.sizes]
+        new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=self.device)  # noqa: E731
+        return MonoSaved([[new(self.batch, 9, h, w) for _ in range(self.n_sources)] for h, w in self.sizes],
+                         [new(self.batch, 1, h, w) for h, w in self.sizes])
 
-    def _set_warped(self, b, warped):
-        if warped is not None:
+    def _set_warped(self, b, saved):
+        if saved is not None:
             for i in range(len(self.sizes)):
+                b.smooth_g[i] = saved.smooth_g[i].data_ptr()
                 for j in range(self.n_sources):
-                    b.warped[i][j] = warped[i][j].data_ptr()
+                    b.warped[i][j] = saved.warped[i][j].data_ptr()
 
     def forward(self, target, source, depth, K, pose, want_argmin=True, out=None, argmin_out=None, warped=None):
         """Runs the forward kernel.  Returns (losses[2], argmin list).  All inputs contiguous fp32 CUDA.

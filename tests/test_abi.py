@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(sde_lib):
 
 
 def test_version_and_strerror(sde_lib):
-    assert sde_lib.sde_version() == 1
+    assert sde_lib.sde_version() == 2
     assert sde_lib.sde_strerror(0) == b"ok"
     assert b"invalid" in sde_lib.sde_strerror(-1)
     assert sde_lib.sde_last_cuda_error() == b""
