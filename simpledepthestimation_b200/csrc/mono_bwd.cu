@@ -26,6 +26,8 @@
 // The smoothness gradient uses the saved per-image mean inverse depth and loss (1-homogeneity,
 // SURVEY.md A.5).  Pose sums: per-warp slots, added by the last CTA of a sample in a fixed order in fp64
 // (deterministic; no float atomics anywhere).
+#include <type_traits>
+
 #include "mono_device.cuh"
 
 namespace sde {
@@ -120,6 +122,9 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
 #pragma unroll
   for (int k = 0; k < kRowsPerWarp; ++k) gd[k] = bc2(0.0f);
   // this lane's pair belongs to the gradient block P (plane columns 3..62) and to the image
+  f2 Gs[kRowsPerWarp];   // SAVED: local smoothness gradient of the same pairs (loaded before the last phase 4)
+#pragma unroll
+  for (int k = 0; k < kRowsPerWarp; ++k) Gs[k] = bc2(0.0f);
   const int gxp = ox + c0 + 1;
   const bool colP = lane >= 1 && lane <= 30;
   const bool col_ok0 = colP && gxp < w, col_ok1 = colP && gxp + 1 < w;
@@ -139,7 +144,8 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
   __syncthreads();
 
   for (int j = 0; j < p.S; ++j) {
-    const int cand = automask ? 2 * j : j;
+    // byte of the argmin plane that selects this source's warped candidate ('mean': every staged pixel holds 254)
+    const int cand = reduce_mean ? 254 : (automask ? 2 * j : j);
     const Cam cam = sh.cam;
     const Proj pj = sh.proj[j];
     const float* __restrict__ sc0 = p.source[s][j] + (size_t)b * 3 * hw;
@@ -181,8 +187,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
           if (rr >= 2) {
             const int row = r0 + rr - 1;  // plane row of the window centre
             const uchar2 m = *reinterpret_cast<const uchar2*>(sh.arg + plane_index(row, c0 + 1));
-            const bool sel0 = reduce_mean ? (m.x != 255) : (m.x == cand);
-            const bool sel1 = reduce_mean ? (m.y != 255) : (m.y == cand);
+            const bool sel0 = m.x == cand, sel1 = m.y == cand;
             f2 ca = bc2(0.0f), cb = bc2(0.0f), cc = bc2(0.0f);
             if (__any_sync(0xffffffffu, sel0 || sel1)) {
               const f2 sA = (hA[0] + hA[1]) + nA, sAA = (hAA[0] + hAA[1]) + nAA;
@@ -219,7 +224,9 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       }
       __syncthreads();
       // -------------------------------------------------------------- phase 3: adjoint gather -> gS_c on P
-      {
+      // instantiated twice: tiles on the left / right image border add the mirrored pad column (block-uniform)
+      auto phase3 = [&](auto lr_tag) {
+        constexpr bool LR = decltype(lr_tag)::value;
         f2 hq[3][2];  // horizontal 3-sums of a, b, c for the two previous coefficient rows
 #pragma unroll
         for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
@@ -229,9 +236,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
             for (int k = 0; k < 3; ++k) {
               const Row4 q = ld_row(planes + (kBCoef + k) * kPlane + plane_index(r0 + rr, c0));
               f2 hsum = (q.c + swp(q.c)) + q.o;
-              if (lr_border) {   // block-uniform: only tiles on the left / right image border
-                hsum = hsum + mk2(eL0 * lo(q.o) + eR0 * hi(q.c), eL1 * lo(q.c) + eR1 * hi(q.o));
-              }
+              if (LR) hsum = hsum + mk2(eL0 * lo(q.o) + eR0 * hi(q.c), eL1 * lo(q.c) + eR1 * hi(q.o));
               nq[k] = hsum;
             }
           }
@@ -248,14 +253,13 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
               const f2 vc = fma2(wu, hq[2][0], fma2(wd, nq[2], hq[2][1]));
               gS = fma2(Sp, vb, fma2(Ap, vc, va));
             }
-            // L1 term on the pixel itself: sign(S - A) where this candidate was selected
+            // L1 term on the pixel itself: g_l1 * sign(S - A) where this candidate was selected (branch-free)
             const uchar2 m = *reinterpret_cast<const uchar2*>(sh.arg + plane_index(row, c0 + 1));
-            const bool sel0 = reduce_mean ? (m.x != 255) : (m.x == cand);
-            const bool sel1 = reduce_mean ? (m.y != 255) : (m.y == cand);
             const f2 df = Sp - Ap;
             const float d0 = lo(df), d1 = hi(df);
-            const float l0 = sel0 ? (d0 > 0.0f ? g_l1 : (d0 < 0.0f ? -g_l1 : 0.0f)) : 0.0f;
-            const float l1 = sel1 ? (d1 > 0.0f ? g_l1 : (d1 < 0.0f ? -g_l1 : 0.0f)) : 0.0f;
+            float l0 = d0 > 0.0f ? g_l1 : -g_l1, l1 = d1 > 0.0f ? g_l1 : -g_l1;
+            l0 = (m.x == cand && d0 != 0.0f) ? l0 : 0.0f;
+            l1 = (m.y == cand && d1 != 0.0f) ? l1 : 0.0f;
             gS = gS + mk2(l0, l1);
             *reinterpret_cast<unsigned long long*>(planes + (kBG + c) * kPlane + plane_index(row, c0 + 1)) = gS.v;
           }
@@ -264,7 +268,9 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
             for (int k = 0; k < 3; ++k) { hq[k][0] = hq[k][1]; hq[k][1] = nq[k]; }
           }
         }
-      }
+      };
+      if (lr_border) phase3(std::true_type{});
+      else           phase3(std::false_type{});
       __syncthreads();
     }
 
@@ -281,6 +287,26 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     // gradient, so each warp first compacts those of its own rows into a dense list -- in a fixed order, so the
     // pose sums stay deterministic -- and the expensive part runs on full warps.  The gS planes of a warp's rows are
     // read and written by that warp only: no CTA barrier until the next source's planes are needed.
+    if (SAVED && j == p.S - 1 && p.smooth_scale[s] > 0.0f) {
+      // local smoothness gradient of this lane's pairs (kept by the forward kernel): the loads overlap phase 4
+      const float* __restrict__ sg = p.smooth_g[s] + (size_t)b * hw;
+      const bool pair = (w & 1) == 0 && (reinterpret_cast<uintptr_t>(sg) & 7) == 0;   // gxp is even
+#pragma unroll
+      for (int o = 0; o < kRowsPerWarp; ++o) {
+        const int row = r0 + 1 + o, gy = oy + row;
+        float G0 = 0.0f, G1 = 0.0f;
+        if (row >= 2 && row <= kBwdH + 1 && gy < h && col_ok0) {
+          if (pair) {
+            const float2 G = __ldg(reinterpret_cast<const float2*>(sg + gy * w + gxp));
+            G0 = G.x; G1 = G.y;
+          } else {
+            G0 = __ldg(sg + gy * w + gxp);
+            if (col_ok1) G1 = __ldg(sg + gy * w + gxp + 1);
+          }
+        }
+        Gs[o] = mk2(G0, G1);
+      }
+    }
     {
       unsigned short* const wlist = sh.list[wid];
       const unsigned lt = (1u << lane) - 1u;
@@ -307,9 +333,26 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
       const float* __restrict__ dw = SAVED ? p.warped[s][j] + ((size_t)b * kSavedPlanes + 3) * hw : nullptr;
       const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
+      // the derivative-plane loads of the NEXT listed pixel are in flight while the current one is processed
+      float nd[6];
+      int npl = 0;
+      auto fetch = [&](int k) {
+        npl = wlist[k];
+        if (SAVED) {
+          const int row = npl / kPitch, col = npl - row * kPitch - kColOff;
+          const float* q = dw + ((oy + row) * w + (ox + col));
+#pragma unroll
+          for (int i = 0; i < 6; ++i) nd[i] = __ldg(q + i * hw);
+        }
+      };
+      if (lane < total) fetch(lane);
 #pragma unroll 1
       for (int k = lane; k < total; k += 32) {
-        const int pl = wlist[k];
+        const int pl = npl;
+        float dv[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dv[i] = nd[i];
+        if (k + 32 < total) fetch(k + 32);
         const int row = pl / kPitch, col = pl - row * kPitch - kColOff;
         const int gy = oy + row, gx = ox + col;
         float* const pg = planes + kBG * kPlane + pl;
@@ -326,11 +369,8 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
           float gX, gY;
           if (SAVED) {
             // derivative planes of the warp kernel (already gated)
-            const float* q = dw + (gy * w + gx);
-            const float x0 = __ldg(q), x1 = __ldg(q + hw), x2 = __ldg(q + 2 * hw);
-            const float y0 = __ldg(q + 3 * hw), y1 = __ldg(q + 4 * hw), y2 = __ldg(q + 5 * hw);
-            gX = g0 * x0; gX += g1 * x1; gX += g2 * x2;
-            gY = g0 * y0; gY += g1 * y1; gY += g2 * y2;
+            gX = g0 * dv[0]; gX += g1 * dv[1]; gX += g2 * dv[2];
+            gY = g0 * dv[3]; gY += g1 * dv[4]; gY += g2 * dv[5];
           } else {
             const Cell cell = bilinear_cell(X, Y, w, h);
             const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
@@ -394,9 +434,8 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     const float rmbar = 1.0f / mbar;
     const float gsm = g_smooth * sscale;
     float* __restrict__ gout = p.grad_depth[s] + (size_t)b * hw;
-    const float* __restrict__ sg = SAVED ? p.smooth_g[s] + (size_t)b * hw : nullptr;
     // the pair (gxp, gxp + 1) is 8-byte aligned in global memory (gxp is even) if the rows and the buffers are
-    const bool even = (w & 1) == 0 && ((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(sg)) & 7) == 0;
+    const bool even = (w & 1) == 0 && (reinterpret_cast<uintptr_t>(gout) & 7) == 0;
 #pragma unroll
     for (int o = 0; o < kRowsPerWarp; ++o) {
       const int row = r0 + 1 + o;
@@ -410,13 +449,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
           const float ic0 = inv_depth(d0), ic1 = inv_depth(d1);
           float G0, G1;
           if (SAVED) {
-            if (even) {
-              const float2 G = __ldg(reinterpret_cast<const float2*>(sg + gy * w + gxp));
-              G0 = G.x; G1 = G.y;
-            } else {
-              G0 = __ldg(sg + gy * w + gxp);
-              G1 = col_ok1 ? __ldg(sg + gy * w + gxp + 1) : 0.0f;
-            }
+            G0 = lo(Gs[o]); G1 = hi(Gs[o]);
           } else {
             G0 = smooth_grad_local(pd, planes + kBA * kPlane + pl, ic0, gxp, gy, w, h, inx, iny);
             G1 = smooth_grad_local(pd + 1, planes + kBA * kPlane + pl + 1, ic1, gxp + 1, gy, w, h, inx, iny);
