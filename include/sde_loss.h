@@ -323,6 +323,50 @@ size_t sde_variance_workspace_bytes(int64_t count);
 int sde_variance_loss_forward(int64_t count, const sde_var_buffers* buf, void* stream);
 int sde_variance_loss_backward(int64_t count, const sde_var_buffers* buf, void* stream);
 
+/* silog_loss(variance_focus)(depth_est, depth_gt), detectron2/modeling/losses/losses.py:5-13 (supervised term,
+ * caller MonoDepth2.py:107-110): mask = depth_gt > 1; d = log(est[mask]) - log(gt[mask]);
+ * loss = sqrt(mean(d^2) - variance_focus * mean(d)^2) * 10.  An empty mask gives NaN, as in the reference. */
+typedef struct sde_silog_buffers {
+  const float* depth_est;     /* [count] */
+  const float* depth_gt;      /* [count] */
+  float* loss;                /* [1] */
+  float* saved_stats;         /* [3] for backward */
+  const float* grad_loss;     /* [1] (device) */
+  float* grad_depth_est;      /* [count] */
+  void* workspace;            /* sde_silog_workspace_bytes(count), zero-filled once */
+} sde_silog_buffers;
+
+size_t sde_silog_workspace_bytes(int64_t count);
+int sde_silog_loss_forward(int64_t count, float variance_focus, const sde_silog_buffers* buf, void* stream);
+int sde_silog_loss_backward(int64_t count, float variance_focus, const sde_silog_buffers* buf, void* stream);
+
+/* disp_to_depth(disp, min_depth, max_depth) -> (scaled_disp, depth), detectron2/layers/depth_decoder.py:9-18
+ * (DepthResNet.py:41,57; PackNet01.py:109): scaled = 1/max_depth + (1/min_depth - 1/max_depth) * disp, depth = 1/scaled.
+ * `scaled_disp`, `grad_scaled_disp` and `grad_depth` are optional (NULL). */
+typedef struct sde_disp_buffers {
+  const float* disp;              /* [count] */
+  float* scaled_disp;             /* [count] or NULL */
+  float* depth;                   /* [count] */
+  const float* grad_scaled_disp;  /* [count] or NULL */
+  const float* grad_depth;        /* [count] or NULL */
+  float* grad_disp;               /* [count] */
+} sde_disp_buffers;
+
+int sde_disp_to_depth_forward(int64_t count, float min_depth, float max_depth, const sde_disp_buffers* buf, void* stream);
+int sde_disp_to_depth_backward(int64_t count, float min_depth, float max_depth, const sde_disp_buffers* buf, void* stream);
+
+/* pose_vec2mat(vec), detectron2/geometry/pose_utils.py:98-137 (PoseNet.py:63; GooglePoseNet.py:85,206):
+ * vec [B,6] = (tx, ty, tz, rx, ry, rz) -> [B,4,4] with R = Rx Ry Rz (euler2mat) and t in the last column. */
+typedef struct sde_posevec_buffers {
+  const float* vec;           /* [B,6] */
+  float* pose;                /* [B,4,4] */
+  const float* grad_pose;     /* [B,4,4] */
+  float* grad_vec;            /* [B,6] */
+} sde_posevec_buffers;
+
+int sde_pose_vec2mat_forward(int32_t batch, const sde_posevec_buffers* buf, void* stream);
+int sde_pose_vec2mat_backward(int32_t batch, const sde_posevec_buffers* buf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

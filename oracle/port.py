@@ -155,6 +155,33 @@ def variance_loss(depth):
     return 1.0 / ((depth / depth.mean() - 1.0) ** 2).mean()
 
 
+def silog_loss(depth_est, depth_gt, variance_focus=0.85):
+    """losses.py:5-13."""
+    mask = depth_gt > 1.0
+    d = torch.log(depth_est[mask]) - torch.log(depth_gt[mask])
+    return torch.sqrt((d ** 2).mean() - variance_focus * (d.mean() ** 2)) * 10.0
+
+
+def disp_to_depth(disp, min_depth, max_depth):
+    """layers/depth_decoder.py:9-18: (scaled_disp, depth)."""
+    min_disp = 1 / max_depth
+    max_disp = 1 / min_depth
+    scaled_disp = min_disp + (max_disp - min_disp) * disp
+    return scaled_disp, 1 / scaled_disp
+
+
+def pose_vec2mat(vec):
+    """geometry/pose_utils.py:98-137: [B,6] (tx,ty,tz,rx,ry,rz) -> [B,4,4], R = Rx Ry Rz."""
+    x, y, z = vec[:, 3], vec[:, 4], vec[:, 5]
+    zero, one = torch.zeros_like(x), torch.ones_like(x)
+    rz = torch.stack([z.cos(), -z.sin(), zero, z.sin(), z.cos(), zero, zero, zero, one], 1).view(-1, 3, 3)
+    ry = torch.stack([y.cos(), zero, y.sin(), zero, one, zero, -y.sin(), zero, y.cos()], 1).view(-1, 3, 3)
+    rx = torch.stack([one, zero, zero, zero, x.cos(), -x.sin(), zero, x.sin(), x.cos()], 1).view(-1, 3, 3)
+    top = torch.cat([rx.bmm(ry).bmm(rz), vec[:, :3].unsqueeze(-1)], 2)
+    bottom = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=vec.dtype, device=vec.device).expand(len(vec), 1, 4)
+    return torch.cat([top, bottom], 1)
+
+
 # --------------------------------------------------------------------------- MonoDepth2 loop
 
 

@@ -118,6 +118,19 @@ class VarBuffers(C.Structure):
     _fields_ = [(n, _f32p) for n in ("depth", "loss", "saved_stats", "grad_loss", "grad_depth", "workspace")]
 
 
+class SilogBuffers(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("depth_est", "depth_gt", "loss", "saved_stats", "grad_loss", "grad_depth_est",
+                                     "workspace")]
+
+
+class DispBuffers(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("disp", "scaled_disp", "depth", "grad_scaled_disp", "grad_depth", "grad_disp")]
+
+
+class PoseVecBuffers(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("vec", "pose", "grad_pose", "grad_vec")]
+
+
 class SdeError(RuntimeError):
     pass
 
@@ -178,6 +191,14 @@ def load():
     for suffix in ("_forward", "_backward"):
         fn = getattr(lib, "sde_variance_loss" + suffix)
         fn.restype, fn.argtypes = C.c_int, [C.c_int64, C.POINTER(VarBuffers), C.c_void_p]
+    lib.sde_silog_workspace_bytes.restype, lib.sde_silog_workspace_bytes.argtypes = C.c_size_t, [C.c_int64]
+    for suffix in ("_forward", "_backward"):
+        fn = getattr(lib, "sde_silog_loss" + suffix)
+        fn.restype, fn.argtypes = C.c_int, [C.c_int64, C.c_float, C.POINTER(SilogBuffers), C.c_void_p]
+        fn = getattr(lib, "sde_disp_to_depth" + suffix)
+        fn.restype, fn.argtypes = C.c_int, [C.c_int64, C.c_float, C.c_float, C.POINTER(DispBuffers), C.c_void_p]
+        fn = getattr(lib, "sde_pose_vec2mat" + suffix)
+        fn.restype, fn.argtypes = C.c_int, [C.c_int32, C.POINTER(PoseVecBuffers), C.c_void_p]
     lib.sde_resize_bilinear.restype = C.c_int
     lib.sde_resize_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p]

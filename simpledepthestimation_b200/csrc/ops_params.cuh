@@ -57,6 +57,7 @@ struct SmoothParams {
   float* g_depth;
 };
 
+
 }  // namespace sde
 
 namespace sde {
@@ -97,6 +98,38 @@ struct VarParams {   // variance_loss
   float* g_depth;
   float* slots;             // [blocks]
   unsigned* counters;       // [1]
+};
+
+struct SilogParams {   // silog_loss
+  long long n;
+  const float* est;
+  const float* gt;
+  float vf;                 // variance_focus
+  float* loss;              // [1]
+  float* stats;             // [3] mean(d), sqrt(mean(d^2) - vf mean(d)^2), number of masked elements
+  const float* g_loss;
+  float* g_est;
+  float* slots;             // [blocks][3]
+  unsigned* counter;        // [1]
+};
+
+struct DispParams {    // disp_to_depth
+  long long n;
+  const float* disp;
+  float min_disp, range;    // 1 / max_depth, 1 / min_depth - 1 / max_depth
+  float* scaled;            // optional
+  float* depth;
+  const float* g_scaled;    // optional
+  const float* g_depth;     // optional
+  float* g_disp;
+};
+
+struct PoseVecParams { // pose_vec2mat
+  int B;
+  const float* vec;         // [B,6]
+  float* mat;               // [B,4,4]
+  const float* g_mat;       // [B,4,4]
+  float* g_vec;             // [B,6]
 };
 
 }  // namespace sde

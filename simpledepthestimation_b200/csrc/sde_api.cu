@@ -25,6 +25,9 @@ cudaError_t launch_mcons_fwd(const McParams& p, cudaStream_t stream);
 cudaError_t launch_mcons_bwd(const McParams& p, float* g_t_ba, cudaStream_t stream);
 cudaError_t launch_mreg(int which, const MregParams& p, cudaStream_t stream);
 cudaError_t launch_var(bool backward, const VarParams& p, cudaStream_t stream);
+cudaError_t launch_silog(bool backward, const SilogParams& p, cudaStream_t stream);
+cudaError_t launch_disp(bool backward, const DispParams& p, cudaStream_t stream);
+cudaError_t launch_posevec(bool backward, const PoseVecParams& p, cudaStream_t stream);
 constexpr int kOpBlock = 256;
 
 static thread_local char g_cuda_err[256] = "";
@@ -654,5 +657,77 @@ static int var_call(bool backward, int64_t count, const sde_var_buffers* b, void
 
 int sde_variance_loss_forward(int64_t count, const sde_var_buffers* buf, void* stream) { return var_call(false, count, buf, stream); }
 int sde_variance_loss_backward(int64_t count, const sde_var_buffers* buf, void* stream) { return var_call(true, count, buf, stream); }
+
+size_t sde_silog_workspace_bytes(int64_t count) {
+  if (count < 1) return 0;
+  return align16(16 + (size_t)((count + kOpBlock - 1) / kOpBlock) * 3 * sizeof(float));
+}
+
+static int silog_call(bool backward, int64_t count, float vf, const sde_silog_buffers* b, void* stream) {
+  if (count < 1 || !b || !b->depth_est || !b->depth_gt || !b->saved_stats) return SDE_ERR_INVALID_ARG;
+  SilogParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = count; p.est = b->depth_est; p.gt = b->depth_gt; p.vf = vf; p.stats = b->saved_stats;
+  if (!backward) {
+    if (!b->loss || !b->workspace) return SDE_ERR_INVALID_ARG;
+    p.loss = b->loss;
+    p.counter = reinterpret_cast<unsigned*>(b->workspace);
+    p.slots = reinterpret_cast<float*>(static_cast<char*>(b->workspace) + 16);
+  } else {
+    if (!b->grad_loss || !b->grad_depth_est) return SDE_ERR_INVALID_ARG;
+    p.g_loss = b->grad_loss; p.g_est = b->grad_depth_est;
+  }
+  SDE_LAUNCH(launch_silog(backward, p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_silog_loss_forward(int64_t count, float variance_focus, const sde_silog_buffers* buf, void* stream) {
+  return silog_call(false, count, variance_focus, buf, stream);
+}
+int sde_silog_loss_backward(int64_t count, float variance_focus, const sde_silog_buffers* buf, void* stream) {
+  return silog_call(true, count, variance_focus, buf, stream);
+}
+
+static int disp_call(bool backward, int64_t count, float min_depth, float max_depth, const sde_disp_buffers* b, void* stream) {
+  if (count < 1 || !b || !b->disp || !(min_depth > 0.0f) || !(max_depth > min_depth)) return SDE_ERR_INVALID_ARG;
+  DispParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = count; p.disp = b->disp;
+  // min_disp = 1 / max_depth, max_disp = 1 / min_depth, in fp32 as the reference's Python floats become on the multiply
+  p.min_disp = (float)(1.0 / (double)max_depth);
+  p.range = (float)(1.0 / (double)min_depth - 1.0 / (double)max_depth);
+  if (!backward) {
+    if (!b->depth) return SDE_ERR_INVALID_ARG;
+    p.scaled = b->scaled_disp; p.depth = b->depth;
+  } else {
+    if (!b->grad_disp || (!b->grad_depth && !b->grad_scaled_disp)) return SDE_ERR_INVALID_ARG;
+    p.g_scaled = b->grad_scaled_disp; p.g_depth = b->grad_depth; p.g_disp = b->grad_disp;
+  }
+  SDE_LAUNCH(launch_disp(backward, p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_disp_to_depth_forward(int64_t count, float min_depth, float max_depth, const sde_disp_buffers* buf, void* stream) {
+  return disp_call(false, count, min_depth, max_depth, buf, stream);
+}
+int sde_disp_to_depth_backward(int64_t count, float min_depth, float max_depth, const sde_disp_buffers* buf, void* stream) {
+  return disp_call(true, count, min_depth, max_depth, buf, stream);
+}
+
+static int posevec_call(bool backward, int32_t batch, const sde_posevec_buffers* b, void* stream) {
+  if (batch < 1 || !b || !b->vec) return SDE_ERR_INVALID_ARG;
+  PoseVecParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = batch; p.vec = b->vec;
+  if (!backward) {
+    if (!b->pose) return SDE_ERR_INVALID_ARG;
+    p.mat = b->pose;
+  } else {
+    if (!b->grad_pose || !b->grad_vec) return SDE_ERR_INVALID_ARG;
+    p.g_mat = b->grad_pose; p.g_vec = b->grad_vec;
+  }
+  SDE_LAUNCH(launch_posevec(backward, p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_pose_vec2mat_forward(int32_t batch, const sde_posevec_buffers* buf, void* stream) { return posevec_call(false, batch, buf, stream); }
+int sde_pose_vec2mat_backward(int32_t batch, const sde_posevec_buffers* buf, void* stream) { return posevec_call(true, batch, buf, stream); }
 
 }  // extern "C"

@@ -10,7 +10,7 @@ import torch.nn as nn
 from ...functional import MonoLossPlan, mono_photometric_smoothness_loss
 from ...geometry.camera import resize_img, view_synthesis
 from ...utils.memory import to_cuda
-from ..losses.losses import variance_loss
+from ..losses.losses import silog_loss, variance_loss
 from ..losses.ssim_loss import SSIM
 from ..nets import build_depth_net, build_pose_net
 from .build import META_ARCH_REGISTRY
@@ -33,10 +33,10 @@ class MonoDepth2Model(nn.Module):
         self.smooth_loss_w = cfg.LOSS.SMOOTHNESS_WEIGHT
         if self.photometric_reduce not in ("min", "mean"):
             raise NotImplementedError(self.photometric_reduce)
-        if self.clip_loss > 0.0 or self.sup_loss_w > 0.0:
-            # off in every shipped config (Base.yaml:8,12,14); not part of the fused path yet
-            raise NotImplementedError("LOSS.CLIP / SUPERVISED_WEIGHT > 0 are not supported "
-                                      "by the fused B200 loss path")
+        if self.clip_loss > 0.0:
+            # off in every shipped config (Base.yaml:8); the per-batch mean + CLIP * std cap is not part of the fused path
+            raise NotImplementedError("LOSS.CLIP > 0 is not supported by the fused B200 loss path")
+        self.supervise_loss = silog_loss(cfg.LOSS.VARIANCE_FOCUS)
 
         self.register_buffer("pixel_mean", torch.Tensor(cfg.MODEL.PIXEL_MEAN).view(1, -1, 1, 1))
         self.register_buffer("pixel_std", torch.Tensor(cfg.MODEL.PIXEL_STD).view(1, -1, 1, 1))
@@ -84,6 +84,11 @@ class MonoDepth2Model(nn.Module):
             output["rec_loss"] = rec
             if self.smooth_loss_w > 0.0:
                 output["smooth_loss"] = smooth
+            if self.sup_loss_w > 0.0:   # MonoDepth2.py:107-110 (weighted by SMOOTHNESS_WEIGHT there, kept as is)
+                n = len(depth_pred)
+                output["sup_loss"] = sum(
+                    self.supervise_loss(d, resize_img(batch["depth"], d.shape[-2:], mode="nearest"))
+                    * (1.0 / 2 ** (n - i - 1)) * self.smooth_loss_w / n for i, d in enumerate(depth_pred))
             if self.var_loss_w > 0.0:   # PackNet (packnet_1a.yaml:12); MonoDepth2.py:112-113
                 n = len(depth_pred)
                 output["var_loss"] = sum(variance_loss(d) * (1.0 / 2 ** (n - i - 1)) * self.var_loss_w / n

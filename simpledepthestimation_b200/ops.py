@@ -344,3 +344,112 @@ class _VarianceFn(torch.autograd.Function):
 
 def variance(depth):
     return _VarianceFn.apply(depth)
+
+
+# ------------------------------------------------------------------------------------------------ silog_loss
+class _SilogFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth_est, depth_gt, variance_focus):
+        lib = _lib.load()
+        est, gt = _cuda_f32(depth_est, "depth_est"), _cuda_f32(depth_gt, "depth_gt")
+        if est.shape != gt.shape:
+            raise _lib.SdeError(f"silog_loss: depth_est {tuple(est.shape)} and depth_gt {tuple(gt.shape)} differ")
+        n = est.numel()
+        ws = _zero_workspace("silog", n, lib.sde_silog_workspace_bytes(n), est.device)
+        loss, stats = torch.empty(1, device=est.device), torch.empty(3, device=est.device)
+        b = _lib.SilogBuffers()
+        b.depth_est, b.depth_gt, b.loss, b.saved_stats, b.workspace = (est.data_ptr(), gt.data_ptr(), loss.data_ptr(),
+                                                                       stats.data_ptr(), ws.data_ptr())
+        _lib.check(lib.sde_silog_loss_forward(n, float(variance_focus), C.byref(b), _stream()), "sde_silog_loss_forward")
+        ctx.save_for_backward(est, gt, stats)
+        ctx.vf = float(variance_focus)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        est, gt, stats = ctx.saved_tensors
+        g = g.reshape(1).contiguous().float()
+        ge = torch.empty_like(est)
+        b = _lib.SilogBuffers()
+        b.depth_est, b.depth_gt, b.saved_stats, b.grad_loss, b.grad_depth_est = (est.data_ptr(), gt.data_ptr(),
+                                                                                stats.data_ptr(), g.data_ptr(), ge.data_ptr())
+        _lib.check(lib.sde_silog_loss_backward(est.numel(), ctx.vf, C.byref(b), _stream()), "sde_silog_loss_backward")
+        return ge, None, None
+
+
+def silog(depth_est, depth_gt, variance_focus):
+    return _SilogFn.apply(depth_est, depth_gt, variance_focus)
+
+
+# ------------------------------------------------------------------------------------------------ disp_to_depth
+class _DispToDepthFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, min_depth, max_depth):
+        lib = _lib.load()
+        disp = _cuda_f32(disp, "disp")
+        scaled, depth = torch.empty_like(disp), torch.empty_like(disp)
+        b = _lib.DispBuffers()
+        b.disp, b.scaled_disp, b.depth = disp.data_ptr(), scaled.data_ptr(), depth.data_ptr()
+        _lib.check(lib.sde_disp_to_depth_forward(disp.numel(), float(min_depth), float(max_depth), C.byref(b), _stream()),
+                   "sde_disp_to_depth_forward")
+        ctx.save_for_backward(disp)
+        ctx.range = (float(min_depth), float(max_depth))
+        return scaled, depth
+
+    @staticmethod
+    def backward(ctx, g_scaled, g_depth):
+        lib = _lib.load()
+        (disp,) = ctx.saved_tensors
+        gd = torch.empty_like(disp)
+        b = _lib.DispBuffers()
+        b.disp, b.grad_disp = disp.data_ptr(), gd.data_ptr()
+        keep = []
+        if g_scaled is not None:
+            keep.append(g_scaled.contiguous().float())
+            b.grad_scaled_disp = keep[-1].data_ptr()
+        if g_depth is not None:
+            keep.append(g_depth.contiguous().float())
+            b.grad_depth = keep[-1].data_ptr()
+        if not keep:
+            return torch.zeros_like(disp), None, None
+        _lib.check(lib.sde_disp_to_depth_backward(disp.numel(), ctx.range[0], ctx.range[1], C.byref(b), _stream()),
+                   "sde_disp_to_depth_backward")
+        return gd, None, None
+
+
+def disp_to_depth(disp, min_depth, max_depth):
+    """(scaled_disp, depth) as detectron2/layers/depth_decoder.py:9-18."""
+    return _DispToDepthFn.apply(disp, min_depth, max_depth)
+
+
+# ------------------------------------------------------------------------------------------------ pose_vec2mat
+class _PoseVec2MatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vec):
+        lib = _lib.load()
+        vec = _cuda_f32(vec, "vec")
+        if vec.dim() != 2 or vec.shape[1] != 6:
+            raise _lib.SdeError(f"pose_vec2mat: expected [B,6], got {tuple(vec.shape)}")
+        pose = torch.empty(vec.shape[0], 4, 4, device=vec.device)
+        b = _lib.PoseVecBuffers()
+        b.vec, b.pose = vec.data_ptr(), pose.data_ptr()
+        _lib.check(lib.sde_pose_vec2mat_forward(vec.shape[0], C.byref(b), _stream()), "sde_pose_vec2mat_forward")
+        ctx.save_for_backward(vec)
+        return pose
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (vec,) = ctx.saved_tensors
+        g = g.contiguous().float()
+        gv = torch.empty_like(vec)
+        b = _lib.PoseVecBuffers()
+        b.vec, b.grad_pose, b.grad_vec = vec.data_ptr(), g.data_ptr(), gv.data_ptr()
+        _lib.check(lib.sde_pose_vec2mat_backward(vec.shape[0], C.byref(b), _stream()), "sde_pose_vec2mat_backward")
+        return gv
+
+
+def pose_vec2mat(vec):
+    """[B,6] (tx,ty,tz,rx,ry,rz) -> [B,4,4] as detectron2/geometry/pose_utils.py:130-137."""
+    return _PoseVec2MatFn.apply(vec)
