@@ -144,7 +144,7 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out)
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -364,9 +364,18 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
             "gpu_launches": (3 if plan.save_warped else 2) * args.steps, "clocks": clocks, "other_configs": extra,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=args.out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _quiet_stdout():
+    """Everything libraries print to fd 1 while the bench runs (NCCL's version banner ...) goes to stderr; returns the
+    stream that writes to the real stdout, which receives exactly one line: the JSON result."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -379,10 +388,12 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs (cfg3, cfg4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.out = _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    args.out.flush()
 
 
 if __name__ == "__main__":

@@ -265,91 +265,9 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
       if (gx0 + 1 < w) { rec += best[o][1]; if (amap) amap[gy * w + gx0 + 1] = (uint8_t)arg[o][1]; }
     }
   }
-  if (p.smooth_scale[s] > 0.0f) {
-    // Edge-aware smoothness (smoothness_loss.py:62-80) on the edges of this lane's pixel pairs.  An edge between
-    // pixels u and v (v right of / below u) with inverse depths iu, iv carries the weight e = exp(-mean_c |dI|);
-    // it adds |iu - iv| e to the loss sums and +-sgn(iu - iv) e / N to d loss / d (1/depth) of u and v (before
-    // the division by the per-image mean) -- kept in smooth_g for the backward pass.
-    // Halo'd rows r0 .. r0+5 (owned rows: r0+1 .. r0+4); columns c0 (left neighbour) .. c0+3 (right neighbour).
-    const float* pd = planes + kPlD * kPlane + plane_index(r0, c0 + 1);
-    const float* pa = planes + kPlA * kPlane + plane_index(r0, c0 + 1);
-    // 1 / clamp(d, min=1e-6); the comparison form keeps a NaN depth NaN, as torch.clamp does
-    auto inv = [](float d) { return 1.0f / (d < 1e-6f ? 1e-6f : d); };
-    auto sgn = [](float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); };
-    const float inx = 1.0f / ((float)p.B * (float)h * (float)(w - 1));
-    const float iny = 1.0f / ((float)p.B * (float)(h - 1) * (float)w);
-    const bool v0 = gx0 < w, v1 = gx0 + 1 < w, v2 = gx0 + 2 < w, vl = gx0 >= 1 && v0;
-    float* __restrict__ gout = p.smooth_g[s] ? p.smooth_g[s] + (size_t)b * hw : nullptr;
-    const bool pair_ok = (w & 1) == 0 && (reinterpret_cast<uintptr_t>(gout) & 7) == 0;   // gx0 is even
-    // vertical edges between halo'd rows rr and rr + 1 (image rows gyu, gyu + 1): signed gradient terms
-    float tv0[kRowsPerWarp + 1], tv1[kRowsPerWarp + 1];
-    f2 du = ld2(pd);
-    float iu0 = inv(lo(du)), iu1 = inv(hi(du));
-    f2 au[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) au[c] = ld2(pa + c * kPlane);
-#pragma unroll
-    for (int rr = 0; rr <= kRowsPerWarp; ++rr) {
-      const int gyu = tc.y0 + r0 + rr - 1;
-      const f2 dl = ld2(pd + (rr + 1) * kPitch);
-      const float il0 = inv(lo(dl)), il1 = inv(hi(dl));
-      float e0 = 0.0f, e1 = 0.0f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const f2 al = ld2(pa + c * kPlane + (rr + 1) * kPitch);
-        e0 += fabsf(lo(au[c]) - lo(al));
-        e1 += fabsf(hi(au[c]) - hi(al));
-        au[c] = al;
-      }
-      const bool ve = gyu >= 0 && gyu + 1 < h;
-      const float w0 = expf(-e0 * (1.0f / 3.0f)), w1 = expf(-e1 * (1.0f / 3.0f));
-      tv0[rr] = (ve && v0) ? sgn(iu0 - il0) * w0 * iny : 0.0f;
-      tv1[rr] = (ve && v1) ? sgn(iu1 - il1) * w1 * iny : 0.0f;
-      if (rr >= 1) {   // the edge below an owned row is counted by this lane
-        if (ve && v0) smy += fabsf(iu0 - il0) * w0;
-        if (ve && v1) smy += fabsf(iu1 - il1) * w1;
-      }
-      iu0 = il0; iu1 = il1;
-    }
-#pragma unroll
-    for (int o = 0; o < kRowsPerWarp; ++o) {
-      const int gy = tc.y0 + r0 + o;
-      const float* pdo = pd + (o + 1) * kPitch;
-      const f2 dc = ld2(pdo);
-      const float iL = inv(pdo[-1]), i0 = inv(lo(dc)), i1 = inv(hi(dc)), iR = inv(pdo[2]);
-      float eL = 0.0f, eM = 0.0f, eR = 0.0f;  // sum_c |dI|
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float* pac = pa + c * kPlane + (o + 1) * kPitch;
-        const f2 ac = ld2(pac);
-        const float aL = pac[-1], a0 = lo(ac), a1 = hi(ac), aR = pac[2];
-        eL += fabsf(aL - a0);
-        eM += fabsf(a0 - a1);
-        eR += fabsf(a1 - aR);
-      }
-      if (gy < h) {
-        const float wL = expf(-eL * (1.0f / 3.0f)), wM = expf(-eM * (1.0f / 3.0f)), wR = expf(-eR * (1.0f / 3.0f));
-        if (v0) sinv += i0;
-        if (v1) sinv += i1;
-        if (v1) smx += fabsf(i0 - i1) * wM;
-        if (v2) smx += fabsf(i1 - iR) * wR;
-        if (gout) {
-          const float tL = vl ? sgn(iL - i0) * wL * inx : 0.0f;
-          const float tM = v1 ? sgn(i0 - i1) * wM * inx : 0.0f;
-          const float tR = v2 ? sgn(i1 - iR) * wR * inx : 0.0f;
-          const float G0 = ((tM - tL) + tv0[o + 1]) - tv0[o];
-          const float G1 = ((tR - tM) + tv1[o + 1]) - tv1[o];
-          float* po = gout + gy * w + gx0;
-          if (v1 && pair_ok) {
-            *reinterpret_cast<float2*>(po) = make_float2(G0, G1);
-          } else {
-            if (v0) po[0] = G0;
-            if (v1) po[1] = G1;
-          }
-        }
-      }
-    }
-  }
+  if (p.smooth_scale[s] > 0.0f)
+    tile_smoothness(planes, kPlD, kPlA, r0, c0, tc.x0, tc.y0, h, w, p.B, p.smooth_g[s] ? p.smooth_g[s] + (size_t)b * hw : nullptr,
+                    smx, smy, sinv);
 
   // ------------------------------------------------------------------ CTA reduction -> partial slot
   rec = warp_sum(rec); smx = warp_sum(smx); smy = warp_sum(smy); sinv = warp_sum(sinv);

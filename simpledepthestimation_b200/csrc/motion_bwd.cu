@@ -54,10 +54,10 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       tma_load_plane(planes + (kNA + c) * kPlane, &maps.frame_a[dir], &sh.bar, bx, oy, b * 3 + c);
-      tma_load_plane(planes + (kNS + c) * kPlane, &maps.warped[dir], &sh.bar, bx, oy, b * 5 + c);
+      tma_load_plane(planes + (kNS + c) * kPlane, &maps.warped[dir], &sh.bar, bx, oy, b * kMotionSaved + c);
     }
-    tma_load_plane(planes + kNU * kPlane, &maps.warped[dir], &sh.bar, bx, oy, b * 5 + 3);
-    tma_load_plane(planes + kNW * kPlane, &maps.warped[dir], &sh.bar, bx, oy, b * 5 + 4);
+    tma_load_plane(planes + kNU * kPlane, &maps.warped[dir], &sh.bar, bx, oy, b * kMotionSaved + 3);
+    tma_load_plane(planes + kNW * kPlane, &maps.warped[dir], &sh.bar, bx, oy, b * kMotionSaved + 4);
     tma_load_plane(planes + kND * kPlane, &maps.depth_a[dir], &sh.bar, bx, oy, b);
   }
   if (tid == 0) load_mcam(sh.cam, p.K, p.pose[dir], b, p.sx, p.sy);
@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
   {
     const MCam mc = sh.cam;
     const float* __restrict__ sc0 = st.frame_b;
+    const float* __restrict__ saved = tma ? p.warped[dir] + (size_t)b * kMotionSaved * hw : nullptr;
     float* __restrict__ gout = p.grad_depth[dir] + (size_t)b * hw;
     float* __restrict__ gfield = p.grad_field[dir] ? p.grad_field[dir] + (size_t)b * 3 * hw : nullptr;
     const float mbar = p.stats[(dir * p.B + b) * 4 + 2], Lb = p.stats[(dir * p.B + b) * 4 + 3];
@@ -283,11 +284,33 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
+    // warp mode: the global operands of a pixel (translation field, derivative planes, smoothness gradient; all
+    // coalesced) are fetched one iteration ahead
+    float nx[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) nx[k] = 0.0f;
+    auto fetch = [&](int it) {
+      const int i = tid + it * kThreads;
+      const int ly = i / kBwdW, lx = i - ly * kBwdW;
+      const int gy = ty0 + ly, gx = tx0 + lx;
+      if (tma && i < kBwdW * kBwdH && gy < h && gx < w) {
+        const int pix = gy * w + gx;
+        if (st.field) { nx[0] = __ldg(st.field + pix); nx[1] = __ldg(st.field + pix + hw); nx[2] = __ldg(st.field + pix + 2 * hw); }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) nx[3 + k] = __ldg(saved + (5 + k) * hw + pix);
+        if (g_smooth != 0.0f) nx[9] = __ldg(saved + 11 * hw + pix);
+      }
+    };
+    fetch(0);
 #pragma unroll 1
     for (int it = 0; it < kMPosPerThread; ++it) {
       const int i = tid + it * kThreads;
       const int ly = i / kBwdW, lx = i - ly * kBwdW;
       const int gy = ty0 + ly, gx = tx0 + lx;
+      float cv[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) cv[k] = nx[k];
+      if (it + 1 < kMPosPerThread) fetch(it + 1);
       if (i < kBwdW * kBwdH && gy < h && gx < w) {
         const int pl = plane_index(ly + 2, lx + kMBwdColOff);
         const int pix = gy * w + gx;
@@ -295,8 +318,8 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
         const float d = planes[kND * kPlane + pl];
         float gd = 0.0f, gt0 = 0.0f, gt1 = 0.0f, gt2 = 0.0f;
         if (g0 != 0.0f || g1 != 0.0f || g2 != 0.0f) {
-          float f0 = 0.0f, f1 = 0.0f, f2v = 0.0f;
-          if (st.field) { f0 = __ldg(st.field + pix); f1 = __ldg(st.field + pix + hw); f2v = __ldg(st.field + pix + 2 * hw); }
+          float f0 = cv[0], f1 = cv[1], f2v = cv[2];
+          if (!tma && st.field) { f0 = __ldg(st.field + pix); f1 = __ldg(st.field + pix + hw); f2v = __ldg(st.field + pix + 2 * hw); }
           const float fxp = (float)gx, fyp = (float)gy;
           float P[3], den, X, Y, Z;
           mproject(mc, fxp, fyp, d, f0, f1, f2v, P, den, X, Y, Z);
@@ -304,20 +327,26 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
           const bool gate_x = (X >= 0.0f) && (X <= wm1);   // nan_to_num + clamp gates (camera.py:184-188)
           const bool gate_y = (Y >= 0.0f) && (Y <= hm1);
           if (gate_x || gate_y) {
-            const Cell cell = bilinear_cell(X, Y, w, h);
-            const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
             float gX = 0.0f, gY = 0.0f;
-            const float gs[3] = {g0, g1, g2};
+            if (tma) {
+              // warp mode: derivative planes of the statistics pass (already gated), coalesced loads
+              gX = g0 * cv[3] + g1 * cv[4] + g2 * cv[5];
+              gY = g0 * cv[6] + g1 * cv[7] + g2 * cv[8];
+            } else {
+              const Cell cell = bilinear_cell(X, Y, w, h);
+              const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
+              const float gs[3] = {g0, g1, g2};
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-              const float* q0 = sc0 + cc * hw + cell.off;
-              const float* q1 = q0 + w;
-              const float v00 = __ldg(q0), v01 = __ldg(q0 + 1), v10 = __ldg(q1), v11 = __ldg(q1 + 1);
-              gX += gs[cc] * ((v01 - v00) * by + (v11 - v10) * cell.ay);
-              gY += gs[cc] * ((v10 - v00) * bx + (v11 - v01) * cell.ax);
+              for (int cc = 0; cc < 3; ++cc) {
+                const float* q0 = sc0 + cc * hw + cell.off;
+                const float* q1 = q0 + w;
+                const float v00 = __ldg(q0), v01 = __ldg(q0 + 1), v10 = __ldg(q1), v11 = __ldg(q1 + 1);
+                gX += gs[cc] * ((v01 - v00) * by + (v11 - v10) * cell.ay);
+                gY += gs[cc] * ((v10 - v00) * bx + (v11 - v01) * cell.ax);
+              }
+              if (!gate_x) gX = 0.0f;
+              if (!gate_y) gY = 0.0f;
             }
-            if (!gate_x) gX = 0.0f;
-            if (!gate_y) gY = 0.0f;
             const float q = 1.0f / den;
             const float u0 = gX * q, u1 = gY * q;
             const float dx = gate_x ? X - mc.cam.cx : 0.0f, dy = gate_y ? Y - mc.cam.cy : 0.0f;
@@ -340,7 +369,8 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
         if (g_smooth != 0.0f) {
           const float* pd = planes + kND * kPlane + pl;
           const float ic = inv_depth(d);
-          const float G = smooth_grad_local(pd, planes + kNA * kPlane + pl, ic, gx, gy, w, h, inx, iny);
+          const float G = tma ? cv[9]
+                              : smooth_grad_local(pd, planes + kNA * kPlane + pl, ic, gx, gy, w, h, inx, iny);
           const float g_inv = G * rmbar - homog;
           if (d >= 1e-6f) gd += -ic * ic * g_inv * g_smooth;
         }

@@ -32,7 +32,8 @@ struct MotionParams {
   float* occ[SDE_MAX_DIRS];
   float* weight[SDE_MAX_DIRS];
   float* coords[SDE_MAX_DIRS];
-  float* warped[SDE_MAX_DIRS];               // [B,5,h,w]: warped rgb, depth error, valid + 2 occlusion (or null)
+  float* warped[SDE_MAX_DIRS];               // [B,12,h,w]: warped rgb, depth error, valid + 2 occlusion, d rgb/dX, d rgb/dY,
+                                             // local smoothness gradient (or null)
   int tma;                                   // loss kernels stage their planes through TMA from `warped`
   // workspace
   unsigned* counters;                        // [0] statistics, [1] forward, [2] backward
@@ -46,6 +47,7 @@ struct MotionParams {
   float* grad_field[SDE_MAX_DIRS];
 };
 
+constexpr int kMotionSaved = 12;   // planes per sample of a `warped` buffer
 constexpr int kStatThreads = 256;
 constexpr int kStatPixPerThread = 4;
 constexpr int kStatPix = kStatThreads * kStatPixPerThread;
@@ -133,13 +135,14 @@ struct MotionStage {
 
 struct MotionSample {
   float S[3], Sd, A[3], d;
+  float dSx[3], dSy[3];                // d S_c / d(X, Y), gated as nan_to_num / clamp gate the gradient (want_deriv)
   float Zc, valid, occ, wgt;
   float Xs, Ys;                        // clamped pixel coordinates
 };
 
 // Projects pixel `pix` = (gy, gx), gathers rgb + depth of B, loads A; no shared memory involved.
 __device__ __forceinline__ void motion_sample(const MotionStage& a, const MCam& mc, int gy, int gx, int pix, bool rgb,
-                                              MotionSample& o, bool load_a = true) {
+                                              MotionSample& o, bool load_a = true, bool want_deriv = false) {
   o.d = __ldg(a.depth_a + pix);
   float f0 = 0.0f, f1 = 0.0f, f2v = 0.0f;
   if (a.field) { f0 = __ldg(a.field + pix); f1 = __ldg(a.field + pix + a.hw); f2v = __ldg(a.field + pix + 2 * a.hw); }
@@ -150,9 +153,18 @@ __device__ __forceinline__ void motion_sample(const MotionStage& a, const MCam& 
   const float w00 = bx * by, w01 = cell.ax * by, w10 = bx * cell.ay, w11 = cell.ax * cell.ay;
   o.Sd = bilinear4(a.depth_b + cell.off, a.w, w00, w01, w10, w11);
   if (rgb) {
+    // gradient gates of nan_to_num and clamp (closed interval, camera.py:184-188); false for NaN / +-inf
+    const float gate_x = (X >= 0.0f && X <= (float)(a.w - 1)) ? 1.0f : 0.0f;
+    const float gate_y = (Y >= 0.0f && Y <= (float)(a.h - 1)) ? 1.0f : 0.0f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      o.S[c] = bilinear4(a.frame_b + cell.off + c * a.hw, a.w, w00, w01, w10, w11);
+      const float* q = a.frame_b + cell.off + c * a.hw;
+      const float t00 = __ldg(q), t01 = __ldg(q + 1), t10 = __ldg(q + a.w), t11 = __ldg(q + a.w + 1);
+      o.S[c] = t00 * w00 + t01 * w01 + t10 * w10 + t11 * w11;   // ATen's order: nw, ne, sw, se
+      if (want_deriv) {
+        o.dSx[c] = gate_x * ((t01 - t00) * by + (t11 - t10) * cell.ay);
+        o.dSy[c] = gate_y * ((t10 - t00) * bx + (t11 - t01) * cell.ax);
+      }
       if (load_a) o.A[c] = __ldg(a.frame_a + pix + c * a.hw);
     }
   }
@@ -182,7 +194,7 @@ __device__ __forceinline__ void decode_motion_tile(int bid, int per_dir, int tx_
 struct alignas(64) MotionTma {
   CUtensorMap frame_a[SDE_MAX_DIRS];   // [B*3, h, w]
   CUtensorMap depth_a[SDE_MAX_DIRS];   // [B, h, w]
-  CUtensorMap warped[SDE_MAX_DIRS];    // [B*5, h, w]
+  CUtensorMap warped[SDE_MAX_DIRS];    // [B*12, h, w]
 };
 
 // proximity weight (MotionLearning.py:279-282) from the planes the warp kernel left: depth error and

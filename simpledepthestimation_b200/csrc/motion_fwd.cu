@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kStatThreads) motion_stats_kernel(const __grid
   st.planes = nullptr; st.oy = 0; st.ox = 0; st.h = p.h; st.w = p.w; st.hw = hw; st.m2 = 1.0f;
   st.frame_b = p.frame_b[dir] + (size_t)b * 3 * hw;
   // warp mode: this pass also gathers the rgb channels and leaves the planes the loss kernels stage by TMA
-  float* __restrict__ wout = p.warped[dir] ? p.warped[dir] + (size_t)b * 5 * hw : nullptr;
+  float* __restrict__ wout = p.warped[dir] ? p.warped[dir] + (size_t)b * kMotionSaved * hw : nullptr;
   float* __restrict__ occ_out = (wout && p.occ[dir]) ? p.occ[dir] + (size_t)b * hw : nullptr;
   float* __restrict__ crd_out = (wout && p.coords[dir]) ? p.coords[dir] + (size_t)b * hw * 2 : nullptr;
   float socc = 0.0f, serr = 0.0f;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kStatThreads) motion_stats_kernel(const __grid
     if (pix < hw) {
       const int gy = pix / p.w, gx = pix - gy * p.w;
       MotionSample sm;
-      motion_sample(st, mc, gy, gx, pix, wout != nullptr, sm, false);
+      motion_sample(st, mc, gy, gx, pix, wout != nullptr, sm, false, wout != nullptr);
       const float e = sm.Zc - sm.Sd;
       const float derr = e * e;
       socc += sm.occ;
@@ -64,6 +64,11 @@ __global__ void __launch_bounds__(kStatThreads) motion_stats_kernel(const __grid
         wout[pix] = sm.S[0]; wout[hw + pix] = sm.S[1]; wout[2 * hw + pix] = sm.S[2];
         wout[3 * hw + pix] = derr;
         wout[4 * hw + pix] = sm.valid + 2.0f * sm.occ;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {   // derivative planes for the backward pass
+          wout[(5 + c) * hw + pix] = sm.dSx[c];
+          wout[(8 + c) * hw + pix] = sm.dSy[c];
+        }
         if (occ_out) occ_out[pix] = sm.occ;
         if (crd_out) {
           float2 cn;
@@ -137,10 +142,10 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       tma_load_plane(planes + (kMA + c) * kPlane, &maps.frame_a[dir], &sh.bar, bx, by, b * 3 + c);
-      tma_load_plane(planes + (kMS + c) * kPlane, &maps.warped[dir], &sh.bar, bx, by, b * 5 + c);
+      tma_load_plane(planes + (kMS + c) * kPlane, &maps.warped[dir], &sh.bar, bx, by, b * kMotionSaved + c);
     }
-    tma_load_plane(planes + kMU * kPlane, &maps.warped[dir], &sh.bar, bx, by, b * 5 + 3);
-    tma_load_plane(planes + kMW * kPlane, &maps.warped[dir], &sh.bar, bx, by, b * 5 + 4);
+    tma_load_plane(planes + kMU * kPlane, &maps.warped[dir], &sh.bar, bx, by, b * kMotionSaved + 3);
+    tma_load_plane(planes + kMW * kPlane, &maps.warped[dir], &sh.bar, bx, by, b * kMotionSaved + 4);
     tma_load_plane(planes + kMD * kPlane, &maps.depth_a[dir], &sh.bar, bx, by, b);
   }
   if (tid == 0) load_mcam(sh.cam, p.K, p.pose[dir], b, p.sx, p.sy);
@@ -314,38 +319,9 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
 
   // ------------------------------------------------------------------ smoothness(depth_A, frame_A)
   float smx = 0.0f, smy = 0.0f, sinv = 0.0f;
-  {
-    const int gx0 = tx0 + c0;
-    const float* pd = planes + kMD * kPlane + plane_index(r0 + 1, c0 + 1);
-    auto inv = [](float d) { return 1.0f / (d < 1e-6f ? 1e-6f : d); };   // NaN-preserving clamp(min=1e-6)
-#pragma unroll
-    for (int o = 0; o < kRowsPerWarp; ++o) {
-      const int gy = ty0 + r0 + o;
-      const f2 dc = ld2(pd + o * kPitch), db = ld2(pd + (o + 1) * kPitch);
-      const float i0 = inv(lo(dc)), i1 = inv(hi(dc)), i2 = inv(pd[o * kPitch + 2]);
-      const float ib0 = inv(lo(db)), ib1 = inv(hi(db));
-      float ex0 = 0.0f, ex1 = 0.0f, ey0 = 0.0f, ey1 = 0.0f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float* pa = planes + (kMA + c) * kPlane + plane_index(r0 + 1 + o, c0 + 1);
-        const f2 ac = ld2(pa), ab = ld2(pa + kPitch);
-        const float a0 = lo(ac), a1 = hi(ac), a2 = pa[2];
-        ex0 += fabsf(a0 - a1);
-        ex1 += fabsf(a1 - a2);
-        ey0 += fabsf(a0 - lo(ab));
-        ey1 += fabsf(a1 - hi(ab));
-      }
-      if (gy < h) {
-        const bool v0 = gx0 < w, v1 = gx0 + 1 < w, v2 = gx0 + 2 < w, vy = gy + 1 < h;
-        if (v0) sinv += i0;
-        if (v1) sinv += i1;
-        if (v1) smx += fabsf(i0 - i1) * expf(-ex0 * (1.0f / 3.0f));
-        if (v2) smx += fabsf(i1 - i2) * expf(-ex1 * (1.0f / 3.0f));
-        if (v0 && vy) smy += fabsf(i0 - ib0) * expf(-ey0 * (1.0f / 3.0f));
-        if (v1 && vy) smy += fabsf(i1 - ib1) * expf(-ey1 * (1.0f / 3.0f));
-      }
-    }
-  }
+  // warp mode: the local smoothness gradient goes to plane 11 of `warped` for the backward pass
+  tile_smoothness(planes, kMD, kMA, r0, c0, tx0, ty0, h, w, p.B,
+                  (tma && p.warped[dir]) ? p.warped[dir] + ((size_t)b * kMotionSaved + 11) * hw : nullptr, smx, smy, sinv);
 
   // ------------------------------------------------------------------ CTA reduction -> partial slot
   l1 = warp_sum(l1); ssim_sum = warp_sum(ssim_sum); smx = warp_sum(smx); smy = warp_sum(smy); sinv = warp_sum(sinv);

@@ -232,7 +232,7 @@ static void motion_tma(const sde_motion_desc* d, const sde_motion_buffers* b, bo
     ok = b->warped[k] != nullptr &&
          encode_planes(&t.frame_a[k], b->frame_a[k], d->batch * 3, d->height, d->width, bw) &&
          encode_planes(&t.depth_a[k], b->depth_a[k], d->batch, d->height, d->width, bw) &&
-         encode_planes(&t.warped[k], b->warped[k], d->batch * 5, d->height, d->width, bw);
+         encode_planes(&t.warped[k], b->warped[k], d->batch * kMotionSaved, d->height, d->width, bw);
   }
   p.tma = ok ? 1 : 0;
   if (!ok)
