@@ -12,6 +12,8 @@
 //   phase 4  warp backward per pixel of P: d/d depth_A, d/d pose (12 sums) and the per-pixel
 //            d/d translation field  K^T g_p.
 // Smoothness gradient from the saved per-image mean and loss.  Deterministic reductions.
+#include <type_traits>
+
 #include "motion_device.cuh"
 
 namespace sde {
@@ -222,7 +224,9 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
     }
     __syncthreads();
     // ---------------------------------------------------------------- phase 3: adjoint -> gS_c on P
-    {
+    // instantiated twice: tiles on the left / right image border add the mirrored pad column (block-uniform)
+    auto phase3 = [&](auto lr_tag) {
+      constexpr bool LR = decltype(lr_tag)::value;
       f2 hq[3][2];
 #pragma unroll
       for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
           for (int k = 0; k < 3; ++k) {
             const Row4 q = ld_row(planes + (kNCoef + k) * kPlane + plane_index(r0 + rr, c0));
             f2 hsum = (q.c + swp(q.c)) + q.o;
-            if (lr_border) hsum = hsum + mk2(eL0 * lo(q.o) + eR0 * hi(q.c), eL1 * lo(q.c) + eR1 * hi(q.o));
+            if (LR) hsum = hsum + mk2(eL0 * lo(q.o) + eR0 * hi(q.c), eL1 * lo(q.c) + eR1 * hi(q.o));
             nq[k] = hsum;
           }
         }
@@ -251,12 +255,13 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
             const f2 Up = ld2(planes + kNU * kPlane + pl);
             gS = Up * fma2(Sp, vb, fma2(Ap, vc, va));
           }
-          // rgb L1 on the pixel itself: occlusion * sign(S - A)
+          // rgb L1 on the pixel itself: occlusion * sign(S - A) (branch-free)
           const uchar2 m = *reinterpret_cast<const uchar2*>(sh.occ + pl);
           const f2 df = Sp - Ap;
           const float d0 = lo(df), d1v = hi(df);
-          const float l0 = m.x ? (d0 > 0.0f ? g_l1 : (d0 < 0.0f ? -g_l1 : 0.0f)) : 0.0f;
-          const float l1 = m.y ? (d1v > 0.0f ? g_l1 : (d1v < 0.0f ? -g_l1 : 0.0f)) : 0.0f;
+          float l0 = d0 > 0.0f ? g_l1 : -g_l1, l1 = d1v > 0.0f ? g_l1 : -g_l1;
+          l0 = (m.x && d0 != 0.0f) ? l0 : 0.0f;
+          l1 = (m.y && d1v != 0.0f) ? l1 : 0.0f;
           gS = gS + mk2(l0, l1);
           *reinterpret_cast<unsigned long long*>(planes + (kNG + c) * kPlane + pl) = gS.v;
         }
@@ -265,7 +270,9 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
           for (int k = 0; k < 3; ++k) { hq[k][0] = hq[k][1]; hq[k][1] = nq[k]; }
         }
       }
-    }
+    };
+    if (lr_border) phase3(std::true_type{});
+    else           phase3(std::false_type{});
     __syncthreads();
   }
 
