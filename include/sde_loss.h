@@ -258,6 +258,17 @@ int sde_smoothness_backward(const sde_smooth_desc* desc, const sde_smooth_buffer
 int sde_resize_bilinear(const float* src, float* dst, int32_t planes, int32_t src_h, int32_t src_w, int32_t dst_h,
                         int32_t dst_w, void* stream);
 
+/* The image pyramid of a training step in one launch: resize_img (camera.py:40-46) of `n_frames` frames (the target
+ * and every source, MonoDepth2.py:82,88) [planes,src_h,src_w] to `n_levels` sizes each; dst[f][l] = [planes,dst_h[l],dst_w[l]].
+ * n_frames <= SDE_MAX_SOURCES + 1, n_levels <= SDE_MAX_SCALES.  Same arithmetic as sde_resize_bilinear. */
+typedef struct sde_pyramid_buffers {
+  const float* src[SDE_MAX_SOURCES + 1];
+  float* dst[SDE_MAX_SOURCES + 1][SDE_MAX_SCALES];
+} sde_pyramid_buffers;
+
+int sde_resize_pyramid(int32_t n_frames, int32_t planes, int32_t src_h, int32_t src_w, int32_t n_levels,
+                       const int32_t* dst_h, const int32_t* dst_w, const sde_pyramid_buffers* buf, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * MotionLearning regularisers, detectron2/modeling/losses/motion_loss.py (callers
  * MotionLearning.py:188-220).

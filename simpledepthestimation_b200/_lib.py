@@ -5,6 +5,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
+ABI_VERSION = 2   # SDE_ABI_VERSION of include/sde_loss.h this binding was written against
 MAX_SCALES = 6
 MAX_SOURCES = 4
 FLAG_AUTOMASK = 1
@@ -131,6 +132,10 @@ class PoseVecBuffers(C.Structure):
     _fields_ = [(n, _f32p) for n in ("vec", "pose", "grad_pose", "grad_vec")]
 
 
+class PyramidBuffers(C.Structure):
+    _fields_ = [("src", _f32p * (MAX_SOURCES + 1)), ("dst", (_f32p * MAX_SCALES) * (MAX_SOURCES + 1))]
+
+
 class SdeError(RuntimeError):
     pass
 
@@ -154,6 +159,8 @@ def load():
                        "(there is no CPU or PyTorch fallback)")
     lib = C.CDLL(path)
     lib.sde_version.restype = C.c_int
+    if lib.sde_version() != ABI_VERSION:
+        raise SdeError(f"libsde_loss.so has ABI version {lib.sde_version()}, the binding expects {ABI_VERSION}: rebuild it")
     lib.sde_strerror.restype = C.c_char_p
     lib.sde_strerror.argtypes = [C.c_int]
     lib.sde_last_cuda_error.restype = C.c_char_p
@@ -202,6 +209,9 @@ def load():
     lib.sde_resize_bilinear.restype = C.c_int
     lib.sde_resize_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p]
+    lib.sde_resize_pyramid.restype = C.c_int
+    lib.sde_resize_pyramid.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32), C.POINTER(PyramidBuffers), C.c_void_p]
     _lib = lib
     return lib
 

@@ -533,4 +533,40 @@ cudaError_t launch_resize_bilinear(const float* src, float* dst, int planes, int
   return cudaGetLastError();
 }
 
+// The image pyramid of a step (MonoDepth2.py:82,88: the target and every source frame resized to every coarser
+// prediction size) in ONE launch: blockIdx.x walks the pixel blocks of all levels, .y the planes, .z the frames.
+__global__ void __launch_bounds__(kOpThreads) resize_pyramid_kernel(const __grid_constant__ PyramidParams p) {
+  int l = 0;
+  while (l + 1 < p.n_levels && (int)blockIdx.x >= p.blk_start[l + 1]) ++l;
+  const int dh = p.dh[l], dw = p.dw[l], sh = p.sh, sw = p.sw;
+  const int pix = ((int)blockIdx.x - p.blk_start[l]) * kOpThreads + threadIdx.x;
+  if (pix >= dh * dw) return;
+  const int y = pix / dw, x = pix - y * dw;
+  const float fy = p.rh[l] * (float)y, fx = p.rw[l] * (float)x;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int yp = y0 < sh - 1 ? 1 : 0, xp = x0 < sw - 1 ? 1 : 0;
+  const float ly1 = fy - (float)y0, ly0 = 1.0f - ly1, lx1 = fx - (float)x0, lx0 = 1.0f - lx1;
+  const float* __restrict__ src = p.src[blockIdx.z];
+  float* __restrict__ dst = p.dst[blockIdx.z][l];
+  for (int pl = blockIdx.y; pl < p.planes; pl += gridDim.y) {
+    const float* s = src + (size_t)pl * sh * sw + (size_t)y0 * sw + x0;
+    const float v00 = __ldg(s), v01 = __ldg(s + xp), v10 = __ldg(s + yp * sw), v11 = __ldg(s + yp * sw + xp);
+    dst[(size_t)pl * dh * dw + pix] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);   // same order as above
+  }
+}
+
+cudaError_t launch_resize_pyramid(PyramidParams& p, cudaStream_t stream) {
+  int start = 0;
+  for (int l = 0; l < p.n_levels; ++l) {
+    p.blk_start[l] = start;
+    start += (p.dh[l] * p.dw[l] + kOpThreads - 1) / kOpThreads;
+    p.rh[l] = p.dh[l] > 1 ? (float)(p.sh - 1) / (float)(p.dh[l] - 1) : 0.0f;
+    p.rw[l] = p.dw[l] > 1 ? (float)(p.sw - 1) / (float)(p.dw[l] - 1) : 0.0f;
+  }
+  p.blk_start[p.n_levels] = start;
+  const dim3 grid(start, p.planes < 65535 ? p.planes : 65535, p.n_frames);
+  resize_pyramid_kernel<<<grid, kOpThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace sde

@@ -2,6 +2,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "../../include/sde_loss.h"
+
 namespace sde {
 
 struct VsParams {
@@ -98,6 +100,17 @@ struct VarParams {   // variance_loss
   float* g_depth;
   float* slots;             // [blocks]
   unsigned* counters;       // [1]
+};
+
+constexpr int kPyrFrames = SDE_MAX_SOURCES + 1;   // target + sources
+
+struct PyramidParams {   // resize_img of several frames to several sizes, one launch
+  int n_frames, n_levels, planes, sh, sw;
+  int dh[SDE_MAX_SCALES], dw[SDE_MAX_SCALES];
+  int blk_start[SDE_MAX_SCALES + 1];   // first pixel block of level l
+  float rh[SDE_MAX_SCALES], rw[SDE_MAX_SCALES];
+  const float* src[kPyrFrames];
+  float* dst[kPyrFrames][SDE_MAX_SCALES];
 };
 
 struct SilogParams {   // silog_loss

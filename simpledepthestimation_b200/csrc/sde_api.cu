@@ -21,6 +21,7 @@ cudaError_t launch_ssim_bwd(const SsimParams& p, cudaStream_t stream);
 cudaError_t launch_smooth_fwd(const SmoothParams& p, cudaStream_t stream);
 cudaError_t launch_smooth_bwd(const SmoothParams& p, cudaStream_t stream);
 cudaError_t launch_resize_bilinear(const float* src, float* dst, int planes, int sh, int sw, int dh, int dw, cudaStream_t stream);
+cudaError_t launch_resize_pyramid(PyramidParams& p, cudaStream_t stream);
 cudaError_t launch_mcons_fwd(const McParams& p, cudaStream_t stream);
 cudaError_t launch_mcons_bwd(const McParams& p, float* g_t_ba, cudaStream_t stream);
 cudaError_t launch_mreg(int which, const MregParams& p, cudaStream_t stream);
@@ -593,6 +594,29 @@ int sde_resize_bilinear(const float* src, float* dst, int32_t planes, int32_t sr
                         int32_t dst_w, void* stream) {
   if (!src || !dst || planes < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return SDE_ERR_INVALID_ARG;
   SDE_LAUNCH(launch_resize_bilinear(src, dst, planes, src_h, src_w, dst_h, dst_w, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_resize_pyramid(int32_t n_frames, int32_t planes, int32_t src_h, int32_t src_w, int32_t n_levels,
+                       const int32_t* dst_h, const int32_t* dst_w, const sde_pyramid_buffers* buf, void* stream) {
+  if (!buf || !dst_h || !dst_w || n_frames < 1 || n_frames > kPyrFrames || n_levels < 1 || n_levels > SDE_MAX_SCALES ||
+      planes < 1 || src_h < 1 || src_w < 1)
+    return SDE_ERR_INVALID_ARG;
+  PyramidParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_frames = n_frames; p.n_levels = n_levels; p.planes = planes; p.sh = src_h; p.sw = src_w;
+  for (int l = 0; l < n_levels; ++l) {
+    if (dst_h[l] < 1 || dst_w[l] < 1) return SDE_ERR_INVALID_ARG;
+    p.dh[l] = dst_h[l]; p.dw[l] = dst_w[l];
+  }
+  for (int f = 0; f < n_frames; ++f) {
+    if (!buf->src[f]) return SDE_ERR_INVALID_ARG;
+    p.src[f] = buf->src[f];
+    for (int l = 0; l < n_levels; ++l) {
+      if (!buf->dst[f][l]) return SDE_ERR_INVALID_ARG;
+      p.dst[f][l] = buf->dst[f][l];
+    }
+  }
+  SDE_LAUNCH(launch_resize_pyramid(p, static_cast<cudaStream_t>(stream)));
 }
 
 size_t sde_motion_consistency_workspace_bytes(const sde_mcons_desc* desc) { return mcons_ok(desc) ? mcons_layout(desc).total : 0; }

@@ -234,8 +234,8 @@ class HostLossRunner:
     finish() waits for the last step and returns its host results."""
 
     def __init__(self, plan: MonoLossPlan, device, slots=2):
-        from .ops import resize_bilinear
-        self._resize = resize_bilinear
+        from .ops import resize_pyramid
+        self._pyramid = resize_pyramid
         self.plan, self.device = plan, torch.device(device)
         B, S = plan.batch, plan.n_sources
         H, W = plan.full_size
@@ -264,8 +264,8 @@ class HostLossRunner:
         outs = [self.losses] + self.grad_depth + self.grad_pose
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in outs)
         self._i = 0
-        # kernels per step: pyramid (3 frames x coarse scales), warp + loss forward, backward
-        self.launches_per_step = (1 + S) * (len(plan.sizes) - 1) + (2 if plan.save_warped else 1) + 1
+        # kernels per step: pyramid (all frames and coarse scales in one launch), warp + loss forward, backward
+        self.launches_per_step = (1 if len(plan.sizes) > 1 else 0) + (2 if plan.save_warped else 1) + 1
 
     @staticmethod
     def pin(host_set):
@@ -292,8 +292,9 @@ class HostLossRunner:
             sl["ready"].record()
         main.wait_event(sl["ready"])
         sizes = self.plan.sizes
-        target = [sl["img"] if tuple(s) == tuple(sl["img"].shape[-2:]) else self._resize(sl["img"], s) for s in sizes]
-        source = [[c if tuple(s) == tuple(c.shape[-2:]) else self._resize(c, s) for c in sl["ctx"]] for s in sizes]
+        pyr = self._pyramid([sl["img"]] + sl["ctx"], sizes)          # [frame][scale]
+        target = pyr[0]
+        source = [[pyr[1 + j][i] for j in range(len(sl["ctx"]))] for i in range(len(sizes))]
         self.plan.forward(target, source, sl["depth"], sl["K"], sl["pose"], out=self.losses, argmin_out=self.argmin,
                           warped=self.warped)
         self.plan.backward(target, source, sl["depth"], sl["K"], sl["pose"], self.argmin, self.ones, self.grad_depth,

@@ -9,6 +9,7 @@ import torch.nn as nn
 
 from ...functional import MonoLossPlan, mono_photometric_smoothness_loss
 from ...geometry.camera import resize_img, view_synthesis
+from ...ops import resize_pyramid
 from ...utils.memory import to_cuda
 from ..losses.losses import silog_loss, variance_loss
 from ..losses.ssim_loss import SSIM
@@ -74,9 +75,15 @@ class MonoDepth2Model(nn.Module):
             pose_pred = list(batch["pose_pred"])
             sizes = [tuple(d.shape[-2:]) for d in depth_pred]
 
-            # image pyramid (resize_img, MonoDepth2.py:82,88); sources resized once per scale
-            target = [resize_img(image, s) for s in sizes]
-            source = [[resize_img(c, s) for c in contexts] for s in sizes]
+            # image pyramid (resize_img, MonoDepth2.py:82,88): every frame to every scale in one launch
+            if image.is_cuda and image.dtype == torch.float32 and len(contexts) + 1 <= 5 and \
+                    all(c.shape == image.shape for c in contexts):
+                pyr = resize_pyramid([image] + list(contexts), sizes)
+                target = pyr[0]
+                source = [[pyr[1 + j][i] for j in range(len(contexts))] for i in range(len(sizes))]
+            else:
+                target = [resize_img(image, s) for s in sizes]
+                source = [[resize_img(c, s) for c in contexts] for s in sizes]
 
             plan = self._plan(image.shape[0], sizes, len(contexts), tuple(image.shape[-2:]))
             rec, smooth, _ = mono_photometric_smoothness_loss(plan, target, source, list(depth_pred),

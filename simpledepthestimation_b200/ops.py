@@ -224,6 +224,34 @@ def resize_bilinear(image: torch.Tensor, dst_size) -> torch.Tensor:
     return out
 
 
+def resize_pyramid(frames, sizes):
+    """resize_img of every frame in `frames` (CUDA fp32 [..., H, W], all the same shape) to every size in `sizes`, in
+    one launch.  Returns out[f][l]; a size equal to the source size returns the frame itself (camera.py:41-42)."""
+    lib = _lib.load()
+    frames = [_cuda_f32(f, "frame") for f in frames]
+    sh, sw = frames[0].shape[-2:]
+    if any(f.shape != frames[0].shape for f in frames):
+        raise _lib.SdeError("resize_pyramid: frames must share one shape")
+    levels = [(int(s[-2]), int(s[-1])) for s in sizes if (int(s[-2]), int(s[-1])) != (sh, sw)]
+    if len(frames) > _lib.MAX_SOURCES + 1 or len(levels) > _lib.MAX_SCALES:
+        raise _lib.SdeError("resize_pyramid: too many frames / levels")
+    out = {}
+    if levels:
+        planes = frames[0].numel() // (sh * sw)
+        b = _lib.PyramidBuffers()
+        for f, fr in enumerate(frames):
+            b.src[f] = fr.data_ptr()
+            for l, (dh, dw) in enumerate(levels):
+                out[f, (dh, dw)] = torch.empty(*fr.shape[:-2], dh, dw, device=fr.device)
+                b.dst[f][l] = out[f, (dh, dw)].data_ptr()
+        dh = (C.c_int32 * len(levels))(*[s[0] for s in levels])
+        dw = (C.c_int32 * len(levels))(*[s[1] for s in levels])
+        _lib.check(lib.sde_resize_pyramid(len(frames), planes, sh, sw, len(levels), dh, dw, C.byref(b), _stream()),
+                   "sde_resize_pyramid")
+    return [[fr if (int(s[-2]), int(s[-1])) == (sh, sw) else out[f, (int(s[-2]), int(s[-1]))] for s in sizes]
+            for f, fr in enumerate(frames)]
+
+
 # ------------------------------------------------------------------------------------------------ motion regularisers
 class _MotionConsistencyFn(torch.autograd.Function):
     @staticmethod

@@ -28,7 +28,9 @@ def test_library_exports_every_declared_symbol(sde_lib):
 
 
 def test_version_and_strerror(sde_lib):
-    assert sde_lib.sde_version() == 2
+    from simpledepthestimation_b200 import _lib
+
+    assert sde_lib.sde_version() == _lib.ABI_VERSION == 2
     assert sde_lib.sde_strerror(0) == b"ok"
     assert b"invalid" in sde_lib.sde_strerror(-1)
     assert sde_lib.sde_last_cuda_error() == b""
@@ -101,3 +103,12 @@ def test_product_does_not_import_oracle():
                 with open(os.path.join(dirpath, f)) as fh:
                     src = fh.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_graft_entry_build_runs_without_a_gpu():
+    """__graft_entry__.build() is the driver's "does it build" check: it must compile, load and version-check the library."""
+    import importlib
+    import sys
+
+    sys.path.insert(0, ROOT)
+    importlib.import_module("__graft_entry__").build()

@@ -406,3 +406,21 @@ def test_disp_to_depth_and_pose_vec2mat(sde_lib):
     torch.cuda.synchronize()
     assert rel_err(T.detach(), g["pose_mat"]) < 1e-6
     assert rel_err(vec.grad, g["pose_grad"]) < 1e-5
+
+
+def test_resize_pyramid_matches_resize_img(sde_lib):
+    """The one-launch pyramid (target + sources to every prediction size, MonoDepth2.py:82,88) gives the bits of
+    resize_img frame by frame and passes full-size frames through."""
+    from simpledepthestimation_b200.geometry.camera import resize_img
+    from simpledepthestimation_b200.ops import resize_pyramid
+
+    gen = torch.Generator().manual_seed(3)
+    frames = [torch.rand(2, 3, 50, 70, generator=gen).to(DEV) for _ in range(3)]
+    sizes = [(50, 70), (25, 35), (13, 18), (7, 9)]
+    pyr = resize_pyramid(frames, sizes)
+    for f, fr in enumerate(frames):
+        assert pyr[f][0] is fr
+        for l, s in enumerate(sizes[1:], 1):
+            assert torch.equal(pyr[f][l], resize_img(fr, s))
+            ref = F.interpolate(fr.cpu(), size=s, mode="bilinear", align_corners=True)
+            assert float((pyr[f][l].cpu() - ref).abs().max()) < 2e-6
