@@ -176,8 +176,9 @@ __device__ __forceinline__ void tile_smoothness(const float* planes, int plD, in
     // Halo'd rows r0 .. r0+5 (owned rows: r0+1 .. r0+4); columns c0 (left neighbour) .. c0+3 (right neighbour).
     const float* pd = planes + plD * kPlane + plane_index(r0, c0 + 1);
     const float* pa = planes + plA * kPlane + plane_index(r0, c0 + 1);
-    // 1 / clamp(d, min=1e-6); the comparison form keeps a NaN depth NaN, as torch.clamp does
-    auto inv = [](float d) { return 1.0f / (d < 1e-6f ? 1e-6f : d); };
+    // 1 / clamp(d, min=1e-6) through a refined hardware reciprocal (<= 1 ulp; NaN stays NaN), exp through ex2.approx
+    // (2 ulp): both far inside the 1e-5 loss tolerance and a fifth of the instructions of the IEEE forms
+    auto inv = [](float d) { return inv_depth(d); };
     auto sgn = [](float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); };
     const float inx = 1.0f / ((float)B * (float)h * (float)(w - 1));
     const float iny = 1.0f / ((float)B * (float)(h - 1) * (float)w);
@@ -185,8 +186,10 @@ __device__ __forceinline__ void tile_smoothness(const float* planes, int plD, in
     const bool pair_ok = (w & 1) == 0 && (reinterpret_cast<uintptr_t>(gout) & 7) == 0;   // gx0 is even
     // vertical edges between halo'd rows rr and rr + 1 (image rows gyu, gyu + 1): signed gradient terms
     float tv0[kRowsPerWarp + 1], tv1[kRowsPerWarp + 1];
+    float ir0[kRowsPerWarp + 2], ir1[kRowsPerWarp + 2];   // inverse depths of this lane's pair in the halo'd rows
     f2 du = ld2(pd);
     float iu0 = inv(lo(du)), iu1 = inv(hi(du));
+    ir0[0] = iu0; ir1[0] = iu1;
     f2 au[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) au[c] = ld2(pa + c * kPlane);
@@ -195,6 +198,7 @@ __device__ __forceinline__ void tile_smoothness(const float* planes, int plD, in
       const int gyu = y0 + r0 + rr - 1;
       const f2 dl = ld2(pd + (rr + 1) * kPitch);
       const float il0 = inv(lo(dl)), il1 = inv(hi(dl));
+      ir0[rr + 1] = il0; ir1[rr + 1] = il1;
       float e0 = 0.0f, e1 = 0.0f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -204,7 +208,7 @@ __device__ __forceinline__ void tile_smoothness(const float* planes, int plD, in
         au[c] = al;
       }
       const bool ve = gyu >= 0 && gyu + 1 < h;
-      const float w0 = expf(-e0 * (1.0f / 3.0f)), w1 = expf(-e1 * (1.0f / 3.0f));
+      const float w0 = __expf(-e0 * (1.0f / 3.0f)), w1 = __expf(-e1 * (1.0f / 3.0f));
       tv0[rr] = (ve && v0) ? sgn(iu0 - il0) * w0 * iny : 0.0f;
       tv1[rr] = (ve && v1) ? sgn(iu1 - il1) * w1 * iny : 0.0f;
       if (rr >= 1) {   // the edge below an owned row is counted by this lane
@@ -217,8 +221,7 @@ __device__ __forceinline__ void tile_smoothness(const float* planes, int plD, in
     for (int o = 0; o < kRowsPerWarp; ++o) {
       const int gy = y0 + r0 + o;
       const float* pdo = pd + (o + 1) * kPitch;
-      const f2 dc = ld2(pdo);
-      const float iL = inv(pdo[-1]), i0 = inv(lo(dc)), i1 = inv(hi(dc)), iR = inv(pdo[2]);
+      const float iL = inv(pdo[-1]), i0 = ir0[o + 1], i1 = ir1[o + 1], iR = inv(pdo[2]);
       float eL = 0.0f, eM = 0.0f, eR = 0.0f;  // sum_c |dI|
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -230,7 +233,7 @@ __device__ __forceinline__ void tile_smoothness(const float* planes, int plD, in
         eR += fabsf(a1 - aR);
       }
       if (gy < h) {
-        const float wL = expf(-eL * (1.0f / 3.0f)), wM = expf(-eM * (1.0f / 3.0f)), wR = expf(-eR * (1.0f / 3.0f));
+        const float wL = __expf(-eL * (1.0f / 3.0f)), wM = __expf(-eM * (1.0f / 3.0f)), wR = __expf(-eR * (1.0f / 3.0f));
         if (v0) sinv += i0;
         if (v1) sinv += i1;
         if (v1) smx += fabsf(i0 - i1) * wM;
