@@ -8,10 +8,11 @@ import torch
 import torch.nn as nn
 
 from ...functional import MonoLossPlan, mono_photometric_smoothness_loss
-from ...geometry.camera import resize_img, view_synthesis
+from ...geometry.camera import resize_img, scale_intrinsics, view_synthesis
 from ...ops import resize_pyramid
 from ...utils.memory import to_cuda
 from ..losses.losses import silog_loss, variance_loss
+from ..losses.smoothness_loss import smoothness_loss
 from ..losses.ssim_loss import SSIM
 from ..nets import build_depth_net, build_pose_net
 from .build import META_ARCH_REGISTRY
@@ -34,9 +35,9 @@ class MonoDepth2Model(nn.Module):
         self.smooth_loss_w = cfg.LOSS.SMOOTHNESS_WEIGHT
         if self.photometric_reduce not in ("min", "mean"):
             raise NotImplementedError(self.photometric_reduce)
-        if self.clip_loss > 0.0:
-            # off in every shipped config (Base.yaml:8); the per-batch mean + CLIP * std cap is not part of the fused path
-            raise NotImplementedError("LOSS.CLIP > 0 is not supported by the fused B200 loss path")
+        # LOSS.CLIP > 0 (off in every shipped config, Base.yaml:8) caps every photometric map at its own mean + CLIP * std
+        # (MonoDepth2.py:146-149), a global statistic per map with a host read: that configuration runs the reference's
+        # loop over the stand-alone CUDA operators (_unfused_losses) instead of the fused kernels
         self.supervise_loss = silog_loss(cfg.LOSS.VARIANCE_FOCUS)
 
         self.register_buffer("pixel_mean", torch.Tensor(cfg.MODEL.PIXEL_MEAN).view(1, -1, 1, 1))
@@ -85,9 +86,13 @@ class MonoDepth2Model(nn.Module):
                 target = [resize_img(image, s) for s in sizes]
                 source = [[resize_img(c, s) for c in contexts] for s in sizes]
 
-            plan = self._plan(image.shape[0], sizes, len(contexts), tuple(image.shape[-2:]))
-            rec, smooth, _ = mono_photometric_smoothness_loss(plan, target, source, list(depth_pred),
-                                                              batch["intrinsics"].float(), pose_pred)
+            if self.clip_loss > 0.0:
+                rec, smooth = self._unfused_losses(target, source, list(depth_pred), batch["intrinsics"].float(),
+                                                   pose_pred, tuple(image.shape[-2:]))
+            else:
+                plan = self._plan(image.shape[0], sizes, len(contexts), tuple(image.shape[-2:]))
+                rec, smooth, _ = mono_photometric_smoothness_loss(plan, target, source, list(depth_pred),
+                                                                  batch["intrinsics"].float(), pose_pred)
             output["rec_loss"] = rec
             if self.smooth_loss_w > 0.0:
                 output["smooth_loss"] = smooth
@@ -104,6 +109,28 @@ class MonoDepth2Model(nn.Module):
             output["depth_pred"] = batch["depth_pred"][0]
         return output
 
+    def _unfused_losses(self, target, source, depth_pred, intrinsics, pose_pred, full_size):
+        """The loss loop of MonoDepth2.py:78-121 over the stand-alone CUDA operators (view_synthesis, SSIM,
+        smoothness_loss); torch only concatenates, reduces and clips.  Used when LOSS.CLIP > 0."""
+        n = len(depth_pred)
+        H, W = full_size
+        rec, smooth = 0.0, 0.0
+        for i, d in enumerate(depth_pred):
+            h, w = d.shape[-2:]
+            K = scale_intrinsics(intrinsics.clone(), w / W, h / H)
+            cand = []
+            for src, T in zip(source[i], pose_pred):
+                cand.append(self.rgb_consistency_loss(target[i], src, d, K, T[:, :3, :3].contiguous(), T[:, :3, 3:, None]))
+                if self.use_automask:
+                    cand.append(self.rgb_consistency_loss(target[i], src, d, K, None, None))
+            if self.photometric_reduce == "mean":
+                rec = rec + sum(c.mean() for c in cand) / len(cand) / n
+            else:
+                rec = rec + torch.cat(cand, 1).min(1, True)[0].mean() / n
+            if self.smooth_loss_w > 0.0:
+                smooth = smooth + smoothness_loss(d, target[i]) * (1.0 / 2 ** (n - i - 1)) * self.smooth_loss_w / n
+        return rec, smooth
+
     def rgb_consistency_loss(self, frame_A, frame_B, depth_A, intrinsics, R_A2B=None, t_A2B=None):
         """Photometric error of one (scale, source) pair, [B,1,H,W] (MonoDepth2.py:130-151): the un-fused
         form of what forward() computes inside the fused kernels -- view_synthesis + SSIM as two CUDA
@@ -117,4 +144,6 @@ class MonoDepth2Model(nn.Module):
         loss = (sampled - frame_A).abs().mean(1, True)
         if self.ssim_loss_weight > 0.0:
             loss = self.ssim(sampled, frame_A).mean(1, True) * self.ssim_loss_weight + loss * (1 - self.ssim_loss_weight)
+        if self.clip_loss > 0.0:   # MonoDepth2.py:146-149 (the float() is the reference's host read)
+            loss = torch.clamp(loss, max=float((loss.mean() + self.clip_loss * loss.std()).detach()))
         return loss

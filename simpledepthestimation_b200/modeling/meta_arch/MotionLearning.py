@@ -13,10 +13,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ...functional import MotionLossPlan, motion_rgbd_smoothness_loss
-from ...geometry.camera import resize_img_avgpool, view_synthesis
+from ...geometry.camera import resize_img, resize_img_avgpool, scale_intrinsics, view_synthesis
 from ...utils.memory import to_cuda
 from ..losses.motion_loss import motion_consistency_loss, motion_smoothness_loss_fn, motion_sparsity_loss_fn
-from ..losses.losses import variance_loss
+from ..losses.losses import silog_loss, variance_loss
 from ..losses.ssim_loss import WeightedSSIM
 from ..nets import build_depth_net, build_pose_net
 from .build import META_ARCH_REGISTRY
@@ -52,10 +52,9 @@ class MotionLearningModel(nn.Module):
         self.with_mask = cfg.MODEL.get("WITH_MASK", False)
         self.mask_dilation = cfg.MODEL.get("MASK_DILATION", 8)
         self.return_loss = cfg.MODEL.get("RETURN_LOSS", False)
-        if self.depth_l1_loss_w > 0 or self.sup_loss_w > 0.0:
-            # 0 in every shipped config (projects/MotionLearning/configs/Base.yaml:11-26)
-            raise NotImplementedError("LOSS.DEPTH_L1_WEIGHT / SUPERVISED_WEIGHT > 0 are not "
-                                      "supported by the fused B200 loss path")
+        # DEPTH_L1_WEIGHT / SUPERVISED_WEIGHT are 0 in every shipped config (projects/MotionLearning/configs/Base.yaml:11-26);
+        # when set, their terms are added next to the fused loss from the stand-alone CUDA operators
+        self.supervise_loss = silog_loss(cfg.LOSS.VARIANCE_FOCUS)
 
         self.register_buffer("pixel_mean", torch.Tensor(cfg.MODEL.PIXEL_MEAN).view(1, -1, 1, 1))
         self.register_buffer("pixel_std", torch.Tensor(cfg.MODEL.PIXEL_STD).view(1, -1, 1, 1))
@@ -160,12 +159,29 @@ class MotionLearningModel(nn.Module):
                     if self.motion_sparsity_loss_w > 0.0:
                         losses["motion_sparsity_loss"] += motion_sparsity_loss_fn(mn) * scale_w * self.motion_sparsity_loss_w
 
+            if self.depth_l1_loss_w > 0:   # MotionLearning.py:264-267, both directions (:166-176)
+                Ki = scale_intrinsics(K.clone(), scale_w, scale_w)
+                for fb, da, db, R, t in ((f2, d1, d2, R12, t12), (f1, d2, d1, R21, t21)):
+                    losses["depth_l1_loss"] += self._depth_l1_loss(fb, da, db, Ki, R.contiguous(), t.contiguous()) * scale_w
+            if self.sup_loss_w > 0.0:   # MotionLearning.py:222-229 (on the un-normalised resized depths)
+                r1, r2 = resize_img_avgpool(depth1[0], (H, W)), resize_img_avgpool(depth2[0], (H, W))
+                g1 = resize_img(batch["depth"], (H, W), mode="nearest")
+                g2 = resize_img(batch["ctx_depth"][0], (H, W), mode="nearest")
+                losses["sup_loss"] += (self.supervise_loss(r1, g1) + self.supervise_loss(r2, g2)) * scale_w * self.sup_loss_w
             if self.var_loss_w > 0.0:   # MotionLearning.py:237-239 (on the un-normalised resized depths)
                 r1, r2 = resize_img_avgpool(depth1[0], (H, W)), resize_img_avgpool(depth2[0], (H, W))
                 losses["var_loss"] += (variance_loss(r1) + variance_loss(r2)) * scale_w * self.var_loss_w
 
         batch.update(losses)
         return batch
+
+    def _depth_l1_loss(self, frame_B, depth_A, depth_B, intrinsics, R_A2B, t_A2B):
+        """depth_l1_loss of one direction (MotionLearning.py:264-267) from the view_synthesis operator."""
+        sampled, depth_in_B, _, valid = view_synthesis(torch.cat([frame_B, depth_B], 1), depth_A, intrinsics, R_A2B, t_A2B)
+        sampled_depth_B = sampled[:, 3:4]
+        occ = (depth_in_B < sampled_depth_B).float() * valid.float()
+        l1 = (sampled_depth_B.detach() - depth_in_B).abs() * occ
+        return (l1.sum([1, 2, 3]) / (occ.sum([1, 2, 3]) + 1)).mean() * self.depth_l1_loss_w
 
     def rgbd_consistency_loss(self, frame_A, frame_B, depth_A, depth_B, intrinsics, R_A2B, t_A2B):
         """One direction of the rgb-d consistency loss as a dict (MotionLearning.py:248-291): the un-fused form
@@ -179,6 +195,9 @@ class MotionLearningModel(nn.Module):
         occ = (depth_in_B < sampled_depth_B).float() * valid.float()
         out["occlusion_mask"] = occ
         normalizer = occ.sum([1, 2, 3]) + 1
+        if self.depth_l1_loss_w > 0:
+            l1 = (sampled_depth_B.detach() - depth_in_B).abs() * occ
+            out["depth_l1_loss"] = (l1.sum([1, 2, 3]) / normalizer).mean() * self.depth_l1_loss_w
         out["rgb_l1_loss"] = ((sampled_frame_B - frame_A).abs() * occ).mean()
         if self.ssim_loss_w > 0.0:
             err = (depth_in_B - sampled_depth_B) ** 2

@@ -300,3 +300,33 @@ def test_motion_model_matches_reference_golden(registered, with_motion, tag):
     w12, w21 = out["depth_proximity_weight"][0]
     assert float((w12.cpu() - f(f"weight12{tag}")).abs().max()) < 1e-3
     assert float((w21.cpu() - f(f"weight21{tag}")).abs().max()) < 1e-3
+
+
+def test_depth_l1_and_supervised_terms(registered):
+    """LOSS.DEPTH_L1_WEIGHT > 0 (MotionLearning.py:264-267) and LOSS.SUPERVISED_WEIGHT > 0 (:222-229) add their terms
+    next to the fused loss; values and the depth gradient of the summed losses against the oracle."""
+    from simpledepthestimation_b200.modeling import build_model
+
+    inp = motion_inputs(2, 32, 64, seed=3)
+    gen = torch.Generator().manual_seed(5)
+    gt1, gt2 = torch.rand(2, 1, 32, 64, generator=gen) * 60, torch.rand(2, 1, 32, 64, generator=gen) * 60
+    model = build_model(motion_cfg(DEPTH_L1_WEIGHT=0.3, SUPERVISED_WEIGHT=0.5)).train()
+    dev = model.device
+    d1, d2 = inp["depth1"].to(dev).requires_grad_(), inp["depth2"].to(dev).requires_grad_()
+    model.depth_net.payload = {"depth_pred": [torch.cat([d1, d2], 0)]}
+    model.pose_net.payload = {"pose_pred": euler_pose(inp["pose_vec"]).to(dev), "motion_pred": inp["motion"].to(dev)}
+    out = model({"img": inp["img1"], "ctx_img": [inp["img2"]], "intrinsics": inp["K"], "depth": gt1, "ctx_depth": [gt2]})
+    keys = sorted(k for k in out if "loss" in k)
+    assert "depth_l1_loss" in keys and "sup_loss" in keys
+    sum(out[k] for k in keys).backward()
+
+    r1, r2 = inp["depth1"].double().requires_grad_(), inp["depth2"].double().requires_grad_()
+    ref = port.motion_loss(inp["img1"].double(), inp["img2"].double(), r1, r2, inp["K"].double(),
+                           euler_pose(inp["pose_vec"].double()), inp["motion"].double(), depth_l1_w=0.3)
+    ref["sup_loss"] = (port.silog_loss(r1, gt1.double(), 0.85) + port.silog_loss(r2, gt2.double(), 0.85)) * 0.5
+    for k in keys:
+        assert abs(float(out[k]) - float(ref[k])) <= 2e-5 * abs(float(ref[k])), k
+    sum(ref[k] for k in keys).backward()
+    for got, want in ((d1.grad, r1.grad), (d2.grad, r2.grad)):
+        err = (got.double().cpu() - want).abs() / want.abs().max()
+        assert float(torch.quantile(err.flatten(), 0.99)) < 1e-4 and float(err.max()) < 1e-2
