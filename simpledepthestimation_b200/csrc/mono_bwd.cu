@@ -225,13 +225,14 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       __syncthreads();
       // -------------------------------------------------------------- phase 3: adjoint gather -> gS_c on P
       // instantiated twice: tiles on the left / right image border add the mirrored pad column (block-uniform)
-      auto phase3 = [&](auto lr_tag) {
+      auto phase3 = [&](auto lr_tag, auto ssim_tag) {
         constexpr bool LR = decltype(lr_tag)::value;
+        constexpr bool SSIM = decltype(ssim_tag)::value;   // compile-time: no control-flow joins inside the unrolled rows
         f2 hq[3][2];  // horizontal 3-sums of a, b, c for the two previous coefficient rows
 #pragma unroll
         for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
           f2 nq[3];
-          if (use_ssim) {
+          if (SSIM) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
               const Row4 q = ld_row(planes + (kBCoef + k) * kPlane + plane_index(r0 + rr, c0));
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
             const f2 Sp = ld2(planes + (kBS + c) * kPlane + plane_index(row, c0 + 1));
             const f2 Ap = ld2(planes + (kBA + c) * kPlane + plane_index(row, c0 + 1));
             f2 gS = bc2(0.0f);
-            if (use_ssim) {
+            if (SSIM) {
               const f2 va = fma2(wu, hq[0][0], fma2(wd, nq[0], hq[0][1]));
               const f2 vb = fma2(wu, hq[1][0], fma2(wd, nq[1], hq[1][1]));
               const f2 vc = fma2(wu, hq[2][0], fma2(wd, nq[2], hq[2][1]));
@@ -263,14 +264,19 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
             gS = gS + mk2(l0, l1);
             *reinterpret_cast<unsigned long long*>(planes + (kBG + c) * kPlane + plane_index(row, c0 + 1)) = gS.v;
           }
-          if (use_ssim) {
+          if (SSIM) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) { hq[k][0] = hq[k][1]; hq[k][1] = nq[k]; }
           }
         }
       };
-      if (lr_border) phase3(std::true_type{});
-      else           phase3(std::false_type{});
+      if (use_ssim) {
+        if (lr_border) phase3(std::true_type{}, std::true_type{});
+        else           phase3(std::false_type{}, std::true_type{});
+      } else {
+        if (lr_border) phase3(std::true_type{}, std::false_type{});
+        else           phase3(std::false_type{}, std::false_type{});
+      }
       __syncthreads();
     }
 

@@ -225,13 +225,14 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
     __syncthreads();
     // ---------------------------------------------------------------- phase 3: adjoint -> gS_c on P
     // instantiated twice: tiles on the left / right image border add the mirrored pad column (block-uniform)
-    auto phase3 = [&](auto lr_tag) {
+    auto phase3 = [&](auto lr_tag, auto ssim_tag) {
       constexpr bool LR = decltype(lr_tag)::value;
+      constexpr bool SSIM = decltype(ssim_tag)::value;   // compile-time: no control-flow joins inside the unrolled rows
       f2 hq[3][2];
 #pragma unroll
       for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
         f2 nq[3];
-        if (use_ssim) {
+        if (SSIM) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             const Row4 q = ld_row(planes + (kNCoef + k) * kPlane + plane_index(r0 + rr, c0));
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
           const f2 Sp = ld2(planes + (kNS + c) * kPlane + pl);
           const f2 Ap = ld2(planes + (kNA + c) * kPlane + pl);
           f2 gS = bc2(0.0f);
-          if (use_ssim) {
+          if (SSIM) {
             const f2 va = fma2(wu, hq[0][0], fma2(wd, nq[0], hq[0][1]));
             const f2 vb = fma2(wu, hq[1][0], fma2(wd, nq[1], hq[1][1]));
             const f2 vc = fma2(wu, hq[2][0], fma2(wd, nq[2], hq[2][1]));
@@ -265,14 +266,19 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
           gS = gS + mk2(l0, l1);
           *reinterpret_cast<unsigned long long*>(planes + (kNG + c) * kPlane + pl) = gS.v;
         }
-        if (use_ssim) {
+        if (SSIM) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) { hq[k][0] = hq[k][1]; hq[k][1] = nq[k]; }
         }
       }
     };
-    if (lr_border) phase3(std::true_type{});
-    else           phase3(std::false_type{});
+    if (use_ssim) {
+      if (lr_border) phase3(std::true_type{}, std::true_type{});
+      else           phase3(std::false_type{}, std::true_type{});
+    } else {
+      if (lr_border) phase3(std::true_type{}, std::false_type{});
+      else           phase3(std::false_type{}, std::false_type{});
+    }
     __syncthreads();
   }
 
