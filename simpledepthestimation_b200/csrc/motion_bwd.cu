@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
 #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
     // ---------------------------------------------------------------- phase 2: coefficients on Q
-    if (use_ssim) {
+    // instantiated per C1/C2 mode (ssim_loss.py:97-105): the unused SSIM factor and the mode switches are compiled out
+    auto phase2 = [&](auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
       const float* pa = planes + (kNA + c) * kPlane + plane_index(r0, c0);
       const float* px = planes + (kNS + c) * kPlane + plane_index(r0, c0);
       const float* pu = planes + kNU * kPlane + plane_index(r0, c0);
@@ -190,8 +192,8 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
           const f2 n2 = fma2(bc2(2.0f), sxy, C2), d2 = (sx + sy) + C2;
           const f2 n1 = fma2(bc2(2.0f), mx * my, C1), d1 = fma2(mx, mx, my * my) + C1;
           f2 N, D;
-          if (p.mode == 1) { N = n2; D = d2; }
-          else if (p.mode == 2) { N = n1; D = d1; }
+          if (MODE == 1) { N = n2; D = d2; }
+          else if (MODE == 2) { N = n1; D = d1; }
           else { N = n1 * n2; D = d1 * d2; }
           const f2 ssim = div2(N, D);
           const uchar2 in = *reinterpret_cast<const uchar2*>(sh.inside + plane_index(row, c0 + 1));
@@ -201,11 +203,11 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
           // d ssim / d x_p = U_p * base * [ ... ]  with  base = 2 g avg_w (inverse_avg_w / 9) / D
           const f2 base = div2((g * avgw[o]) * (k * bc2(2.0f)), D);
           f2 ca, cb, cc;
-          if (p.mode == 1) {
+          if (MODE == 1) {
             cc = base;
             cb = (base * ssim) * bc2(-1.0f);
             ca = (cb * mx + cc * my) * bc2(-1.0f);
-          } else if (p.mode == 2) {
+          } else if (MODE == 2) {
             cc = bc2(0.0f); cb = bc2(0.0f);
             ca = base * (my - ssim * mx);
           } else {
@@ -221,6 +223,11 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
         hX[0] = hX[1]; hX[1] = nX; hA[0] = hA[1]; hA[1] = nA;
         hXX[0] = hXX[1]; hXX[1] = nXX; hAA[0] = hAA[1]; hAA[1] = nAA; hXA[0] = hXA[1]; hXA[1] = nXA;
       }
+    };
+    if (use_ssim) {
+      if (p.mode == 1) phase2(std::integral_constant<int, 1>{});
+      else if (p.mode == 2) phase2(std::integral_constant<int, 2>{});
+      else phase2(std::integral_constant<int, 0>{});
     }
     __syncthreads();
     // ---------------------------------------------------------------- phase 3: adjoint -> gS_c on P
