@@ -321,3 +321,18 @@ def test_shape_errors_raise(dev):
         plan.forward([z(1, 3, 16, 32).cpu()], [[z(1, 3, 16, 32)]], [z(1, 1, 16, 32)], z(1, 3, 3), [z(1, 4, 4)])
     with pytest.raises(NotImplementedError):
         MonoLossPlan(1, [(16, 32)], 1, (16, 32), dev, reduce="median")
+
+
+def test_tma_and_thread_staged_planes_give_the_same_bits(dev, monkeypatch):
+    """SDE_DISABLE_TMA=1 forces the thread-staged planes on a shape that takes the TMA path (row pitch a multiple of
+    16 bytes): same warp kernel, same arithmetic, so losses, argmin maps and gradients must be bit-identical; the
+    thread-staged path is also checked against the oracle."""
+    inp = mono_inputs(2, 48, 160, seed=23)
+    monkeypatch.delenv("SDE_DISABLE_TMA", raising=False)
+    a = gpu_mono_from_vec(inp, dev)
+    monkeypatch.setenv("SDE_DISABLE_TMA", "1")
+    b = gpu_mono_from_vec(inp, dev)
+    assert torch.equal(a["rec_loss"], b["rec_loss"]) and torch.equal(a["smooth_loss"], b["smooth_loss"])
+    for x, y in zip(a["argmin"] + a["grad_depth"] + a["grad_pose_vec"], b["argmin"] + b["grad_depth"] + b["grad_pose_vec"]):
+        assert torch.equal(x, y)
+    _against_oracle(inp, dev)

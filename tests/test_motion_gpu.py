@@ -330,3 +330,16 @@ def test_depth_l1_and_supervised_terms(registered):
     for got, want in ((d1.grad, r1.grad), (d2.grad, r2.grad)):
         err = (got.double().cpu() - want).abs() / want.abs().max()
         assert float(torch.quantile(err.flatten(), 0.99)) < 1e-4 and float(err.max()) < 1e-2
+
+
+def test_motion_without_tma_matches_oracle(monkeypatch):
+    """SDE_DISABLE_TMA=1: the MotionLearning kernels fall back to in-kernel projection + gather (no kept planes) on a
+    TMA-eligible shape; still within tolerance of the oracle and of the warp-mode result."""
+    inp = motion_inputs(2, 32, 64, seed=2)
+    monkeypatch.delenv("SDE_DISABLE_TMA", raising=False)
+    a = gpu_motion(inp, True)
+    monkeypatch.setenv("SDE_DISABLE_TMA", "1")
+    b = gpu_motion(inp, True)
+    assert rel_err(a["losses"], b["losses"]) < 1e-6
+    for k in ("gd1", "gd2", "gpose", "gmo"):   # same bound as test_motion_warp_mode_and_recompute_agree
+        assert rel_err(a[k], b[k]) < 1e-4, k
