@@ -71,13 +71,22 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
   // reflect-pad adjoint: pixels next to the image border also receive the mirrored pad position
   const bool lr_border = ox + 2 <= 1 || ox + kHW - 3 >= w - 2;
 
-  if (tid < p.S) {
-    Cam cam;
-    float k[9];
-    load_cam(cam, k, p.K, b, p.sx[s], p.sy[s]);
-    if (tid == 0) sh.cam = cam;
-    load_proj(sh.proj[tid], k, p.pose[tid], b);
-  }
+  // Camera terms (needed from phase 4 on; SAVED = false: from phase 1 on): threads 32 .. 32+S-1 issue the raw loads
+  // of K and the pose now and form the terms after the argmin bytes are staged, so that nobody waits at the first
+  // barrier for two threads' global-memory round trip.
+  const bool cam_thread = tid >= 32 && tid < 32 + p.S;
+  CamRaw raw;
+  if (cam_thread) load_cam_raw(raw, p.K, p.pose[tid - 32], b);
+  auto make_camera = [&]() {
+    if (cam_thread) {
+      Cam cam;
+      float k[9];
+      load_cam(cam, k, raw.k, 0, p.sx[s], p.sy[s]);
+      if (tid == 32) sh.cam = cam;
+      load_proj(sh.proj[tid - 32], k, raw.T, 0);
+    }
+  };
+  if (!SAVED) make_camera();
   // TMA path (saved warps, row pitch a multiple of 16 bytes): one thread hands the tile planes -- target,
   // depth and the first source's warp -- to the copy engine before anything else happens in the CTA
   const bool tma = SAVED && p.tma[s] != 0;
@@ -141,6 +150,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
     if (interior) stage_target<true, true>(sa, tid, reduce_mean);
     else          stage_target<false, true>(sa, tid, reduce_mean);
   }
+  if (SAVED) make_camera();
   __syncthreads();
 
   for (int j = 0; j < p.S; ++j) {

@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
     }
     tma_load_plane(planes + kPlD * kPlane, &maps.depth[s], &sh.bar, ox - kColOff, oy, b);
   }
-  if (tid < p.S) {
+  // camera terms: only the in-kernel gather needs them (with the warp kernel's planes the CTA never projects, and
+  // nobody waits at this barrier for two threads' global-memory round trip)
+  if (tid < p.S && !(tma && prewarp)) {
     Cam cam;
     float k[9];
     load_cam(cam, k, p.K, b, p.sx[s], p.sy[s]);

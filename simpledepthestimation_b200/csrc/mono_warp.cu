@@ -40,14 +40,21 @@ __global__ void __launch_bounds__(kWarpThreads, 4) mono_warp_kernel(const __grid
     if (tid == 0) sh.cam = cam;
     load_proj(sh.proj[tid], k, p.pose[tid], b);
   }
+  // this thread's depths are loaded before the barrier, so that their latency overlaps the camera threads' loads
+  float dv[kWarpPixPerThread];
+#pragma unroll
+  for (int it = 0; it < kWarpPixPerThread; ++it) {
+    const int pix = chunk * kWarpChunk + it * kWarpThreads + tid;
+    dv[it] = pix < hw ? __ldg(p.depth[s] + (size_t)b * hw + pix) : 0.0f;
+  }
   __syncthreads();
   const Cam& cam = sh.cam;
-#pragma unroll 1
+#pragma unroll
   for (int it = 0; it < kWarpPixPerThread; ++it) {
     const int pix = chunk * kWarpChunk + it * kWarpThreads + tid;
     if (pix >= hw) return;
     const int gy = pix / w, gx = pix - gy * w;
-    const float d = __ldg(p.depth[s] + (size_t)b * hw + pix);
+    const float d = dv[it];
 #pragma unroll 1
     for (int j = 0; j < p.S; ++j) {
       const Proj& pj = sh.proj[j];

@@ -98,6 +98,7 @@ struct Proj {
 __device__ __forceinline__ void load_cam(Cam& c, float k[9], const float* __restrict__ K, int b, float sx, float sy) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) k[i] = K[b * 9 + i];
+  // (pointer form: K + b * 9 may also be the k[] of a CamRaw with b == 0)
   // scale_intrinsics, camera.py:14-22
   k[0] *= sx; k[2] *= sx; k[4] *= sy; k[5] *= sy;
 #pragma unroll
@@ -107,6 +108,18 @@ __device__ __forceinline__ void load_cam(Cam& c, float k[9], const float* __rest
   c.ki[2] = -1.0f * k[2] / k[0];
   c.ki[5] = -1.0f * k[5] / k[4];
   c.fx = k[0]; c.sk = k[1]; c.cx = k[2]; c.fy = k[4]; c.cy = k[5];
+}
+
+// The same in two steps, so that the global loads can be in flight while the thread does something else:
+// raw loads (no dependent arithmetic) now, camera terms later.
+struct CamRaw {
+  float k[9], T[16];
+};
+__device__ __forceinline__ void load_cam_raw(CamRaw& r, const float* __restrict__ K, const float* __restrict__ pose, int b) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r.k[i] = __ldg(K + b * 9 + i);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r.T[i] = __ldg(pose + b * 16 + i);
 }
 
 __device__ __forceinline__ void load_proj(Proj& q, const float k[9], const float* __restrict__ pose, int b) {
