@@ -239,56 +239,82 @@ class HostLossRunner:
         self.plan, self.device = plan, torch.device(device)
         B, S = plan.batch, plan.n_sources
         H, W = plan.full_size
+        # One arena per direction: the inputs of a step travel as ONE host->device copy and the results as ONE
+        # device->host copy (ten / seven separate copies cost ~8 us of launch gap each on a PCIe-bound step).
+        # Every tensor is a 16-byte aligned view into the arena (TMA needs aligned plane bases).
+        self.in_shapes = ([("img", (B, 3, H, W))] + [(f"ctx{j}", (B, 3, H, W)) for j in range(S)] +
+                          [(f"depth{i}", (B, 1, h, w)) for i, (h, w) in enumerate(plan.sizes)] + [("K", (B, 3, 3))] +
+                          [(f"pose{j}", (B, 4, 4)) for j in range(S)])
+        self.out_shapes = ([("losses", (2,))] + [(f"grad_depth{i}", (B, 1, h, w)) for i, (h, w) in enumerate(plan.sizes)] +
+                           [(f"grad_pose{j}", (B, 4, 4)) for j in range(S)])
+        self.in_floats, self.out_floats = self._arena_floats(self.in_shapes), self._arena_floats(self.out_shapes)
         new = lambda *shape, dt=torch.float32: torch.empty(*shape, dtype=dt, device=self.device)  # noqa: E731
         self.slots = []
         for _ in range(slots):
-            sl = dict(img=new(B, 3, H, W), ctx=[new(B, 3, H, W) for _ in range(S)],
-                      depth=[new(B, 1, h, w) for h, w in plan.sizes], K=new(B, 3, 3), pose=[new(B, 4, 4) for _ in range(S)],
-                      ready=torch.cuda.Event(), free=torch.cuda.Event())
+            arena = new(self.in_floats)
+            v = self._views(arena, self.in_shapes)
+            sl = dict(arena=arena, img=v["img"], ctx=[v[f"ctx{j}"] for j in range(S)],
+                      depth=[v[f"depth{i}"] for i in range(len(plan.sizes))], K=v["K"],
+                      pose=[v[f"pose{j}"] for j in range(S)], ready=torch.cuda.Event(), free=torch.cuda.Event())
             sl["free"].record()
             self.slots.append(sl)
-        self.losses = new(2)
+        self.out_arena = new(self.out_floats)
+        ov = self._views(self.out_arena, self.out_shapes)
+        self.losses = ov["losses"]
+        self.grad_depth = [ov[f"grad_depth{i}"] for i in range(len(plan.sizes))]
+        self.grad_pose = [ov[f"grad_pose{j}"] for j in range(S)]
         self.argmin = [new(B, h, w, dt=torch.uint8) for h, w in plan.sizes]
-        self.grad_depth = [new(B, 1, h, w) for h, w in plan.sizes]
-        self.grad_pose = [new(B, 4, 4) for _ in range(S)]
         self.ones = torch.ones(2, device=self.device)
         self.warped = plan.new_warped()
-        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
-        self.h_losses = pin(self.losses)
-        self.h_grad_depth = [pin(t) for t in self.grad_depth]
-        self.h_grad_pose = [pin(t) for t in self.grad_pose]
+        self.h_out = torch.empty(self.out_floats, dtype=torch.float32, pin_memory=True)
+        hv = self._views(self.h_out, self.out_shapes)
+        self.h_losses = hv["losses"]
+        self.h_grad_depth = [hv[f"grad_depth{i}"] for i in range(len(plan.sizes))]
+        self.h_grad_pose = [hv[f"grad_pose{j}"] for j in range(S)]
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        sl = self.slots[0]
-        dev_in = [sl["img"]] + sl["ctx"] + sl["depth"] + [sl["K"]] + sl["pose"]
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in dev_in)
-        outs = [self.losses] + self.grad_depth + self.grad_pose
-        self.d2h_bytes = sum(t.numel() * t.element_size() for t in outs)
+        # bytes per step, counted from the tensors (the arenas add at most 12 bytes of padding per tensor)
+        count = lambda shapes: 4 * sum(int(torch.Size(shape).numel()) for _, shape in shapes)  # noqa: E731
+        self.h2d_bytes, self.d2h_bytes = count(self.in_shapes), count(self.out_shapes)
         self._i = 0
         # kernels per step: pyramid (all frames and coarse scales in one launch), warp + loss forward, backward
         self.launches_per_step = (1 if len(plan.sizes) > 1 else 0) + (2 if plan.save_warped else 1) + 1
 
     @staticmethod
-    def pin(host_set):
-        """Pins an (img, ctx list, depth list, K, pose list) tuple of CPU tensors."""
-        img, ctx, depth, K, pose = host_set
-        p = lambda t: t.contiguous().pin_memory()  # noqa: E731
-        return (p(img), [p(c) for c in ctx], [p(d) for d in depth], p(K), [p(x) for x in pose])
+    def _arena_floats(shapes):
+        return sum((int(torch.Size(shape).numel()) + 3) // 4 * 4 for _, shape in shapes)
 
-    def step(self, host_set):
+    @staticmethod
+    def _views(arena, shapes):
+        out, off = {}, 0
+        for name, shape in shapes:
+            n = int(torch.Size(shape).numel())
+            out[name] = arena[off:off + n].view(*shape)
+            off += (n + 3) // 4 * 4
+        return out
+
+    def pin(self, host_set):
+        """Packs an (img, ctx list, depth list, K, pose list) tuple of CPU tensors into one pinned arena (the layout of
+        the device slots) -- what a data loader that writes into pinned memory hands over."""
         img, ctx, depth, K, pose = host_set
+        arena = torch.empty(self.in_floats, dtype=torch.float32, pin_memory=True)
+        v = self._views(arena, self.in_shapes)
+        v["img"].copy_(img)
+        for j, c in enumerate(ctx):
+            v[f"ctx{j}"].copy_(c)
+        for i, d in enumerate(depth):
+            v[f"depth{i}"].copy_(d)
+        v["K"].copy_(K)
+        for j, x in enumerate(pose):
+            v[f"pose{j}"].copy_(x)
+        return arena
+
+    def step(self, host_arena):
         sl = self.slots[self._i % len(self.slots)]
         self._i += 1
         main = torch.cuda.current_stream()
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(sl["free"])       # the kernels that last read this slot are done
-            sl["img"].copy_(img, non_blocking=True)
-            for d, h in zip(sl["ctx"], ctx):
-                d.copy_(h, non_blocking=True)
-            for d, h in zip(sl["depth"], depth):
-                d.copy_(h, non_blocking=True)
-            sl["K"].copy_(K, non_blocking=True)
-            for d, h in zip(sl["pose"], pose):
-                d.copy_(h, non_blocking=True)
+            sl["arena"].copy_(host_arena, non_blocking=True)
             sl["ready"].record()
         main.wait_event(sl["ready"])
         sizes = self.plan.sizes
@@ -300,11 +326,7 @@ class HostLossRunner:
         self.plan.backward(target, source, sl["depth"], sl["K"], sl["pose"], self.argmin, self.ones, self.grad_depth,
                            self.grad_pose, warped=self.warped)
         sl["free"].record()
-        self.h_losses.copy_(self.losses, non_blocking=True)
-        for h, d in zip(self.h_grad_depth, self.grad_depth):
-            h.copy_(d, non_blocking=True)
-        for h, d in zip(self.h_grad_pose, self.grad_pose):
-            h.copy_(d, non_blocking=True)
+        self.h_out.copy_(self.out_arena, non_blocking=True)
 
     def finish(self):
         torch.cuda.current_stream().synchronize()
