@@ -32,8 +32,12 @@
 
 namespace sde {
 
-constexpr int kBwdPlanes = 13;  // A[3], S[3], depth, coef a/b/c, gS[3]
-constexpr int kBA = 0, kBS = 3, kBD = 6, kBCoef = 7, kBG = 10;
+// Ten planes: A[3], depth and two 3-plane regions X, Y.  For an even source the warped planes S sit in X and the
+// coefficient planes in Y, for an odd one the other way round: gS_c overwrites S_c in place (S_c is dead once the
+// adjoint pass of channel c has read its own pixel), the next source's S planes are prefetched into the region whose
+// coefficients were just consumed, and 10 planes (53 KB) instead of 13 let a fourth CTA fit on an SM.
+constexpr int kBwdPlanes = 10;
+constexpr int kBA = 0, kBD = 3, kBX = 4, kBY = 7;
 #ifndef SDE_NB
 #define SDE_NB 2
 #endif
@@ -54,7 +58,7 @@ struct BwdShared {
 };
 
 template <bool SAVED>
-__global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_constant__ MonoParams p,
+__global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_constant__ MonoParams p,
                                                                const __grid_constant__ MonoTma maps) {
   extern __shared__ __align__(128) float planes[];  // [kBwdPlanes][kPlane]
   __shared__ BwdShared sh;
@@ -97,12 +101,12 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       tma_load_plane(planes + (kBA + c) * kPlane, &maps.target[s], &sh.bar, ox - kColOff, oy, b * 3 + c);
-      tma_load_plane(planes + (kBS + c) * kPlane, &maps.warped[s][0], &sh.bar, ox - kColOff, oy, b * kSavedPlanes + c);
+      tma_load_plane(planes + (kBX + c) * kPlane, &maps.warped[s][0], &sh.bar, ox - kColOff, oy, b * kSavedPlanes + c);
     }
     tma_load_plane(planes + kBD * kPlane, &maps.depth[s], &sh.bar, ox - kColOff, oy, b);
   }
   // coefficient planes: the 1-pixel border is never written and must read as zero
-  for (int i = tid; i < 3 * kPlane; i += kThreads) planes[kBCoef * kPlane + i] = 0.0f;
+  for (int i = tid; i < 3 * kPlane; i += kThreads) planes[kBY * kPlane + i] = 0.0f;
   __syncthreads();
 
   const float* __restrict__ depth = p.depth[s] + (size_t)b * hw;
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
   StageArgs sa;
   sa.depth = depth; sa.src = nullptr; sa.tgt = tg0; sa.amap = amap;
   sa.planes = planes; sa.arg = sh.arg; sa.oy = oy; sa.ox = ox; sa.h = h; sa.w = w; sa.hw = hw;
-  sa.plS = kBS; sa.plI = 0; sa.plA = kBA; sa.plD = kBD;
+  sa.plS = kBX; sa.plI = 0; sa.plA = kBA; sa.plD = kBD;
   // ------------------------------------------------------------------ phase 0: depth + target + argmin
   unsigned tma_phase = 0;
   if (tma) {
@@ -156,6 +160,20 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
   for (int j = 0; j < p.S; ++j) {
     // byte of the argmin plane that selects this source's warped candidate ('mean': every staged pixel holds 254)
     const int cand = reduce_mean ? 254 : (automask ? 2 * j : j);
+    // plane regions of this source: S (later gS, in place) and the coefficients
+    const int bS = (j & 1) ? kBY : kBX, bC = (j & 1) ? kBX : kBY;
+    sa.plS = bS;
+    if (j > 0) {
+      // the coefficient region held the previous source's S / gS planes: its one-pixel border ring (never written
+      // by the coefficient pass, never read by phase 4) must read as zero
+      for (int i = tid; i < 3 * (2 * kHW + 2 * kHH); i += kThreads) {
+        const int k = i / (2 * kHW + 2 * kHH), r = i - k * (2 * kHW + 2 * kHH);
+        int yy, xx;
+        if (r < 2 * kHW) { yy = r < kHW ? 0 : kHH - 1; xx = r < kHW ? r : r - kHW; }
+        else { const int q = r - 2 * kHW; yy = q < kHH ? q : q - kHH; xx = q < kHH ? 0 : kHW - 1; }
+        planes[(bC + k) * kPlane + plane_index(yy, xx)] = 0.0f;
+      }
+    }
     const Cam cam = sh.cam;
     const Proj pj = sh.proj[j];
     const float* __restrict__ sc0 = p.source[s][j] + (size_t)b * 3 * hw;
@@ -168,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       tma_phase ^= 1u;
       if (!interior) {
         if (j == 0) reflect_fixup(planes, kBA, 3, oy, ox, h, w, tid), reflect_fixup(planes, kBD, 1, oy, ox, h, w, tid);
-        reflect_fixup(planes, kBS, 3, oy, ox, h, w, tid);
+        reflect_fixup(planes, bS, 3, oy, ox, h, w, tid);
       }
     } else if (SAVED) {
       const float* wsrc = p.warped[s][j] + (size_t)b * kSavedPlanes * hw;
@@ -189,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
 #pragma unroll
         for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
           const Row4 a = ld_row(pa + rr * kPitch);
-          const Row4 x = ld_row(pa + (kBS - kBA) * kPlane + rr * kPitch);
+          const Row4 x = ld_row(pa + (bS - kBA) * kPlane + rr * kPitch);
           const f2 aa = a.c * a.c, xx2 = x.c * x.c, xa = x.c * a.c;
           const f2 nA = (a.c + swp(a.c)) + a.o, nAA = fma2(a.o, a.o, aa + swp(aa));
           const f2 nX = (x.c + swp(x.c)) + x.o, nXX = fma2(x.o, x.o, xx2 + swp(xx2));
@@ -223,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
               cb = (gi * bc2(-18.0f)) * (ssim * d1);
               cc = (gi * bc2(18.0f)) * n1;
             }
-            float* pc = planes + kBCoef * kPlane + plane_index(row, c0 + 1);
+            float* pc = planes + bC * kPlane + plane_index(row, c0 + 1);
             *reinterpret_cast<unsigned long long*>(pc) = ca.v;
             *reinterpret_cast<unsigned long long*>(pc + kPlane) = cb.v;
             *reinterpret_cast<unsigned long long*>(pc + 2 * kPlane) = cc.v;
@@ -245,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
           if (SSIM) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              const Row4 q = ld_row(planes + (kBCoef + k) * kPlane + plane_index(r0 + rr, c0));
+              const Row4 q = ld_row(planes + (bC + k) * kPlane + plane_index(r0 + rr, c0));
               f2 hsum = (q.c + swp(q.c)) + q.o;
               if (LR) hsum = hsum + mk2(eL0 * lo(q.o) + eR0 * hi(q.c), eL1 * lo(q.c) + eR1 * hi(q.o));
               nq[k] = hsum;
@@ -255,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
             const int row = r0 + rr - 1;        // plane row of pixel p
             const int py = oy + row;
             const f2 wu = bc2(py == 1 ? 2.0f : 1.0f), wd = bc2(py == h - 2 ? 2.0f : 1.0f);
-            const f2 Sp = ld2(planes + (kBS + c) * kPlane + plane_index(row, c0 + 1));
+            const f2 Sp = ld2(planes + (bS + c) * kPlane + plane_index(row, c0 + 1));
             const f2 Ap = ld2(planes + (kBA + c) * kPlane + plane_index(row, c0 + 1));
             f2 gS = bc2(0.0f);
             if (SSIM) {
@@ -272,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
             l0 = (m.x == cand && d0 != 0.0f) ? l0 : 0.0f;
             l1 = (m.y == cand && d1 != 0.0f) ? l1 : 0.0f;
             gS = gS + mk2(l0, l1);
-            *reinterpret_cast<unsigned long long*>(planes + (kBG + c) * kPlane + plane_index(row, c0 + 1)) = gS.v;
+            *reinterpret_cast<unsigned long long*>(planes + (bS + c) * kPlane + plane_index(row, c0 + 1)) = gS.v;   // in place of S_c
           }
           if (SSIM) {
 #pragma unroll
@@ -290,13 +308,14 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       __syncthreads();
     }
 
-    // the S planes are dead from here on: let the copy engine fetch the next source's warp during phase 4
+    // this source's coefficient planes are dead from here on: let the copy engine put the next source's warp there
+    // during phase 4 (the regions swap roles)
     if (tma && j + 1 < p.S && tid == 0) {
       proxy_fence();
       mbar_arrive_expect_tx(&sh.bar, 3 * kPlaneBytesTma);
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        tma_load_plane(planes + (kBS + c) * kPlane, &maps.warped[s][j + 1], &sh.bar, ox - kColOff, oy, b * kSavedPlanes + c);
+        tma_load_plane(planes + (bC + c) * kPlane, &maps.warped[s][j + 1], &sh.bar, ox - kColOff, oy, b * kSavedPlanes + c);
     }
     // ---------------------------------------------------------------- phase 4: warp backward on P
     // Only pixels whose 3x3 neighbourhood holds a window that selected this source's warped candidate carry a
@@ -332,8 +351,8 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
         const int row = r0 + 1 + o;
         const int pl = plane_index(row, c0 + 1);
         const bool row_ok = row >= 2 && row <= kBwdH + 1 && oy + row < h;
-        const f2 g0 = ld2(planes + kBG * kPlane + pl), g1 = ld2(planes + (kBG + 1) * kPlane + pl),
-                 g2 = ld2(planes + (kBG + 2) * kPlane + pl);
+        const f2 g0 = ld2(planes + bS * kPlane + pl), g1 = ld2(planes + (bS + 1) * kPlane + pl),
+                 g2 = ld2(planes + (bS + 2) * kPlane + pl);
         const bool s0 = row_ok && col_ok0 && (lo(g0) != 0.0f || lo(g1) != 0.0f || lo(g2) != 0.0f);
         const bool s1 = row_ok && col_ok1 && (hi(g0) != 0.0f || hi(g1) != 0.0f || hi(g2) != 0.0f);
         const unsigned b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1);
@@ -371,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
         if (k + 32 < total) fetch(k + 32);
         const int row = pl / kPitch, col = pl - row * kPitch - kColOff;
         const int gy = oy + row, gx = ox + col;
-        float* const pg = planes + kBG * kPlane + pl;
+        float* const pg = planes + bS * kPlane + pl;
         const float g0 = pg[0], g1 = pg[kPlane], g2 = pg[2 * kPlane];
         const float d = planes[kBD * kPlane + pl];
         const float fxp = (float)gx, fyp = (float)gy;
@@ -436,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 3) mono_bwd_kernel(const __grid_cons
       __syncwarp();
       // pick up the depth gradients of this lane's own pixels (pairs outside P / the image hold garbage that is never stored)
 #pragma unroll
-      for (int o = 0; o < kRowsPerWarp; ++o) gd[o] = gd[o] + ld2(planes + kBG * kPlane + plane_index(r0 + 1 + o, c0 + 1));
+      for (int o = 0; o < kRowsPerWarp; ++o) gd[o] = gd[o] + ld2(planes + bS * kPlane + plane_index(r0 + 1 + o, c0 + 1));
     }
   }
 
@@ -536,7 +555,7 @@ size_t mono_bwd_smem_bytes() { return (size_t)kBwdPlanes * kPlane * sizeof(float
 cudaError_t launch_mono_bwd(const MonoParams& p, const MonoTma& t, cudaStream_t stream) {
   const bool saved = p.warped[0][0] != nullptr;   // all-or-nothing, checked by the caller
   auto kernel = saved ? mono_bwd_kernel<true> : mono_bwd_kernel<false>;
-  // 61.8 KB of dynamic shared memory needs the opt-in attribute (per device; cheap and idempotent)
+  // 47.8 KB of dynamic shared memory (+ 4 KB static): four CTAs per SM; the opt-in attribute is per device, cheap and idempotent
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mono_bwd_smem_bytes());
   if (e != cudaSuccess) return e;
   kernel<<<p.btile_start[p.n_scales], kThreads, mono_bwd_smem_bytes(), stream>>>(p, t);
