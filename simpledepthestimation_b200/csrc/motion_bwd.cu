@@ -18,9 +18,11 @@
 
 namespace sde {
 
-// WZ (zero-padded weight) is only read before the first phase 3 (avg_w), so it shares gS plane 0
-constexpr int kNA = 0, kNS = 3, kNU = 6, kND = 7, kNCoef = 8, kNG = 11, kNW = kNG;
-constexpr int kMotionBwdPlanes = 14;
+// Eleven planes so that four CTAs fit on an SM: gS_c overwrites S_c in place (S_c is dead once the adjoint pass of
+// channel c has read its own pixel); WZ (zero-padded weight) is only read before the channel loop (avg_w), so it
+// shares coefficient plane 0 (whose border ring is zeroed afterwards).
+constexpr int kNA = 0, kNS = 3, kNU = 6, kND = 7, kNCoef = 8, kNG = kNS, kNW = kNCoef;
+constexpr int kMotionBwdPlanes = 11;
 // the gradient block P starts at plane column 3: with 60-wide tiles plane index 0 is image column tile_x0 - 4 (TMA)
 constexpr int kMBwdColOff = 3;
 constexpr int kMPosPerThread = (kBwdW * kBwdH + kThreads - 1) / kThreads;  // 7
@@ -30,11 +32,10 @@ struct MotionBwdShared {
   float red[12][kThreads / 32];
   unsigned ticket;
   __align__(8) uint64_t bar;             // TMA completion barrier
-  __align__(8) uint8_t occ[kPlane];      // occlusion mask of the staged positions (0 / 1)
-  __align__(8) uint8_t inside[kPlane];   // window centre lies in the image
+  __align__(8) uint8_t flag[kPlane];     // bit 0: occlusion mask of the staged position, bit 1: it lies in the image
 };
 
-__global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_constant__ MotionParams p,
+__global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_constant__ MotionParams p,
                                                                  const __grid_constant__ MotionTma maps) {
   extern __shared__ __align__(128) float planes[];  // [kMotionBwdPlanes][kPlane]
   __shared__ MotionBwdShared sh;
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
     tma_load_plane(planes + kND * kPlane, &maps.depth_a[dir], &sh.bar, bx, oy, b);
   }
   if (tid == 0) load_mcam(sh.cam, p.K, p.pose[dir], b, p.sx, p.sy);
-  for (int i = tid; i < 3 * kPlane; i += kThreads) planes[kNCoef * kPlane + i] = 0.0f;
+  // coefficient planes 1, 2: the border ring is never written and must read as zero (plane 0 holds WZ for now)
+  for (int i = tid; i < 2 * kPlane; i += kThreads) planes[(kNCoef + 1) * kPlane + i] = 0.0f;
   __syncthreads();
 
   MotionStage st;
@@ -100,8 +102,7 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
       planes[kNU * kPlane + pl] = wgt + 1e-2f;
       planes[kNW * kPlane + pl] = wgt;
       const int ty = oy + yy, tx = ox + xx;
-      sh.occ[pl] = vo >= 2.0f ? 1 : 0;
-      sh.inside[pl] = (ty >= 0 && ty < h && tx >= 0 && tx < w) ? 1 : 0;
+      sh.flag[pl] = (vo >= 2.0f ? 1 : 0) | ((ty >= 0 && ty < h && tx >= 0 && tx < w) ? 2 : 0);
     }
     if (!interior) {
       __syncthreads();
@@ -128,8 +129,7 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
       planes[kNU * kPlane + pl] = sm.wgt + 1e-2f;
       planes[kNW * kPlane + pl] = inside ? sm.wgt : 0.0f;
       planes[kND * kPlane + pl] = sm.d;
-      sh.occ[pl] = sm.occ != 0.0f ? 1 : 0;
-      sh.inside[pl] = inside ? 1 : 0;
+      sh.flag[pl] = (sm.occ != 0.0f ? 1 : 0) | (inside ? 2 : 0);
     }
   }
   __syncthreads();
@@ -158,6 +158,15 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
       }
       hW[0] = hW[1]; hW[1] = nW;
     }
+  }
+  // WZ is dead: its plane becomes coefficient plane 0, whose border ring must read as zero (the coefficient pass
+  // rewrites the interior of all three planes every channel)
+  __syncthreads();
+  for (int i = tid; i < 2 * kHW + 2 * kHH; i += kThreads) {
+    int yy, xx;
+    if (i < 2 * kHW) { yy = i < kHW ? 0 : kHH - 1; xx = i < kHW ? i : i - kHW; }
+    else { const int q = i - 2 * kHW; yy = q < kHH ? q : q - kHH; xx = q < kHH ? 0 : kHW - 1; }
+    planes[kNCoef * kPlane + plane_index(yy, xx)] = 0.0f;
   }
 
 #pragma unroll 1
@@ -196,10 +205,11 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
           else if (MODE == 2) { N = n1; D = d1; }
           else { N = n1 * n2; D = d1 * d2; }
           const f2 ssim = div2(N, D);
-          const uchar2 in = *reinterpret_cast<const uchar2*>(sh.inside + plane_index(row, c0 + 1));
+          const uchar2 fl = *reinterpret_cast<const uchar2*>(sh.flag + plane_index(row, c0 + 1));
+          const bool in_x = (fl.x & 2) != 0, in_y = (fl.y & 2) != 0;
           const float h0 = fmaf(lo(ssim), -0.5f, 0.5f), h1 = fmaf(hi(ssim), -0.5f, 0.5f);
           // torch.clamp passes the gradient on the closed interval; windows centred outside the image do not exist
-          const f2 g = mk2((in.x && h0 >= 0.0f && h0 <= 1.0f) ? g_ss : 0.0f, (in.y && h1 >= 0.0f && h1 <= 1.0f) ? g_ss : 0.0f);
+          const f2 g = mk2((in_x && h0 >= 0.0f && h0 <= 1.0f) ? g_ss : 0.0f, (in_y && h1 >= 0.0f && h1 <= 1.0f) ? g_ss : 0.0f);
           // d ssim / d x_p = U_p * base * [ ... ]  with  base = 2 g avg_w (inverse_avg_w / 9) / D
           const f2 base = div2((g * avgw[o]) * (k * bc2(2.0f)), D);
           f2 ca, cb, cc;
@@ -264,12 +274,12 @@ __global__ void __launch_bounds__(kThreads, 3) motion_bwd_kernel(const __grid_co
             gS = Up * fma2(Sp, vb, fma2(Ap, vc, va));
           }
           // rgb L1 on the pixel itself: occlusion * sign(S - A) (branch-free)
-          const uchar2 m = *reinterpret_cast<const uchar2*>(sh.occ + pl);
+          const uchar2 m = *reinterpret_cast<const uchar2*>(sh.flag + pl);
           const f2 df = Sp - Ap;
           const float d0 = lo(df), d1v = hi(df);
           float l0 = d0 > 0.0f ? g_l1 : -g_l1, l1 = d1v > 0.0f ? g_l1 : -g_l1;
-          l0 = (m.x && d0 != 0.0f) ? l0 : 0.0f;
-          l1 = (m.y && d1v != 0.0f) ? l1 : 0.0f;
+          l0 = ((m.x & 1) && d0 != 0.0f) ? l0 : 0.0f;
+          l1 = ((m.y & 1) && d1v != 0.0f) ? l1 : 0.0f;
           gS = gS + mk2(l0, l1);
           *reinterpret_cast<unsigned long long*>(planes + (kNG + c) * kPlane + pl) = gS.v;
         }
