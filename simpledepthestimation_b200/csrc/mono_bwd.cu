@@ -79,6 +79,15 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
   // of K and the pose now and form the terms after the argmin bytes are staged, so that nobody waits at the first
   // barrier for two threads' global-memory round trip.
   const bool cam_thread = tid >= 32 && tid < 32 + p.S;
+  // coefficient planes: the 1-pixel border is never written and must read as zero (shared memory only: before the
+  // dependency wait)
+  for (int i = tid; i < 3 * kPlane; i += kThreads) planes[kBY * kPlane + i] = 0.0f;
+  const bool tma = SAVED && p.tma[s] != 0;
+  if (tma && tid == 0) {
+    mbar_init(&sh.bar, 1);
+    mbar_init_fence();
+  }
+  pdl_wait();   // the forward pass's outputs (and every other tensor) are complete and visible from here on
   CamRaw raw;
   if (cam_thread) load_cam_raw(raw, p.K, p.pose[tid - 32], b);
   auto make_camera = [&]() {
@@ -93,10 +102,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
   if (!SAVED) make_camera();
   // TMA path (saved warps, row pitch a multiple of 16 bytes): one thread hands the tile planes -- target,
   // depth and the first source's warp -- to the copy engine before anything else happens in the CTA
-  const bool tma = SAVED && p.tma[s] != 0;
   if (tma && tid == 0) {
-    mbar_init(&sh.bar, 1);
-    mbar_init_fence();
     mbar_arrive_expect_tx(&sh.bar, 7 * kPlaneBytesTma);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -105,8 +111,6 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
     }
     tma_load_plane(planes + kBD * kPlane, &maps.depth[s], &sh.bar, ox - kColOff, oy, b);
   }
-  // coefficient planes: the 1-pixel border is never written and must read as zero
-  for (int i = tid; i < 3 * kPlane; i += kThreads) planes[kBY * kPlane + i] = 0.0f;
   __syncthreads();
 
   const float* __restrict__ depth = p.depth[s] + (size_t)b * hw;
@@ -459,6 +463,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
     }
   }
 
+  pdl_launch_dependents();   // see mono_fwd.cu
   // ------------------------------------------------------------------ smoothness gradient + store
   {
     const float sscale = p.smooth_scale[s];
@@ -558,8 +563,7 @@ cudaError_t launch_mono_bwd(const MonoParams& p, const MonoTma& t, cudaStream_t 
   // 47.8 KB of dynamic shared memory (+ 4 KB static): four CTAs per SM; the opt-in attribute is per device, cheap and idempotent
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mono_bwd_smem_bytes());
   if (e != cudaSuccess) return e;
-  kernel<<<p.btile_start[p.n_scales], kThreads, mono_bwd_smem_bytes(), stream>>>(p, t);
-  return cudaGetLastError();
+  return launch_chained(2, kernel, (unsigned)p.btile_start[p.n_scales], kThreads, mono_bwd_smem_bytes(), stream, p, t);
 }
 
 }  // namespace sde

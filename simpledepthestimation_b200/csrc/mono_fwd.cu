@@ -66,6 +66,9 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   if (tma && tid == 0) {
     mbar_init(&sh.bar, 1);
     mbar_init_fence();
+  }
+  pdl_wait();   // the warp kernel's planes (and every other tensor) are complete and visible from here on
+  if (tma && tid == 0) {
     mbar_arrive_expect_tx(&sh.bar, (4 + (AUTOMASK ? 3 : 0) + (p.prewarp[s] ? 3 : 0)) * kPlaneBytesTma);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -255,6 +258,9 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
     }
   }
 
+  // the heavy part of this tile is done: once that holds for every tile, the next kernel of the stream may be
+  // scheduled (it waits for this grid to complete before it touches memory)
+  pdl_launch_dependents();
   // ------------------------------------------------------------------ per-thread sums, argmin, smoothness
   float rec = 0.0f, smx = 0.0f, smy = 0.0f, sinv = 0.0f;
   const int gx0 = tc.x0 + c0;  // image column of this lane's first pixel
@@ -354,8 +360,7 @@ cudaError_t launch_mono_fwd(const MonoParams& p, const MonoTma& t, cudaStream_t 
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mono_fwd_smem_bytes());
   if (e != cudaSuccess) return e;
   if (SDE_FWD_CARVEOUT >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, SDE_FWD_CARVEOUT);
-  kernel<<<p.tile_start[p.n_scales], kThreads, mono_fwd_smem_bytes(), stream>>>(p, t);
-  return cudaGetLastError();
+  return launch_chained(1, kernel, (unsigned)p.tile_start[p.n_scales], kThreads, mono_fwd_smem_bytes(), stream, p, t);
 }
 
 }  // namespace sde

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kWarpThreads, 4) mono_warp_kernel(const __grid
   const int chunks = (hw + kWarpChunk - 1) / kWarpChunk;
   const int b = bid / chunks, chunk = bid - b * chunks;
   const int tid = threadIdx.x;
+  pdl_wait();   // K, pose and depth may come from the kernel ahead; the planes written below may still be read by it
   if (tid < p.S) {
     Cam cam;
     float k[9];
@@ -51,6 +52,9 @@ __global__ void __launch_bounds__(kWarpThreads, 4) mono_warp_kernel(const __grid
   const Cam& cam = sh.cam;
 #pragma unroll
   for (int it = 0; it < kWarpPixPerThread; ++it) {
+    // once every block is on its last pixel, the next kernel of the stream may be scheduled (it waits for this grid
+    // to complete before it touches memory): its launch latency overlaps this kernel's tail
+    if (it == kWarpPixPerThread - 1) pdl_launch_dependents();
     const int pix = chunk * kWarpChunk + it * kWarpThreads + tid;
     if (pix >= hw) return;
     const int gy = pix / w, gx = pix - gy * w;
@@ -89,8 +93,7 @@ __global__ void __launch_bounds__(kWarpThreads, 4) mono_warp_kernel(const __grid
 cudaError_t launch_mono_warp(const MonoParams& p, cudaStream_t stream) {
   const int grid = p.warp_start[p.n_scales];
   if (grid == 0) return cudaSuccess;
-  mono_warp_kernel<<<grid, kWarpThreads, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_chained(0, mono_warp_kernel, (unsigned)grid, kWarpThreads, 0, stream, p);
 }
 
 }  // namespace sde

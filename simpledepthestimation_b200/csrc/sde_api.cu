@@ -189,6 +189,19 @@ static bool encode_planes(CUtensorMap* m, const float* base, int planes, int h, 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Which launches carry the programmatic-dependent-launch attribute: bit 0 warp kernel, bit 1 forward, bit 2 backward.
+// Measured at cfg2 (profiles/r1_notes.md): chaining the forward kernel behind the warp kernel and the backward
+// kernel behind whatever precedes it saves 2.1 + 2.4 us per step; chaining the warp kernel costs 9 us (its blocks,
+// parked on the SMs until the predecessor has drained, then start in lock-step and their gathers collide in L1),
+// hence the default mask 6.  SDE_DISABLE_PDL=1 / SDE_PDL_MASK=<bits> override it (read per call, like SDE_DISABLE_TMA).
+bool pdl_enabled(int which) {
+  const char* off = getenv("SDE_DISABLE_PDL");
+  if (off && off[0] == '1') return false;
+  const char* m = getenv("SDE_PDL_MASK");
+  const int mask = m ? atoi(m) : 6;
+  return (mask >> which) & 1;
+}
+
 // Decides per scale whether the tile planes are staged by TMA (row pitch a multiple of 16 bytes, encoder
 // available; the backward pass also needs the saved warps) and builds the descriptors.
 static void mono_tma(const sde_mono_desc* d, const sde_mono_buffers* b, bool backward, MonoParams& p, MonoTma& t) {

@@ -70,6 +70,34 @@ __device__ __forceinline__ f2 ld2(const float* p) {   // 8-byte aligned
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): the kernels of a step are chained on one stream, and each one lets the
+// next be scheduled while it drains (launch_dependents, once the heavy part of a CTA is done) and itself touches no tensor
+// before the kernels ahead of it in the stream have completed and flushed (pdl_wait).  What runs before pdl_wait
+// is index arithmetic, shared-memory initialisation and barrier set-up only, so the effect is that the launch
+// latency and the CTA prologue of a kernel overlap the tail of its predecessor.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+#ifndef __CUDACC_RTC__
+// Host side: launch with the programmatic-stream-serialization attribute (SDE_DISABLE_PDL=1: plain launch).
+bool pdl_enabled(int which);
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chained(int which, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled(which) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
