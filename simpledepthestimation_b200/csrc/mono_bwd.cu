@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
   // ------------------------------------------------------------------ phase 0: depth + target + argmin
   unsigned tma_phase = 0;
   if (tma) {
-    stage_arg(sh.arg, amap, oy, ox, h, w, reduce_mean, tid);   // argmin bytes: plain loads while the copy engine works
+    // argmin bytes: plain loads while the copy engine works (the TMA path implies w % 4 == 0 and ox - kColOff is a
+    // multiple of 4 by construction of the tiles, so whole words can be moved if the map itself is word-aligned)
+    if ((reinterpret_cast<uintptr_t>(amap) & 3) == 0) stage_arg_words(sh.arg, amap, oy, ox, h, w, reduce_mean, tid);
+    else stage_arg(sh.arg, amap, oy, ox, h, w, reduce_mean, tid);
   } else {
     if (interior) stage_target<true, true>(sa, tid, reduce_mean);
     else          stage_target<false, true>(sa, tid, reduce_mean);
@@ -232,18 +235,19 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
               const f2 d1 = (xs + aa2) + C1;
               const f2 d2 = (fma2(xs, bc2(-1.0f), sXX * bc2(9.0f)) + vA) + C2;
               const f2 N = n1 * n2, D = d1 * d2;
-              const f2 ssim = div2(N, D);
-              const f2 invD = div2(bc2(1.0f), D);
+              // both quotients negated (ndiv2: one packed instruction less each); the signs fold into the constants below
+              const f2 nssim = ndiv2(N, D);
+              const f2 ninvD = ndiv2(bc2(1.0f), D);
               // torch.clamp passes the gradient on the closed interval 0 <= (1-ssim)/2 <= 1
-              const float h0 = fmaf(lo(ssim), -0.5f, 0.5f), h1 = fmaf(hi(ssim), -0.5f, 0.5f);
+              const float h0 = fmaf(lo(nssim), 0.5f, 0.5f), h1 = fmaf(hi(nssim), 0.5f, 0.5f);
               const f2 g = mk2((sel0 && h0 >= 0.0f && h0 <= 1.0f) ? g_ss : 0.0f,
                                (sel1 && h1 >= 0.0f && h1 <= 1.0f) ? g_ss : 0.0f);
-              const f2 gi = g * invD;
+              const f2 ngi = g * ninvD;
               // d ssim / d(sum S), d(sum S^2), d(sum S A)   (SURVEY.md A.6 in window-sum form)
-              const f2 u = (sA * (n2 - n1)) - ((sX * ssim) * (d2 - d1));
-              ca = (gi * bc2(2.0f)) * u;
-              cb = (gi * bc2(-18.0f)) * (ssim * d1);
-              cc = (gi * bc2(18.0f)) * n1;
+              const f2 u = fma2(sX * nssim, d2 - d1, sA * (n2 - n1));
+              ca = (ngi * bc2(-2.0f)) * u;
+              cb = (ngi * bc2(-18.0f)) * (nssim * d1);
+              cc = (ngi * bc2(-18.0f)) * n1;
             }
             float* pc = planes + bC * kPlane + plane_index(row, c0 + 1);
             *reinterpret_cast<unsigned long long*>(pc) = ca.v;

@@ -208,9 +208,9 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
               const f2 n2 = fma2(bc2(2.0f), fma2(t, bc2(-1.0f), sXA * bc2(9.0f)), C2);
               const f2 d1 = (xs + aa2) + C1;
               const f2 d2 = (fma2(xs, bc2(-1.0f), sXX * bc2(9.0f)) + vA) + C2;
-              const f2 ssim = div2(n1 * n2, d1 * d2);
+              const f2 nssim = ndiv2(n1 * n2, d1 * d2);   // -ssim
               // clamp((1 - ssim) / 2, 0, 1), ssim_loss.py:53
-              const f2 l = mk2(__saturatef(fmaf(lo(ssim), -0.5f, 0.5f)), __saturatef(fmaf(hi(ssim), -0.5f, 0.5f)));
+              const f2 l = mk2(__saturatef(fmaf(lo(nssim), 0.5f, 0.5f)), __saturatef(fmaf(hi(nssim), 0.5f, 0.5f)));
               a2 = fma2(l, bc2(wS), a2);
             }
             acc[k][o] = mk2(fmaf(fabsf(lo(dXA[k])), wL, lo(a2)), fmaf(fabsf(hi(dXA[k])), wL, hi(a2)));

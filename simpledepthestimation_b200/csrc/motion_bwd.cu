@@ -204,10 +204,10 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
           if (MODE == 1) { N = n2; D = d2; }
           else if (MODE == 2) { N = n1; D = d1; }
           else { N = n1 * n2; D = d1 * d2; }
-          const f2 ssim = div2(N, D);
+          const f2 nssim = ndiv2(N, D);   // -ssim: one packed instruction less, and the minus signs below disappear
           const uchar2 fl = *reinterpret_cast<const uchar2*>(sh.flag + plane_index(row, c0 + 1));
           const bool in_x = (fl.x & 2) != 0, in_y = (fl.y & 2) != 0;
-          const float h0 = fmaf(lo(ssim), -0.5f, 0.5f), h1 = fmaf(hi(ssim), -0.5f, 0.5f);
+          const float h0 = fmaf(lo(nssim), 0.5f, 0.5f), h1 = fmaf(hi(nssim), 0.5f, 0.5f);
           // torch.clamp passes the gradient on the closed interval; windows centred outside the image do not exist
           const f2 g = mk2((in_x && h0 >= 0.0f && h0 <= 1.0f) ? g_ss : 0.0f, (in_y && h1 >= 0.0f && h1 <= 1.0f) ? g_ss : 0.0f);
           // d ssim / d x_p = U_p * base * [ ... ]  with  base = 2 g avg_w (inverse_avg_w / 9) / D
@@ -215,15 +215,16 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
           f2 ca, cb, cc;
           if (MODE == 1) {
             cc = base;
-            cb = (base * ssim) * bc2(-1.0f);
+            cb = base * nssim;
             ca = (cb * mx + cc * my) * bc2(-1.0f);
           } else if (MODE == 2) {
             cc = bc2(0.0f); cb = bc2(0.0f);
-            ca = base * (my - ssim * mx);
+            ca = base * fma2(nssim, mx, my);
           } else {
             cc = base * n1;
-            cb = ((base * ssim) * d1) * bc2(-1.0f);
-            ca = (base * my) * n2 - ((base * ssim) * mx) * d2 - (cb * mx + cc * my);
+            const f2 bns = base * nssim;
+            cb = bns * d1;
+            ca = fma2(bns * mx, d2, (base * my) * n2) - (cb * mx + cc * my);
           }
           float* pc = planes + kNCoef * kPlane + plane_index(row, c0 + 1);
           *reinterpret_cast<unsigned long long*>(pc) = ca.v;

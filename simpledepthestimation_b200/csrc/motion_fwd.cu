@@ -298,8 +298,8 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
             n = fma2(bc2(2.0f), sxy, C2) * fma2(bc2(2.0f), mx * my, C1);
             d = ((sx + sy) + C2) * (fma2(mx, mx, my * my) + C1);
           }
-          const f2 ssim = div2(n, d);
-          const f2 l = mk2(__saturatef(fmaf(lo(ssim), -0.5f, 0.5f)), __saturatef(fmaf(hi(ssim), -0.5f, 0.5f)));
+          const f2 nssim = ndiv2(n, d);   // -ssim
+          const f2 l = mk2(__saturatef(fmaf(lo(nssim), 0.5f, 0.5f)), __saturatef(fmaf(hi(nssim), 0.5f, 0.5f)));
           acc[o] = fma2(l, avgw[o], acc[o]);
         }
         hX[0] = hX[1]; hX[1] = nX; hA[0] = hA[1]; hA[1] = nA;

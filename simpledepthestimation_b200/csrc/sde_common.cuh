@@ -63,6 +63,14 @@ __device__ __forceinline__ f2 div2(f2 a, f2 b) {
   const f2 q = a * r;
   return fma2(r, fma2(q * bc2(-1.0f), b, a), q);
 }
+// -(a / b), bit for bit the negated div2(a, b), in one packed instruction less: the sign rides on the reciprocal
+// (the negation of b folds into the MUFU operand, rcp(-b) == -rcp(b) exactly), so the residual a - q b is
+// fma(-q, b, a) without a separate negation.  Callers fold the sign into their next constant.
+__device__ __forceinline__ f2 ndiv2(f2 a, f2 b) {
+  const f2 r = mk2(rcp_approx(-lo(b)), rcp_approx(-hi(b)));   // -1/b
+  const f2 q = a * r;                                           // -q
+  return fma2(r, fma2(q, b, a), q);                             // -(q + (a - q b)/b)
+}
 __device__ __forceinline__ f2 ld2(const float* p) {   // 8-byte aligned
   f2 r;
   r.v = *reinterpret_cast<const unsigned long long*>(p);
