@@ -144,6 +144,9 @@ _lib = None
 
 
 def lib_path() -> str:
+    # SDE_LIB_PATH: developer switch for A/B timing of two builds in one GPU session (scratch/ab.sh)
+    if os.environ.get("SDE_LIB_PATH"):
+        return os.environ["SDE_LIB_PATH"]
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsde_loss.so")
 
 

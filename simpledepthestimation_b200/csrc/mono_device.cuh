@@ -59,17 +59,24 @@ __device__ __forceinline__ void divide2(float p0, float p1, float den, float& X,
 
 // Back-project pixel (gx, gy) with depth d through K^-1, move by (R, t), project with K
 // (camera.py:125-163,172-178).  P = K^-1 [x d, y d, d], p = (K R) P + K t, X = p0 / (p2 + 1e-6).
-__device__ __forceinline__ void project_full(const Cam& c, const Proj& pj, float gx, float gy, float d, float P[3],
-                                             float& den, float& X, float& Y) {
+// Two halves, so that a caller that projects one pixel into several sources back-projects once.
+__device__ __forceinline__ void backproject(const Cam& c, float gx, float gy, float d, float P[3]) {
   const float xd = gx * d, yd = gy * d;
   P[0] = c.ki[0] * xd + c.ki[1] * yd + c.ki[2] * d;
   P[1] = c.ki[3] * xd + c.ki[4] * yd + c.ki[5] * d;
   P[2] = c.ki[6] * xd + c.ki[7] * yd + c.ki[8] * d;
+}
+__device__ __forceinline__ void project_point(const Proj& pj, const float P[3], float& den, float& X, float& Y) {
   const float p0 = pj.m[0] * P[0] + pj.m[1] * P[1] + pj.m[2] * P[2] + pj.tau[0];
   const float p1 = pj.m[3] * P[0] + pj.m[4] * P[1] + pj.m[5] * P[2] + pj.tau[1];
   const float p2 = pj.m[6] * P[0] + pj.m[7] * P[1] + pj.m[8] * P[2] + pj.tau[2];
   den = p2 + 1e-6f;
   divide2(p0, p1, den, X, Y);
+}
+__device__ __forceinline__ void project_full(const Cam& c, const Proj& pj, float gx, float gy, float d, float P[3],
+                                             float& den, float& X, float& Y) {
+  backproject(c, gx, gy, d, P);
+  project_point(pj, P, den, X, Y);
 }
 
 // nan_to_num + clamp (camera.py:184-188) and the bilinear cell of grid_sample(align_corners=True).

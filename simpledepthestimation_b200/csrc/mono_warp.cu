@@ -42,33 +42,52 @@ __global__ void __launch_bounds__(kWarpThreads, 4) mono_warp_kernel(const __grid
     load_proj(sh.proj[tid], k, p.pose[tid], b);
   }
   // this thread's depths are loaded before the barrier, so that their latency overlaps the camera threads' loads
+  const int pix0 = chunk * kWarpChunk + tid;
   float dv[kWarpPixPerThread];
 #pragma unroll
   for (int it = 0; it < kWarpPixPerThread; ++it) {
-    const int pix = chunk * kWarpChunk + it * kWarpThreads + tid;
+    const int pix = pix0 + it * kWarpThreads;
     dv[it] = pix < hw ? __ldg(p.depth[s] + (size_t)b * hw + pix) : 0.0f;
   }
+  // pixel coordinates: one integer division per thread, the other pixels follow by stepping kWarpThreads columns
+  int gy = pix0 / w, gx = pix0 - gy * w;
   __syncthreads();
-  const Cam& cam = sh.cam;
+  // camera-space points of this thread's pixels (independent of the source); K^-1 stays in registers meanwhile
+  float P[kWarpPixPerThread][3];
+  {
+    const Cam cam = sh.cam;
 #pragma unroll
-  for (int it = 0; it < kWarpPixPerThread; ++it) {
-    // once every block is on its last pixel, the next kernel of the stream may be scheduled (it waits for this grid
-    // to complete before it touches memory): its launch latency overlaps this kernel's tail
-    if (it == kWarpPixPerThread - 1) pdl_launch_dependents();
-    const int pix = chunk * kWarpChunk + it * kWarpThreads + tid;
-    if (pix >= hw) return;
-    const int gy = pix / w, gx = pix - gy * w;
-    const float d = dv[it];
+    for (int it = 0; it < kWarpPixPerThread; ++it) {
+      backproject(cam, (float)gx, (float)gy, dv[it], P[it]);
+      gx += kWarpThreads;
+      while (gx >= w) { gx -= w; ++gy; }
+    }
+  }
 #pragma unroll 1
-    for (int j = 0; j < p.S; ++j) {
-      const Proj& pj = sh.proj[j];
-      float P[3], den, X, Y;
-      project_full(cam, pj, (float)gx, (float)gy, d, P, den, X, Y);
+  for (int j = 0; j < p.S; ++j) {
+    // K R and K t of this source: registers for the thread's four pixels (they were 21 shared-memory loads per
+    // pixel and source, 15 % of the kernel's L1 wavefronts)
+    Proj pj;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) pj.m[k] = sh.proj[j].m[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pj.tau[k] = sh.proj[j].tau[k];
+    const float* __restrict__ srcb = p.source[s][j] + (size_t)b * 3 * hw;
+    float* __restrict__ dstb = p.warped[s][j] + (size_t)b * kSavedPlanes * hw;
+#pragma unroll
+    for (int it = 0; it < kWarpPixPerThread; ++it) {
+      // once every block is on its last pixel, the next kernel of the stream may be scheduled (it waits for this grid
+      // to complete before it touches memory): its launch latency overlaps this kernel's tail
+      if (j == p.S - 1 && it == kWarpPixPerThread - 1) pdl_launch_dependents();
+      const int pix = pix0 + it * kWarpThreads;
+      if (pix >= hw) break;
+      float den, X, Y;
+      project_point(pj, P[it], den, X, Y);
       const Cell cell = bilinear_cell(X, Y, w, h);
       const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
       const float w00 = bx * by, w01 = cell.ax * by, w10 = bx * cell.ay, w11 = cell.ax * cell.ay;
-      const float* src = p.source[s][j] + (size_t)b * 3 * hw + cell.off;
-      float* dst = p.warped[s][j] + (size_t)b * kSavedPlanes * hw + pix;
+      const float* src = srcb + cell.off;
+      float* dst = dstb + pix;
       // gradient gates of nan_to_num and clamp (closed interval): false for NaN / +-inf
       const float gate_x = (X >= 0.0f && X <= (float)(w - 1)) ? 1.0f : 0.0f;
       const float gate_y = (Y >= 0.0f && Y <= (float)(h - 1)) ? 1.0f : 0.0f;
