@@ -338,6 +338,26 @@ def test_tma_and_thread_staged_planes_give_the_same_bits(dev, monkeypatch):
     _against_oracle(inp, dev)
 
 
+def test_chained_and_plain_launches_give_the_same_bits(dev, monkeypatch):
+    """Programmatic dependent launch (forward kernel chained behind the warp kernel, backward kernel behind its
+    predecessor) only moves launch latency: every output must be bit-identical to plain launches (SDE_DISABLE_PDL=1)
+    and to the all-chained configuration (SDE_PDL_MASK=7), over repeated back-to-back steps."""
+    inp = mono_inputs(2, 96, 320, seed=29)
+    runs = []
+    for env in ({"SDE_DISABLE_PDL": "1"}, {}, {"SDE_PDL_MASK": "7"}):
+        for k in ("SDE_DISABLE_PDL", "SDE_PDL_MASK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for _ in range(3):
+            runs.append(gpu_mono_from_vec(inp, dev))
+    a = runs[0]
+    for b in runs[1:]:
+        assert torch.equal(a["rec_loss"], b["rec_loss"]) and torch.equal(a["smooth_loss"], b["smooth_loss"])
+        for x, y in zip(a["argmin"] + a["grad_depth"] + a["grad_pose_vec"], b["argmin"] + b["grad_depth"] + b["grad_pose_vec"]):
+            assert torch.equal(x, y)
+
+
 def test_host_runner_end_to_end_matches_device_path(dev):
     """HostLossRunner (pinned host arena -> one H2D copy -> device pyramid -> fused fwd + bwd -> one D2H copy, two
     pipelined slots) returns the bits of the device-resident path, step after step."""
