@@ -57,6 +57,26 @@ struct BwdShared {
   __align__(8) uint8_t arg[kPlane];
 };
 
+// zeroes the one-pixel ring (rows 0 and kHH-1, columns 0 and kHW-1) of the three planes b0 .. b0+2: threads 0..65
+// take the two rows, 18 threads of the last warp the two columns -- no index arithmetic beyond the thread id
+__device__ __forceinline__ void zero_ring3(float* planes, int b0, int tid) {
+  static_assert(kHW <= 96 && 96 + kHH <= kThreads, "thread ranges of zero_ring3");
+  if (tid < kHW) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      planes[(b0 + k) * kPlane + plane_index(0, tid)] = 0.0f;
+      planes[(b0 + k) * kPlane + plane_index(kHH - 1, tid)] = 0.0f;
+    }
+  } else if (tid >= 96 && tid < 96 + kHH) {
+    const int yy = tid - 96;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      planes[(b0 + k) * kPlane + plane_index(yy, 0)] = 0.0f;
+      planes[(b0 + k) * kPlane + plane_index(yy, kHW - 1)] = 0.0f;
+    }
+  }
+}
+
 template <bool SAVED>
 __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_constant__ MonoParams p,
                                                                const __grid_constant__ MonoTma maps) {
@@ -79,9 +99,9 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
   // of K and the pose now and form the terms after the argmin bytes are staged, so that nobody waits at the first
   // barrier for two threads' global-memory round trip.
   const bool cam_thread = tid >= 32 && tid < 32 + p.S;
-  // coefficient planes: the 1-pixel border is never written and must read as zero (shared memory only: before the
-  // dependency wait)
-  for (int i = tid; i < 3 * kPlane; i += kThreads) planes[kBY * kPlane + i] = 0.0f;
+  // coefficient planes: the coefficient pass writes every window centre of the block, the one-pixel ring around it
+  // is never written and must read as zero (shared memory only: before the dependency wait)
+  zero_ring3(planes, kBY, tid);
   const bool tma = SAVED && p.tma[s] != 0;
   if (tma && tid == 0) {
     mbar_init(&sh.bar, 1);
@@ -118,10 +138,8 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
   const uint8_t* __restrict__ amap = reduce_mean ? nullptr : p.argmin[s] + (size_t)b * hw;
 
   const float g_rec = __ldg(p.grad_losses), g_smooth = __ldg(p.grad_losses + 1);
-  const int ncand_total = (automask ? 2 : 1) * p.S;
-  // d rec_loss / d pe_q for a selected pixel (MonoDepth2.py:116-124)
-  const float g_pe = g_rec / ((float)p.n_scales * (float)p.B * (float)h * (float)w) /
-                     (reduce_mean ? (float)ncand_total : 1.0f);
+  // d rec_loss / d pe_q for a selected pixel (MonoDepth2.py:116-124); the normaliser comes from the host
+  const float g_pe = g_rec * p.inv_norm[s];
   const float g_l1 = g_pe * p.l1_w * (1.0f / 3.0f);
   const float g_ss = g_pe * p.ssim_w * (1.0f / 3.0f) * -0.5f;  // d pe / d ssim (ssim_loss.py:53)
 
@@ -173,13 +191,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
     if (j > 0) {
       // the coefficient region held the previous source's S / gS planes: its one-pixel border ring (never written
       // by the coefficient pass, never read by phase 4) must read as zero
-      for (int i = tid; i < 3 * (2 * kHW + 2 * kHH); i += kThreads) {
-        const int k = i / (2 * kHW + 2 * kHH), r = i - k * (2 * kHW + 2 * kHH);
-        int yy, xx;
-        if (r < 2 * kHW) { yy = r < kHW ? 0 : kHH - 1; xx = r < kHW ? r : r - kHW; }
-        else { const int q = r - 2 * kHW; yy = q < kHH ? q : q - kHH; xx = q < kHH ? 0 : kHW - 1; }
-        planes[(bC + k) * kPlane + plane_index(yy, xx)] = 0.0f;
-      }
+      zero_ring3(planes, bC, tid);
     }
     const Cam cam = sh.cam;
     const Proj pj = sh.proj[j];
@@ -294,7 +306,9 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
             const uchar2 m = *reinterpret_cast<const uchar2*>(sh.arg + plane_index(row, c0 + 1));
             const f2 df = Sp - Ap;
             const float d0 = lo(df), d1 = hi(df);
-            float l0 = d0 > 0.0f ? g_l1 : -g_l1, l1 = d1 > 0.0f ? g_l1 : -g_l1;
+            // g_l1 * sign(d): the sign bit of d flips g_l1 (one LOP3), sign(0) = 0 and unselected pixels through the select
+            float l0 = __int_as_float(__float_as_int(g_l1) ^ (__float_as_int(d0) & 0x80000000));
+            float l1 = __int_as_float(__float_as_int(g_l1) ^ (__float_as_int(d1) & 0x80000000));
             l0 = (m.x == cand && d0 != 0.0f) ? l0 : 0.0f;
             l1 = (m.y == cand && d1 != 0.0f) ? l1 : 0.0f;
             gS = gS + mk2(l0, l1);

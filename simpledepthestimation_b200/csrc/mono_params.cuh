@@ -34,6 +34,7 @@ struct MonoParams {
   float* stats;           // [n_scales*B][2] = (mean inverse depth, per-image smoothness)
   float ssim_w, l1_w, c1, c2;
   float smooth_scale[SDE_MAX_SCALES];  // scale_w * SMOOTHNESS_WEIGHT / n_scales (MonoDepth2.py:80,103-105)
+  float inv_norm[SDE_MAX_SCALES];      // 1 / (n_scales * B * h * w [* candidates for 'mean']): d rec_loss / d pe of a selected pixel
   unsigned flags;
   // forward workspace
   float* partials;        // [grid][4]

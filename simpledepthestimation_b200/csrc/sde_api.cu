@@ -112,6 +112,11 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
     }
     const double scale_w = 1.0 / (double)(1 << (d->n_scales - i - 1));
     p.smooth_scale[i] = d->smooth_weight > 0.0f ? (float)(scale_w * (double)d->smooth_weight / d->n_scales) : 0.0f;
+    {
+      const bool mean = (d->flags & SDE_MONO_REDUCE_MEAN) != 0, am = (d->flags & SDE_MONO_AUTOMASK) != 0;
+      const double ncand = mean ? (double)((am ? 2 : 1) * d->n_sources) : 1.0;
+      p.inv_norm[i] = (float)(1.0 / ((double)d->n_scales * (double)d->batch * (double)p.h[i] * (double)p.w[i] * ncand));
+    }
   }
   for (int i = d->n_scales; i <= SDE_MAX_SCALES; ++i) {
     p.tile_start[i] = start;
