@@ -53,7 +53,7 @@ struct BwdShared {
   double dred[12][kWarps];
   unsigned ticket;
   __align__(8) uint64_t bar;                     // TMA completion barrier
-  unsigned short list[kWarps][kListPerWarp];     // per warp: dense list (plane indices) of its pixels of P that carry a gradient
+  unsigned short list[kWarps][kListPerWarp];     // per warp: dense list ((plane row << 7) | stored column) of its pixels of P that carry a gradient
   __align__(8) uint8_t arg[kPlane];
 };
 
@@ -378,9 +378,9 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
         const bool s0 = row_ok && col_ok0 && (lo(g0) != 0.0f || lo(g1) != 0.0f || lo(g2) != 0.0f);
         const bool s1 = row_ok && col_ok1 && (hi(g0) != 0.0f || hi(g1) != 0.0f || hi(g2) != 0.0f);
         const unsigned b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1);
-        if (s0) wlist[total + __popc(b0 & lt)] = (unsigned short)pl;
+        if (s0) wlist[total + __popc(b0 & lt)] = (unsigned short)((row << 7) | (c0 + 1 + kColOff));
         total += __popc(b0);
-        if (s1) wlist[total + __popc(b1 & lt)] = (unsigned short)(pl + 1);
+        if (s1) wlist[total + __popc(b1 & lt)] = (unsigned short)((row << 7) | (c0 + 2 + kColOff));
         total += __popc(b1);
       }
       __syncwarp();
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
       auto fetch = [&](int k) {
         npl = wlist[k];
         if (SAVED) {
-          const int row = npl / kPitch, col = npl - row * kPitch - kColOff;
+          const int row = npl >> 7, col = (npl & 127) - kColOff;
           const float* q = dw + ((oy + row) * w + (ox + col));
 #pragma unroll
           for (int i = 0; i < 6; ++i) nd[i] = __ldg(q + i * hw);
@@ -405,13 +405,13 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
       if (lane < total) fetch(lane);
 #pragma unroll 1
       for (int k = lane; k < total; k += 32) {
-        const int pl = npl;
+        const int ent = npl;   // (plane row << 7) | stored column index
         float dv[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) dv[i] = nd[i];
         if (k + 32 < total) fetch(k + 32);
-        const int row = pl / kPitch, col = pl - row * kPitch - kColOff;
-        const int gy = oy + row, gx = ox + col;
+        const int row = ent >> 7, ci = ent & 127, pl = row * kPitch + ci;
+        const int gy = oy + row, gx = ox + ci - kColOff;
         float* const pg = planes + bS * kPlane + pl;
         const float g0 = pg[0], g1 = pg[kPlane], g2 = pg[2 * kPlane];
         const float d = planes[kBD * kPlane + pl];
@@ -467,13 +467,14 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
         pg[0] = gdep;   // in place of gS_0: unlisted pixels of P hold gS_0 == 0 there
       }
       // the 12 pose sums of this (warp, source) -> per-warp slot
-      float mine = 0.0f;
+      {
+        float v16[16];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        const float v = warp_sum(acc[k]);
-        if (lane == k) mine = v;
+        for (int k = 0; k < 16; ++k) v16[k] = k < 12 ? acc[k] : 0.0f;
+        const float mine = warp_sum16(v16, lane);
+        const int slot = warp_slot(lane);
+        if ((lane & 1) == 0 && slot < 12) p.pose_partials[(((size_t)blockIdx.x * kWarps + wid) * p.S + j) * 12 + slot] = mine;
       }
-      if (lane < 12) p.pose_partials[(((size_t)blockIdx.x * kWarps + wid) * p.S + j) * 12 + lane] = mine;
       __syncwarp();
       // pick up the depth gradients of this lane's own pixels (pairs outside P / the image hold garbage that is never stored)
 #pragma unroll

@@ -112,6 +112,26 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Sums 16 per-lane values over the warp with 16 shuffles instead of 80: at every step a lane keeps one half of its
+// values and hands the other half to its partner (offsets 16, 8, 4, 2), then the last exchange (offset 1) completes
+// the sums.  Returns the total of value warp_slot(lane) -- lanes 2k and 2k+1 hold the same total.  Fixed order.
+__device__ __forceinline__ int warp_slot(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+__device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = up ? v[i + half] : v[i];
+      const float send = up ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // reflect index as nn.ReflectionPad2d(1) does (-1 -> 1, n -> n-2), then clamp for tiles that
 // overhang the image (those positions are never used by a valid output)
 __device__ __forceinline__ int reflect_clamp(int i, int n) {
