@@ -186,7 +186,11 @@ __device__ __forceinline__ void tile_smoothness(const float* planes, int plD, in
     // 1 / clamp(d, min=1e-6) through a refined hardware reciprocal (<= 1 ulp; NaN stays NaN), exp through ex2.approx
     // (2 ulp): both far inside the 1e-5 loss tolerance and a fifth of the instructions of the IEEE forms
     auto inv = [](float d) { return inv_depth(d); };
-    auto sgn = [](float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); };
+    // sgn(v) * ws for ws >= 0 (sgn(0) = sgn(NaN) = 0): the sign bit of v rides onto ws, one compare selects
+    auto sgn_mul = [](float v, float ws) {
+      const float sw = __int_as_float(__float_as_int(ws) ^ (__float_as_int(v) & 0x80000000));
+      return fabsf(v) > 0.0f ? sw : 0.0f;
+    };
     const float inx = 1.0f / ((float)B * (float)h * (float)(w - 1));
     const float iny = 1.0f / ((float)B * (float)(h - 1) * (float)w);
     const bool v0 = gx0 < w, v1 = gx0 + 1 < w, v2 = gx0 + 2 < w, vl = gx0 >= 1 && v0;
@@ -216,8 +220,8 @@ __device__ __forceinline__ void tile_smoothness(const float* planes, int plD, in
       }
       const bool ve = gyu >= 0 && gyu + 1 < h;
       const float w0 = __expf(-e0 * (1.0f / 3.0f)), w1 = __expf(-e1 * (1.0f / 3.0f));
-      tv0[rr] = (ve && v0) ? sgn(iu0 - il0) * w0 * iny : 0.0f;
-      tv1[rr] = (ve && v1) ? sgn(iu1 - il1) * w1 * iny : 0.0f;
+      tv0[rr] = (ve && v0) ? sgn_mul(iu0 - il0, w0 * iny) : 0.0f;
+      tv1[rr] = (ve && v1) ? sgn_mul(iu1 - il1, w1 * iny) : 0.0f;
       if (rr >= 1) {   // the edge below an owned row is counted by this lane
         if (ve && v0) smy += fabsf(iu0 - il0) * w0;
         if (ve && v1) smy += fabsf(iu1 - il1) * w1;
@@ -246,9 +250,9 @@ __device__ __forceinline__ void tile_smoothness(const float* planes, int plD, in
         if (v1) smx += fabsf(i0 - i1) * wM;
         if (v2) smx += fabsf(i1 - iR) * wR;
         if (gout) {
-          const float tL = vl ? sgn(iL - i0) * wL * inx : 0.0f;
-          const float tM = v1 ? sgn(i0 - i1) * wM * inx : 0.0f;
-          const float tR = v2 ? sgn(i1 - iR) * wR * inx : 0.0f;
+          const float tL = vl ? sgn_mul(iL - i0, wL * inx) : 0.0f;
+          const float tM = v1 ? sgn_mul(i0 - i1, wM * inx) : 0.0f;
+          const float tR = v2 ? sgn_mul(i1 - iR, wR * inx) : 0.0f;
           const float G0 = ((tM - tL) + tv0[o + 1]) - tv0[o];
           const float G1 = ((tR - tM) + tv1[o + 1]) - tv1[o];
           float* po = gout + gy * w + gx0;

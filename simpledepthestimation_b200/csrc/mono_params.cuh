@@ -34,6 +34,8 @@ struct MonoParams {
   float* stats;           // [n_scales*B][2] = (mean inverse depth, per-image smoothness)
   float ssim_w, l1_w, c1, c2;
   float smooth_scale[SDE_MAX_SCALES];  // scale_w * SMOOTHNESS_WEIGHT / n_scales (MonoDepth2.py:80,103-105)
+  // reciprocals of the tile counts (forward: x, y; backward: x, y) for the division-free tile decoding
+  float rtiles[SDE_MAX_SCALES][4];
   float inv_norm[SDE_MAX_SCALES];      // 1 / (n_scales * B * h * w [* candidates for 'mean']): d rec_loss / d pe of a selected pixel
   unsigned flags;
   // forward workspace
@@ -67,16 +69,23 @@ struct TileCoord {
   int s, b, x0, y0;
 };
 
+// t / d and t % d for 0 <= t < 2^22 through the host-rounded reciprocal rd = 1.0f / d: (t + 0.5) / d is at least
+// 0.5 / d away from an integer while the rounding error of (t + 0.5) * rd stays below (t / d) * 2^-23, so the
+// truncation is exact (the host rejects descriptors with 2^22 or more tiles per scale).
+__device__ __forceinline__ void small_divmod(int t, int d, float rd, int& q, int& r) {
+  q = (int)(((float)t + 0.5f) * rd);
+  r = t - q * d;
+}
+
 __device__ __forceinline__ TileCoord decode_tile(const MonoParams& p, int bid) {
   int s = 0;
   while (s + 1 < p.n_scales && bid >= p.tile_start[s + 1]) ++s;
-  int t = bid - p.tile_start[s];
-  const int tx = t % p.tiles_x[s];
-  t /= p.tiles_x[s];
-  const int ty = t % p.tiles_y[s];
+  int t = bid - p.tile_start[s], tx, ty, b;
+  small_divmod(t, p.tiles_x[s], p.rtiles[s][0], t, tx);
+  small_divmod(t, p.tiles_y[s], p.rtiles[s][1], b, ty);
   TileCoord c;
   c.s = s;
-  c.b = t / p.tiles_y[s];
+  c.b = b;
   c.x0 = tx * kTileW;
   c.y0 = ty * kTileH;
   return c;
@@ -86,13 +95,12 @@ __device__ __forceinline__ TileCoord decode_tile(const MonoParams& p, int bid) {
 __device__ __forceinline__ TileCoord decode_btile(const MonoParams& p, int bid) {
   int s = 0;
   while (s + 1 < p.n_scales && bid >= p.btile_start[s + 1]) ++s;
-  int t = bid - p.btile_start[s];
-  const int tx = t % p.btiles_x[s];
-  t /= p.btiles_x[s];
-  const int ty = t % p.btiles_y[s];
+  int t = bid - p.btile_start[s], tx, ty, b;
+  small_divmod(t, p.btiles_x[s], p.rtiles[s][2], t, tx);
+  small_divmod(t, p.btiles_y[s], p.rtiles[s][3], b, ty);
   TileCoord c;
   c.s = s;
-  c.b = t / p.btiles_y[s];
+  c.b = b;
   c.x0 = tx * kBwdW;
   c.y0 = ty * kBwdH;
   return c;

@@ -98,6 +98,10 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
     p.btiles_y[i] = (p.h[i] + kBwdH - 1) / kBwdH;
     p.btile_start[i] = bstart;
     bstart += p.B * p.btiles_x[i] * p.btiles_y[i];
+    if ((long long)p.B * p.tiles_x[i] * p.tiles_y[i] >= (1 << 22) || (long long)p.B * p.btiles_x[i] * p.btiles_y[i] >= (1 << 22))
+      return SDE_ERR_INVALID_ARG;   // small_divmod (mono_params.cuh) is exact below 2^22 tiles per scale
+    p.rtiles[i][0] = 1.0f / (float)p.tiles_x[i]; p.rtiles[i][1] = 1.0f / (float)p.tiles_y[i];
+    p.rtiles[i][2] = 1.0f / (float)p.btiles_x[i]; p.rtiles[i][3] = 1.0f / (float)p.btiles_y[i];
     // x_scale = w_i / W as the reference forms it (MonoDepth2.py:83-85), then cast to fp32 by the multiply
     p.sx[i] = (float)((double)p.w[i] / (double)d->full_width);
     p.sy[i] = (float)((double)p.h[i] / (double)d->full_height);
