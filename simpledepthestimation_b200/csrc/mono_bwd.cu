@@ -529,8 +529,8 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
 
   // ------------------------------------------------------------------ last tile of a sample: pose gradients
   // The tile that finishes a sample last (over all scales) adds that sample's per-CTA slots in a fixed
-  // order in fp64, while other samples are still being computed.
-  __threadfence();
+  // order in fp64, while other samples are still being computed.  Only the lanes that wrote pose slots fence.
+  if ((lane & 1) == 0 && warp_slot(lane) < 12) __threadfence();
   __syncthreads();
   int total_b = 0;
   for (int ss = 0; ss < p.n_scales; ++ss) total_b += p.btiles_x[ss] * p.btiles_y[ss];

@@ -281,19 +281,22 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   rec = warp_sum(rec); smx = warp_sum(smx); smy = warp_sum(smy); sinv = warp_sum(sinv);
   if (lane == 0) { sh.red[0][wid] = rec; sh.red[1][wid] = smx; sh.red[2][wid] = smy; sh.red[3][wid] = sinv; }
   __syncthreads();
-  if (tid < 4) {
-    float v = 0.0f;
-#pragma unroll
-    for (int k = 0; k < kThreads / 32; ++k) v += sh.red[tid][k];
-    p.partials[(size_t)blockIdx.x * 4 + tid] = v;
-  }
-  __threadfence();
-  __syncthreads();
   // ------------------------------------------------------------------ two-level fixed-order reduction
   // The last tile of a (scale, image) pair adds that image's partial slots (while other images are still
   // being computed); the last pair to finish adds the per-image results.  Same order every run.
+  // One thread publishes the slot, fences it and takes the ticket: the other threads' stores (argmin bytes,
+  // smoothness gradient) are consumed by later kernels only and need no fence here.
   const int q = s * p.B + b, per = p.tiles_x[s] * p.tiles_y[s];
-  if (tid == 0) sh.ticket = atomicAdd(p.img_counter + q, 1u);
+  if (tid == 0) {
+    float4 v;
+    v.x = ((sh.red[0][0] + sh.red[0][1]) + sh.red[0][2]) + sh.red[0][3];
+    v.y = ((sh.red[1][0] + sh.red[1][1]) + sh.red[1][2]) + sh.red[1][3];
+    v.z = ((sh.red[2][0] + sh.red[2][1]) + sh.red[2][2]) + sh.red[2][3];
+    v.w = ((sh.red[3][0] + sh.red[3][1]) + sh.red[3][2]) + sh.red[3][3];
+    *reinterpret_cast<float4*>(p.partials + (size_t)blockIdx.x * 4) = v;
+    __threadfence();
+    sh.ticket = atomicAdd(p.img_counter + q, 1u);
+  }
   __syncthreads();
   if (sh.ticket != (unsigned)(per - 1)) return;
   __threadfence();
