@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SDE_ABI_VERSION 2
+#define SDE_ABI_VERSION 3
 #define SDE_MAX_SCALES 6
 #define SDE_MAX_SOURCES 4
 
@@ -147,9 +147,10 @@ typedef struct sde_motion_buffers {
   float* occlusion[SDE_MAX_DIRS];       /* optional [B,1,h,w] occlusion_mask (MotionLearning.py:257-259) */
   float* weight[SDE_MAX_DIRS];          /* optional [B,1,h,w] depth_proximity_weight (MotionLearning.py:279-282) */
   float* coords[SDE_MAX_DIRS];          /* optional [B,h,w,2] coords_A_in_B, normalised (camera.py:190-193) */
-  /* optional, forward output / backward input: [B,12,h,w] per direction = warped rgb (3), depth_error (1),
+  /* optional, forward output / backward input: [B,16,h,w] per direction = warped rgb (3), depth_error (1),
    * valid + 2 * occlusion (1), d warped_c / dX (3) and d warped_c / dY (3) w.r.t. the sample coordinate (zero where
-   * nan_to_num / clamp gate the gradient) and the local smoothness gradient d smoothness / d (1/depth_A) (1).  When
+   * nan_to_num / clamp gate the gradient), the local smoothness gradient d smoothness / d (1/depth_A) (1), and four
+   * planes of scratch (frame B and depth B interleaved per pixel for the gather of the forward pass).  When
    * given (and the row pitch is a multiple of 16 bytes) the statistics pre-pass doubles as the warp kernel, the loss
    * kernels take these planes through TMA instead of re-projecting and re-gathering, and the backward kernel never
    * touches frame B again.  NULL = recompute. */

@@ -5,7 +5,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 2   # SDE_ABI_VERSION of include/sde_loss.h this binding was written against
+ABI_VERSION = 3   # SDE_ABI_VERSION of include/sde_loss.h this binding was written against
 MAX_SCALES = 6
 MAX_SOURCES = 4
 FLAG_AUTOMASK = 1

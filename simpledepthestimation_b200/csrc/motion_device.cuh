@@ -47,7 +47,9 @@ struct MotionParams {
   float* grad_field[SDE_MAX_DIRS];
 };
 
-constexpr int kMotionSaved = 12;   // planes per sample of a `warped` buffer
+constexpr int kMotionSaved = 16;   // planes per sample of a `warped` buffer: 12 kept planes + 4 planes of scratch
+constexpr int kMotionPacked = 12;  // first scratch plane: frame B and depth B of the sample interleaved per pixel
+                                   // ([h*w] float4 = r, g, b, depth), written by motion_pack_kernel for the gather
 constexpr int kStatThreads = 256;
 constexpr int kStatPixPerThread = 4;
 constexpr int kStatPix = kStatThreads * kStatPixPerThread;
@@ -128,6 +130,7 @@ struct MotionStage {
   const float* __restrict__ frame_a;
   const float* __restrict__ frame_b;
   const float* __restrict__ field;     // nullptr = rigid
+  const float4* __restrict__ packed = nullptr;   // frame_b + depth_b interleaved per pixel (warp mode) or nullptr
   float* planes;
   int oy, ox, h, w, hw;
   float m2;                            // depth_err_2nd_mom of this sample
@@ -151,6 +154,26 @@ __device__ __forceinline__ void motion_sample(const MotionStage& a, const MCam& 
   const Cell cell = bilinear_cell(X, Y, a.w, a.h);
   const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
   const float w00 = bx * by, w01 = cell.ax * by, w10 = bx * cell.ay, w11 = cell.ax * cell.ay;
+  if (a.packed && rgb) {
+    // one 16-byte load per tap brings r, g, b and depth: 4 requests per pixel instead of 16, and every byte of the
+    // sectors they touch is used (the planar taps of a 1920-wide noisy-depth gather hit 23 sectors per request)
+    const float4* q = a.packed + cell.off;
+    const float4 t00 = __ldg(q), t01 = __ldg(q + 1), t10 = __ldg(q + a.w), t11 = __ldg(q + a.w + 1);
+    const float gate_x = (X >= 0.0f && X <= (float)(a.w - 1)) ? 1.0f : 0.0f;
+    const float gate_y = (Y >= 0.0f && Y <= (float)(a.h - 1)) ? 1.0f : 0.0f;
+    o.Sd = t00.w * w00 + t01.w * w01 + t10.w * w10 + t11.w * w11;   // ATen's order: nw, ne, sw, se
+    const float a00[3] = {t00.x, t00.y, t00.z}, a01[3] = {t01.x, t01.y, t01.z};
+    const float a10[3] = {t10.x, t10.y, t10.z}, a11[3] = {t11.x, t11.y, t11.z};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o.S[c] = a00[c] * w00 + a01[c] * w01 + a10[c] * w10 + a11[c] * w11;
+      if (want_deriv) {
+        o.dSx[c] = gate_x * ((a01[c] - a00[c]) * by + (a11[c] - a10[c]) * cell.ay);
+        o.dSy[c] = gate_y * ((a10[c] - a00[c]) * bx + (a11[c] - a01[c]) * cell.ax);
+      }
+      if (load_a) o.A[c] = __ldg(a.frame_a + pix + c * a.hw);
+    }
+  } else {
   o.Sd = bilinear4(a.depth_b + cell.off, a.w, w00, w01, w10, w11);
   if (rgb) {
     // gradient gates of nan_to_num and clamp (closed interval, camera.py:184-188); false for NaN / +-inf
@@ -167,6 +190,7 @@ __device__ __forceinline__ void motion_sample(const MotionStage& a, const MCam& 
       }
       if (load_a) o.A[c] = __ldg(a.frame_a + pix + c * a.hw);
     }
+  }
   }
   o.valid = valid_mask(X, Y, Z, a.w, a.h);
   o.Zc = clamp_depth(Z);

@@ -26,6 +26,23 @@ constexpr int kMA = 0, kMS = 3, kMU = 6, kMW = 7, kMD = 8;
 constexpr int kMotionFwdPlanes = 9;
 
 // ------------------------------------------------------------------------------------------------
+// Warp mode only: frame B and depth B of every (direction, sample) interleaved per pixel into the scratch planes of
+// the `warped` buffer, so that the gather of the statistics / warp pass is one 16-byte load per tap.  Coalesced
+// planar reads, coalesced 16-byte stores; 32 bytes of traffic per pixel.
+__global__ void __launch_bounds__(kStatThreads) motion_pack_kernel(const __grid_constant__ MotionParams p) {
+  const int img = blockIdx.x / p.stat_blocks, chunk = blockIdx.x - img * p.stat_blocks;
+  const int dir = img / p.B, b = img - dir * p.B;
+  const int hw = p.h * p.w;
+  const float* __restrict__ fb = p.frame_b[dir] + (size_t)b * 3 * hw;
+  const float* __restrict__ db = p.depth_b[dir] + (size_t)b * hw;
+  float4* __restrict__ out = reinterpret_cast<float4*>(p.warped[dir] + ((size_t)b * kMotionSaved + kMotionPacked) * hw);
+#pragma unroll
+  for (int k = 0; k < kStatPixPerThread; ++k) {
+    const int pix = chunk * kStatPix + k * kStatThreads + threadIdx.x;
+    if (pix < hw) out[pix] = make_float4(__ldg(fb + pix), __ldg(fb + hw + pix), __ldg(fb + 2 * hw + pix), __ldg(db + pix));
+  }
+}
+
 __global__ void __launch_bounds__(kStatThreads) motion_stats_kernel(const __grid_constant__ MotionParams p) {
   __shared__ MCam s_cam;
   __shared__ float red[2][kStatThreads / 32];
@@ -46,6 +63,7 @@ __global__ void __launch_bounds__(kStatThreads) motion_stats_kernel(const __grid
   st.frame_b = p.frame_b[dir] + (size_t)b * 3 * hw;
   // warp mode: this pass also gathers the rgb channels and leaves the planes the loss kernels stage by TMA
   float* __restrict__ wout = p.warped[dir] ? p.warped[dir] + (size_t)b * kMotionSaved * hw : nullptr;
+  if (wout) st.packed = reinterpret_cast<const float4*>(wout + (size_t)kMotionPacked * hw);   // motion_pack_kernel ran
   float* __restrict__ occ_out = (wout && p.occ[dir]) ? p.occ[dir] + (size_t)b * hw : nullptr;
   float* __restrict__ crd_out = (wout && p.coords[dir]) ? p.coords[dir] + (size_t)b * hw * 2 : nullptr;
   float socc = 0.0f, serr = 0.0f;
@@ -382,6 +400,11 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
 size_t motion_fwd_smem_bytes() { return (size_t)kMotionFwdPlanes * kPlane * sizeof(float); }
 
 cudaError_t launch_motion_fwd(const MotionParams& p, const MotionTma& t, cudaStream_t stream) {
+  if (p.warped[0]) {   // warp mode (all directions or none, motion_tma): interleave frame B + depth B for the gather
+    motion_pack_kernel<<<p.n_dirs * p.B * p.stat_blocks, kStatThreads, 0, stream>>>(p);
+    cudaError_t e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) return e0;
+  }
   motion_stats_kernel<<<p.n_dirs * p.B * p.stat_blocks, kStatThreads, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -384,12 +384,13 @@ class MotionLossPlan:
             raise _lib.SdeError("intrinsics must be contiguous [B,3,3]")
 
     def new_warped(self):
-        """Buffers for what one step keeps from the forward to the backward pass (per direction [B,12,h,w]: warped
-        rgb, depth error, valid/occlusion, derivatives of the warp, local smoothness gradient), or None."""
+        """Buffers for what one step keeps from the forward to the backward pass (per direction [B,16,h,w]: warped
+        rgb, depth error, valid/occlusion, derivatives of the warp, local smoothness gradient, and four planes of
+        scratch for the interleaved copy of frame B + depth B that the gather reads), or None."""
         if not self.save_warped:
             return None
         h, w = self.size
-        return [torch.empty(self.batch, 12, h, w, dtype=torch.float32, device=self.device) for _ in range(self.n_dirs)]
+        return [torch.empty(self.batch, 16, h, w, dtype=torch.float32, device=self.device) for _ in range(self.n_dirs)]
 
     def _buffers(self, frame_a, frame_b, depth_a, depth_b, K, pose, field, warped=None):
         b = _lib.MotionBuffers()
