@@ -51,7 +51,8 @@ constexpr int kMotionSaved = 16;   // planes per sample of a `warped` buffer: 12
 constexpr int kMotionPacked = 12;  // first scratch plane: frame B and depth B of the sample interleaved per pixel
                                    // ([h*w] float4 = r, g, b, depth), written by motion_pack_kernel for the gather
 constexpr int kStatThreads = 256;
-constexpr int kStatPixPerThread = 4;
+constexpr int kStatPixPerThread = 16;   // 4096 pixels per block: the camera prologue (one thread's global loads + barrier) and the
+                                        // ticket epilogue were 20 % of a 1024-pixel block's lifetime
 constexpr int kStatPix = kStatThreads * kStatPixPerThread;
 
 // Per-(direction, sample) camera terms: scaled K, K^-1, M = K R, R and the pose translation.

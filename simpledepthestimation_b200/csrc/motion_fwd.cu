@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kStatThreads) motion_pack_kernel(const __grid_
   const float* __restrict__ fb = p.frame_b[dir] + (size_t)b * 3 * hw;
   const float* __restrict__ db = p.depth_b[dir] + (size_t)b * hw;
   float4* __restrict__ out = reinterpret_cast<float4*>(p.warped[dir] + ((size_t)b * kMotionSaved + kMotionPacked) * hw);
-#pragma unroll
+#pragma unroll 4
   for (int k = 0; k < kStatPixPerThread; ++k) {
     const int pix = chunk * kStatPix + k * kStatThreads + threadIdx.x;
     if (pix < hw) out[pix] = make_float4(__ldg(fb + pix), __ldg(fb + hw + pix), __ldg(fb + 2 * hw + pix), __ldg(db + pix));
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kStatThreads) motion_stats_kernel(const __grid
 #pragma unroll
     for (int k = 0; k < kStatThreads / 32; ++k) v += red[tid][k];
     p.stat_partials[(size_t)blockIdx.x * 2 + tid] = v;
+    __threadfence();   // only the two threads that publish the slot fence (the planes are consumed by later kernels)
   }
-  __threadfence();
   __syncthreads();
   if (tid == 0) ticket = atomicAdd(p.counters, 1u);
   __syncthreads();
