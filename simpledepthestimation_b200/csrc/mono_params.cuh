@@ -13,6 +13,17 @@ constexpr int kRowsPerWarp = 4;
 constexpr int kSavedPlanes = 9;   // planes per sample of a `warped` buffer: warp[3], d/dX[3], d/dY[3]
 // backward: a CTA recomputes SSIM on a kTileW x kTileH block of window centres and emits
 // gradients for its interior (the 3x3 adjoint needs one ring of neighbours)
+// warp kernel (mono_warp.cu): threads per block, pixels per thread, pixels per block.  Measured at cfg2 (full step,
+// same box): 128 x 4: 274.7 us, 256 x 4: 273.8, 512 x 4: 270.9, 1024 x 4: 273.9, 512 x 2: 274.0, 512 x 8: 281.7
+#ifndef SDE_WARP_THREADS
+#define SDE_WARP_THREADS 512
+#endif
+constexpr int kWarpThreads = SDE_WARP_THREADS;
+#ifndef SDE_WARP_PIX
+#define SDE_WARP_PIX 4
+#endif
+constexpr int kWarpPixPerThread = SDE_WARP_PIX;
+constexpr int kWarpChunk = kWarpThreads * kWarpPixPerThread;
 constexpr int kBwdW = kTileW - 4;   // 60: a multiple of 4, so that TMA boxes of the backward tiles start 16-byte aligned
 constexpr int kBwdH = kTileH - 2;   // 14
 
@@ -53,7 +64,7 @@ struct MonoParams {
   int btile_start[SDE_MAX_SCALES + 1];
   int tma[SDE_MAX_SCALES];   // tile planes of this scale are staged by TMA (tensor maps in MonoTma are valid)
   int prewarp[SDE_MAX_SCALES];            // forward: the loss kernel takes warped[s][*] (filled by the warp kernel) through TMA
-  int warp_start[SDE_MAX_SCALES + 1];     // warp kernel: first block of scale s (blocks of 1024 pixels per sample)
+  int warp_start[SDE_MAX_SCALES + 1];     // warp kernel: first block of scale s (blocks of kWarpChunk pixels per sample)
 };
 
 // Tensor maps over the [planes, h, w] inputs of every scale, box {68, 18, 1} (tma.cuh).  Second kernel

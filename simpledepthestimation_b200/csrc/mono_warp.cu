@@ -14,18 +14,15 @@
 
 namespace sde {
 
-constexpr int kWarpThreads = 256;
-constexpr int kWarpPixPerThread = 4;
-constexpr int kWarpChunk = kWarpThreads * kWarpPixPerThread;   // pixels per block
 
 struct WarpShared {
   Cam cam;
   Proj proj[SDE_MAX_SOURCES];
 };
 
-__global__ void __launch_bounds__(kWarpThreads, 4) mono_warp_kernel(const __grid_constant__ MonoParams p) {
+__global__ void __launch_bounds__(kWarpThreads, 1024 / kWarpThreads) mono_warp_kernel(const __grid_constant__ MonoParams p) {
   __shared__ WarpShared sh;
-  // blockIdx.x -> (scale, sample, chunk of 1024 pixels)
+  // blockIdx.x -> (scale, sample, chunk of kWarpChunk pixels)
   int s = 0, bid = blockIdx.x;
   while (s + 1 < p.n_scales && bid >= p.warp_start[s + 1]) ++s;
   bid -= p.warp_start[s];

@@ -240,7 +240,7 @@ static void mono_tma(const sde_mono_desc* d, const sde_mono_buffers* b, bool bac
     p.warp_start[i] = start;
     // the warp kernel fills the `warped` buffers of every scale (the loss kernels of a scale that cannot take
     // the TMA path stage them with plain loads / gather themselves)
-    if (i < d->n_scales && !backward && b->warped[i][0]) start += d->batch * ((d->height[i] * d->width[i] + 1023) / 1024);   // kWarpChunk pixels per block
+    if (i < d->n_scales && !backward && b->warped[i][0]) start += d->batch * ((d->height[i] * d->width[i] + kWarpChunk - 1) / kWarpChunk);
   }
 }
 
