@@ -164,7 +164,8 @@ typedef struct sde_motion_buffers {
 } sde_motion_buffers;
 
 size_t sde_motion_workspace_bytes(const sde_motion_desc* desc);
-/* writes losses, saved_stats and the optional maps (two launches: statistics pre-pass + fused loss) */
+/* writes losses, saved_stats and the optional maps (launches: [interleave frame B + depth B, warp mode only,]
+ * statistics / warp pre-pass, fused loss) */
 int sde_motion_loss_forward(const sde_motion_desc* desc, const sde_motion_buffers* buf, void* stream);
 /* reads saved_stats, grad_losses; recomputes the warp; writes grad_depth_a, grad_pose, grad_field */
 int sde_motion_loss_backward(const sde_motion_desc* desc, const sde_motion_buffers* buf, void* stream);
