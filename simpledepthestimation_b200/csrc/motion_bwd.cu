@@ -30,6 +30,7 @@ constexpr int kMPosPerThread = (kBwdW * kBwdH + kThreads - 1) / kThreads;  // 7
 struct MotionBwdShared {
   MCam cam;
   float red[12][kThreads / 32];
+  double dred[12][kThreads / 32];
   unsigned ticket;
   __align__(8) uint64_t bar;             // TMA completion barrier
   __align__(8) uint8_t flag[kPlane];     // bit 0: occlusion mask of the staged position, bit 1: it lies in the image
@@ -420,24 +421,25 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
 #pragma unroll
       for (int k = 0; k < kThreads / 32; ++k) v += sh.red[tid][k];
       p.pose_partials[(size_t)blockIdx.x * 12 + tid] = v;
+      __threadfence();   // only the publishing threads fence
     }
   }
 
-  // ------------------------------------------------------------------ last CTA: pose gradients
-  __threadfence();
+  // ------------------------------------------------------------------ last tile of an image: its pose gradient
+  // Every (direction, sample) has its own grad_pose, so the tile that finishes an image last adds that image's slots
+  // in a fixed order in fp64 while the other images are still being computed (no serial last-CTA tail).
   __syncthreads();
-  if (tid == 0) sh.ticket = atomicAdd(p.counters + 2, 1u);
+  const int per_img = p.btiles_x * p.btiles_y, img = dir * p.B + b;
+  if (tid == 0) sh.ticket = atomicAdd(p.img_counter_b + img, 1u);
   __syncthreads();
-  if (sh.ticket != gridDim.x - 1) return;
+  if (sh.ticket != (unsigned)(per_img - 1)) return;
   __threadfence();
-  const int per_img = p.btiles_x * p.btiles_y;
-  for (int task = wid; task < p.n_dirs * p.B; task += kThreads / 32) {   // one warp per (direction, sample)
-    const int td = task / p.B, tb = task - td * p.B;
+  {
     double a[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) a[k] = 0.0;
-    const size_t first = (size_t)td * p.btiles_per_dir + (size_t)tb * per_img;
-    for (int t = lane; t < per_img; t += 32) {
+    const size_t first = (size_t)dir * p.btiles_per_dir + (size_t)b * per_img;
+    for (int t = tid; t < per_img; t += kThreads) {
       const float4* part = reinterpret_cast<const float4*>(p.pose_partials + (first + t) * 12);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -450,13 +452,15 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
     if (lane == 0) {
-      float* gp = p.grad_pose[td] + tb * 16;
 #pragma unroll
-      for (int k = 0; k < 12; ++k) gp[k] = (float)a[k];
-      gp[12] = gp[13] = gp[14] = gp[15] = 0.0f;
+      for (int k = 0; k < 12; ++k) sh.dred[k][wid] = a[k];
     }
+    __syncthreads();
+    float* gp = p.grad_pose[dir] + b * 16;
+    if (tid < 12) gp[tid] = (float)(((sh.dred[tid][0] + sh.dred[tid][1]) + sh.dred[tid][2]) + sh.dred[tid][3]);
+    if (tid < 4) gp[12 + tid] = 0.0f;
+    if (tid == 0) p.img_counter_b[img] = 0u;   // leave the workspace zeroed for the next call
   }
-  if (tid == 0) p.counters[2] = 0u;
 }
 
 size_t motion_bwd_smem_bytes() { return (size_t)kMotionBwdPlanes * kPlane * sizeof(float); }

@@ -36,7 +36,10 @@ struct MotionParams {
                                              // local smoothness gradient (or null)
   int tma;                                   // loss kernels stage their planes through TMA from `warped`
   // workspace
-  unsigned* counters;                        // [0] statistics, [1] forward, [2] backward
+  unsigned* counters;                        // [0] statistics, [1] forward: images finished, [2] unused
+  unsigned* img_counter_f;                   // [n_dirs*B] forward tiles finished per (direction, sample)
+  unsigned* img_counter_b;                   // [n_dirs*B] backward tiles finished per (direction, sample)
+  double* fin;                               // [n_dirs*B][4] per-image results of the forward pass (l1 sum, ssim sum, smoothness)
   float* stat_partials;                      // [n_dirs*B*stat_blocks][2]
   float* partials;                           // [forward grid][8]
   float* pose_partials;                      // [backward grid][12]

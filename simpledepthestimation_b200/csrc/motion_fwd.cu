@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kStatThreads) motion_stats_kernel(const __grid
 struct MotionFwdShared {
   MCam cam;
   float red[5][kThreads / 32];
+  double dred[5][kThreads / 32];
   unsigned ticket;
   __align__(8) uint64_t bar;   // TMA completion barrier
 };
@@ -352,47 +353,65 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
 #pragma unroll
     for (int k = 0; k < kThreads / 32; ++k) v += sh.red[tid][k];
     p.partials[(size_t)blockIdx.x * 8 + tid] = v;
+    __threadfence();   // only the publishing threads fence
   }
-  __threadfence();
   __syncthreads();
-  if (tid == 0) sh.ticket = atomicAdd(p.counters + 1, 1u);
+  // ------------------------------------------------------------------ two-level fixed-order reduction
+  // The last tile of a (direction, sample) image adds that image's partial slots while other images are still being
+  // computed; the last image to finish adds the per-image results.  (One last CTA adding all 19 200 slots of cfg4
+  // was a serial tail of ~60 us.)  Same order every run.
+  const int per_img = p.tiles_x * p.tiles_y, img = dir * p.B + b, n_img = p.n_dirs * p.B;
+  if (tid == 0) sh.ticket = atomicAdd(p.img_counter_f + img, 1u);
   __syncthreads();
-  if (sh.ticket != gridDim.x - 1) return;
-
-  // ------------------------------------------------------------------ last CTA: fixed-order final reduction
+  if (sh.ticket != (unsigned)(per_img - 1)) return;
   __threadfence();
-  const int per_img = p.tiles_x * p.tiles_y;
-  if (wid < p.n_dirs) {   // one warp per direction; samples in order
-    const int qd = wid;
+  {
+    const float* part = p.partials + ((size_t)dir * p.tiles_per_dir + (size_t)b * per_img) * 8;
+    double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int t = tid; t < per_img; t += kThreads) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (size_t)t * 8));
+      const float v4 = __ldcg(part + (size_t)t * 8 + 4);
+      a[0] += (double)v.x; a[1] += (double)v.y; a[2] += (double)v.z; a[3] += (double)v.w; a[4] += (double)v4;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) sh.dred[k][wid] = a[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double t5[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) t5[k] = ((sh.dred[k][0] + sh.dred[k][1]) + sh.dred[k][2]) + sh.dred[k][3];
+      const double qh = h, qw = w, nB = p.B;
+      const double mbar = fmax(t5[4] / (qh * qw), 1e-6);
+      const double Lb = (t5[2] / (nB * qh * (qw - 1.0)) + t5[3] / (nB * (qh - 1.0) * qw)) / mbar;
+      p.stats[img * 4 + 2] = (float)mbar;
+      p.stats[img * 4 + 3] = (float)Lb;
+      p.fin[img * 4 + 0] = t5[0]; p.fin[img * 4 + 1] = t5[1]; p.fin[img * 4 + 2] = Lb;
+      p.img_counter_f[img] = 0u;   // leave the workspace zeroed for the next call
+      __threadfence();
+      sh.ticket = atomicAdd(p.counters + 1, 1u);
+    }
+  }
+  __syncthreads();
+  if (sh.ticket != (unsigned)(n_img - 1)) return;
+  __threadfence();
+  if (tid < p.n_dirs) {   // one thread per direction; samples in order
+    const int qd = tid;
     double L1 = 0.0, LS = 0.0, LSm = 0.0;
     for (int qb = 0; qb < p.B; ++qb) {
-      const float* part = p.partials + ((size_t)qd * p.tiles_per_dir + (size_t)qb * per_img) * 8;
-      double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-      for (int t = lane; t < per_img; t += 32) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (size_t)t * 8));
-        const float v4 = __ldcg(part + (size_t)t * 8 + 4);
-        a[0] += (double)v.x; a[1] += (double)v.y; a[2] += (double)v.z; a[3] += (double)v.w; a[4] += (double)v4;
-      }
-#pragma unroll
-      for (int k = 0; k < 5; ++k)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
-      const double qh = h, qw = w, nB = p.B;
-      const double mbar = fmax(a[4] / (qh * qw), 1e-6);
-      const double Lb = (a[2] / (nB * qh * (qw - 1.0)) + a[3] / (nB * (qh - 1.0) * qw)) / mbar;
-      L1 += a[0]; LS += a[1]; LSm += Lb;
-      if (lane == 0) {
-        p.stats[(qd * p.B + qb) * 4 + 2] = (float)mbar;
-        p.stats[(qd * p.B + qb) * 4 + 3] = (float)Lb;
-      }
+      const double* f = p.fin + (size_t)(qd * p.B + qb) * 4;
+      L1 += __ldcg(f); LS += __ldcg(f + 1); LSm += __ldcg(f + 2);
     }
-    if (lane == 0) {
-      const double n = (double)p.B * 3.0 * h * w;
-      p.losses[qd * 4 + 0] = (float)(L1 / n);
-      p.losses[qd * 4 + 1] = (float)(LS / n * (double)p.ssim_w * 0.5);   // MotionLearning.py:286-289
-      p.losses[qd * 4 + 2] = (float)LSm;
-      p.losses[qd * 4 + 3] = 0.0f;
-    }
+    const double n = (double)p.B * 3.0 * h * w;
+    p.losses[qd * 4 + 0] = (float)(L1 / n);
+    p.losses[qd * 4 + 1] = (float)(LS / n * (double)p.ssim_w * 0.5);   // MotionLearning.py:286-289
+    p.losses[qd * 4 + 2] = (float)LSm;
+    p.losses[qd * 4 + 3] = 0.0f;
   }
   if (tid == 0) p.counters[1] = 0u;
 }

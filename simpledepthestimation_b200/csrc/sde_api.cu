@@ -265,7 +265,7 @@ static void motion_tma(const sde_motion_desc* d, const sde_motion_buffers* b, bo
 // ------------------------------------------------------------------------------------------------
 struct MotionLayout {
   int tiles_x, tiles_y, btiles_x, btiles_y, stat_blocks, grid, bgrid;
-  size_t off_stat, off_partials, off_pose, total;
+  size_t off_imgc, off_fin, off_stat, off_partials, off_pose, total;
 };
 
 static int motion_check(const sde_motion_desc* d) {
@@ -287,6 +287,10 @@ static MotionLayout motion_layout(const sde_motion_desc* d) {
   L.grid = d->n_dirs * d->batch * L.tiles_x * L.tiles_y;
   L.bgrid = d->n_dirs * d->batch * L.btiles_x * L.btiles_y;
   size_t off = 16;  // three counters
+  L.off_imgc = off;   // per-image tile tickets, forward and backward
+  off = align16(off + (size_t)2 * d->n_dirs * d->batch * sizeof(unsigned));
+  L.off_fin = off;
+  off = align16(off + (size_t)d->n_dirs * d->batch * 4 * sizeof(double));
   L.off_stat = off;
   off = align16(off + (size_t)d->n_dirs * d->batch * L.stat_blocks * 2 * sizeof(float));
   L.off_partials = off;
@@ -328,6 +332,9 @@ static int motion_params(const sde_motion_desc* d, const sde_motion_buffers* b, 
   p.losses = b->losses; p.stats = b->saved_stats;
   char* ws = static_cast<char*>(b->workspace);
   p.counters = reinterpret_cast<unsigned*>(ws);
+  p.img_counter_f = reinterpret_cast<unsigned*>(ws + L.off_imgc);
+  p.img_counter_b = p.img_counter_f + d->n_dirs * d->batch;
+  p.fin = reinterpret_cast<double*>(ws + L.off_fin);
   p.stat_partials = reinterpret_cast<float*>(ws + L.off_stat);
   p.partials = reinterpret_cast<float*>(ws + L.off_partials);
   p.pose_partials = reinterpret_cast<float*>(ws + L.off_pose);
