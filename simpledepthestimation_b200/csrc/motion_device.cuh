@@ -148,11 +148,22 @@ struct MotionSample {
 };
 
 // Projects pixel `pix` = (gy, gx), gathers rgb + depth of B, loads A; no shared memory involved.
+// (the depth of A and the residual translation of the pixel are passed in, so that a caller can have them in flight
+// for the next pixel while this one is processed)
+__device__ __forceinline__ void motion_sample_pre(const MotionStage& a, const MCam& mc, int gy, int gx, int pix, float dA,
+                                                  float f0, float f1, float f2v, bool rgb, MotionSample& o,
+                                                  bool load_a = true, bool want_deriv = false);
 __device__ __forceinline__ void motion_sample(const MotionStage& a, const MCam& mc, int gy, int gx, int pix, bool rgb,
                                               MotionSample& o, bool load_a = true, bool want_deriv = false) {
-  o.d = __ldg(a.depth_a + pix);
+  const float dA = __ldg(a.depth_a + pix);
   float f0 = 0.0f, f1 = 0.0f, f2v = 0.0f;
   if (a.field) { f0 = __ldg(a.field + pix); f1 = __ldg(a.field + pix + a.hw); f2v = __ldg(a.field + pix + 2 * a.hw); }
+  motion_sample_pre(a, mc, gy, gx, pix, dA, f0, f1, f2v, rgb, o, load_a, want_deriv);
+}
+__device__ __forceinline__ void motion_sample_pre(const MotionStage& a, const MCam& mc, int gy, int gx, int pix, float dA,
+                                                  float f0, float f1, float f2v, bool rgb, MotionSample& o,
+                                                  bool load_a, bool want_deriv) {
+  o.d = dA;
   float P[3], den, X, Y, Z;
   mproject(mc, (float)gx, (float)gy, o.d, f0, f1, f2v, P, den, X, Y, Z);
   const Cell cell = bilinear_cell(X, Y, a.w, a.h);

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kStatThreads) motion_pack_kernel(const __grid_
   }
 }
 
-__global__ void __launch_bounds__(kStatThreads) motion_stats_kernel(const __grid_constant__ MotionParams p) {
+__global__ void __launch_bounds__(kStatThreads, 3) motion_stats_kernel(const __grid_constant__ MotionParams p) {
   __shared__ MCam s_cam;
   __shared__ float red[2][kStatThreads / 32];
   __shared__ unsigned ticket;
@@ -67,13 +67,26 @@ __global__ void __launch_bounds__(kStatThreads) motion_stats_kernel(const __grid
   float* __restrict__ occ_out = (wout && p.occ[dir]) ? p.occ[dir] + (size_t)b * hw : nullptr;
   float* __restrict__ crd_out = (wout && p.coords[dir]) ? p.coords[dir] + (size_t)b * hw * 2 : nullptr;
   float socc = 0.0f, serr = 0.0f;
+  // depth of A and the residual translation of the NEXT pixel are in flight while the current one is projected,
+  // gathered and stored (two dependent round trips per pixel otherwise)
+  float nd = 0.0f, nf0 = 0.0f, nf1 = 0.0f, nf2 = 0.0f;
+  auto prefetch = [&](int k) {
+    const int pix = chunk * kStatPix + k * kStatThreads + tid;
+    if (k < kStatPixPerThread && pix < hw) {
+      nd = __ldg(st.depth_a + pix);
+      if (st.field) { nf0 = __ldg(st.field + pix); nf1 = __ldg(st.field + pix + hw); nf2 = __ldg(st.field + pix + 2 * hw); }
+    }
+  };
+  prefetch(0);
 #pragma unroll 1
   for (int k = 0; k < kStatPixPerThread; ++k) {
     const int pix = chunk * kStatPix + k * kStatThreads + tid;
+    const float cd = nd, cf0 = nf0, cf1 = nf1, cf2 = nf2;
+    prefetch(k + 1);
     if (pix < hw) {
       const int gy = pix / p.w, gx = pix - gy * p.w;
       MotionSample sm;
-      motion_sample(st, mc, gy, gx, pix, wout != nullptr, sm, false, wout != nullptr);
+      motion_sample_pre(st, mc, gy, gx, pix, cd, cf0, cf1, cf2, wout != nullptr, sm, false, wout != nullptr);
       const float e = sm.Zc - sm.Sd;
       const float derr = e * e;
       socc += sm.occ;
