@@ -94,16 +94,22 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
       reflect_fixup(planes, kND, 1, oy, ox, h, w, tid);
       __syncthreads();
     }
-    for (int i = tid; i < kPositions; i += kThreads) {
-      int yy, xx;
-      position_of(i, yy, xx);
-      const int pl = plane_index(yy, xx);
-      const float derr = planes[kNU * kPlane + pl], vo = planes[kNW * kPlane + pl];
-      const float wgt = proximity_weight(derr, vo, st.m2);
-      planes[kNU * kPlane + pl] = wgt + 1e-2f;
-      planes[kNW * kPlane + pl] = wgt;
-      const int ty = oy + yy, tx = ox + xx;
-      sh.flag[pl] = (vo >= 2.0f ? 1 : 0) | ((ty >= 0 && ty < h && tx >= 0 && tx < w) ? 2 : 0);
+    // depth error, valid/occlusion -> U = weight + 0.01, WZ = weight and the flag bytes, two stored positions (an
+    // aligned pair of the plane row, pad columns included) per iteration
+    constexpr int kPairs = kPitch / 2;
+    for (int i = tid; i < kHH * kPairs; i += kThreads) {
+      const int yy = i / kPairs, j = i - yy * kPairs;
+      const int pl = yy * kPitch + 2 * j;
+      const f2 derr = ld2(planes + kNU * kPlane + pl), vo = ld2(planes + kNW * kPlane + pl);
+      const float w0 = proximity_weight(lo(derr), lo(vo), st.m2), w1 = proximity_weight(hi(derr), hi(vo), st.m2);
+      *reinterpret_cast<unsigned long long*>(planes + kNU * kPlane + pl) = mk2(w0 + 1e-2f, w1 + 1e-2f).v;
+      *reinterpret_cast<unsigned long long*>(planes + kNW * kPlane + pl) = mk2(w0, w1).v;
+      const int ty = oy + yy, tx = ox + 2 * j - kColOff;   // image position of the pair's first element
+      const bool row_in = ty >= 0 && ty < h;
+      uchar2 f;
+      f.x = (uint8_t)((lo(vo) >= 2.0f ? 1 : 0) | ((row_in && tx >= 0 && tx < w) ? 2 : 0));
+      f.y = (uint8_t)((hi(vo) >= 2.0f ? 1 : 0) | ((row_in && tx + 1 >= 0 && tx + 1 < w) ? 2 : 0));
+      *reinterpret_cast<uchar2*>(sh.flag + pl) = f;
     }
     if (!interior) {
       __syncthreads();

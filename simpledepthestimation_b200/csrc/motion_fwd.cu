@@ -207,22 +207,30 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
       __syncthreads();
     }
     // depth error, valid/occlusion -> U = weight + 0.01 and WZ = weight (zero outside the image: valid = 0 there)
-    for (int i = tid; i < kPositions; i += kThreads) {
-      int yy, xx;
-      position_of(i, yy, xx);
-      const int pl = plane_index(yy, xx);
-      const float derr = planes[kMU * kPlane + pl], vo = planes[kMW * kPlane + pl];
-      const float wgt = proximity_weight(derr, vo, st.m2);
-      planes[kMU * kPlane + pl] = wgt + 1e-2f;
-      planes[kMW * kPlane + pl] = wgt;
-      const int ty = st.oy + yy, tx = st.ox + xx;
-      if (ty >= 0 && ty < h && tx >= 0 && tx < w && yy >= 1 && yy <= kTileH && xx >= 1 && xx <= kTileW) {
-        const float occ = vo >= 2.0f ? 1.0f : 0.0f;
-        float e = 0.0f;
+    // two stored positions (an aligned pair of the plane row, pad columns included) per iteration
+    constexpr int kPairs = kPitch / 2;
+    for (int i = tid; i < kHH * kPairs; i += kThreads) {
+      const int yy = i / kPairs, j = i - yy * kPairs;
+      const int pl = yy * kPitch + 2 * j;
+      const f2 derr = ld2(planes + kMU * kPlane + pl), vo = ld2(planes + kMW * kPlane + pl);
+      const float wg[2] = {proximity_weight(lo(derr), lo(vo), st.m2), proximity_weight(hi(derr), hi(vo), st.m2)};
+      const float vv[2] = {lo(vo), hi(vo)};
+      *reinterpret_cast<unsigned long long*>(planes + kMU * kPlane + pl) = mk2(wg[0] + 1e-2f, wg[1] + 1e-2f).v;
+      *reinterpret_cast<unsigned long long*>(planes + kMW * kPlane + pl) = mk2(wg[0], wg[1]).v;
+      const int ty = st.oy + yy;
+      if (ty >= 0 && ty < h && yy >= 1 && yy <= kTileH) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) e += fabsf(planes[(kMS + c) * kPlane + pl] - planes[(kMA + c) * kPlane + pl]);
-        l1 += e * occ;
-        if (wgt_out) wgt_out[ty * w + tx] = wgt;
+        for (int e2 = 0; e2 < 2; ++e2) {
+          const int xx = 2 * j + e2 - kColOff, tx = st.ox + xx;
+          if (tx >= 0 && tx < w && xx >= 1 && xx <= kTileW) {
+            const float occ = vv[e2] >= 2.0f ? 1.0f : 0.0f;
+            float e = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) e += fabsf(planes[(kMS + c) * kPlane + pl + e2] - planes[(kMA + c) * kPlane + pl + e2]);
+            l1 += e * occ;
+            if (wgt_out) wgt_out[ty * w + tx] = wg[e2];
+          }
+        }
       }
     }
     if (!interior) {
