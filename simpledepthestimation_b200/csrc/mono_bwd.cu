@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
   __shared__ BwdShared sh;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const TileCoord tc = decode_btile(p, blockIdx.x);
+  const int vbid = (int)blockIdx.x;   // list order (the forward kernel runs in reverse order, see mono_fwd.cu)
+  const TileCoord tc = decode_btile(p, vbid);
   const int s = tc.s, b = tc.b, h = p.h[s], w = p.w[s], hw = h * w;
   const bool automask = (p.flags & SDE_MONO_AUTOMASK) != 0;
   const bool reduce_mean = (p.flags & SDE_MONO_REDUCE_MEAN) != 0;
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
         for (int k = 0; k < 16; ++k) v16[k] = k < 12 ? acc[k] : 0.0f;
         const float mine = warp_sum16(v16, lane);
         const int slot = warp_slot(lane);
-        if ((lane & 1) == 0 && slot < 12) p.pose_partials[(((size_t)blockIdx.x * kWarps + wid) * p.S + j) * 12 + slot] = mine;
+        if ((lane & 1) == 0 && slot < 12) p.pose_partials[(((size_t)vbid * kWarps + wid) * p.S + j) * 12 + slot] = mine;
       }
       __syncwarp();
       // pick up the depth gradients of this lane's own pixels (pairs outside P / the image hold garbage that is never stored)
