@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int dir, b, tx0, ty0;
-  decode_motion_tile(blockIdx.x, p.tiles_per_dir, p.tiles_x, p.tiles_y, kTileW, kTileH, dir, b, tx0, ty0);
+  // tiles in reverse list order: the planes the statistics / warp pass wrote last are still in L2 (cf. mono_fwd.cu)
+  const int vbid = (int)(gridDim.x - 1 - blockIdx.x);
+  decode_motion_tile(vbid, p.tiles_per_dir, p.tiles_x, p.tiles_y, kTileW, kTileH, dir, b, tx0, ty0);
   const int h = p.h, w = p.w, hw = h * w;
   const bool tma = p.tma != 0;
   if (tma && tid == 0) {
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
     float v = 0.0f;
 #pragma unroll
     for (int k = 0; k < kThreads / 32; ++k) v += sh.red[tid][k];
-    p.partials[(size_t)blockIdx.x * 8 + tid] = v;
+    p.partials[(size_t)vbid * 8 + tid] = v;
     __threadfence();   // only the publishing threads fence
   }
   __syncthreads();
