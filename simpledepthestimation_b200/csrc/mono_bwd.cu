@@ -57,26 +57,6 @@ struct BwdShared {
   __align__(8) uint8_t arg[kPlane];
 };
 
-// zeroes the one-pixel ring (rows 0 and kHH-1, columns 0 and kHW-1) of the three planes b0 .. b0+2: threads 0..65
-// take the two rows, 18 threads of the last warp the two columns -- no index arithmetic beyond the thread id
-__device__ __forceinline__ void zero_ring3(float* planes, int b0, int tid) {
-  static_assert(kHW <= 96 && 96 + kHH <= kThreads, "thread ranges of zero_ring3");
-  if (tid < kHW) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      planes[(b0 + k) * kPlane + plane_index(0, tid)] = 0.0f;
-      planes[(b0 + k) * kPlane + plane_index(kHH - 1, tid)] = 0.0f;
-    }
-  } else if (tid >= 96 && tid < 96 + kHH) {
-    const int yy = tid - 96;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      planes[(b0 + k) * kPlane + plane_index(yy, 0)] = 0.0f;
-      planes[(b0 + k) * kPlane + plane_index(yy, kHW - 1)] = 0.0f;
-    }
-  }
-}
-
 template <bool SAVED>
 __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_constant__ MonoParams p,
                                                                const __grid_constant__ MonoTma maps) {
@@ -102,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
   const bool cam_thread = tid >= 32 && tid < 32 + p.S;
   // coefficient planes: the coefficient pass writes every window centre of the block, the one-pixel ring around it
   // is never written and must read as zero (shared memory only: before the dependency wait)
-  zero_ring3(planes, kBY, tid);
+  zero_ring<3>(planes, kBY, tid);
   const bool tma = SAVED && p.tma[s] != 0;
   if (tma && tid == 0) {
     mbar_init(&sh.bar, 1);
@@ -192,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
     if (j > 0) {
       // the coefficient region held the previous source's S / gS planes: its one-pixel border ring (never written
       // by the coefficient pass, never read by phase 4) must read as zero
-      zero_ring3(planes, bC, tid);
+      zero_ring<3>(planes, bC, tid);
     }
     const Cam cam = sh.cam;
     const Proj pj = sh.proj[j];

@@ -463,6 +463,27 @@ __device__ __forceinline__ void stage_arg(uint8_t* arg, const uint8_t* __restric
     if (pl[k] >= 0) arg[pl[k]] = m[k];
 }
 
+// zeroes the one-pixel ring (rows 0 and kHH-1, columns 0 and kHW-1) of the N planes b0 .. b0+N-1: threads 0..65
+// take the two rows, 18 threads of the last warp the two columns -- no index arithmetic beyond the thread id
+template <int N>
+__device__ __forceinline__ void zero_ring(float* planes, int b0, int tid) {
+  static_assert(kHW <= 96 && 96 + kHH <= kThreads, "thread ranges of zero_ring");
+  if (tid < kHW) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      planes[(b0 + k) * kPlane + plane_index(0, tid)] = 0.0f;
+      planes[(b0 + k) * kPlane + plane_index(kHH - 1, tid)] = 0.0f;
+    }
+  } else if (tid >= 96 && tid < 96 + kHH) {
+    const int yy = tid - 96;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      planes[(b0 + k) * kPlane + plane_index(yy, 0)] = 0.0f;
+      planes[(b0 + k) * kPlane + plane_index(yy, kHW - 1)] = 0.0f;
+    }
+  }
+}
+
 // The same plane, four bytes per load: possible when the image column of plane index 0 (ox - kColOff) and the row
 // pitch of the map are multiples of 4 -- then every aligned word of a plane row lies entirely inside or entirely
 // outside the image.  18 x 17 word loads per tile instead of 1188 byte loads.

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
   }
   if (tid == 0) load_mcam(sh.cam, p.K, p.pose[dir], b, p.sx, p.sy);
   // coefficient planes 1, 2: the border ring is never written and must read as zero (plane 0 holds WZ for now)
-  for (int i = tid; i < 2 * kPlane; i += kThreads) planes[(kNCoef + 1) * kPlane + i] = 0.0f;
+  zero_ring<2>(planes, kNCoef + 1, tid);
   __syncthreads();
 
   MotionStage st;
@@ -169,12 +169,7 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
   // WZ is dead: its plane becomes coefficient plane 0, whose border ring must read as zero (the coefficient pass
   // rewrites the interior of all three planes every channel)
   __syncthreads();
-  for (int i = tid; i < 2 * kHW + 2 * kHH; i += kThreads) {
-    int yy, xx;
-    if (i < 2 * kHW) { yy = i < kHW ? 0 : kHH - 1; xx = i < kHW ? i : i - kHW; }
-    else { const int q = i - 2 * kHW; yy = q < kHH ? q : q - kHH; xx = q < kHH ? 0 : kHW - 1; }
-    planes[kNCoef * kPlane + plane_index(yy, xx)] = 0.0f;
-  }
+  zero_ring<1>(planes, kNCoef, tid);
 
 #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
@@ -416,10 +411,13 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
         if (gfield) { gfield[pix] = gt0; gfield[pix + hw] = gt1; gfield[pix + 2 * hw] = gt2; }
       }
     }
+    {
+      float v16[16];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-      const float v = warp_sum(acc[k]);
-      if (lane == 0) sh.red[k][wid] = v;
+      for (int k = 0; k < 16; ++k) v16[k] = k < 12 ? acc[k] : 0.0f;
+      const float mine = warp_sum16(v16, lane);   // 16 shuffles instead of 60
+      const int slot = warp_slot(lane);
+      if ((lane & 1) == 0 && slot < 12) sh.red[slot][wid] = mine;
     }
     __syncthreads();
     if (tid < 12) {
