@@ -29,9 +29,10 @@
 extern "C" {
 #endif
 
-#define SDE_ABI_VERSION 3
+#define SDE_ABI_VERSION 4
 #define SDE_MAX_SCALES 6
 #define SDE_MAX_SOURCES 4
+#define SDE_MONO_SAVED_PLANES 11   /* planes per sample of sde_mono_buffers.warped[i][j] */
 
 typedef enum sde_status {
   SDE_OK = 0,
@@ -85,9 +86,12 @@ typedef struct sde_mono_buffers {
   float* saved_stats;                 /* [n_scales*B*2] per-image (mean inverse depth, smoothness) for backward */
   /* optional, forward output / backward input, all-or-nothing (every warped[i][j] and every smooth_g[i], or none):
    * what the forward pass keeps for the backward pass.
-   *   warped[i][j]  [B,9,h_i,w_i]: planes 0..2 the warped source, planes 3..5 / 6..8 its derivatives
-   *                 d warped_c / dX and d warped_c / dY w.r.t. the sample coordinate (zero where nan_to_num /
-   *                 clamp gate the gradient, camera.py:184-188), written by the warp kernel;
+   *   warped[i][j]  [B,SDE_MONO_SAVED_PLANES,h_i,w_i]: planes 0..2 the warped source; planes 3..5 / 6..8 its
+   *                 derivatives d warped_c / dX and d warped_c / dY w.r.t. the sample coordinate, already divided by
+   *                 the projective denominator p2 + 1e-6 (camera.py:150-151) and zero where nan_to_num / clamp gate
+   *                 the gradient (camera.py:184-188); planes 9 / 10 the sample coordinate relative to the principal
+   *                 point, X - cx and Y - cy (zero where gated) -- everything the backward kernel needs to turn
+   *                 d loss / d warped into d loss / d (depth, R, t) without projecting again; written by the warp kernel;
    *   smooth_g[i]   [B,1,h_i,w_i]: d smoothness / d (1/depth) before the division by the per-image mean.
    * With them the loss kernels take the warped planes through TMA and the backward kernel neither re-projects
    * the halo nor re-gathers (trades 72 B/pixel/source + 4 B/pixel of HBM traffic, which this issue-bound path

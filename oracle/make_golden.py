@@ -108,15 +108,73 @@ def motion_case(name, B, H, W, seed=0):
     print(name, {k: float(v) for k, v in data.items() if "loss" in k and k.endswith("f64")})
 
 
+MOTION_VARIANTS = {
+    # tag: (LOSS overrides, MODEL overrides, needs masks)      -- MotionLearning.py:108-117,126-161
+    "scales2": (dict(NUM_SCALES=2), {}, False),
+    "scalenorm": (dict(SCALE_NORMALIZE=True), {}, False),
+    "scales2_scalenorm": (dict(NUM_SCALES=2, SCALE_NORMALIZE=True), {}, False),
+    "mask": ({}, dict(WITH_MASK=True, MASK_DILATION=2), True),
+}
+
+
+def motion_masks(B, H, W):
+    """Instance-mask stand-ins (batch['mask'], batch['ctx_mask'][0]): a few rectangles, int64 ids."""
+    gen = torch.Generator().manual_seed(17)
+    masks = []
+    for _ in range(2):
+        m = torch.zeros(B, 1, H, W, dtype=torch.int64)
+        for b in range(B):
+            for k in range(2):
+                y0, x0 = int(torch.randint(0, H - 8, (1,), generator=gen)), int(torch.randint(0, W - 12, (1,), generator=gen))
+                m[b, 0, y0:y0 + 8, x0:x0 + 12] = k + 1
+        masks.append(m)
+    return masks
+
+
+def motion_variants_case(name, base="motion_2x32x64"):
+    """MotionLearningModel variants the shipped configs leave off -- NUM_SCALES = 2 (resize_img_avgpool,
+    camera.py:49-54), SCALE_NORMALIZE, WITH_MASK -- run by the real reference on the inputs of `base`."""
+    g = np.load(os.path.join(OUT, base + ".npz"))
+    inp = {k: torch.from_numpy(g[k]) for k in ("img1", "img2", "depth1", "depth2", "K", "pose_vec", "motion")}
+    B, _, H, W = inp["img1"].shape
+    m1, m2 = motion_masks(B, H, W)
+    data = {"mask1": m1.numpy().astype(np.uint8), "mask2": m2.numpy().astype(np.uint8)}
+    for tag, (loss_over, model_over, need_mask) in MOTION_VARIANTS.items():
+        extra = {"mask": m1, "ctx_mask": [m2]} if need_mask else None
+        for dt, dn in ((torch.float64, "f64"), (torch.float32, "f32")):
+            r = ref_import.run_motion(inp, dt, model_over=model_over, extra_batch=extra, **loss_over)
+            for k, v in r.items():
+                if torch.is_tensor(v):
+                    data[f"{tag}.{k}_{dn}"] = v.numpy()
+            if dn == "f64":
+                for i, (a, b) in enumerate(r["overall_motion"]):
+                    data[f"{tag}.overall_motion{i}_12"] = a.numpy().astype(np.float32)
+                    data[f"{tag}.overall_motion{i}_21"] = b.numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **data)
+    print(name, {k: float(v) for k, v in data.items() if "loss" in k and k.endswith("f64")})
+
+
 def main():
+    import sys
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])
+    want = lambda n: not only or n in only  # noqa: E731
     variants = (("_noauto", dict(AUTOMASK=False)), ("_mean", dict(PHOTOMETRIC_REDUCE="mean")),
                 ("_l1", dict(SSIM_WEIGHT=0.0)))
-    mono_case("mono_2x32x64", 2, 32, 64, variants=variants)
-    mono_case("mono_1x50x70", 1, 50, 70, seed=3, pose_scale=2.0)
-    mono_case("mono_1x48x160_bigpose", 1, 48, 160, seed=5, pose_scale=8.0)
-    mono_case("mono_cfg1_1x192x640", 1, 192, 640, store_inputs=False)
-    motion_case("motion_2x32x64", 2, 32, 64)
+    if want("mono_2x32x64"):
+        mono_case("mono_2x32x64", 2, 32, 64, variants=variants)
+    if want("mono_1x50x70"):
+        mono_case("mono_1x50x70", 1, 50, 70, seed=3, pose_scale=2.0)
+    if want("mono_1x48x160_bigpose"):
+        mono_case("mono_1x48x160_bigpose", 1, 48, 160, seed=5, pose_scale=8.0)
+    if want("mono_cfg1_1x192x640"):
+        mono_case("mono_cfg1_1x192x640", 1, 192, 640, store_inputs=False)
+    if want("mono_cfg3_1x320x1024"):
+        mono_case("mono_cfg3_1x320x1024", 1, 320, 1024, store_inputs=False, seed=3)
+    if want("motion_2x32x64"):
+        motion_case("motion_2x32x64", 2, 32, 64)
+    if want("motion_variants_2x32x64"):
+        motion_variants_case("motion_variants_2x32x64")
 
 
 if __name__ == "__main__":

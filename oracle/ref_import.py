@@ -1,7 +1,8 @@
-"""Import the real reference (read-only, /root/reference) for oracle validation.
+"""Import the real reference (read-only) for oracle validation and for the CPU arm of bench.py.
 
-TEST INFRASTRUCTURE ONLY.  Works only in the build container: /root/reference is
-not present on the GPU box, so nothing run there may import this module.
+TEST / BENCH INFRASTRUCTURE ONLY.  In the build container the reference is /root/reference; on the GPU box
+(where /root/reference does not exist) it is the unmodified copy that oracle/make_ref.sh stages under the
+git-ignored oracle/_ref/ -- available() tells whether either is present.
 
 ``import detectron2`` fails in this image (fvcore/iopath/... absent), so the
 package ``__init__`` files are bypassed with empty module stubs whose
@@ -23,7 +24,16 @@ import types
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("SDE_REFERENCE_ROOT", "/root/reference")
+def _ref_root():
+    """/root/reference in the build container; on the GPU box the copy staged by oracle/make_ref.sh (git-ignored)."""
+    staged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    for root in (os.environ.get("SDE_REFERENCE_ROOT"), "/root/reference", staged):
+        if root and os.path.isdir(os.path.join(root, "detectron2", "modeling", "meta_arch")):
+            return root
+    return "/root/reference"
+
+
+REF_ROOT = _ref_root()
 _REF = os.path.join(REF_ROOT, "detectron2")
 
 
@@ -141,10 +151,13 @@ def run_mono(inp, dtype=torch.float64, grads=True, **cfg_over):
     return res
 
 
-def run_motion(inp, dtype=torch.float64, grads=True, with_motion=True, **cfg_over):
-    """Runs the reference's MotionLearningModel.forward (+backward of summed *loss* keys)."""
+def run_motion(inp, dtype=torch.float64, grads=True, with_motion=True, model_over=None, extra_batch=None, **cfg_over):
+    """Runs the reference's MotionLearningModel.forward (+backward of summed *loss* keys).  `model_over` updates
+    cfg.MODEL (WITH_MASK, MASK_DILATION), `extra_batch` adds batch entries (mask, ctx_mask)."""
     ns = load()
-    model = ns.MotionLearning.MotionLearningModel(motion_cfg(**cfg_over)).train().to(dtype)
+    cfg = motion_cfg(**cfg_over)
+    cfg.MODEL.update(model_over or {})
+    model = ns.MotionLearning.MotionLearningModel(cfg).train().to(dtype)
     d1 = inp["depth1"].to(dtype).clone().requires_grad_(grads)
     d2 = inp["depth2"].to(dtype).clone().requires_grad_(grads)
     vec = inp["pose_vec"].to(dtype).clone().requires_grad_(grads)
@@ -154,10 +167,12 @@ def run_motion(inp, dtype=torch.float64, grads=True, with_motion=True, **cfg_ove
     if with_motion:
         payload["motion_pred"] = mo
     model.pose_net.payload = payload
-    batch = model({"img": inp["img1"].to(dtype), "ctx_img": [inp["img2"].to(dtype)],
-                   "intrinsics": inp["K"].to(dtype)})
+    feed = {"img": inp["img1"].to(dtype), "ctx_img": [inp["img2"].to(dtype)], "intrinsics": inp["K"].to(dtype)}
+    feed.update(extra_batch or {})
+    batch = model(feed)
     res = {k: v.detach() for k, v in batch.items() if "loss" in k and torch.is_tensor(v)}
     res["depth_proximity_weight"] = [tuple(t.detach() for t in pair) for pair in batch["depth_proximity_weight"]]
+    res["overall_motion"] = [tuple(t.detach() for t in pair) for pair in batch["overall_motion"]]
     if grads:
         total = sum(v for k, v in batch.items() if "loss" in k)
         total.backward()

@@ -5,9 +5,10 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 3   # SDE_ABI_VERSION of include/sde_loss.h this binding was written against
+ABI_VERSION = 4   # SDE_ABI_VERSION of include/sde_loss.h this binding was written against
 MAX_SCALES = 6
 MAX_SOURCES = 4
+MONO_SAVED_PLANES = 11   # SDE_MONO_SAVED_PLANES: planes per sample of a `warped` buffer
 FLAG_AUTOMASK = 1
 FLAG_REDUCE_MEAN = 2
 MAX_DIRS = 2

@@ -50,6 +50,9 @@ constexpr int kListPerWarp = kRowsPerWarp * kTileW;   // a warp lists pixels of 
 struct BwdShared {
   Cam cam;
   Proj proj[SDE_MAX_SOURCES];
+  // SAVED: d depth-gradient / d (a0, a1, a2) as an affine function of the (centred) pixel coordinates, per source:
+  // rows of diag-combined K^T-weights times R K^-1 (see phase 4); row 2 is stored negated
+  float wmat[SDE_MAX_SOURCES][9];
   double dred[12][kWarps];
   unsigned ticket;
   __align__(8) uint64_t bar;                     // TMA completion barrier
@@ -97,7 +100,27 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
       float k[9];
       load_cam(cam, k, raw.k, 0, p.sx[s], p.sy[s]);
       if (tid == 32) sh.cam = cam;
-      load_proj(sh.proj[tid - 32], k, raw.T, 0);
+      Proj& pj = sh.proj[tid - 32];
+      load_proj(pj, k, raw.T, 0);
+      if (SAVED) {
+        // d (R P + t) / d depth = R K^-1 [x, y, 1]^T =: V [x, y, 1]^T; d loss / d depth = (K^T g_p) . V [x, y, 1]^T with
+        // K^T g_p = (fx a0, sk a0 + fy a1, a2): rows of W = (fx V0 + sk V1, fy V1, V2), re-centred on (w/2, h/2)
+        float V[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) V[r * 3 + c] = pj.r[r * 3] * cam.ki[c] + pj.r[r * 3 + 1] * cam.ki[3 + c] + pj.r[r * 3 + 2] * cam.ki[6 + c];
+        const float x0c = (float)(w >> 1), y0c = (float)(h >> 1);
+        float* wm = sh.wmat[tid - 32];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          wm[c] = cam.fx * V[c] + cam.sk * V[3 + c];
+          wm[3 + c] = cam.fy * V[3 + c];
+          wm[6 + c] = -V[6 + c];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) wm[r * 3 + 2] += wm[r * 3] * x0c + wm[r * 3 + 1] * y0c;
+      }
     }
   };
   if (!SAVED) make_camera();
@@ -345,6 +368,92 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
         Gs[o] = mk2(G0, G1);
       }
     }
+    if constexpr (SAVED) {
+      // Dense form: every lane processes its own pixel pairs in packed fp32; nothing is projected or divided here --
+      // the warp kernel left q dS_c/dX, q dS_c/dY and the centred sample coordinate (ex, ey) = (X - cx, Y - cy):
+      //   a0 = sum_c gS_c (q dS_c/dX), a1 = sum_c gS_c (q dS_c/dY), a2 = -(a0 ex + a1 ey)      [= g_p in camera units]
+      //   K^T g_p = (fx a0, sk a0 + fy a1, a2);  d loss / d depth = a0 w0 + a1 w1 + a2 w2 with w = W [x, y, 1]^T (wmat)
+      //   d loss / d [R | t] = K^T g_p (x) [P, 1] with P = depth K^-1 [x, y, 1]^T, i.e. linear in the twelve sums of
+      //   a_i depth x, a_i depth y, a_i depth, a_i -- the linear map is applied once per (sample, scale) in fp64 by the
+      //   tile that finishes the sample.  x is fixed per lane: sum(b x) = x sum(b), formed after the rows.
+      // Pairs outside the gradient block / the image load zeros, so they add nothing.
+      const float* __restrict__ dwp = p.warped[s][j] + (size_t)b * kSavedPlanes * hw;
+      const float* wm = sh.wmat[j];
+      const bool pair = (w & 1) == 0 && (reinterpret_cast<uintptr_t>(dwp) & 7) == 0;   // gxp is even
+      const float xc0 = (float)(gxp - (w >> 1));
+      const f2 xc = mk2(xc0, xc0 + 1.0f);
+      f2 Sa[3], Sb[3], Sy[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Sa[k] = Sb[k] = Sy[k] = bc2(0.0f);
+      // all loads of the source's rows are issued before the first multiply-add: one L2 round trip per (warp, source)
+      // (instantiated on the alignment switch, so that the loads sit in one basic block)
+      auto rows = [&](auto pair_tag) {
+        constexpr bool PAIR = decltype(pair_tag)::value;
+        f2 dq[kRowsPerWarp][8];
+        bool ok[kRowsPerWarp];
+#pragma unroll
+        for (int o = 0; o < kRowsPerWarp; ++o) {
+          const int row = r0 + 1 + o, gy = oy + row;
+          const bool row_ok = row >= 2 && row <= kBwdH + 1 && gy < h;   // warp-uniform
+          ok[o] = row_ok && col_ok0;
+          if (PAIR) {
+            // branch-free: pairs outside the block / the image read the sample's first pixel instead (always a valid
+            // address) and are switched off through gS below
+            const float* q = dwp + (ok[o] ? gy * w + gxp : 0) + 3 * hw;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dq[o][i].v = __ldg(reinterpret_cast<const unsigned long long*>(q + i * hw));
+          } else {
+            const float* q = dwp + (gy * w + gxp) + 3 * hw;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              dq[o][i] = mk2(ok[o] ? __ldg(q + i * hw) : 0.0f, row_ok && col_ok1 ? __ldg(q + i * hw + 1) : 0.0f);
+          }
+        }
+        f2 wb[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) wb[k] = fma2(bc2(wm[3 * k]), xc, bc2(wm[3 * k + 2]));
+        const float wy0 = wm[1], wy1 = wm[4], wy2 = wm[7];
+#pragma unroll
+        for (int o = 0; o < kRowsPerWarp; ++o) {
+          const int row = r0 + 1 + o, gy = oy + row;
+          const int pl = plane_index(row, c0 + 1);
+          f2 g0 = ld2(planes + bS * kPlane + pl), g1 = ld2(planes + (bS + 1) * kPlane + pl),
+             g2 = ld2(planes + (bS + 2) * kPlane + pl);
+          if (PAIR && !ok[o]) g0 = g1 = g2 = bc2(0.0f);
+          const f2 dd = ld2(planes + kBD * kPlane + pl);
+          const f2 a0 = fma2(g2, dq[o][2], fma2(g1, dq[o][1], g0 * dq[o][0]));
+          const f2 a1 = fma2(g2, dq[o][5], fma2(g1, dq[o][4], g0 * dq[o][3]));
+          const f2 a2 = fma2(a1, dq[o][7], a0 * dq[o][6]);   // -a2 (the sign lives in wmat row 2 and in the final map)
+          const float yc = (float)(gy - (h >> 1));
+          const f2 b0 = a0 * dd, b1 = a1 * dd, b2 = a2 * dd;
+          Sa[0] = Sa[0] + a0; Sa[1] = Sa[1] + a1; Sa[2] = Sa[2] + a2;
+          Sb[0] = Sb[0] + b0; Sb[1] = Sb[1] + b1; Sb[2] = Sb[2] + b2;
+          const f2 ycc = bc2(yc);
+          Sy[0] = fma2(b0, ycc, Sy[0]); Sy[1] = fma2(b1, ycc, Sy[1]); Sy[2] = fma2(b2, ycc, Sy[2]);
+          const f2 w0 = wb[0] + bc2(wy0 * yc), w1 = wb[1] + bc2(wy1 * yc), w2 = wb[2] + bc2(wy2 * yc);
+          gd[o] = fma2(a2, w2, fma2(a1, w1, fma2(a0, w0, gd[o])));
+        }
+      };
+      if (pair) rows(std::true_type{});
+      else      rows(std::false_type{});
+      // the 12 sums of this (warp, source) -> per-warp slot: [i][x', y', 1 (all times depth), plain]
+      {
+        float v16[16];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const f2 sx = Sb[i] * xc;
+          v16[4 * i] = lo(sx) + hi(sx);
+          v16[4 * i + 1] = lo(Sy[i]) + hi(Sy[i]);
+          v16[4 * i + 2] = lo(Sb[i]) + hi(Sb[i]);
+          v16[4 * i + 3] = lo(Sa[i]) + hi(Sa[i]);
+        }
+#pragma unroll
+        for (int k = 12; k < 16; ++k) v16[k] = 0.0f;
+        const float mine = warp_sum16(v16, lane);
+        const int slot = warp_slot(lane);
+        if ((lane & 1) == 0 && slot < 12) p.pose_partials[(((size_t)vbid * kWarps + wid) * p.S + j) * 12 + slot] = mine;
+      }
+    } else
     {
       unsigned short* const wlist = sh.list[wid];
       const unsigned lt = (1u << lane) - 1u;
@@ -464,6 +573,14 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
   }
 
   pdl_launch_dependents();   // see mono_fwd.cu
+#ifdef SDE_BWD_EARLY_TICKET
+  // publish the pose slots and take the sample's ticket BEFORE the gradient stores: the fence then waits for the few
+  // slot stores only, not for this warp's share of the gradient planes
+  if ((lane & 1) == 0 && warp_slot(lane) < 12) publish_fence();
+  __syncthreads();
+  if (tid == 0) sh.ticket = atomicAdd(p.smp_counter + b, 1u);
+  __syncthreads();
+#endif
   // ------------------------------------------------------------------ smoothness gradient + store
   {
     const float sscale = p.smooth_scale[s];
@@ -511,14 +628,16 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
   // ------------------------------------------------------------------ last tile of a sample: pose gradients
   // The tile that finishes a sample last (over all scales) adds that sample's per-CTA slots in a fixed
   // order in fp64, while other samples are still being computed.  Only the lanes that wrote pose slots fence.
-  if ((lane & 1) == 0 && warp_slot(lane) < 12) __threadfence();
-  __syncthreads();
   int total_b = 0;
   for (int ss = 0; ss < p.n_scales; ++ss) total_b += p.btiles_x[ss] * p.btiles_y[ss];
+#ifndef SDE_BWD_EARLY_TICKET
+  if ((lane & 1) == 0 && warp_slot(lane) < 12) publish_fence();
+  __syncthreads();
   if (tid == 0) sh.ticket = atomicAdd(p.smp_counter + b, 1u);
   __syncthreads();
+#endif
   if (sh.ticket != (unsigned)(total_b - 1)) return;
-  __threadfence();
+  publish_fence();
   for (int tj = 0; tj < p.S; ++tj) {
     double a[12];
 #pragma unroll
@@ -526,13 +645,42 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
     for (int ss = 0; ss < p.n_scales; ++ss) {
       const int per = p.btiles_x[ss] * p.btiles_y[ss] * kWarps;   // one slot per warp of every tile of the sample
       const size_t first = ((size_t)p.btile_start[ss] + (size_t)b * p.btiles_x[ss] * p.btiles_y[ss]) * kWarps;
+      double q[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) q[k] = 0.0;
       for (int t = tid; t < per; t += kThreads) {
         const float4* part = reinterpret_cast<const float4*>(p.pose_partials + ((first + t) * p.S + tj) * 12);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const float4 v = __ldcg(part + k);
-          a[4 * k] += (double)v.x; a[4 * k + 1] += (double)v.y; a[4 * k + 2] += (double)v.z; a[4 * k + 3] += (double)v.w;
+          q[4 * k] += (double)v.x; q[4 * k + 1] += (double)v.y; q[4 * k + 2] += (double)v.z; q[4 * k + 3] += (double)v.w;
         }
+      }
+      if (SAVED) {
+        // the slots hold, per i, the sums of a_i depth x', a_i depth y', a_i depth, a_i over the scale's pixels (x', y'
+        // centred on (w/2, h/2); i = 2 with the opposite sign): the linear map to d loss / d [R | t] uses the
+        // intrinsics of this scale (applied to this thread's partial sums; the map is linear)
+        Cam cam;
+        float kk[9];
+        load_cam(cam, kk, p.K, b, p.sx[ss], p.sy[ss]);
+        const double x0 = (double)(p.w[ss] >> 1), y0 = (double)(p.h[ss] >> 1);
+        double A[3][4];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double sb = q[4 * i + 2], sx = q[4 * i] + x0 * sb, sy = q[4 * i + 1] + y0 * sb;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) A[i][c] = (double)cam.ki[3 * c] * sx + (double)cam.ki[3 * c + 1] * sy + (double)cam.ki[3 * c + 2] * sb;
+          A[i][3] = q[4 * i + 3];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          a[c] += (double)cam.fx * A[0][c];
+          a[4 + c] += (double)cam.sk * A[0][c] + (double)cam.fy * A[1][c];
+          a[8 + c] -= A[2][c];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) a[k] += q[k];
       }
     }
 #pragma unroll

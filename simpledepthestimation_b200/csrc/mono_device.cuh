@@ -42,7 +42,8 @@ __device__ __forceinline__ Row4 ld_row(const float* p) {  // p -> stored index o
 
 // p0/den and p1/den through one refined reciprocal and a residual correction (<= 1 ulp from the
 // IEEE quotient the reference's torch division produces); exotic denominators take the IEEE path.
-__device__ __forceinline__ void divide2(float p0, float p1, float den, float& X, float& Y) {
+// The variant with `q` also returns the reciprocal itself (refined, <= 1 ulp): the scale of d (X, Y) / d p.
+__device__ __forceinline__ void divide2(float p0, float p1, float den, float& X, float& Y, float& q) {
   const float ad = fabsf(den);
   if (ad > 1e-30f && ad < 1e30f) {
     float r = rcp_approx(den);
@@ -51,10 +52,16 @@ __device__ __forceinline__ void divide2(float p0, float p1, float den, float& X,
     Y = p1 * r;
     X = fmaf(fmaf(-X, den, p0), r, X);
     Y = fmaf(fmaf(-Y, den, p1), r, Y);
+    q = r;
   } else {
     X = p0 / den;
     Y = p1 / den;
+    q = 1.0f / den;
   }
+}
+__device__ __forceinline__ void divide2(float p0, float p1, float den, float& X, float& Y) {
+  float q;
+  divide2(p0, p1, den, X, Y, q);
 }
 
 // Back-project pixel (gx, gy) with depth d through K^-1, move by (R, t), project with K
@@ -66,12 +73,16 @@ __device__ __forceinline__ void backproject(const Cam& c, float gx, float gy, fl
   P[1] = c.ki[3] * xd + c.ki[4] * yd + c.ki[5] * d;
   P[2] = c.ki[6] * xd + c.ki[7] * yd + c.ki[8] * d;
 }
-__device__ __forceinline__ void project_point(const Proj& pj, const float P[3], float& den, float& X, float& Y) {
+__device__ __forceinline__ void project_point(const Proj& pj, const float P[3], float& den, float& X, float& Y, float& q) {
   const float p0 = pj.m[0] * P[0] + pj.m[1] * P[1] + pj.m[2] * P[2] + pj.tau[0];
   const float p1 = pj.m[3] * P[0] + pj.m[4] * P[1] + pj.m[5] * P[2] + pj.tau[1];
   const float p2 = pj.m[6] * P[0] + pj.m[7] * P[1] + pj.m[8] * P[2] + pj.tau[2];
   den = p2 + 1e-6f;
-  divide2(p0, p1, den, X, Y);
+  divide2(p0, p1, den, X, Y, q);
+}
+__device__ __forceinline__ void project_point(const Proj& pj, const float P[3], float& den, float& X, float& Y) {
+  float q;
+  project_point(pj, P, den, X, Y, q);
 }
 __device__ __forceinline__ void project_full(const Cam& c, const Proj& pj, float gx, float gy, float d, float P[3],
                                              float& den, float& X, float& Y) {

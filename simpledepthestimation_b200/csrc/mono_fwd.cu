@@ -299,12 +299,12 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
     v.z = ((sh.red[2][0] + sh.red[2][1]) + sh.red[2][2]) + sh.red[2][3];
     v.w = ((sh.red[3][0] + sh.red[3][1]) + sh.red[3][2]) + sh.red[3][3];
     *reinterpret_cast<float4*>(p.partials + (size_t)vbid * 4) = v;
-    __threadfence();
+    publish_fence();
     sh.ticket = atomicAdd(p.img_counter + q, 1u);
   }
   __syncthreads();
   if (sh.ticket != (unsigned)(per - 1)) return;
-  __threadfence();
+  publish_fence();
   {
     const float* part = p.partials + ((size_t)p.tile_start[s] + (size_t)b * per) * 4;
     double a[4] = {0.0, 0.0, 0.0, 0.0};
@@ -338,14 +338,14 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
       p.fin[q * 2 + 0] = rec_q;
       p.fin[q * 2 + 1] = Lb * (double)p.smooth_scale[s];
       p.img_counter[q] = 0u;   // leave the workspace zeroed for the next call
-      __threadfence();
+      publish_fence();
       sh.ticket = atomicAdd(p.counter, 1u);
     }
   }
   __syncthreads();
   const int pairs = p.n_scales * p.B;
   if (sh.ticket != (unsigned)(pairs - 1)) return;
-  __threadfence();
+  publish_fence();
   if (wid == 0) {
     double r = 0.0, sm = 0.0;
     for (int k = lane; k < pairs; k += 32) { r += __ldcg(p.fin + k * 2); sm += __ldcg(p.fin + k * 2 + 1); }

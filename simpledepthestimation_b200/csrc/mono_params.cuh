@@ -10,7 +10,8 @@ constexpr int kTileW = 64;   // 32 lanes x 2 pixels (one f2 per lane)
 constexpr int kTileH = 16;   // 4 warps x 4 rows
 constexpr int kThreads = 128;
 constexpr int kRowsPerWarp = 4;
-constexpr int kSavedPlanes = 9;   // planes per sample of a `warped` buffer: warp[3], d/dX[3], d/dY[3]
+// planes per sample of a `warped` buffer: warp[3], q d/dX[3], q d/dY[3], X - cx, Y - cy (include/sde_loss.h)
+constexpr int kSavedPlanes = SDE_MONO_SAVED_PLANES;
 // backward: a CTA recomputes SSIM on a kTileW x kTileH block of window centres and emits
 // gradients for its interior (the 3x3 adjoint needs one ring of neighbours)
 // warp kernel (mono_warp.cu): threads per block, pixels per thread, pixels per block.  Measured at cfg2 (full step,
@@ -39,7 +40,7 @@ struct MonoParams {
   const float* K;
   const float* pose[SDE_MAX_SOURCES];
   uint8_t* argmin[SDE_MAX_SCALES];
-  float* warped[SDE_MAX_SCALES][SDE_MAX_SOURCES];   // optional [B,9,h,w]: warp + d warp/dX + d warp/dY (nullptr = recompute)
+  float* warped[SDE_MAX_SCALES][SDE_MAX_SOURCES];   // optional [B,kSavedPlanes,h,w] (nullptr = recompute)
   float* smooth_g[SDE_MAX_SCALES];                  // optional [B,h,w]: local smoothness gradient kept by the forward pass
   float* losses;
   float* stats;           // [n_scales*B][2] = (mean inverse depth, per-image smoothness)

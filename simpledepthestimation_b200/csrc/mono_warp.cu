@@ -1,8 +1,9 @@
 // Warp kernel of the MonoDepth2 loss (sm_100a): project + bilinear gather of every source at every scale,
-// one thread per target pixel, written as [B,9,h,w] planes (the `warped` buffers of sde_mono_buffers):
-// the warped source (planes 0..2) and, from the same four taps, its derivatives w.r.t. the sample coordinate
-// (planes 3..5: d/dX, 6..8: d/dY; zero where nan_to_num / clamp gate the reference's gradient,
-// camera.py:184-188), so that the backward kernel never touches the source frames again.
+// one thread per target pixel, written as [B,11,h,w] planes (the `warped` buffers of sde_mono_buffers):
+// the warped source (planes 0..2); from the same four taps its derivatives w.r.t. the sample coordinate, times
+// q = 1 / (p2 + 1e-6) (planes 3..5: q d/dX, 6..8: q d/dY; zero where nan_to_num / clamp gate the reference's
+// gradient, camera.py:184-188); and the sample coordinate relative to the principal point (planes 9, 10: X - cx,
+// Y - cy, zero where gated) -- so that the backward kernel neither touches the source frames nor projects again.
 //
 // The fused loss kernels are stencil kernels with fat threads (128-160 registers, 12-16 warps per SM),
 // which is the wrong shape for the gather: it is latency-bound and wants many thin threads.  Run on its own
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(kWarpThreads, 1024 / kWarpThreads) mono_warp_k
   __syncthreads();
   // camera-space points of this thread's pixels (independent of the source); K^-1 stays in registers meanwhile
   float P[kWarpPixPerThread][3];
+  const float ccx = sh.cam.cx, ccy = sh.cam.cy;
   {
     const Cam cam = sh.cam;
 #pragma unroll
@@ -78,30 +80,37 @@ __global__ void __launch_bounds__(kWarpThreads, 1024 / kWarpThreads) mono_warp_k
       if (j == p.S - 1 && it == kWarpPixPerThread - 1) pdl_launch_dependents();
       const int pix = pix0 + it * kWarpThreads;
       if (pix >= hw) break;
-      float den, X, Y;
-      project_point(pj, P[it], den, X, Y);
+      float den, X, Y, q;
+      project_point(pj, P[it], den, X, Y, q);
       const Cell cell = bilinear_cell(X, Y, w, h);
       const float bx = 1.0f - cell.ax, by = 1.0f - cell.ay;
       const float w00 = bx * by, w01 = cell.ax * by, w10 = bx * cell.ay, w11 = cell.ax * cell.ay;
       const float* src = srcb + cell.off;
       float* dst = dstb + pix;
       // gradient gates of nan_to_num and clamp (closed interval): false for NaN / +-inf
-      const float gate_x = (X >= 0.0f && X <= (float)(w - 1)) ? 1.0f : 0.0f;
-      const float gate_y = (Y >= 0.0f && Y <= (float)(h - 1)) ? 1.0f : 0.0f;
+      const bool gate_x = X >= 0.0f && X <= (float)(w - 1);
+      const bool gate_y = Y >= 0.0f && Y <= (float)(h - 1);
+      // d (X, Y) / d p carries the factor q = 1 / (p2 + 1e-6): folded into the derivative planes here, where the
+      // issue slots are free (this kernel waits on L1), so that the backward kernel is a stream of multiply-adds
       float t[3][4];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         // scalar taps: a 16-byte load per lane is served quarter-warp by quarter-warp and touched MORE L1
         // sectors on the scattered addresses of this gather (measured: 100 us against 62 us)
-        const float* q = src + c * hw;
-        t[c][0] = __ldg(q); t[c][1] = __ldg(q + 1); t[c][2] = __ldg(q + w); t[c][3] = __ldg(q + w + 1);
+        const float* q4 = src + c * hw;
+        t[c][0] = __ldg(q4); t[c][1] = __ldg(q4 + 1); t[c][2] = __ldg(q4 + w); t[c][3] = __ldg(q4 + w + 1);
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {  // ATen's accumulation order: nw, ne, sw, se
         dst[c * hw] = t[c][0] * w00 + t[c][1] * w01 + t[c][2] * w10 + t[c][3] * w11;
-        dst[(3 + c) * hw] = gate_x * ((t[c][1] - t[c][0]) * by + (t[c][3] - t[c][2]) * cell.ay);
-        dst[(6 + c) * hw] = gate_y * ((t[c][2] - t[c][0]) * bx + (t[c][3] - t[c][1]) * cell.ax);
+        const float ddx = (t[c][1] - t[c][0]) * by + (t[c][3] - t[c][2]) * cell.ay;
+        const float ddy = (t[c][2] - t[c][0]) * bx + (t[c][3] - t[c][1]) * cell.ax;
+        dst[(3 + c) * hw] = gate_x ? ddx * q : 0.0f;
+        dst[(6 + c) * hw] = gate_y ? ddy * q : 0.0f;
       }
+      // sample coordinate relative to the principal point (the third row of K^T g_p is formed from it)
+      dst[9 * hw] = gate_x ? X - ccx : 0.0f;
+      dst[10 * hw] = gate_y ? Y - ccy : 0.0f;
     }
   }
 }

@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
 #pragma unroll
       for (int k = 0; k < kThreads / 32; ++k) v += sh.red[tid][k];
       p.pose_partials[(size_t)blockIdx.x * 12 + tid] = v;
-      __threadfence();   // only the publishing threads fence
+      publish_fence();   // only the publishing threads fence
     }
   }
 
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
   if (tid == 0) sh.ticket = atomicAdd(p.img_counter_b + img, 1u);
   __syncthreads();
   if (sh.ticket != (unsigned)(per_img - 1)) return;
-  __threadfence();
+  publish_fence();
   {
     double a[12];
 #pragma unroll

@@ -118,13 +118,13 @@ __global__ void __launch_bounds__(kStatThreads, 3) motion_stats_kernel(const __g
 #pragma unroll
     for (int k = 0; k < kStatThreads / 32; ++k) v += red[tid][k];
     p.stat_partials[(size_t)blockIdx.x * 2 + tid] = v;
-    __threadfence();   // only the two threads that publish the slot fence (the planes are consumed by later kernels)
+    publish_fence();   // only the two threads that publish the slot fence (the planes are consumed by later kernels)
   }
   __syncthreads();
   if (tid == 0) ticket = atomicAdd(p.counters, 1u);
   __syncthreads();
   if (ticket != gridDim.x - 1) return;
-  __threadfence();
+  publish_fence();
   for (int q = wid; q < p.n_dirs * p.B; q += kStatThreads / 32) {   // one warp per (direction, sample)
     double a0 = 0.0, a1 = 0.0;
     for (int t = lane; t < p.stat_blocks; t += 32) {
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
 #pragma unroll
     for (int k = 0; k < kThreads / 32; ++k) v += sh.red[tid][k];
     p.partials[(size_t)vbid * 8 + tid] = v;
-    __threadfence();   // only the publishing threads fence
+    publish_fence();   // only the publishing threads fence
   }
   __syncthreads();
   // ------------------------------------------------------------------ two-level fixed-order reduction
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
   if (tid == 0) sh.ticket = atomicAdd(p.img_counter_f + img, 1u);
   __syncthreads();
   if (sh.ticket != (unsigned)(per_img - 1)) return;
-  __threadfence();
+  publish_fence();
   {
     const float* part = p.partials + ((size_t)dir * p.tiles_per_dir + (size_t)b * per_img) * 8;
     double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -416,13 +416,13 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
       p.stats[img * 4 + 3] = (float)Lb;
       p.fin[img * 4 + 0] = t5[0]; p.fin[img * 4 + 1] = t5[1]; p.fin[img * 4 + 2] = Lb;
       p.img_counter_f[img] = 0u;   // leave the workspace zeroed for the next call
-      __threadfence();
+      publish_fence();
       sh.ticket = atomicAdd(p.counters + 1, 1u);
     }
   }
   __syncthreads();
   if (sh.ticket != (unsigned)(n_img - 1)) return;
-  __threadfence();
+  publish_fence();
   if (tid < p.n_dirs) {   // one thread per direction; samples in order
     const int qd = tid;
     double L1 = 0.0, LS = 0.0, LSm = 0.0;

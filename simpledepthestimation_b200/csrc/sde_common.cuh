@@ -106,6 +106,16 @@ inline cudaError_t launch_chained(int which, void (*kernel)(KArgs...), unsigned 
 }
 #endif
 
+// Fence between publishing a partial-result slot and taking the ticket (and, on the reading side, between the ticket and
+// the slots).  SDE_FENCE_ACQREL: the release / acquire form instead of the sequentially consistent __threadfence().
+__device__ __forceinline__ void publish_fence() {
+#ifdef SDE_FENCE_ACQREL
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#else
+  __threadfence();
+#endif
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -111,12 +111,12 @@ class MonoLossPlan:
 
     def new_warped(self):
         """What one step keeps from the forward to the backward pass (sde_mono_buffers.warped / .smooth_g), or None:
-        per (scale, source) a [B,9,h,w] buffer -- the warped source and its derivatives w.r.t. the sample coordinate
-        -- and per scale the [B,1,h,w] local smoothness gradient."""
+        per (scale, source) a [B,11,h,w] buffer -- the warped source, its derivatives w.r.t. the sample coordinate
+        and the centred sample coordinate -- and per scale the [B,1,h,w] local smoothness gradient."""
         if not self.save_warped:
             return None
         new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=self.device)  # noqa: E731
-        return MonoSaved([[new(self.batch, 9, h, w) for _ in range(self.n_sources)] for h, w in self.sizes],
+        return MonoSaved([[new(self.batch, _lib.MONO_SAVED_PLANES, h, w) for _ in range(self.n_sources)] for h, w in self.sizes],
                          [new(self.batch, 1, h, w) for h, w in self.sizes])
 
     def _set_warped(self, b, saved):

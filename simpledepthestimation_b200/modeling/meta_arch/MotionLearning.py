@@ -119,18 +119,20 @@ class MotionLearningModel(nn.Module):
             m12 = m21 = None
             if with_field:
                 m12, m21 = resize_img_avgpool(motion_1to2, (H, W)), resize_img_avgpool(motion_2to1, (H, W))
+            # overall translation fields (MotionLearning.py:143-155): the output dict carries them un-normalised
+            # (:154 comes before the SCALE_NORMALIZE block), the losses use the normalised ones
+            def overall(P, m):
+                t = P[:, :3, 3][:, :, None, None]
+                return t + m if with_field else t.expand(-1, -1, H, W)
+            t12, t21 = overall(P12, m12), overall(P21, m21)
+            batch["overall_motion"].append((t12, t21))
             if self.scale_normalize:
                 depth_mean = torch.mean(torch.cat([d1, d2], 0))
                 d1, d2 = d1 / depth_mean, d2 / depth_mean
                 P12, P21 = _scaled_translation(P12, depth_mean), _scaled_translation(P21, depth_mean)
                 if with_field:
                     m12, m21 = m12 / depth_mean, m21 / depth_mean
-            # overall translation fields (MotionLearning.py:143-155), needed by the regularisers only
-            t12 = P12[:, :3, 3][:, :, None, None]
-            t21 = P21[:, :3, 3][:, :, None, None]
-            t12 = t12 + m12 if with_field else t12.expand(-1, -1, H, W)
-            t21 = t21 + m21 if with_field else t21.expand(-1, -1, H, W)
-            batch["overall_motion"].append((t12, t21))
+                t12, t21 = overall(P12, m12), overall(P21, m21)
 
             plan = self._plan(B, (H, W), scale_w, with_field)
             out, maps = motion_rgbd_smoothness_loss(

@@ -302,6 +302,64 @@ def test_motion_model_matches_reference_golden(registered, with_motion, tag):
     assert float((w21.cpu() - f(f"weight21{tag}")).abs().max()) < 1e-3
 
 
+VARIANTS = {   # tag: (LOSS overrides, MODEL overrides, masks) -- the same table as oracle/make_golden.py:MOTION_VARIANTS
+    "scales2": (dict(NUM_SCALES=2), {}, False),
+    "scalenorm": (dict(SCALE_NORMALIZE=True), {}, False),
+    "scales2_scalenorm": (dict(NUM_SCALES=2, SCALE_NORMALIZE=True), {}, False),
+    "mask": ({}, dict(WITH_MASK=True, MASK_DILATION=2), True),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(VARIANTS))
+def test_motion_model_variants_match_reference_golden(registered, tag):
+    """NUM_SCALES = 2 (resize_img_avgpool, camera.py:49-54; MotionLearning.py:126-144), SCALE_NORMALIZE (:157-166) and
+    WITH_MASK (:108-117): MotionLearningModel.forward + backward against the outputs of the REAL reference
+    (tests/golden/motion_variants_2x32x64.npz, oracle/make_golden.py), including the un-normalised
+    batch['overall_motion'] (:154)."""
+    from parity_log import record
+    from simpledepthestimation_b200.modeling import build_model
+
+    g0, g = load_golden("motion_2x32x64"), load_golden("motion_variants_2x32x64")
+    t = lambda k: torch.from_numpy(g0[k])  # noqa: E731
+    loss_over, model_over, need_mask = VARIANTS[tag]
+    cfg = motion_cfg(**loss_over)
+    cfg.MODEL.update(model_over)
+    model = build_model(cfg).train()
+    dev = model.device
+    d1, d2 = t("depth1").to(dev).requires_grad_(), t("depth2").to(dev).requires_grad_()
+    vec = t("pose_vec").to(dev).requires_grad_()
+    mo = t("motion").to(dev).requires_grad_()
+    model.depth_net.payload = {"depth_pred": [torch.cat([d1, d2], 0)]}
+    model.pose_net.payload = {"pose_pred": euler_pose(vec), "motion_pred": mo}
+    feed = {"img": t("img1"), "ctx_img": [t("img2")], "intrinsics": t("K")}
+    if need_mask:
+        feed["mask"] = torch.from_numpy(g["mask1"]).long()
+        feed["ctx_mask"] = [torch.from_numpy(g["mask2"]).long()]
+    out = model(feed)
+    keys = ["rgb_l1_loss", "ssim_loss", "rot_loss", "trans_loss", "smooth_loss", "motion_smooth_loss", "motion_sparsity_loss"]
+    assert sorted(k for k in out if "loss" in k) == sorted(keys)
+    sum(out[k] for k in keys).backward()
+    torch.cuda.synchronize()
+    achieved = {}
+    for k in keys:
+        ref, ref32 = float(g[f"{tag}.{k}_f64"]), float(g[f"{tag}.{k}_f32"])
+        tol = max(1e-5, 3.0 * abs(ref32 - ref) / abs(ref))
+        achieved[k] = abs(float(out[k]) - ref) / abs(ref)
+        assert achieved[k] <= tol, (k, achieved[k], tol)
+    f = lambda k: torch.from_numpy(g[f"{tag}.{k}"])  # noqa: E731
+    for name, got in (("grad_depth1", d1.grad), ("grad_depth2", d2.grad), ("grad_pose_vec", vec.grad), ("grad_motion", mo.grad)):
+        f64 = f(f"{name}_f64")
+        achieved[name] = float((got.cpu().double() - f64).abs().max() / f64.abs().max())
+        achieved[name + "_reference_fp32"] = float((f(f"{name}_f32").double() - f64).abs().max() / f64.abs().max())
+        check_grad(name, got.cpu(), f64, f(f"{name}_f32"))
+    n_scales = loss_over.get("NUM_SCALES", 1)
+    assert len(out["overall_motion"]) == n_scales
+    for i, (t12, t21) in enumerate(out["overall_motion"]):
+        assert float((t12.detach().cpu() - f(f"overall_motion{i}_12")).abs().max()) < 1e-6
+        assert float((t21.detach().cpu() - f(f"overall_motion{i}_21")).abs().max()) < 1e-6
+    record(variant=tag, **achieved)
+
+
 def test_depth_l1_and_supervised_terms(registered):
     """LOSS.DEPTH_L1_WEIGHT > 0 (MotionLearning.py:264-267) and LOSS.SUPERVISED_WEIGHT > 0 (:222-229) add their terms
     next to the fused loss; values and the depth gradient of the summed losses against the oracle."""

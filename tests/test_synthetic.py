@@ -21,3 +21,21 @@ def test_euler_pose_is_a_rigid_transform():
     assert float((R @ R.T - torch.eye(3, dtype=torch.float64)).abs().max()) < 1e-14
     assert abs(float(torch.det(R)) - 1.0) < 1e-14
     assert torch.equal(T[0, :3, 3], v[0, :3])
+
+
+def test_per_sample_oracle_assembly_equals_the_batch_oracle():
+    """tests/test_fullsize_gpu.py evaluates the oracle sample by sample at the full GPU sizes; the assembly (loss =
+    mean of the per-sample losses, gradients = per-sample gradients / B) must reproduce the batch oracle."""
+    import torch
+    from helpers import port_mono_from_vec, rel_err
+    from test_fullsize_gpu import _oracle_per_sample
+
+    inp = mono_inputs(3, 32, 64, seed=4)
+    full = port_mono_from_vec(inp, torch.float64)
+    parts = _oracle_per_sample(inp, torch.float64)
+    assert abs(parts["rec_loss"] - float(full["rec_loss"])) < 1e-13
+    assert abs(parts["smooth_loss"] - float(full["smooth_loss"])) < 1e-15
+    for a, b in zip(parts["grad_depth"] + parts["grad_pose_vec"], full["grad_depth"] + full["grad_pose_vec"]):
+        assert rel_err(a, b) < 1e-12
+    for a, b in zip(parts["argmin"], full["argmin"]):
+        assert torch.equal(a.reshape(b.shape), b)
