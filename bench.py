@@ -317,8 +317,8 @@ def model_step(dev, inp):
     """MonoDepth2Model.forward(batch) + backward of rec_loss + smooth_loss (depth / pose predictions injected in place
     of the networks), cfg2, CUDA events.  Includes the image pyramid, the pose matrices, the
     autograd.Function plumbing and every allocation the model path makes."""
+    from simpledepthestimation_b200.geometry.pose_utils import pose_vec2mat
     from simpledepthestimation_b200.modeling import DEPTH_NET_REGISTRY, POSE_NET_REGISTRY, build_model
-    from simpledepthestimation_b200.synthetic import euler_pose
     if "BenchInjectDepth" not in DEPTH_NET_REGISTRY:
         DEPTH_NET_REGISTRY._do_register("BenchInjectDepth", _Inject)
         POSE_NET_REGISTRY._do_register("BenchInjectPose", _Inject)
@@ -338,7 +338,7 @@ def model_step(dev, inp):
         for t in depth + vecs:
             t.grad = None
         model.depth_net.payload = {"depth_pred": depth}
-        model.pose_net.payload = {"pose_pred": [euler_pose(v) for v in vecs]}
+        model.pose_net.payload = {"pose_pred": [pose_vec2mat(v) for v in vecs]}   # PoseNet.py:63
         out = model({"img": img, "ctx_img": ctx, "img_orig": img, "ctx_img_orig": ctx, "intrinsics": K})
         (out["rec_loss"] + out["smooth_loss"]).backward()
     ms = event_time(step, 30, warm=3)
@@ -510,32 +510,32 @@ def run_ours(args):
                 "fwd_ms": ms_fwd, "bwd_ms": ms_bwd,
                 "step_frac_of_hbm_roofline": (target_px * 84.0 / (ms_step * 1e-3) / 1e9) / peak}
 
-    # end to end through host buffers: headline leg = everything copied (fp32 frames, depth pyramid, K, poses)
+    # End to end through host buffers.  Headline leg: everything a step consumes travels from pinned host memory --
+    # the three frames as the DECODED uint8 images (converted by byte / 255 = torchvision's ToTensor inside the pyramid
+    # kernel), the predicted depth pyramid, intrinsics and poses as fp32 -- and the losses and all gradients travel back.
     e_steps = max(3, min(args.steps, 20))
-    runner = HostLossRunner(plan, dev)
-    pinned = [runner.pin(h) for h in host]
-    e2e_t = timed(lambda i: runner.step(pinned[i % nsets]), e_steps, 3, 0.3)
-    runner.finish()
-    e2e_ms = e2e_t["ms"]
-    e2e = {"value": world * warped_px / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
-           "h2d_bytes_per_step": runner.h2d_bytes, "d2h_bytes_per_step": runner.d2h_bytes, "ms_per_step": e2e_ms,
-           "per_rank_ms": e2e_t["per_rank"], "gpu_launches_per_step": runner.launches_per_step,
-           "path": "pinned host frames/depth/K/pose -> H2D -> device pyramid -> warp + loss fwd + loss bwd -> D2H losses+grads"}
-    del runner
-    # further legs of the same path with fewer bytes on the wire (HostLossRunner options; not the headline)
+
+    def e2e_leg(**kw):
+        r = HostLossRunner(plan, dev, **kw)
+        pins = [r.pin(h) for h in host]
+        if kw.get("frames_only"):
+            r.set_resident(sets[0][2], sets[0][3], sets[0][4])
+        t = timed(lambda i: r.step(pins[i % nsets]), e_steps, 3, 0.3)
+        r.finish()
+        return {"value": world * warped_px / (t["ms"] * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": r.h2d_bytes,
+                "d2h_bytes_per_step": r.d2h_bytes, "ms_per_step": t["ms"], "per_rank_ms": t["per_rank"],
+                "gpu_launches_per_step": r.launches_per_step, "what": r.describe()}
+
+    e2e = e2e_leg(u8_frames=True)
+    e2e["path"] = ("pinned host: uint8 frames + fp32 depth pyramid / K / poses -> one H2D copy -> device pyramid (byte / 255, "
+                   "resize) -> warp + loss fwd + loss bwd -> one D2H copy of losses + gradients; two pipelined slots")
+    # further legs of the same path (not the headline): fp32 frames as in round 1; depth / K / poses device-resident as
+    # in the trainer, where they are network outputs
     e2e_variants = {}
-    for name, kw in (("e2e_u8_frames", dict(u8_frames=True)), ("e2e_frames_only", dict(frames_only=True)),
+    for name, kw in (("e2e_f32_frames", dict()), ("e2e_f32_frames_only", dict(frames_only=True)),
                      ("e2e_u8_frames_only", dict(u8_frames=True, frames_only=True))):
         try:
-            r = HostLossRunner(plan, dev, **kw)
-            pins = [r.pin(h) for h in host]
-            if kw.get("frames_only"):
-                r.set_resident(sets[0][2], sets[0][3], sets[0][4])
-            t = timed(lambda i: r.step(pins[i % nsets]), e_steps, 3, 0.3)
-            r.finish()
-            e2e_variants[name] = {"value": world * warped_px / (t["ms"] * 1e-3) / 1e6, "ms_per_step": t["ms"],
-                                  "h2d_bytes_per_step": r.h2d_bytes, "d2h_bytes_per_step": r.d2h_bytes, "what": r.describe()}
-            del r, pins
+            e2e_variants[name] = e2e_leg(**kw)
         except Exception as exc:
             e2e_variants[name] = {"error": repr(exc)[:200]}
     e2e["variants"] = e2e_variants

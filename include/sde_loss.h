@@ -45,6 +45,10 @@ typedef enum sde_status {
 /* flags of sde_mono_desc.flags */
 #define SDE_MONO_AUTOMASK 1u       /* LOSS.AUTOMASK (MonoDepth2.py:96-101) */
 #define SDE_MONO_REDUCE_MEAN 2u    /* LOSS.PHOTOMETRIC_REDUCE == 'mean' (MonoDepth2.py:116-117); default 'min' */
+/* values of sde_mono_desc.depth_mode */
+#define SDE_DEPTH_IS_DEPTH 0
+#define SDE_DEPTH_IS_DISP 1
+#define SDE_DEPTH_IS_LOGIT 2
 
 int sde_version(void);
 const char* sde_strerror(int status);
@@ -71,6 +75,18 @@ typedef struct sde_mono_desc {
   float c1, c2;                     /* LOSS.C1, LOSS.C2 */
   float smooth_weight;              /* LOSS.SMOOTHNESS_WEIGHT (1e-3); 0 -> smooth_loss = 0 */
   uint32_t flags;                   /* SDE_MONO_* */
+  /* What depth[i] holds (the decoder's tail folded into the loss kernels, so that no depth map is
+   * written and re-read between the network and the loss, and the backward pass emits the gradient w.r.t. what the
+   * network produced):
+   *   SDE_DEPTH_IS_DEPTH  depth (default);
+   *   SDE_DEPTH_IS_DISP   the decoder's disparity output `disp`: depth = disp_to_depth(disp, min_depth, max_depth)[1] =
+   *                       1 / (1/max_depth + (1/min_depth - 1/max_depth) disp), detectron2/layers/depth_decoder.py:9-18
+   *                       (DepthResNet.py:41,57);
+   *   SDE_DEPTH_IS_LOGIT  the pre-activation output of the last convolution: disp = softplus(x) (nn.Softplus(),
+   *                       depth_decoder.py:93,108), then as SDE_DEPTH_IS_DISP.
+   * grad_depth[i] receives d loss / d depth[i] in the same representation. */
+  int32_t depth_mode;
+  float min_depth, max_depth;       /* used unless depth_mode == SDE_DEPTH_IS_DEPTH; 0 < min_depth < max_depth */
 } sde_mono_desc;
 
 typedef struct sde_mono_buffers {
@@ -264,6 +280,14 @@ int sde_smoothness_backward(const sde_smooth_desc* desc, const sde_smooth_buffer
 int sde_resize_bilinear(const float* src, float* dst, int32_t planes, int32_t src_h, int32_t src_w, int32_t dst_h,
                         int32_t dst_w, void* stream);
 
+/* resize_img_avgpool(image, dst_size) = F.adaptive_avg_pool2d, detectron2/geometry/camera.py:49-54 (MotionLearning.py:
+ * 126-144 resizes frames, depths and motion fields with it when NUM_SCALES > 1): src [planes,sh,sw] -> dst
+ * [planes,dh,dw]; the backward entry is its adjoint (grad_dst [planes,dh,dw] -> grad_src [planes,sh,sw]). */
+int sde_resize_avgpool_forward(const float* src, float* dst, int32_t planes, int32_t src_h, int32_t src_w, int32_t dst_h,
+                               int32_t dst_w, void* stream);
+int sde_resize_avgpool_backward(const float* grad_dst, float* grad_src, int32_t planes, int32_t src_h, int32_t src_w,
+                                int32_t dst_h, int32_t dst_w, void* stream);
+
 /* The image pyramid of a training step in one launch: resize_img (camera.py:40-46) of `n_frames` frames (the target
  * and every source, MonoDepth2.py:82,88) [planes,src_h,src_w] to `n_levels` sizes each; dst[f][l] = [planes,dst_h[l],dst_w[l]].
  * n_frames <= SDE_MAX_SOURCES + 1, n_levels <= SDE_MAX_SCALES.  Same arithmetic as sde_resize_bilinear. */
@@ -274,6 +298,18 @@ typedef struct sde_pyramid_buffers {
 
 int sde_resize_pyramid(int32_t n_frames, int32_t planes, int32_t src_h, int32_t src_w, int32_t n_levels,
                        const int32_t* dst_h, const int32_t* dst_w, const sde_pyramid_buffers* buf, void* stream);
+
+/* The same from the DECODED frames: src[f] is uint8 [planes,src_h,src_w] (what the data loader reads before
+ * torchvision's ToTensor, detectron2/data/datasets/kitti_v2.py:207-208); every tap is byte / 255 in fp32, so dst[f][l]
+ * holds the bits resize_img gives on the converted frame, and a level of the source size is the conversion itself.
+ * A host-side integration then copies a quarter of the bytes per frame. */
+typedef struct sde_pyramid_u8_buffers {
+  const uint8_t* src[SDE_MAX_SOURCES + 1];
+  float* dst[SDE_MAX_SOURCES + 1][SDE_MAX_SCALES];
+} sde_pyramid_u8_buffers;
+
+int sde_resize_pyramid_u8(int32_t n_frames, int32_t planes, int32_t src_h, int32_t src_w, int32_t n_levels,
+                          const int32_t* dst_h, const int32_t* dst_w, const sde_pyramid_u8_buffers* buf, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * MotionLearning regularisers, detectron2/modeling/losses/motion_loss.py (callers

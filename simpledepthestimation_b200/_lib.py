@@ -11,6 +11,7 @@ MAX_SOURCES = 4
 MONO_SAVED_PLANES = 11   # SDE_MONO_SAVED_PLANES: planes per sample of a `warped` buffer
 FLAG_AUTOMASK = 1
 FLAG_REDUCE_MEAN = 2
+DEPTH_MODES = {"depth": 0, "disp": 1, "logit": 2}   # SDE_DEPTH_IS_*
 MAX_DIRS = 2
 MOTION_FLAG_FIELD = 1
 MOTION_N_LOSSES = 4
@@ -25,6 +26,7 @@ class MonoDesc(C.Structure):
         ("full_height", C.c_int32), ("full_width", C.c_int32),
         ("ssim_weight", C.c_float), ("c1", C.c_float), ("c2", C.c_float), ("smooth_weight", C.c_float),
         ("flags", C.c_uint32),
+        ("depth_mode", C.c_int32), ("min_depth", C.c_float), ("max_depth", C.c_float),
     ]
 
 
@@ -216,6 +218,11 @@ def load():
     lib.sde_resize_pyramid.restype = C.c_int
     lib.sde_resize_pyramid.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), C.POINTER(PyramidBuffers), C.c_void_p]
+    for name in ("sde_resize_avgpool_forward", "sde_resize_avgpool_backward"):
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = C.c_int, lib.sde_resize_bilinear.argtypes
+    lib.sde_resize_pyramid_u8.restype = C.c_int
+    lib.sde_resize_pyramid_u8.argtypes = lib.sde_resize_pyramid.argtypes
     _lib = lib
     return lib
 

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
   const bool col_ok0 = colP && gxp < w, col_ok1 = colP && gxp + 1 < w;
 
   StageArgs sa;
+  sa.depth_mode = p.depth_mode; sa.min_disp = p.min_disp; sa.disp_range = p.disp_range;
   sa.depth = depth; sa.src = nullptr; sa.tgt = tg0; sa.amap = amap;
   sa.planes = planes; sa.arg = sh.arg; sa.oy = oy; sa.ox = ox; sa.h = h; sa.w = w; sa.hw = hw;
   sa.plS = kBX; sa.plI = 0; sa.plA = kBA; sa.plD = kBD;
@@ -207,6 +208,10 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
     if (tma) {
       mbar_wait(&sh.bar, tma_phase);
       tma_phase ^= 1u;
+      if (j == 0 && p.depth_mode != SDE_DEPTH_IS_DEPTH) {
+        decode_depth_plane(planes + kBD * kPlane, p.depth_mode, p.min_disp, p.disp_range, tid);
+        if (!interior) __syncthreads();   // the fix-up copies decoded values
+      }
       if (!interior) {
         if (j == 0) reflect_fixup(planes, kBA, 3, oy, ox, h, w, tid), reflect_fixup(planes, kBD, 1, oy, ox, h, w, tid);
         reflect_fixup(planes, bS, 3, oy, ox, h, w, tid);
@@ -613,6 +618,15 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
           }
           if (d0 >= 1e-6f) g0 += -ic0 * ic0 * (G0 * rmbar - homog) * gsm;
           if (d1 >= 1e-6f) g1 += -ic1 * ic1 * (G1 * rmbar - homog) * gsm;
+        }
+        if (p.depth_mode != SDE_DEPTH_IS_DEPTH) {
+          // chain rule through disp_to_depth (and softplus): the gradient leaves w.r.t. what depth[] holds
+          const int pl = plane_index(row, c0 + 1);
+          const float* praw = depth + gy * w + gxp;
+          const float raw0 = p.depth_mode == SDE_DEPTH_IS_LOGIT ? __ldg(praw) : 0.0f;
+          const float raw1 = (p.depth_mode == SDE_DEPTH_IS_LOGIT && col_ok1) ? __ldg(praw + 1) : 0.0f;
+          g0 *= decode_depth_grad(planes[kBD * kPlane + pl], raw0, p.depth_mode, p.disp_range);
+          g1 *= decode_depth_grad(planes[kBD * kPlane + pl + 1], raw1, p.depth_mode, p.disp_range);
         }
         float* po = gout + gy * w + gxp;
         if (even && col_ok1) {

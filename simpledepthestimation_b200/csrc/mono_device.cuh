@@ -113,6 +113,8 @@ __device__ __forceinline__ Cell bilinear_cell(float X, float Y, int w, int h) {
 // Everything phase 1 needs about one (tile, source): where the halo'd tile sits, which planes
 // receive what.
 struct StageArgs {
+  int depth_mode;                    // SDE_DEPTH_IS_*: how stage_target decodes what it loads from `depth`
+  float min_disp, disp_range;
   const float* __restrict__ depth;   // [h*w] of this sample
   const float* __restrict__ src;     // [3*h*w] source frame of this sample
   const float* __restrict__ tgt;     // [3*h*w] target frame of this sample
@@ -308,7 +310,7 @@ __device__ __forceinline__ void stage_target(const StageArgs& a0, int tid, bool 
       position_of(ok[u] ? i : tid, yy, xx);
       const int pix = pixel_of<INTERIOR>(a, yy, xx, gy, gx);
       pl[u] = plane_index(yy, xx);
-      d[u] = __ldg(a.depth + pix);
+      d[u] = decode_depth(__ldg(a.depth + pix), a.depth_mode, a.min_disp, a.disp_range);
 #pragma unroll
       for (int c = 0; c < 3; ++c) t[u][c] = __ldg(a.tgt + (pix + c * a.hw));
       if (ARG) {
@@ -416,6 +418,13 @@ __device__ __forceinline__ void stage_saved(const StageArgs& a0, const float* __
         for (int c = 0; c < 3; ++c) a.planes[(a.plS + c) * kPlane + pl[u]] = v[u][c];
       }
   }
+}
+
+// A depth plane that arrived through TMA as disparity / logits is decoded in place, every stored
+// element once (out-of-image zeros become some finite depth that no valid output reads).
+__device__ __forceinline__ void decode_depth_plane(float* plane, int mode, float min_disp, float range, int tid) {
+  if (mode == SDE_DEPTH_IS_DEPTH) return;
+  for (int i = tid; i < kHH * kPitch; i += kThreads) plane[i] = decode_depth(plane[i], mode, min_disp, range);
 }
 
 // After a TMA box load of a tile that touches the image border: out-of-image elements arrived as zeros.

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   }
 
   StageArgs sa;
+  sa.depth_mode = p.depth_mode; sa.min_disp = p.min_disp; sa.disp_range = p.disp_range;
   sa.depth = depth; sa.src = nullptr; sa.tgt = tg0; sa.amap = nullptr;
   sa.planes = planes; sa.arg = nullptr; sa.oy = tc.y0 - 1; sa.ox = tc.x0 - 1; sa.h = h; sa.w = w; sa.hw = hw;
   sa.plS = kPlS; sa.plI = kPlI; sa.plA = kPlA; sa.plD = kPlD;
@@ -123,6 +124,8 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   if (tma) {
     mbar_wait(&sh.bar, tma_phase);
     tma_phase ^= 1u;
+    decode_depth_plane(planes + kPlD * kPlane, p.depth_mode, p.min_disp, p.disp_range, tid);
+    if (p.depth_mode != SDE_DEPTH_IS_DEPTH && !interior) __syncthreads();   // the fix-up copies decoded values
     if (!interior) {
       reflect_fixup(planes, kPlA, 3, oy, ox, h, w, tid);
       reflect_fixup(planes, kPlD, 1, oy, ox, h, w, tid);

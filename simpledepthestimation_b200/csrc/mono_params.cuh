@@ -50,6 +50,9 @@ struct MonoParams {
   float rtiles[SDE_MAX_SCALES][4];
   float inv_norm[SDE_MAX_SCALES];      // 1 / (n_scales * B * h * w [* candidates for 'mean']): d rec_loss / d pe of a selected pixel
   unsigned flags;
+  // what depth[] holds (SDE_DEPTH_IS_*): disparity / logits are decoded where a kernel stages them
+  int depth_mode;
+  float min_disp, disp_range;   // 1 / max_depth, 1 / min_depth - 1 / max_depth
   // forward workspace
   float* partials;        // [grid][4]
   double* fin;            // [n_scales*B][2]
@@ -76,6 +79,22 @@ struct alignas(64) MonoTma {
   CUtensorMap source[SDE_MAX_SCALES][SDE_MAX_SOURCES];
   CUtensorMap warped[SDE_MAX_SCALES][SDE_MAX_SOURCES];
 };
+
+// depth of one element of depth[]: depth itself, disp_to_depth of a disparity
+// (depth_decoder.py:9-18: scaled = min_disp + (max_disp - min_disp) * disp, depth = 1 / scaled -- separately rounded
+// multiply, add and IEEE division, as the reference's three ATen operations), or of softplus(logit) (depth_decoder.py:108)
+__device__ __forceinline__ float decode_depth(float v, int mode, float min_disp, float range) {
+  if (mode == SDE_DEPTH_IS_DEPTH) return v;
+  if (mode == SDE_DEPTH_IS_LOGIT) v = v > 20.0f ? v : log1pf(expf(v));   // nn.Softplus(beta=1, threshold=20)
+  return __fdiv_rn(1.0f, __fadd_rn(min_disp, __fmul_rn(range, v)));
+}
+// d depth / d (what depth[] holds), given the decoded depth and the raw element
+__device__ __forceinline__ float decode_depth_grad(float depth, float raw, int mode, float range) {
+  if (mode == SDE_DEPTH_IS_DEPTH) return 1.0f;
+  float g = -range * depth * depth;
+  if (mode == SDE_DEPTH_IS_LOGIT && raw <= 20.0f) g *= 1.0f / (1.0f + expf(-raw));   // softplus' = sigmoid
+  return g;
+}
 
 struct TileCoord {
   int s, b, x0, y0;

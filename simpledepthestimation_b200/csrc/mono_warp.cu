@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kWarpThreads, 1024 / kWarpThreads) mono_warp_k
 #pragma unroll
   for (int it = 0; it < kWarpPixPerThread; ++it) {
     const int pix = pix0 + it * kWarpThreads;
-    dv[it] = pix < hw ? __ldg(p.depth[s] + (size_t)b * hw + pix) : 0.0f;
+    dv[it] = pix < hw ? decode_depth(__ldg(p.depth[s] + (size_t)b * hw + pix), p.depth_mode, p.min_disp, p.disp_range) : 0.0f;
   }
   // pixel coordinates: one integer division per thread, the other pixels follow by stepping kWarpThreads columns
   int gy = pix0 / w, gx = pix0 - gy * w;

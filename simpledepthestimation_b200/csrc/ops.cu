@@ -533,8 +533,65 @@ cudaError_t launch_resize_bilinear(const float* src, float* dst, int planes, int
   return cudaGetLastError();
 }
 
+// resize_img_avgpool(image, dst_size) = F.adaptive_avg_pool2d (camera.py:49-54; MotionLearning.py:126-144 at
+// NUM_SCALES > 1): output cell (i, j) averages the source rows floor(i sh / dh) .. ceil((i + 1) sh / dh) - 1 and the
+// columns likewise.  One thread per output element; the backward kernel is the adjoint, one thread per source
+// element gathering from the (at most two per axis when shrinking) cells that contain it -- no atomics.
+__device__ __forceinline__ int pool_start(int i, int src, int dst) { return (int)(((long long)i * src) / dst); }
+__device__ __forceinline__ int pool_end(int i, int src, int dst) { return (int)((((long long)i + 1) * src + dst - 1) / dst); }
+
+__global__ void __launch_bounds__(kOpThreads) avgpool_fwd_kernel(const float* __restrict__ src, float* __restrict__ dst, int sh,
+                                                                  int sw, int dh, int dw) {
+  const int pix = blockIdx.x * kOpThreads + threadIdx.x;
+  if (pix >= dh * dw) return;
+  const int i = pix / dw, j = pix - i * dw;
+  const int y0 = pool_start(i, sh, dh), y1 = pool_end(i, sh, dh), x0 = pool_start(j, sw, dw), x1 = pool_end(j, sw, dw);
+  const float* s = src + (size_t)blockIdx.y * sh * sw;
+  float sum = 0.0f;
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x) sum += __ldg(s + (size_t)y * sw + x);
+  dst[(size_t)blockIdx.y * dh * dw + pix] = sum / (float)((y1 - y0) * (x1 - x0));
+}
+
+__global__ void __launch_bounds__(kOpThreads) avgpool_bwd_kernel(const float* __restrict__ g_dst, float* __restrict__ g_src, int sh,
+                                                                  int sw, int dh, int dw) {
+  const int pix = blockIdx.x * kOpThreads + threadIdx.x;
+  if (pix >= sh * sw) return;
+  const int y = pix / sw, x = pix - y * sw;
+  const float* g = g_dst + (size_t)blockIdx.y * dh * dw;
+  // cells whose row range contains y: a superset is floor(y dh / sh) - 1 .. ceil((y + 1) dh / sh)
+  const int i_lo = max(0, (int)(((long long)y * dh) / sh) - 1), i_hi = min(dh - 1, (int)((((long long)y + 1) * dh + sh - 1) / sh));
+  const int j_lo = max(0, (int)(((long long)x * dw) / sw) - 1), j_hi = min(dw - 1, (int)((((long long)x + 1) * dw + sw - 1) / sw));
+  float sum = 0.0f;
+  for (int i = i_lo; i <= i_hi; ++i) {
+    const int y0 = pool_start(i, sh, dh), y1 = pool_end(i, sh, dh);
+    if (y < y0 || y >= y1) continue;
+    for (int j = j_lo; j <= j_hi; ++j) {
+      const int x0 = pool_start(j, sw, dw), x1 = pool_end(j, sw, dw);
+      if (x < x0 || x >= x1) continue;
+      sum += __ldg(g + (size_t)i * dw + j) / (float)((y1 - y0) * (x1 - x0));
+    }
+  }
+  g_src[(size_t)blockIdx.y * sh * sw + pix] = sum;
+}
+
+cudaError_t launch_avgpool(bool backward, const float* in, float* out, int planes, int sh, int sw, int dh, int dw, cudaStream_t stream) {
+  const int n = backward ? sh * sw : dh * dw;
+  for (int p0 = 0; p0 < planes; p0 += 65535) {   // gridDim.y limit
+    const int np = planes - p0 < 65535 ? planes - p0 : 65535;
+    const dim3 grid((n + kOpThreads - 1) / kOpThreads, np);
+    if (backward) avgpool_bwd_kernel<<<grid, kOpThreads, 0, stream>>>(in + (size_t)p0 * dh * dw, out + (size_t)p0 * sh * sw, sh, sw, dh, dw);
+    else          avgpool_fwd_kernel<<<grid, kOpThreads, 0, stream>>>(in + (size_t)p0 * sh * sw, out + (size_t)p0 * dh * dw, sh, sw, dh, dw);
+  }
+  return cudaGetLastError();
+}
+
 // The image pyramid of a step (MonoDepth2.py:82,88: the target and every source frame resized to every coarser
 // prediction size) in ONE launch: blockIdx.x walks the pixel blocks of all levels, .y the planes, .z the frames.
+// U8: the frames are the decoded uint8 images; a tap is byte / 255 in fp32 -- the bits torchvision's ToTensor produces
+// (kitti_v2.py:207-208) -- so the pyramid equals the one built from the converted frames, and a level of the source
+// size is the conversion itself.
+template <bool U8>
 __global__ void __launch_bounds__(kOpThreads) resize_pyramid_kernel(const __grid_constant__ PyramidParams p) {
   int l = 0;
   while (l + 1 < p.n_levels && (int)blockIdx.x >= p.blk_start[l + 1]) ++l;
@@ -546,11 +603,18 @@ __global__ void __launch_bounds__(kOpThreads) resize_pyramid_kernel(const __grid
   const int y0 = (int)fy, x0 = (int)fx;
   const int yp = y0 < sh - 1 ? 1 : 0, xp = x0 < sw - 1 ? 1 : 0;
   const float ly1 = fy - (float)y0, ly0 = 1.0f - ly1, lx1 = fx - (float)x0, lx0 = 1.0f - lx1;
-  const float* __restrict__ src = p.src[blockIdx.z];
   float* __restrict__ dst = p.dst[blockIdx.z][l];
   for (int pl = blockIdx.y; pl < p.planes; pl += gridDim.y) {
-    const float* s = src + (size_t)pl * sh * sw + (size_t)y0 * sw + x0;
-    const float v00 = __ldg(s), v01 = __ldg(s + xp), v10 = __ldg(s + yp * sw), v11 = __ldg(s + yp * sw + xp);
+    const size_t off = (size_t)pl * sh * sw + (size_t)y0 * sw + x0;
+    float v00, v01, v10, v11;
+    if (U8) {
+      const uint8_t* s = static_cast<const uint8_t*>(p.src[blockIdx.z]) + off;
+      v00 = (float)__ldg(s) / 255.0f; v01 = (float)__ldg(s + xp) / 255.0f;
+      v10 = (float)__ldg(s + yp * sw) / 255.0f; v11 = (float)__ldg(s + yp * sw + xp) / 255.0f;
+    } else {
+      const float* s = static_cast<const float*>(p.src[blockIdx.z]) + off;
+      v00 = __ldg(s); v01 = __ldg(s + xp); v10 = __ldg(s + yp * sw); v11 = __ldg(s + yp * sw + xp);
+    }
     dst[(size_t)pl * dh * dw + pix] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);   // same order as above
   }
 }
@@ -565,7 +629,8 @@ cudaError_t launch_resize_pyramid(PyramidParams& p, cudaStream_t stream) {
   }
   p.blk_start[p.n_levels] = start;
   const dim3 grid(start, p.planes < 65535 ? p.planes : 65535, p.n_frames);
-  resize_pyramid_kernel<<<grid, kOpThreads, 0, stream>>>(p);
+  if (p.src_u8) resize_pyramid_kernel<true><<<grid, kOpThreads, 0, stream>>>(p);
+  else          resize_pyramid_kernel<false><<<grid, kOpThreads, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -109,8 +109,9 @@ struct PyramidParams {   // resize_img of several frames to several sizes, one l
   int dh[SDE_MAX_SCALES], dw[SDE_MAX_SCALES];
   int blk_start[SDE_MAX_SCALES + 1];   // first pixel block of level l
   float rh[SDE_MAX_SCALES], rw[SDE_MAX_SCALES];
-  const float* src[kPyrFrames];
+  const void* src[kPyrFrames];          // fp32 planes, or uint8 planes (src_u8: value = byte / 255, torchvision ToTensor)
   float* dst[kPyrFrames][SDE_MAX_SCALES];
+  int src_u8;
 };
 
 struct SilogParams {   // silog_loss

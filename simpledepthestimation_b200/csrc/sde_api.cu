@@ -22,6 +22,7 @@ cudaError_t launch_smooth_fwd(const SmoothParams& p, cudaStream_t stream);
 cudaError_t launch_smooth_bwd(const SmoothParams& p, cudaStream_t stream);
 cudaError_t launch_resize_bilinear(const float* src, float* dst, int planes, int sh, int sw, int dh, int dw, cudaStream_t stream);
 cudaError_t launch_resize_pyramid(PyramidParams& p, cudaStream_t stream);
+cudaError_t launch_avgpool(bool backward, const float* in, float* out, int planes, int sh, int sw, int dh, int dw, cudaStream_t stream);
 cudaError_t launch_mcons_fwd(const McParams& p, cudaStream_t stream);
 cudaError_t launch_mcons_bwd(const McParams& p, float* g_t_ba, cudaStream_t stream);
 cudaError_t launch_mreg(int which, const MregParams& p, cudaStream_t stream);
@@ -54,6 +55,8 @@ static int mono_check(const sde_mono_desc* d) {
   for (int i = 0; i < d->n_scales; ++i)
     if (d->height[i] < 2 || d->width[i] < 2) return SDE_ERR_INVALID_ARG;  // reflect pad needs >= 2
   if (!(d->ssim_weight >= 0.0f) || !(d->smooth_weight >= 0.0f)) return SDE_ERR_INVALID_ARG;
+  if (d->depth_mode < SDE_DEPTH_IS_DEPTH || d->depth_mode > SDE_DEPTH_IS_LOGIT) return SDE_ERR_INVALID_ARG;
+  if (d->depth_mode != SDE_DEPTH_IS_DEPTH && !(d->min_depth > 0.0f && d->max_depth > d->min_depth)) return SDE_ERR_INVALID_ARG;
   return SDE_OK;
 }
 
@@ -137,6 +140,12 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
   p.l1_w = d->ssim_weight > 0.0f ? 1.0f - d->ssim_weight : 1.0f;  // MonoDepth2.py:137-144
   p.c1 = d->c1; p.c2 = d->c2;
   p.flags = d->flags;
+  p.depth_mode = d->depth_mode;
+  if (d->depth_mode != SDE_DEPTH_IS_DEPTH) {
+    // min_disp = 1 / max_depth, max_disp - min_disp: Python floats in the reference, fp32 on the multiply / add
+    p.min_disp = (float)(1.0 / (double)d->max_depth);
+    p.disp_range = (float)(1.0 / (double)d->min_depth - 1.0 / (double)d->max_depth);
+  }
   const MonoLayout L = mono_layout(d);
   char* ws = static_cast<char*>(b->workspace);
   p.counter = reinterpret_cast<unsigned*>(ws);
@@ -625,27 +634,54 @@ int sde_resize_bilinear(const float* src, float* dst, int32_t planes, int32_t sr
   SDE_LAUNCH(launch_resize_bilinear(src, dst, planes, src_h, src_w, dst_h, dst_w, static_cast<cudaStream_t>(stream)));
 }
 
-int sde_resize_pyramid(int32_t n_frames, int32_t planes, int32_t src_h, int32_t src_w, int32_t n_levels,
-                       const int32_t* dst_h, const int32_t* dst_w, const sde_pyramid_buffers* buf, void* stream) {
-  if (!buf || !dst_h || !dst_w || n_frames < 1 || n_frames > kPyrFrames || n_levels < 1 || n_levels > SDE_MAX_SCALES ||
+int sde_resize_avgpool_forward(const float* src, float* dst, int32_t planes, int32_t src_h, int32_t src_w, int32_t dst_h,
+                               int32_t dst_w, void* stream) {
+  if (!src || !dst || planes < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return SDE_ERR_INVALID_ARG;
+  SDE_LAUNCH(launch_avgpool(false, src, dst, planes, src_h, src_w, dst_h, dst_w, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_resize_avgpool_backward(const float* grad_dst, float* grad_src, int32_t planes, int32_t src_h, int32_t src_w,
+                                int32_t dst_h, int32_t dst_w, void* stream) {
+  if (!grad_dst || !grad_src || planes < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return SDE_ERR_INVALID_ARG;
+  SDE_LAUNCH(launch_avgpool(true, grad_dst, grad_src, planes, src_h, src_w, dst_h, dst_w, static_cast<cudaStream_t>(stream)));
+}
+
+static int pyramid_call(bool u8, int32_t n_frames, int32_t planes, int32_t src_h, int32_t src_w, int32_t n_levels,
+                        const int32_t* dst_h, const int32_t* dst_w, const void* const* src, float* const (*dst)[SDE_MAX_SCALES],
+                        void* stream) {
+  if (!src || !dst || !dst_h || !dst_w || n_frames < 1 || n_frames > kPyrFrames || n_levels < 1 || n_levels > SDE_MAX_SCALES ||
       planes < 1 || src_h < 1 || src_w < 1)
     return SDE_ERR_INVALID_ARG;
   PyramidParams p;
   memset(&p, 0, sizeof(p));
-  p.n_frames = n_frames; p.n_levels = n_levels; p.planes = planes; p.sh = src_h; p.sw = src_w;
+  p.n_frames = n_frames; p.n_levels = n_levels; p.planes = planes; p.sh = src_h; p.sw = src_w; p.src_u8 = u8 ? 1 : 0;
   for (int l = 0; l < n_levels; ++l) {
     if (dst_h[l] < 1 || dst_w[l] < 1) return SDE_ERR_INVALID_ARG;
     p.dh[l] = dst_h[l]; p.dw[l] = dst_w[l];
   }
   for (int f = 0; f < n_frames; ++f) {
-    if (!buf->src[f]) return SDE_ERR_INVALID_ARG;
-    p.src[f] = buf->src[f];
+    if (!src[f]) return SDE_ERR_INVALID_ARG;
+    p.src[f] = src[f];
     for (int l = 0; l < n_levels; ++l) {
-      if (!buf->dst[f][l]) return SDE_ERR_INVALID_ARG;
-      p.dst[f][l] = buf->dst[f][l];
+      if (!dst[f][l]) return SDE_ERR_INVALID_ARG;
+      p.dst[f][l] = dst[f][l];
     }
   }
   SDE_LAUNCH(launch_resize_pyramid(p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_resize_pyramid(int32_t n_frames, int32_t planes, int32_t src_h, int32_t src_w, int32_t n_levels,
+                       const int32_t* dst_h, const int32_t* dst_w, const sde_pyramid_buffers* buf, void* stream) {
+  if (!buf) return SDE_ERR_INVALID_ARG;
+  return pyramid_call(false, n_frames, planes, src_h, src_w, n_levels, dst_h, dst_w,
+                      reinterpret_cast<const void* const*>(buf->src), buf->dst, stream);
+}
+
+int sde_resize_pyramid_u8(int32_t n_frames, int32_t planes, int32_t src_h, int32_t src_w, int32_t n_levels,
+                          const int32_t* dst_h, const int32_t* dst_w, const sde_pyramid_u8_buffers* buf, void* stream) {
+  if (!buf) return SDE_ERR_INVALID_ARG;
+  return pyramid_call(true, n_frames, planes, src_h, src_w, n_levels, dst_h, dst_w,
+                      reinterpret_cast<const void* const*>(buf->src), buf->dst, stream);
 }
 
 size_t sde_motion_consistency_workspace_bytes(const sde_mcons_desc* desc) { return mcons_ok(desc) ? mcons_layout(desc).total : 0; }

@@ -48,9 +48,11 @@ class MonoLossPlan:
 
     def __init__(self, batch: int, sizes: Sequence[Sequence[int]], n_sources: int, full_size: Sequence[int],
                  device, ssim_weight=0.85, c1=1e-4, c2=9e-4, smooth_weight=1e-3, automask=True, reduce="min",
-                 save_warped=True):
+                 save_warped=True, depth_mode="depth", min_depth=0.1, max_depth=80.0):
         if reduce not in ("min", "mean"):
             raise NotImplementedError(reduce)  # same as MonoDepth2.py:120-121
+        if depth_mode not in _lib.DEPTH_MODES:
+            raise _lib.SdeError(f"depth_mode must be one of {sorted(_lib.DEPTH_MODES)}")
         if len(sizes) > _lib.MAX_SCALES or n_sources > _lib.MAX_SOURCES:
             raise _lib.SdeError("too many scales / sources")
         self.lib = _lib.load()
@@ -69,6 +71,11 @@ class MonoLossPlan:
         d.full_height, d.full_width = self.full_size
         d.ssim_weight, d.c1, d.c2, d.smooth_weight = ssim_weight, c1, c2, smooth_weight
         d.flags = (_lib.FLAG_AUTOMASK if automask else 0) | (_lib.FLAG_REDUCE_MEAN if reduce == "mean" else 0)
+        # depth_mode "disp" / "logit": the `depth` tensors hold the decoder's disparity / pre-softplus output and the
+        # kernels apply disp_to_depth(., min_depth, max_depth) (depth_decoder.py:9-18,108) themselves; the gradient comes
+        # back w.r.t. that tensor
+        self.depth_mode = depth_mode
+        d.depth_mode, d.min_depth, d.max_depth = _lib.DEPTH_MODES[depth_mode], float(min_depth), float(max_depth)
         self.desc = d
         nbytes = self.lib.sde_mono_workspace_bytes(C.byref(d))
         if nbytes == 0:
@@ -231,34 +238,47 @@ class HostLossRunner:
     Copies and compute are software-pipelined over two input slots: the H2D copy of step i+1 (copy stream)
     overlaps the kernels and the D2H copy of step i (compute stream).  Every step still performs its own H2D
     and D2H; `h2d_bytes` / `d2h_bytes` count exactly the tensors copied per step.  step() is asynchronous;
-    finish() waits for the last step and returns its host results."""
+    finish() waits for the last step and returns its host results.
 
-    def __init__(self, plan: MonoLossPlan, device, slots=2):
-        from .ops import resize_pyramid
-        self._pyramid = resize_pyramid
+    Options (fewer bytes on the wire; the default copies everything as fp32):
+      u8_frames    the frames travel as the decoded uint8 images and become fp32 inside the pyramid kernel
+                   (byte / 255 = torchvision's ToTensor, kitti_v2.py:207-208): a quarter of the frame bytes;
+      frames_only  the depth pyramid, intrinsics and poses are device-resident (set_resident()): in the trainer
+                   they are network outputs that never leave the device, only the frames come from the host."""
+
+    def __init__(self, plan: MonoLossPlan, device, slots=2, u8_frames=False, frames_only=False):
+        from .ops import resize_pyramid, resize_pyramid_u8
+        self._pyramid, self._pyramid_u8 = resize_pyramid, resize_pyramid_u8
         self.plan, self.device = plan, torch.device(device)
+        self.u8_frames, self.frames_only = bool(u8_frames), bool(frames_only)
         B, S = plan.batch, plan.n_sources
         H, W = plan.full_size
         # One arena per direction: the inputs of a step travel as ONE host->device copy and the results as ONE
         # device->host copy (ten / seven separate copies cost ~8 us of launch gap each on a PCIe-bound step).
-        # Every tensor is a 16-byte aligned view into the arena (TMA needs aligned plane bases).
-        self.in_shapes = ([("img", (B, 3, H, W))] + [(f"ctx{j}", (B, 3, H, W)) for j in range(S)] +
-                          [(f"depth{i}", (B, 1, h, w)) for i, (h, w) in enumerate(plan.sizes)] + [("K", (B, 3, 3))] +
-                          [(f"pose{j}", (B, 4, 4)) for j in range(S)])
-        self.out_shapes = ([("losses", (2,))] + [(f"grad_depth{i}", (B, 1, h, w)) for i, (h, w) in enumerate(plan.sizes)] +
-                           [(f"grad_pose{j}", (B, 4, 4)) for j in range(S)])
-        self.in_floats, self.out_floats = self._arena_floats(self.in_shapes), self._arena_floats(self.out_shapes)
+        # Every tensor is a 16-byte aligned view into the byte arena (TMA needs aligned plane bases).
+        fdt = torch.uint8 if self.u8_frames else torch.float32
+        self.in_shapes = [("img", (B, 3, H, W), fdt)] + [(f"ctx{j}", (B, 3, H, W), fdt) for j in range(S)]
+        if not self.frames_only:
+            self.in_shapes += ([(f"depth{i}", (B, 1, h, w), torch.float32) for i, (h, w) in enumerate(plan.sizes)] +
+                               [("K", (B, 3, 3), torch.float32)] + [(f"pose{j}", (B, 4, 4), torch.float32) for j in range(S)])
+        self.out_shapes = ([("losses", (2,), torch.float32)] +
+                           [(f"grad_depth{i}", (B, 1, h, w), torch.float32) for i, (h, w) in enumerate(plan.sizes)] +
+                           [(f"grad_pose{j}", (B, 4, 4), torch.float32) for j in range(S)])
+        self.in_bytes, self.out_bytes = self._arena_bytes(self.in_shapes), self._arena_bytes(self.out_shapes)
         new = lambda *shape, dt=torch.float32: torch.empty(*shape, dtype=dt, device=self.device)  # noqa: E731
         self.slots = []
         for _ in range(slots):
-            arena = new(self.in_floats)
+            arena = new(self.in_bytes, dt=torch.uint8)
             v = self._views(arena, self.in_shapes)
-            sl = dict(arena=arena, img=v["img"], ctx=[v[f"ctx{j}"] for j in range(S)],
-                      depth=[v[f"depth{i}"] for i in range(len(plan.sizes))], K=v["K"],
-                      pose=[v[f"pose{j}"] for j in range(S)], ready=torch.cuda.Event(), free=torch.cuda.Event())
+            sl = dict(arena=arena, img=v["img"], ctx=[v[f"ctx{j}"] for j in range(S)], ready=torch.cuda.Event(),
+                      free=torch.cuda.Event())
+            if not self.frames_only:
+                sl.update(depth=[v[f"depth{i}"] for i in range(len(plan.sizes))], K=v["K"],
+                          pose=[v[f"pose{j}"] for j in range(S)])
             sl["free"].record()
             self.slots.append(sl)
-        self.out_arena = new(self.out_floats)
+        self.resident = None
+        self.out_arena = new(self.out_bytes, dt=torch.uint8)
         ov = self._views(self.out_arena, self.out_shapes)
         self.losses = ov["losses"]
         self.grad_depth = [ov[f"grad_depth{i}"] for i in range(len(plan.sizes))]
@@ -266,46 +286,61 @@ class HostLossRunner:
         self.argmin = [new(B, h, w, dt=torch.uint8) for h, w in plan.sizes]
         self.ones = torch.ones(2, device=self.device)
         self.warped = plan.new_warped()
-        self.h_out = torch.empty(self.out_floats, dtype=torch.float32, pin_memory=True)
+        self.h_out = torch.empty(self.out_bytes, dtype=torch.uint8, pin_memory=True)
         hv = self._views(self.h_out, self.out_shapes)
         self.h_losses = hv["losses"]
         self.h_grad_depth = [hv[f"grad_depth{i}"] for i in range(len(plan.sizes))]
         self.h_grad_pose = [hv[f"grad_pose{j}"] for j in range(S)]
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        # bytes per step, counted from the tensors (the arenas add at most 12 bytes of padding per tensor)
-        count = lambda shapes: 4 * sum(int(torch.Size(shape).numel()) for _, shape in shapes)  # noqa: E731
+        # bytes per step, counted from the tensors (the arenas add at most 15 bytes of padding per tensor)
+        count = lambda shapes: sum(int(torch.Size(shape).numel()) * torch.empty((), dtype=dt).element_size()  # noqa: E731
+                                   for _, shape, dt in shapes)
         self.h2d_bytes, self.d2h_bytes = count(self.in_shapes), count(self.out_shapes)
         self._i = 0
-        # kernels per step: pyramid (all frames and coarse scales in one launch), warp + loss forward, backward
-        self.launches_per_step = (1 if len(plan.sizes) > 1 else 0) + (2 if plan.save_warped else 1) + 1
+        # kernels per step: pyramid (all frames and scales in one launch), warp + loss forward, backward
+        pyr = 1 if (self.u8_frames or len(plan.sizes) > 1) else 0
+        self.launches_per_step = pyr + (2 if plan.save_warped else 1) + 1
+
+    def describe(self):
+        frames = "uint8 frames (byte / 255 in the pyramid kernel)" if self.u8_frames else "fp32 frames"
+        rest = "depth pyramid / K / poses device-resident" if self.frames_only else "depth pyramid, K, poses copied too"
+        return f"{frames}; {rest}; losses + gradients copied back"
 
     @staticmethod
-    def _arena_floats(shapes):
-        return sum((int(torch.Size(shape).numel()) + 3) // 4 * 4 for _, shape in shapes)
+    def _arena_bytes(shapes):
+        return sum((int(torch.Size(shape).numel()) * torch.empty((), dtype=dt).element_size() + 15) // 16 * 16
+                   for _, shape, dt in shapes)
 
     @staticmethod
     def _views(arena, shapes):
         out, off = {}, 0
-        for name, shape in shapes:
-            n = int(torch.Size(shape).numel())
-            out[name] = arena[off:off + n].view(*shape)
-            off += (n + 3) // 4 * 4
+        for name, shape, dt in shapes:
+            n = int(torch.Size(shape).numel()) * torch.empty((), dtype=dt).element_size()
+            out[name] = arena[off:off + n].view(dt).view(*shape)
+            off += (n + 15) // 16 * 16
         return out
+
+    def set_resident(self, depth, K, pose):
+        """frames_only: the device tensors that stand for the network outputs (depth pyramid, poses) and intrinsics."""
+        self.resident = dict(depth=list(depth), K=K, pose=list(pose))
 
     def pin(self, host_set):
         """Packs an (img, ctx list, depth list, K, pose list) tuple of CPU tensors into one pinned arena (the layout of
-        the device slots) -- what a data loader that writes into pinned memory hands over."""
+        the device slots) -- what a data loader that writes into pinned memory hands over.  With u8_frames the fp32
+        frames are quantised to the uint8 images a decoder delivers (round(x * 255))."""
         img, ctx, depth, K, pose = host_set
-        arena = torch.empty(self.in_floats, dtype=torch.float32, pin_memory=True)
+        arena = torch.empty(self.in_bytes, dtype=torch.uint8, pin_memory=True)
         v = self._views(arena, self.in_shapes)
-        v["img"].copy_(img)
+        q = (lambda t: (t * 255.0).round().clamp(0, 255).to(torch.uint8)) if self.u8_frames else (lambda t: t)
+        v["img"].copy_(q(img))
         for j, c in enumerate(ctx):
-            v[f"ctx{j}"].copy_(c)
-        for i, d in enumerate(depth):
-            v[f"depth{i}"].copy_(d)
-        v["K"].copy_(K)
-        for j, x in enumerate(pose):
-            v[f"pose{j}"].copy_(x)
+            v[f"ctx{j}"].copy_(q(c))
+        if not self.frames_only:
+            for i, d in enumerate(depth):
+                v[f"depth{i}"].copy_(d)
+            v["K"].copy_(K)
+            for j, x in enumerate(pose):
+                v[f"pose{j}"].copy_(x)
         return arena
 
     def step(self, host_arena):
@@ -318,12 +353,16 @@ class HostLossRunner:
             sl["ready"].record()
         main.wait_event(sl["ready"])
         sizes = self.plan.sizes
-        pyr = self._pyramid([sl["img"]] + sl["ctx"], sizes)          # [frame][scale]
+        frames = [sl["img"]] + sl["ctx"]
+        pyr = self._pyramid_u8(frames, sizes) if self.u8_frames else self._pyramid(frames, sizes)   # [frame][scale]
         target = pyr[0]
         source = [[pyr[1 + j][i] for j in range(len(sl["ctx"]))] for i in range(len(sizes))]
-        self.plan.forward(target, source, sl["depth"], sl["K"], sl["pose"], out=self.losses, argmin_out=self.argmin,
+        rest = self.resident if self.frames_only else sl
+        if rest is None:
+            raise _lib.SdeError("HostLossRunner(frames_only=True): call set_resident(depth, K, pose) first")
+        self.plan.forward(target, source, rest["depth"], rest["K"], rest["pose"], out=self.losses, argmin_out=self.argmin,
                           warped=self.warped)
-        self.plan.backward(target, source, sl["depth"], sl["K"], sl["pose"], self.argmin, self.ones, self.grad_depth,
+        self.plan.backward(target, source, rest["depth"], rest["K"], rest["pose"], self.argmin, self.ones, self.grad_depth,
                            self.grad_pose, warped=self.warped)
         sl["free"].record()
         self.h_out.copy_(self.out_arena, non_blocking=True)

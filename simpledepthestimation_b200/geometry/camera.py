@@ -43,9 +43,14 @@ def resize_img(image, dst_size, mode="bilinear"):
 
 
 def resize_img_avgpool(image, dst_size):
-    """adaptive average pooling resize (camera.py:49-54)."""
+    """adaptive average pooling resize, identity when the size already matches (camera.py:49-54).  CUDA fp32 tensors
+    (frames, depths and motion fields of MotionLearning at NUM_SCALES > 1, MotionLearning.py:126-144) go through the
+    sde_resize_avgpool kernels (differentiable); host tensors use F.adaptive_avg_pool2d as the reference does."""
     if image.shape[-2] == dst_size[-2] and image.shape[-1] == dst_size[-1]:
         return image
+    if image.is_cuda and image.dtype == torch.float32:
+        from ..ops import resize_avgpool
+        return resize_avgpool(image, dst_size)
     return F.adaptive_avg_pool2d(image, tuple(dst_size))
 
 

@@ -44,19 +44,24 @@ class MonoDepth2Model(nn.Module):
         self.register_buffer("pixel_std", torch.Tensor(cfg.MODEL.PIXEL_STD).view(1, -1, 1, 1))
         self._plans = {}
         self.ssim = SSIM(self.c1, self.c2)
+        # disp_to_depth range of the depth nets (DepthResNet.py:41: min_depth=0.1, max_depth=cfg.MODEL.MAX_DEPTH): used when
+        # a depth net hands over `disp_pred` / `disp_logit_pred` instead of `depth_pred`
+        self.min_depth = float(cfg.MODEL.get("MIN_DEPTH", 0.1)) if hasattr(cfg.MODEL, "get") else 0.1
+        self.max_depth = float(cfg.MODEL.get("MAX_DEPTH", 80.0)) if hasattr(cfg.MODEL, "get") else 80.0
 
     @property
     def device(self):
         return self.pixel_mean.device
 
-    def _plan(self, batch, sizes, n_sources, full_size):
-        key = (batch, tuple(sizes), n_sources, tuple(full_size), str(self.device))
+    def _plan(self, batch, sizes, n_sources, full_size, depth_mode="depth"):
+        key = (batch, tuple(sizes), n_sources, tuple(full_size), str(self.device), depth_mode)
         plan = self._plans.get(key)
         if plan is None:
             plan = MonoLossPlan(batch, sizes, n_sources, full_size, self.device,
                                 ssim_weight=self.ssim_loss_weight, c1=self.c1, c2=self.c2,
                                 smooth_weight=self.smooth_loss_w, automask=self.use_automask,
-                                reduce=self.photometric_reduce)
+                                reduce=self.photometric_reduce, depth_mode=depth_mode,
+                                min_depth=self.min_depth, max_depth=self.max_depth)
             self._plans[key] = plan
         return plan
 
@@ -72,6 +77,16 @@ class MonoDepth2Model(nn.Module):
 
             image = batch["img_orig"]
             contexts = batch["ctx_img_orig"]
+            # A depth net may skip its tail (softplus + disp_to_depth, depth_decoder.py:9-18,108; DepthResNet.py:57) and
+            # hand over the disparities (`disp_pred`) or the last convolution's output (`disp_logit_pred`): the fused
+            # loss decodes them in-kernel and returns the gradient w.r.t. that tensor
+            depth_mode = "depth"
+            if "depth_pred" not in batch:
+                depth_mode = "disp" if "disp_pred" in batch else "logit"
+                batch["depth_pred"] = batch["disp_pred"] if depth_mode == "disp" else batch["disp_logit_pred"]
+                if self.clip_loss > 0.0 or self.sup_loss_w > 0.0 or self.var_loss_w > 0.0:
+                    raise NotImplementedError("disp_pred / disp_logit_pred need the fused loss (CLIP, SUPERVISED_WEIGHT and "
+                                              "VAR_LOSS_WEIGHT off): hand over depth_pred for those terms")
             depth_pred = batch["depth_pred"]
             pose_pred = list(batch["pose_pred"])
             sizes = [tuple(d.shape[-2:]) for d in depth_pred]
@@ -90,7 +105,7 @@ class MonoDepth2Model(nn.Module):
                 rec, smooth = self._unfused_losses(target, source, list(depth_pred), batch["intrinsics"].float(),
                                                    pose_pred, tuple(image.shape[-2:]))
             else:
-                plan = self._plan(image.shape[0], sizes, len(contexts), tuple(image.shape[-2:]))
+                plan = self._plan(image.shape[0], sizes, len(contexts), tuple(image.shape[-2:]), depth_mode)
                 rec, smooth, _ = mono_photometric_smoothness_loss(plan, target, source, list(depth_pred),
                                                                   batch["intrinsics"].float(), pose_pred)
             output["rec_loss"] = rec

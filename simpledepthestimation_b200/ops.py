@@ -224,6 +224,34 @@ def resize_bilinear(image: torch.Tensor, dst_size) -> torch.Tensor:
     return out
 
 
+class _AvgPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, dh, dw):
+        lib = _lib.load()
+        image = _cuda_f32(image, "image")
+        sh, sw = image.shape[-2:]
+        planes = image.numel() // (sh * sw)
+        out = torch.empty(*image.shape[:-2], dh, dw, device=image.device)
+        _lib.check(lib.sde_resize_avgpool_forward(image.data_ptr(), out.data_ptr(), planes, sh, sw, dh, dw, _stream()),
+                   "sde_resize_avgpool_forward")
+        ctx.geom = (tuple(image.shape), planes, sh, sw, dh, dw)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, planes, sh, sw, dh, dw = ctx.geom
+        g = _cuda_f32(g, "grad")
+        out = torch.empty(shape, device=g.device)
+        _lib.check(_lib.load().sde_resize_avgpool_backward(g.data_ptr(), out.data_ptr(), planes, sh, sw, dh, dw, _stream()),
+                   "sde_resize_avgpool_backward")
+        return out, None, None
+
+
+def resize_avgpool(image: torch.Tensor, dst_size) -> torch.Tensor:
+    """F.adaptive_avg_pool2d(image, dst_size) for a CUDA fp32 [..., H, W] tensor (camera.py:49-54), differentiable."""
+    return _AvgPoolFn.apply(image, int(dst_size[-2]), int(dst_size[-1]))
+
+
 def resize_pyramid(frames, sizes):
     """resize_img of every frame in `frames` (CUDA fp32 [..., H, W], all the same shape) to every size in `sizes`, in
     one launch.  Returns out[f][l]; a size equal to the source size returns the frame itself (camera.py:41-42)."""
@@ -250,6 +278,38 @@ def resize_pyramid(frames, sizes):
                    "sde_resize_pyramid")
     return [[fr if (int(s[-2]), int(s[-1])) == (sh, sw) else out[f, (int(s[-2]), int(s[-1]))] for s in sizes]
             for f, fr in enumerate(frames)]
+
+
+def resize_pyramid_u8(frames, sizes):
+    """The pyramid from DECODED frames: `frames` are CUDA uint8 [..., H, W] tensors of one shape; returns out[f][l] fp32
+    with the bits of resize_img(frame / 255, sizes[l]) (a size equal to the source size is the conversion itself,
+    torchvision ToTensor).  One launch."""
+    lib = _lib.load()
+    for f in frames:
+        if not f.is_cuda or f.dtype != torch.uint8:
+            raise _lib.SdeError("resize_pyramid_u8: frames must be CUDA uint8 tensors")
+    frames = [f.contiguous() for f in frames]
+    sh, sw = frames[0].shape[-2:]
+    if any(f.shape != frames[0].shape for f in frames):
+        raise _lib.SdeError("resize_pyramid_u8: frames must share one shape")
+    levels = [(int(s[-2]), int(s[-1])) for s in sizes]
+    if len(frames) > _lib.MAX_SOURCES + 1 or not 1 <= len(levels) <= _lib.MAX_SCALES:
+        raise _lib.SdeError("resize_pyramid_u8: too many frames / levels")
+    planes = frames[0].numel() // (sh * sw)
+    b = _lib.PyramidBuffers()
+    out = []
+    for f, fr in enumerate(frames):
+        b.src[f] = fr.data_ptr()
+        row = []
+        for l, (dh, dw) in enumerate(levels):
+            row.append(torch.empty(*fr.shape[:-2], dh, dw, dtype=torch.float32, device=fr.device))
+            b.dst[f][l] = row[-1].data_ptr()
+        out.append(row)
+    dh = (C.c_int32 * len(levels))(*[s[0] for s in levels])
+    dw = (C.c_int32 * len(levels))(*[s[1] for s in levels])
+    _lib.check(lib.sde_resize_pyramid_u8(len(frames), planes, sh, sw, len(levels), dh, dw, C.byref(b), _stream()),
+               "sde_resize_pyramid_u8")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ motion regularisers

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import port
 from helpers import (build_pyramid, golden_mono_inputs, gpu_mono_from_pose, gpu_mono_from_vec, load_golden, oracle_mono,
                      port_mono_from_vec, rel_err, stable_mask)
 from simpledepthestimation_b200.synthetic import euler_pose, mono_inputs
@@ -387,3 +388,101 @@ def test_host_runner_end_to_end_matches_device_path(dev):
         assert torch.equal(losses, ref_l.cpu())
         for a, b in zip(gd + gp, ref_gd + ref_gp):
             assert torch.equal(a, b.cpu())
+
+
+@pytest.mark.parametrize("u8,frames_only", [(True, False), (False, True), (True, True)])
+def test_host_runner_options_match_device_path(dev, u8, frames_only):
+    """HostLossRunner(u8_frames / frames_only): uint8 frames converted inside the pyramid kernel, and depth / K / poses
+    kept device-resident, give the bits of the device-resident path on the same (quantised) frames."""
+    from simpledepthestimation_b200.functional import HostLossRunner, MonoLossPlan
+    from simpledepthestimation_b200.geometry.camera import resize_img
+
+    B, H, W = 2, 48, 160
+    s = mono_inputs(B, H, W, seed=44)
+    sizes = [tuple(d.shape[-2:]) for d in s["depth"]]
+    plan = MonoLossPlan(B, sizes, 2, (H, W), dev)
+    g = lambda t: t.to(dev).contiguous()  # noqa: E731
+    depth, K, pose = [g(d) for d in s["depth"]], g(s["K"]), [g(euler_pose(v)) for v in s["pose_vec"]]
+    runner = HostLossRunner(plan, dev, u8_frames=u8, frames_only=frames_only)
+    if frames_only:
+        runner.set_resident(depth, K, pose)
+    arena = runner.pin((s["img"], list(s["ctx"]), list(s["depth"]), s["K"], [euler_pose(v) for v in s["pose_vec"]]))
+    frame_bytes = 3 * B * 3 * H * W * (1 if u8 else 4)
+    rest_bytes = 0 if frames_only else 4 * (sum(B * h * w for h, w in sizes) + B * 9 + 2 * B * 16)
+    assert runner.h2d_bytes == frame_bytes + rest_bytes
+    for _ in range(3):
+        runner.step(arena)
+    losses, gd, gp = runner.finish()
+    quant = (lambda t: (t * 255.0).round().clamp(0, 255) / 255.0) if u8 else (lambda t: t)
+    img, ctx = g(quant(s["img"])), [g(quant(c)) for c in s["ctx"]]
+    tgt = [resize_img(img, sz) for sz in sizes]
+    src = [[resize_img(c, sz) for c in ctx] for sz in sizes]
+    saved = plan.new_warped()
+    ref_l, argm = plan.forward(tgt, src, depth, K, pose, warped=saved)
+    ref_gd, ref_gp = plan.backward(tgt, src, depth, K, pose, argm, torch.ones(2, device=dev), warped=saved)
+    torch.cuda.synchronize()
+    assert torch.equal(losses, ref_l.cpu())
+    for a, b in zip(gd + gp, ref_gd + ref_gp):
+        assert torch.equal(a, b.cpu())
+
+
+@pytest.mark.parametrize("mode", ["disp", "logit"])
+@pytest.mark.parametrize("B,H,W,save", [(2, 32, 64, True), (1, 50, 70, True), (2, 32, 64, False)])
+def test_depth_decoder_tail_folded_into_the_loss(dev, mode, B, H, W, save):
+    """the loss kernels take the decoder's disparity (or its pre-softplus logits) and apply
+    disp_to_depth (layers/depth_decoder.py:9-18; softplus :108; DepthResNet.py:41,57) themselves; the gradient comes back
+    w.r.t. that tensor.  Against (a) the oracle in fp64 and (b) the same kernels fed the depth torch decodes, with
+    autograd through the decode."""
+    from parity_log import record
+    from simpledepthestimation_b200.functional import MonoLossPlan, mono_photometric_smoothness_loss
+
+    inp = mono_inputs(B, H, W, seed=21)
+    min_d, max_d = 0.1, 80.0
+    gen = torch.Generator().manual_seed(6)
+    # what the network hands over: disparities in (0, 1) or logits; the same smooth fields as the depth generator
+    raw = []
+    for d in inp["depth"]:
+        disp = ((1.0 / d.double() - 1.0 / max_d) / (1.0 / min_d - 1.0 / max_d)).clamp(1e-4, 0.999)
+        raw.append((disp if mode == "disp" else torch.log(torch.expm1(disp))).float())
+    tgt, src = build_pyramid(inp)
+    g = lambda t: t.to(dev).contiguous()  # noqa: E731
+    sizes = [tuple(d.shape[-2:]) for d in inp["depth"]]
+    pose = [g(euler_pose(v)) for v in inp["pose_vec"]]
+    T, S_, K = [g(t) for t in tgt], [[g(x) for x in row] for row in src], g(inp["K"])
+
+    def decode(x):   # depth_decoder.py:9-18 (+ nn.Softplus, :93,108)
+        disp = torch.nn.functional.softplus(x) if mode == "logit" else x
+        return 1 / (1 / max_d + (1 / min_d - 1 / max_d) * disp)
+
+    # (b) torch decodes, the kernels see depth
+    x1 = [g(r).requires_grad_() for r in raw]
+    p1 = [p.clone().requires_grad_() for p in pose]
+    plan1 = MonoLossPlan(B, sizes, 2, (H, W), dev, save_warped=save)
+    rec1, sm1, arg1 = mono_photometric_smoothness_loss(plan1, T, S_, [decode(x) for x in x1], K, p1)
+    (rec1 + sm1).backward()
+    # folded: the kernels see the raw tensor
+    x2 = [g(r).requires_grad_() for r in raw]
+    p2 = [p.clone().requires_grad_() for p in pose]
+    plan2 = MonoLossPlan(B, sizes, 2, (H, W), dev, save_warped=save, depth_mode=mode, min_depth=min_d, max_depth=max_d)
+    rec2, sm2, arg2 = mono_photometric_smoothness_loss(plan2, T, S_, x2, K, p2)
+    (rec2 + sm2).backward()
+    torch.cuda.synchronize()
+    e = dict(rec=rel_err(rec2.detach(), rec1.detach()), smooth=rel_err(sm2.detach(), sm1.detach()),
+             grad_raw=max(rel_err(a.grad, b.grad) for a, b in zip(x2, x1)),
+             grad_pose=max(rel_err(a.grad, b.grad) for a, b in zip(p2, p1)))
+    for a, b in zip(arg2, arg1):
+        assert float((a != b).double().mean()) < 1e-3
+    assert e["rec"] < 2e-6 and e["smooth"] < 2e-6 and e["grad_raw"] < 2e-5 and e["grad_pose"] < 2e-5, e
+    # (a) the oracle in fp64 on the same raw tensors
+    xd = [r.double().requires_grad_() for r in raw]
+    pd_ = [euler_pose(v.float()).double().requires_grad_() for v in inp["pose_vec"]]
+    pyr = [(t.double(), [s_.double() for s_ in ss]) for t, ss in zip(tgt, src)]
+    out = port.mono_loss(inp["img"].double(), None, inp["K"].double(), [decode(x) for x in xd], pd_, pyramid=pyr)
+    (out["rec_loss"] + out["smooth_loss"]).backward()
+    e["rec_vs_oracle"] = rel_err(rec2.detach(), out["rec_loss"].detach())
+    e["smooth_vs_oracle"] = rel_err(sm2.detach(), out["smooth_loss"].detach())
+    e["grad_raw_vs_oracle_q999"] = max(
+        float(torch.quantile(((a.grad.cpu().double() - b.grad).abs() / b.grad.abs().max()).flatten(), 0.999))
+        for a, b in zip(x2, xd))
+    record(mode=mode, shape=[B, H, W], save_warped=save, **e)
+    assert e["rec_vs_oracle"] < LOSS_TOL and e["smooth_vs_oracle"] < LOSS_TOL and e["grad_raw_vs_oracle_q999"] < GRAD_TOL, e

@@ -7,6 +7,7 @@ import torch.nn.functional as F
 
 from helpers import rel_err
 from oracle import port
+from simpledepthestimation_b200 import _lib
 from simpledepthestimation_b200.synthetic import euler_pose, motion_inputs
 
 pytestmark = pytest.mark.gpu
@@ -424,3 +425,42 @@ def test_resize_pyramid_matches_resize_img(sde_lib):
             assert torch.equal(pyr[f][l], resize_img(fr, s))
             ref = F.interpolate(fr.cpu(), size=s, mode="bilinear", align_corners=True)
             assert float((pyr[f][l].cpu() - ref).abs().max()) < 2e-6
+
+
+def test_resize_pyramid_from_uint8_frames(sde_lib):
+    """sde_resize_pyramid_u8: the pyramid built from the decoded uint8 frames has the bits of the pyramid built from
+    the frames torchvision's ToTensor makes of them (byte / 255, kitti_v2.py:207-208), level 0 included."""
+    from simpledepthestimation_b200.ops import resize_pyramid, resize_pyramid_u8
+
+    gen = torch.Generator().manual_seed(9)
+    u8 = [torch.randint(0, 256, (2, 3, 50, 70), generator=gen, dtype=torch.uint8) for _ in range(3)]
+    sizes = [(50, 70), (25, 35), (13, 18), (7, 9)]
+    as_float = [(f.float() / 255.0).to(DEV) for f in u8]           # ToTensor: uint8 -> float32, div(255)
+    ref = resize_pyramid(as_float, sizes)
+    got = resize_pyramid_u8([f.to(DEV) for f in u8], sizes)
+    for f in range(3):
+        for l in range(len(sizes)):
+            assert got[f][l].dtype == torch.float32 and torch.equal(got[f][l], ref[f][l]), (f, l)
+    with pytest.raises(_lib.SdeError):
+        resize_pyramid_u8(as_float, sizes)
+
+
+@pytest.mark.parametrize("src,dst", [((32, 64), (16, 32)), ((50, 70), (25, 35)), ((37, 53), (11, 17)), ((8, 12), (16, 20)),
+                                     ((192, 320), (96, 160))])
+def test_resize_img_avgpool_matches_adaptive_avg_pool(sde_lib, src, dst):
+    """resize_img_avgpool (camera.py:49-54) = F.adaptive_avg_pool2d: forward and adjoint, including ragged windows
+    (sizes that do not divide) and enlarging."""
+    from simpledepthestimation_b200.geometry.camera import resize_img_avgpool
+
+    gen = torch.Generator().manual_seed(12)
+    x = torch.rand(2, 3, *src, generator=gen)
+    w = torch.rand(2, 3, *dst, generator=gen)
+    xr = x.double().requires_grad_()
+    ref = F.adaptive_avg_pool2d(xr, dst)
+    (ref * w.double()).sum().backward()
+    xg = x.to(DEV).requires_grad_()
+    got = resize_img_avgpool(xg, dst)
+    (got * w.to(DEV)).sum().backward()
+    assert rel_err(got.detach(), ref.detach()) < 1e-6
+    assert rel_err(xg.grad, xr.grad) < 1e-6
+    assert resize_img_avgpool(xg, src) is xg
