@@ -15,7 +15,10 @@
  *   - device pointers, fp32, contiguous NCHW, 4-byte aligned; intrinsics [B,3,3]
  *     row-major; poses [B,4,4] row-major (R = [:3,:3], t = [:3,3]);
  *   - workspaces must be zero-filled ONCE after allocation; every call leaves them
- *     zeroed again, so they can be reused call after call on the same stream;
+ *     zeroed again, so they can be reused call after call on the same stream.  A workspace
+ *     belongs to ONE stream at a time (its ticket counters are shared by the CTAs of a call);
+ *     after a call that returned an error, or a launch that faulted, zero-fill it again
+ *     before reuse (the tickets may be left non-zero);
  *   - re-entrant for distinct (stream, workspace) pairs; no mutable globals;
  *   - results are deterministic: fixed-order reductions, no floating-point atomics.
  */
@@ -45,6 +48,8 @@ typedef enum sde_status {
 /* flags of sde_mono_desc.flags */
 #define SDE_MONO_AUTOMASK 1u       /* LOSS.AUTOMASK (MonoDepth2.py:96-101) */
 #define SDE_MONO_REDUCE_MEAN 2u    /* LOSS.PHOTOMETRIC_REDUCE == 'mean' (MonoDepth2.py:116-117); default 'min' */
+#define SDE_MONO_NO_TMA 4u         /* stage the tile planes with plain loads even where TMA boxes are possible (testing);
+                                      part of the descriptor so that the forward and the backward call of a step agree */
 /* values of sde_mono_desc.depth_mode */
 #define SDE_DEPTH_IS_DEPTH 0
 #define SDE_DEPTH_IS_DISP 1
@@ -54,6 +59,9 @@ int sde_version(void);
 const char* sde_strerror(int status);
 /* text of the last CUDA error seen by this thread ("" if none) */
 const char* sde_last_cuda_error(void);
+/* Developer switches (SDE_DISABLE_PDL, SDE_PDL_MASK) are read from the environment once, at the first call; this
+ * re-reads them (tests that flip a switch between two plans).  Not on the hot path. */
+void sde_reload_env(void);
 
 /* ------------------------------------------------------------------------------------------
  * MonoDepth2 multi-scale loss (fused).  Replaces the loss loop of
@@ -140,6 +148,7 @@ int sde_mono_loss_backward(const sde_mono_desc* desc, const sde_mono_buffers* bu
  * ------------------------------------------------------------------------------------------ */
 #define SDE_MAX_DIRS 2
 #define SDE_MOTION_FIELD 1u        /* field[d] given: residual translation [B,3,h,w] (motion_pred) */
+#define SDE_MOTION_NO_TMA 2u       /* recompute mode even where the kept planes could be boxed (testing); see SDE_MONO_NO_TMA */
 #define SDE_MOTION_N_LOSSES 4      /* per direction: rgb_l1_loss, ssim_loss, smooth_loss, reserved */
 
 typedef struct sde_motion_desc {
@@ -224,7 +233,9 @@ typedef struct sde_vs_buffers {
   float* grad_rotation;        /* [B,3,3] */
   float* grad_translation;     /* same shape as translation */
   float* grad_image_b;         /* [B,C,h,w], optional: bilinear scatter, accumulated in 64-bit fixed point
-                                  (integer atomics: order-independent, hence deterministic; |sum| < 5e5) */
+                                  (integer atomics: order-independent, hence deterministic).  A contribution of 2^15
+                                  or more in magnitude, a sum beyond 2^16, or a NaN / inf contribution gives NaN in
+                                  that element (ATen's float scatter would overflow / propagate likewise). */
   void* workspace;             /* sde_view_synthesis_workspace_bytes(), zero-filled once */
 } sde_vs_buffers;
 
@@ -328,14 +339,23 @@ typedef struct sde_mcons_buffers {
   const float* coords;        /* [B,h,w,2] normalised (x,y) */
   const float* mask;          /* [B,1,h,w] */
   const float* rotation;      /* [B,3,3] R_A2B */
-  const float* t_ab;          /* [B,3,h,w] */
-  const float* t_ba;          /* [B,3,h,w] */
+  const float* t_ab;          /* [B,3,h,w]: the translation field t_A2B -- or, with pose_ab, only its residual part */
+  const float* t_ba;          /* [B,3,h,w] likewise for B->A */
   float* loss;                /* [1] trans_error */
   const float* grad_loss;     /* [1] (device) */
   float* grad_t_ab;           /* [B,3,h,w] */
   float* grad_t_ba;           /* [B,3,h,w]: bilinear scatter, 64-bit fixed point + integer atomics (deterministic) */
   float* grad_rotation;       /* [B,3,3] */
   void* workspace;            /* sde_motion_consistency_workspace_bytes(), zero-filled once */
+  /* Optional split form (MotionLearning.py:143-147 builds t = pose[:, :3, [3], None] + motion field; here the sum is
+   * formed per pixel, the [B,3,h,w] overall field is never materialised): pose_ab / pose_ba [B,4,4] contribute their
+   * translation column; t_ab / t_ba are then the residual fields and may be NULL (rigid motion).  The backward pass
+   * writes d / d pose_*[:, :3, 3] to grad_pose_t_* [B,3] and the field gradients to grad_t_* (required iff the
+   * field is given). */
+  const float* pose_ab;
+  const float* pose_ba;
+  float* grad_pose_t_ab;
+  float* grad_pose_t_ba;
 } sde_mcons_buffers;
 
 size_t sde_motion_consistency_workspace_bytes(const sde_mcons_desc* desc);
@@ -361,6 +381,25 @@ int sde_motion_smoothness_forward(const sde_mreg_desc* desc, const sde_mreg_buff
 int sde_motion_smoothness_backward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream);
 int sde_motion_sparsity_forward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream);
 int sde_motion_sparsity_backward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream);
+
+/* The field regularisers as the model applies them (detectron2/modeling/meta_arch/MotionLearning.py:203-220), fused:
+ * t = pose[:, :3, 3] + field; s = 1 / sqrt(3 mean_{c,h,w}(t^2) + 1e-12) per sample (not detached); mn = field * s;
+ * losses[0] = motion_smoothness_loss_fn(mn), losses[1] = motion_sparsity_loss_fn(mn) (motion_loss.py:51-64).
+ * Neither t nor mn is materialised; the gradient reaches the field and the pose translation (through s). */
+typedef struct sde_mfield_buffers {
+  const float* pose;          /* [B,4,4] A->B, or NULL (zero translation) */
+  const float* field;         /* [B,3,h,w] residual translation (motion_pred, after masking / resizing) */
+  float* losses;              /* [2] */
+  float* saved_stats;         /* [B*12] for backward */
+  const float* grad_losses;   /* [2] upstream gradients (device) */
+  float* grad_field;          /* [B,3,h,w] */
+  float* grad_pose_t;         /* [B,3] d / d pose[:, :3, 3], or NULL */
+  void* workspace;            /* sde_motion_field_reg_workspace_bytes(), zero-filled once */
+} sde_mfield_buffers;
+
+size_t sde_motion_field_reg_workspace_bytes(const sde_mreg_desc* desc);   /* desc->channels must be 3 */
+int sde_motion_field_reg_forward(const sde_mreg_desc* desc, const sde_mfield_buffers* buf, void* stream);
+int sde_motion_field_reg_backward(const sde_mreg_desc* desc, const sde_mfield_buffers* buf, void* stream);
 
 /* variance_loss(depth) = 1 / mean((depth / mean(depth) - 1)^2), detectron2/modeling/losses/losses.py:16-18
  * (PackNet config, projects/MonoDepth2/configs/packnet_1a.yaml:12; callers MonoDepth2.py:112-113,

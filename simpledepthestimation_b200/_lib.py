@@ -11,6 +11,8 @@ MAX_SOURCES = 4
 MONO_SAVED_PLANES = 11   # SDE_MONO_SAVED_PLANES: planes per sample of a `warped` buffer
 FLAG_AUTOMASK = 1
 FLAG_REDUCE_MEAN = 2
+FLAG_NO_TMA = 4            # SDE_MONO_NO_TMA
+MOTION_FLAG_NO_TMA = 2     # SDE_MOTION_NO_TMA
 DEPTH_MODES = {"depth": 0, "disp": 1, "logit": 2}   # SDE_DEPTH_IS_*
 MAX_DIRS = 2
 MOTION_FLAG_FIELD = 1
@@ -107,7 +109,13 @@ class McDesc(C.Structure):
 
 class McBuffers(C.Structure):
     _fields_ = [(n, _f32p) for n in ("coords", "mask", "rotation", "t_ab", "t_ba", "loss", "grad_loss", "grad_t_ab",
-                                     "grad_t_ba", "grad_rotation", "workspace")]
+                                     "grad_t_ba", "grad_rotation", "workspace", "pose_ab", "pose_ba", "grad_pose_t_ab",
+                                     "grad_pose_t_ba")]
+
+
+class MfieldBuffers(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("pose", "field", "losses", "saved_stats", "grad_losses", "grad_field", "grad_pose_t",
+                                     "workspace")]
 
 
 class MregDesc(C.Structure):
@@ -170,6 +178,7 @@ def load():
     lib.sde_strerror.restype = C.c_char_p
     lib.sde_strerror.argtypes = [C.c_int]
     lib.sde_last_cuda_error.restype = C.c_char_p
+    lib.sde_reload_env.restype = None
     lib.sde_mono_workspace_bytes.restype = C.c_size_t
     lib.sde_mono_workspace_bytes.argtypes = [C.POINTER(MonoDesc)]
     for name in ("sde_mono_loss_forward", "sde_mono_loss_backward"):
@@ -200,6 +209,11 @@ def load():
         for suffix in ("_forward", "_backward"):
             fn = getattr(lib, f"sde_motion_{name}{suffix}")
             fn.restype, fn.argtypes = C.c_int, [C.POINTER(MregDesc), C.POINTER(MregBuffers), C.c_void_p]
+    lib.sde_motion_field_reg_workspace_bytes.restype = C.c_size_t
+    lib.sde_motion_field_reg_workspace_bytes.argtypes = [C.POINTER(MregDesc)]
+    for suffix in ("_forward", "_backward"):
+        fn = getattr(lib, "sde_motion_field_reg" + suffix)
+        fn.restype, fn.argtypes = C.c_int, [C.POINTER(MregDesc), C.POINTER(MfieldBuffers), C.c_void_p]
     lib.sde_variance_workspace_bytes.restype, lib.sde_variance_workspace_bytes.argtypes = C.c_size_t, [C.c_int64]
     for suffix in ("_forward", "_backward"):
         fn = getattr(lib, "sde_variance_loss" + suffix)
@@ -225,6 +239,12 @@ def load():
     lib.sde_resize_pyramid_u8.argtypes = lib.sde_resize_pyramid.argtypes
     _lib = lib
     return lib
+
+
+def tma_disabled() -> bool:
+    """SDE_DISABLE_TMA=1 (testing): plans built while it is set stage their tile planes with plain loads; the choice is
+    recorded in the plan's descriptor, so its forward and backward calls always agree."""
+    return os.environ.get("SDE_DISABLE_TMA", "") == "1"
 
 
 def check(status: int, what: str):

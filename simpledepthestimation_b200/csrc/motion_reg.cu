@@ -11,8 +11,6 @@
 namespace sde {
 
 constexpr int kRegThreads = 256;
-constexpr double kRegFixScale = 17592186044416.0;   // 2^44
-constexpr double kRegFixInv = 1.0 / 17592186044416.0;
 
 // block sum of `v` -> slot; the last block adds all slots of its group (fixed order, fp64) and returns true on
 // thread 0 with the total in `total`
@@ -77,18 +75,30 @@ struct McTerms {
   float th[3], z[3], ta[3], n, dn, m;
 };
 
-__device__ __forceinline__ void mcons_terms(const McParams& p, int b, int pix, int hw, const float* R, TapSet& taps, McTerms& t) {
+// t_ab(p) = [pose_ab translation] + [field t_ab(p)]; t_hat(p) = grid_sample(t_B2A, coords(p)) with zero padding -- the
+// constant part of t_B2A contributes its value times the weight of the in-range taps (win)
+__device__ __forceinline__ void mcons_terms(const McParams& p, int b, int pix, int hw, const float* R, TapSet& taps, McTerms& t,
+                                            float& win) {
   const float2 c = *reinterpret_cast<const float2*>(p.coords + ((size_t)b * hw + pix) * 2);
   taps = grid_taps(c.x, c.y, p.w, p.h);
+  win = 0.0f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (taps.off[q] >= 0) win += taps.wgt[q];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const float* plane = p.t_ba + ((size_t)b * 3 + k) * hw;
-    float s = 0.0f;
+    float s = p.pose_ba ? __ldg(p.pose_ba + b * 16 + k * 4 + 3) * win : 0.0f;
+    if (p.t_ba) {
+      const float* plane = p.t_ba + ((size_t)b * 3 + k) * hw;
+      float f = 0.0f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (taps.off[q] >= 0) s += __ldg(plane + taps.off[q]) * taps.wgt[q];
+      for (int q = 0; q < 4; ++q)
+        if (taps.off[q] >= 0) f += __ldg(plane + taps.off[q]) * taps.wgt[q];
+      s += f;
+    }
     t.th[k] = s;
-    t.ta[k] = __ldg(p.t_ab + ((size_t)b * 3 + k) * hw + pix);
+    t.ta[k] = (p.pose_ab ? __ldg(p.pose_ab + b * 16 + k * 4 + 3) : 0.0f) +
+              (p.t_ab ? __ldg(p.t_ab + ((size_t)b * 3 + k) * hw + pix) : 0.0f);
   }
 #pragma unroll
   for (int k = 0; k < 3; ++k) t.z[k] = R[k * 3] * t.th[0] + R[k * 3 + 1] * t.th[1] + R[k * 3 + 2] * t.th[2] + t.ta[k];
@@ -108,7 +118,8 @@ __global__ void __launch_bounds__(kRegThreads) mcons_fwd_kernel(const __grid_con
   if (pix < hw) {
     TapSet taps;
     McTerms t;
-    mcons_terms(p, b, pix, hw, R, taps, t);
+    float win;
+    mcons_terms(p, b, pix, hw, R, taps, t, win);
     e = t.m * fdiv(t.n, t.dn);
   }
   double total;
@@ -117,8 +128,9 @@ __global__ void __launch_bounds__(kRegThreads) mcons_fwd_kernel(const __grid_con
 }
 
 __global__ void __launch_bounds__(kRegThreads) mcons_bwd_kernel(const __grid_constant__ McParams p) {
-  __shared__ float red[9][kRegThreads / 32];
-  __shared__ double dred[9][kRegThreads / 32];
+  constexpr int NS = 15;   // d / d R [9], sum d / d t_ab [3], sum d / d t_hat over the in-range taps [3]
+  __shared__ float red[NS][kRegThreads / 32];
+  __shared__ double dred[NS][kRegThreads / 32];
   __shared__ unsigned ticket;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int b = blockIdx.y, hw = p.h * p.w;
@@ -127,13 +139,14 @@ __global__ void __launch_bounds__(kRegThreads) mcons_bwd_kernel(const __grid_con
 #pragma unroll
   for (int k = 0; k < 9; ++k) R[k] = __ldg(p.R + b * 9 + k);
   const float g = __ldg(p.g_loss) / ((float)p.B * (float)p.h * (float)p.w);
-  float gR[9];
+  float gs[NS];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) gR[k] = 0.0f;
+  for (int k = 0; k < NS; ++k) gs[k] = 0.0f;
   if (pix < hw) {
     TapSet taps;
     McTerms t;
-    mcons_terms(p, b, pix, hw, R, taps, t);
+    float win;
+    mcons_terms(p, b, pix, hw, R, taps, t, win);
     const float inv = fdiv(1.0f, t.dn);
     const float ge = g * t.m;                       // d loss / d (n / dn)
     const float cz = 2.0f * ge * inv;               // d / d z = cz * z
@@ -141,33 +154,36 @@ __global__ void __launch_bounds__(kRegThreads) mcons_bwd_kernel(const __grid_con
     float gth[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      p.g_t_ab[((size_t)b * 3 + k) * hw + pix] = cz * t.z[k] + cd * t.ta[k];
+      const float gab = cz * t.z[k] + cd * t.ta[k];
+      if (p.g_t_ab) p.g_t_ab[((size_t)b * 3 + k) * hw + pix] = gab;
+      gs[9 + k] = gab;
       gth[k] = cz * (R[k] * t.z[0] + R[3 + k] * t.z[1] + R[6 + k] * t.z[2]) + cd * t.th[k];   // R^T z
+      gs[12 + k] = gth[k] * win;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) gR[k * 3 + c] = cz * t.z[k] * t.th[c];
+      for (int c = 0; c < 3; ++c) gs[k * 3 + c] = cz * t.z[k] * t.th[c];
     }
+    if (p.scatter) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      long long* plane = p.g_t_ba_fix + ((size_t)b * 3 + k) * hw;
+      for (int k = 0; k < 3; ++k) {
+        long long* plane = p.g_t_ba_fix + ((size_t)b * 3 + k) * hw;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (taps.off[q] >= 0 && gth[k] != 0.0f)
-          atomicAdd(reinterpret_cast<unsigned long long*>(plane + taps.off[q]),
-                    (unsigned long long)__double2ll_rn((double)(gth[k] * taps.wgt[q]) * kRegFixScale));
+        for (int q = 0; q < 4; ++q)
+          if (taps.off[q] >= 0 && gth[k] != 0.0f) fix_add(plane + taps.off[q], gth[k] * taps.wgt[q]);
+      }
     }
   }
-  // d / d R: per-block slots, last block of the sample adds them
+  // per-sample sums: per-block slots, last block of the sample adds them
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const float v = warp_sum(gR[k]);
+  for (int k = 0; k < NS; ++k) {
+    const float v = warp_sum(gs[k]);
     if (lane == 0) red[k][wid] = v;
   }
   __syncthreads();
-  if (tid < 9) {
+  if (tid < NS) {
     float v = 0.0f;
 #pragma unroll
     for (int k = 0; k < kRegThreads / 32; ++k) v += red[tid][k];
-    p.slots[((size_t)b * gridDim.x + blockIdx.x) * 12 + tid] = v;
+    p.slots[((size_t)b * gridDim.x + blockIdx.x) * 16 + tid] = v;
   }
   __threadfence();
   __syncthreads();
@@ -175,29 +191,31 @@ __global__ void __launch_bounds__(kRegThreads) mcons_bwd_kernel(const __grid_con
   __syncthreads();
   if (ticket != gridDim.x - 1) return;
   __threadfence();
-  double a[9];
+  double a[NS];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) a[k] = 0.0;
+  for (int k = 0; k < NS; ++k) a[k] = 0.0;
   for (int t = tid; t < (int)gridDim.x; t += kRegThreads) {
-    const float* s = p.slots + ((size_t)b * gridDim.x + t) * 12;
+    const float* s = p.slots + ((size_t)b * gridDim.x + t) * 16;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) a[k] += (double)__ldcg(s + k);
+    for (int k = 0; k < NS; ++k) a[k] += (double)__ldcg(s + k);
   }
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
+  for (int k = 0; k < NS; ++k) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
   }
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) dred[k][wid] = a[k];
+    for (int k = 0; k < NS; ++k) dred[k][wid] = a[k];
   }
   __syncthreads();
-  if (tid < 9) {
+  if (tid < NS) {
     double v = 0.0;
 #pragma unroll
     for (int k = 0; k < kRegThreads / 32; ++k) v += dred[tid][k];
-    p.g_R[b * 9 + tid] = (float)v;
+    if (tid < 9) p.g_R[b * 9 + tid] = (float)v;
+    else if (tid < 12) { if (p.g_pose_t_ab) p.g_pose_t_ab[b * 3 + tid - 9] = (float)v; }
+    else if (p.g_pose_t_ba) p.g_pose_t_ba[b * 3 + tid - 12] = (float)v;
   }
   if (tid == 0) p.counters[1 + b] = 0u;
 }
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(kRegThreads) mcons_bwd_kernel(const __grid_con
 __global__ void __launch_bounds__(kRegThreads) reg_fix_to_float_kernel(long long* __restrict__ acc, float* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * kRegThreads + threadIdx.x;
   if (i < n) {
-    out[i] = (float)((double)acc[i] * kRegFixInv);
+    out[i] = fix_to_float(acc[i]);
     acc[i] = 0;
   }
 }
@@ -221,6 +239,7 @@ cudaError_t launch_mcons_bwd(const McParams& p, float* g_t_ba, cudaStream_t stre
   mcons_bwd_kernel<<<grid, kRegThreads, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (!p.scatter) return cudaSuccess;
   const size_t n = (size_t)p.B * 3 * p.h * p.w;
   reg_fix_to_float_kernel<<<(unsigned)((n + kRegThreads - 1) / kRegThreads), kRegThreads, 0, stream>>>(p.g_t_ba_fix, g_t_ba, n);
   return cudaGetLastError();

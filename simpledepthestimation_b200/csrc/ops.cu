@@ -14,8 +14,6 @@
 namespace sde {
 
 constexpr int kOpThreads = 256;
-constexpr double kFixScale = 17592186044416.0;        // 2^44: resolution 5.7e-14, range +-5.2e5
-constexpr double kFixInv = 1.0 / 17592186044416.0;
 
 __device__ __forceinline__ int reflect1(int i, int n) {   // nn.ReflectionPad2d(1): -1 -> 1, n -> n-2
   i = i < 0 ? -i : i;
@@ -100,10 +98,6 @@ __global__ void __launch_bounds__(kOpThreads) vs_fwd_kernel(const __grid_constan
     cn.y = __fdiv_rn(2.0f * Ys, (float)(p.h - 1)) - 1.0f;
     *reinterpret_cast<float2*>(p.coords + ((size_t)b * hw + pix) * 2) = cn;
   }
-}
-
-__device__ __forceinline__ void fix_add(long long* dst, float v) {
-  atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__double2ll_rn((double)v * kFixScale));
 }
 
 // backward: one thread per pixel; per-CTA slots for d/dR (9) and rigid d/dt (3), added by the last CTA of a sample
@@ -236,7 +230,7 @@ __global__ void __launch_bounds__(kOpThreads) vs_bwd_kernel(const __grid_constan
 __global__ void __launch_bounds__(kOpThreads) fix_to_float_kernel(long long* __restrict__ acc, float* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * kOpThreads + threadIdx.x;
   if (i < n) {
-    out[i] = (float)((double)acc[i] * kFixInv);
+    out[i] = fix_to_float(acc[i]);
     acc[i] = 0;
   }
 }

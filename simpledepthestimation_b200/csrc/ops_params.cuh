@@ -69,14 +69,33 @@ struct McParams {   // motion_consistency_loss, translation term
   const float* coords;      // [B,h,w,2]
   const float* mask;        // [B,1,h,w]
   const float* R;           // [B,3,3] A->B
-  const float* t_ab;        // [B,3,h,w]
-  const float* t_ba;        // [B,3,h,w]
+  const float* t_ab;        // [B,3,h,w] translation field A->B, or its residual part when pose_ab is given (may then be nullptr)
+  const float* t_ba;        // [B,3,h,w] likewise B->A
+  const float* pose_ab;     // optional [B,4,4]: its translation column is added to t_ab (the field is never materialised)
+  const float* pose_ba;     // optional [B,4,4]
   float* loss;              // [1]
   const float* g_loss;
-  float* g_t_ab;
+  float* g_t_ab;            // [B,3,h,w] (nullptr when t_ab is)
   long long* g_t_ba_fix;    // [B,3,h,w] fixed-point accumulator (zero on entry and exit)
   float* g_R;               // [B,3,3]
-  float* slots;             // forward: [B*blocks]; backward: [B*blocks][12]
+  float* g_pose_t_ab;       // optional [B,3]: sum over pixels of d / d t_ab
+  float* g_pose_t_ba;       // optional [B,3]: sum over pixels and in-range taps of d / d t_hat
+  int scatter;              // backward: scatter d / d t_hat into g_t_ba_fix (t_ba given)
+  float* slots;             // forward: [B*blocks]; backward: [B*blocks][16]
+  unsigned* counters;       // [1 + B]
+};
+
+struct MfieldParams {   // fused regularisers of the residual translation field (motion_field.cu)
+  int B, h, w;
+  const float* pose;        // [B,4,4] or nullptr (zero translation)
+  const float* field;       // [B,3,h,w]
+  float* losses;            // [2] smoothness, sparsity
+  float* stats;             // [B][12]
+  const float* g_losses;    // [2]
+  float* g_field;           // [B,3,h,w]
+  float* g_pose_t;          // [B,3] or nullptr
+  float* slots;             // [B][blocks][8]
+  double* fin;              // [B][2]
   unsigned* counters;       // [1 + B]
 };
 

@@ -26,6 +26,7 @@ cudaError_t launch_avgpool(bool backward, const float* in, float* out, int plane
 cudaError_t launch_mcons_fwd(const McParams& p, cudaStream_t stream);
 cudaError_t launch_mcons_bwd(const McParams& p, float* g_t_ba, cudaStream_t stream);
 cudaError_t launch_mreg(int which, const MregParams& p, cudaStream_t stream);
+cudaError_t launch_mfield(bool backward, const MfieldParams& p, cudaStream_t stream);
 cudaError_t launch_var(bool backward, const VarParams& p, cudaStream_t stream);
 cudaError_t launch_silog(bool backward, const SilogParams& p, cudaStream_t stream);
 cudaError_t launch_disp(bool backward, const DispParams& p, cudaStream_t stream);
@@ -211,22 +212,26 @@ static bool encode_planes(CUtensorMap* m, const float* base, int planes, int h, 
 // Measured at cfg2 (profiles/r1_notes.md): chaining the forward kernel behind the warp kernel and the backward
 // kernel behind whatever precedes it saves 2.1 + 2.4 us per step; chaining the warp kernel costs 9 us (its blocks,
 // parked on the SMs until the predecessor has drained, then start in lock-step and their gathers collide in L1),
-// hence the default mask 6.  SDE_DISABLE_PDL=1 / SDE_PDL_MASK=<bits> override it (read per call, like SDE_DISABLE_TMA).
-bool pdl_enabled(int which) {
+// hence the default mask 6.  SDE_DISABLE_PDL=1 / SDE_PDL_MASK=<bits> override it (read once; sde_reload_env() re-reads).
+static int g_pdl_mask = -1;   // cached developer switches (sde_reload_env)
+static int read_pdl_mask() {
   const char* off = getenv("SDE_DISABLE_PDL");
-  if (off && off[0] == '1') return false;
+  if (off && off[0] == '1') return 0;
   const char* m = getenv("SDE_PDL_MASK");
-  const int mask = m ? atoi(m) : 6;
-  return (mask >> which) & 1;
+  return m ? (atoi(m) & 7) : 6;
+}
+bool pdl_enabled(int which) {
+  if (g_pdl_mask < 0) g_pdl_mask = read_pdl_mask();
+  return (g_pdl_mask >> which) & 1;
 }
 
 // Decides per scale whether the tile planes are staged by TMA (row pitch a multiple of 16 bytes, encoder
 // available; the backward pass also needs the saved warps) and builds the descriptors.
 static void mono_tma(const sde_mono_desc* d, const sde_mono_buffers* b, bool backward, MonoParams& p, MonoTma& t) {
   memset(&t, 0, sizeof(t));
-  // SDE_DISABLE_TMA=1 forces the thread-staged path on every shape (used by the parity tests to cover it)
-  const char* off = getenv("SDE_DISABLE_TMA");
-  const bool disabled = off && off[0] == '1';
+  // SDE_MONO_NO_TMA forces the thread-staged path on every shape (the parity tests cover it that way); it travels in
+  // the descriptor, so the forward and the backward call of a step take the same path
+  const bool disabled = (d->flags & SDE_MONO_NO_TMA) != 0;
   for (int i = 0; i < d->n_scales; ++i) {
     p.tma[i] = 0;
     if (disabled) continue;
@@ -257,8 +262,7 @@ static void mono_tma(const sde_mono_desc* d, const sde_mono_buffers* b, bool bac
 static void motion_tma(const sde_motion_desc* d, const sde_motion_buffers* b, bool backward, MotionParams& p, MotionTma& t) {
   memset(&t, 0, sizeof(t));
   p.tma = 0;
-  const char* off = getenv("SDE_DISABLE_TMA");
-  bool ok = !(off && off[0] == '1');
+  bool ok = (d->flags & SDE_MOTION_NO_TMA) == 0;
   const int bw = backward ? 68 : 72;
   for (int k = 0; ok && k < d->n_dirs; ++k) {
     ok = b->warped[k] != nullptr &&
@@ -448,28 +452,48 @@ static McLayout mcons_layout(const sde_mcons_desc* d) {
   L.blocks = (d->height * d->width + kOpBlock - 1) / kOpBlock;
   size_t off = align16((size_t)(1 + d->batch) * sizeof(unsigned));
   L.off_slots = off;
-  off = align16(off + (size_t)d->batch * L.blocks * 12 * sizeof(float));
+  off = align16(off + (size_t)d->batch * L.blocks * 16 * sizeof(float));
   L.off_fix = off;
   off = align16(off + (size_t)d->batch * 3 * d->height * d->width * sizeof(long long));
   L.total = off;
   return L;
 }
 static int mcons_params(const sde_mcons_desc* d, const sde_mcons_buffers* b, bool backward, McParams& p) {
-  if (!mcons_ok(d) || !b || !b->coords || !b->mask || !b->rotation || !b->t_ab || !b->t_ba || !b->workspace)
-    return SDE_ERR_INVALID_ARG;
+  if (!mcons_ok(d) || !b || !b->coords || !b->mask || !b->rotation || !b->workspace) return SDE_ERR_INVALID_ARG;
+  // either the full fields, or pose + optional residual field per direction
+  if ((!b->t_ab && !b->pose_ab) || (!b->t_ba && !b->pose_ba)) return SDE_ERR_INVALID_ARG;
   memset(&p, 0, sizeof(p));
   const McLayout L = mcons_layout(d);
   char* ws = static_cast<char*>(b->workspace);
   p.B = d->batch; p.h = d->height; p.w = d->width;
   p.coords = b->coords; p.mask = b->mask; p.R = b->rotation; p.t_ab = b->t_ab; p.t_ba = b->t_ba;
+  p.pose_ab = b->pose_ab; p.pose_ba = b->pose_ba;
   p.loss = b->loss;
   p.counters = reinterpret_cast<unsigned*>(ws);
   p.slots = reinterpret_cast<float*>(ws + L.off_slots);
   p.g_t_ba_fix = reinterpret_cast<long long*>(ws + L.off_fix);
   if (!backward) return b->loss ? SDE_OK : SDE_ERR_INVALID_ARG;
-  if (!b->grad_loss || !b->grad_t_ab || !b->grad_t_ba || !b->grad_rotation) return SDE_ERR_INVALID_ARG;
-  p.g_loss = b->grad_loss; p.g_t_ab = b->grad_t_ab; p.g_R = b->grad_rotation;
+  if (!b->grad_loss || !b->grad_rotation) return SDE_ERR_INVALID_ARG;
+  if ((b->t_ab && !b->grad_t_ab) || (b->t_ba && !b->grad_t_ba)) return SDE_ERR_INVALID_ARG;
+  if ((b->pose_ab && !b->grad_pose_t_ab) || (b->pose_ba && !b->grad_pose_t_ba)) return SDE_ERR_INVALID_ARG;
+  p.g_loss = b->grad_loss; p.g_t_ab = b->t_ab ? b->grad_t_ab : nullptr; p.g_R = b->grad_rotation;
+  p.g_pose_t_ab = b->pose_ab ? b->grad_pose_t_ab : nullptr;
+  p.g_pose_t_ba = b->pose_ba ? b->grad_pose_t_ba : nullptr;
+  p.scatter = b->t_ba ? 1 : 0;
   return SDE_OK;
+}
+
+struct MfieldLayout { int blocks; size_t off_fin, off_slots, total; };
+static MfieldLayout mfield_layout(const sde_mreg_desc* d) {
+  MfieldLayout L;
+  L.blocks = (d->height * d->width + kOpBlock - 1) / kOpBlock;
+  size_t off = align16((size_t)(1 + d->batch) * sizeof(unsigned));
+  L.off_fin = off;
+  off = align16(off + (size_t)d->batch * 2 * sizeof(double));
+  L.off_slots = off;
+  off = align16(off + (size_t)d->batch * L.blocks * 8 * sizeof(float));
+  L.total = off;
+  return L;
 }
 
 static bool mreg_ok(const sde_mreg_desc* d) {
@@ -523,6 +547,8 @@ const char* sde_strerror(int status) {
 }
 
 const char* sde_last_cuda_error(void) { return g_cuda_err; }
+
+void sde_reload_env(void) { g_pdl_mask = read_pdl_mask(); }
 
 size_t sde_mono_workspace_bytes(const sde_mono_desc* desc) {
   if (mono_check(desc) != SDE_OK) return 0;
@@ -720,6 +746,38 @@ int sde_motion_sparsity_forward(const sde_mreg_desc* desc, const sde_mreg_buffer
 }
 int sde_motion_sparsity_backward(const sde_mreg_desc* desc, const sde_mreg_buffers* buf, void* stream) {
   return mreg_call(3, true, true, desc, buf, stream);
+}
+
+size_t sde_motion_field_reg_workspace_bytes(const sde_mreg_desc* desc) {
+  return (mreg_ok(desc) && desc->channels == 3) ? mfield_layout(desc).total : 0;
+}
+
+static int mfield_call(bool backward, const sde_mreg_desc* d, const sde_mfield_buffers* b, void* stream) {
+  if (!mreg_ok(d) || d->channels != 3 || !b || !b->field || !b->saved_stats) return SDE_ERR_INVALID_ARG;
+  MfieldParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->batch; p.h = d->height; p.w = d->width;
+  p.pose = b->pose; p.field = b->field; p.stats = b->saved_stats;
+  if (!backward) {
+    if (!b->losses || !b->workspace) return SDE_ERR_INVALID_ARG;
+    const MfieldLayout L = mfield_layout(d);
+    char* ws = static_cast<char*>(b->workspace);
+    p.losses = b->losses;
+    p.counters = reinterpret_cast<unsigned*>(ws);
+    p.fin = reinterpret_cast<double*>(ws + L.off_fin);
+    p.slots = reinterpret_cast<float*>(ws + L.off_slots);
+  } else {
+    if (!b->grad_losses || !b->grad_field) return SDE_ERR_INVALID_ARG;
+    p.g_losses = b->grad_losses; p.g_field = b->grad_field; p.g_pose_t = b->grad_pose_t;
+  }
+  SDE_LAUNCH(launch_mfield(backward, p, static_cast<cudaStream_t>(stream)));
+}
+
+int sde_motion_field_reg_forward(const sde_mreg_desc* desc, const sde_mfield_buffers* buf, void* stream) {
+  return mfield_call(false, desc, buf, stream);
+}
+int sde_motion_field_reg_backward(const sde_mreg_desc* desc, const sde_mfield_buffers* buf, void* stream) {
+  return mfield_call(true, desc, buf, stream);
 }
 
 size_t sde_variance_workspace_bytes(int64_t count) {

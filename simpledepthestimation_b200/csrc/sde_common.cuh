@@ -116,6 +116,25 @@ __device__ __forceinline__ void publish_fence() {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// Deterministic scatter accumulation: 64-bit fixed point (scale 2^44, resolution 5.7e-14) with INTEGER atomics -- the
+// sum does not depend on the order of the additions, unlike a float atomicAdd.  Range: a contribution must be below
+// 2^15 in magnitude and a sum below 2^16; what is not -- including NaN / inf, which ATen's float scatter would
+// propagate -- poisons the element (atomicMax to 2^62, idempotent), and fix_to_float returns NaN for any accumulator at
+// or beyond +-2^60.
+// ---------------------------------------------------------------------------------------------
+constexpr double kFixScale = 17592186044416.0;        // 2^44
+constexpr double kFixInv = 1.0 / 17592186044416.0;
+__device__ __forceinline__ void fix_add(long long* dst, float v) {
+  if (fabsf(v) < 32768.0f)
+    atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__double2ll_rn((double)v * kFixScale));
+  else
+    atomicMax(dst, 1LL << 62);   // NaN, inf or out of range
+}
+__device__ __forceinline__ float fix_to_float(long long a) {
+  return (a >= (1LL << 60) || a <= -(1LL << 60)) ? __int_as_float(0x7fc00000) : (float)((double)a * kFixInv);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

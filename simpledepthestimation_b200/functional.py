@@ -41,8 +41,10 @@ class MonoLossPlan:
     """Shape-specialised launcher of the fused MonoDepth2 loss (forward + backward).
 
     Holds the descriptor, the zero-initialised workspace and the output buffers for one
-    (B, scales, S, sizes, loss options) signature so that a training step costs two kernel
-    launches and no allocation.  Mirrors the options read by the reference's
+    (B, scales, S, sizes, loss options) signature so that a training step costs three kernel
+    launches and no allocation.  A plan (its workspace: ticket counters and partial-sum slots)
+    belongs to ONE stream at a time -- use one plan per stream; the workspace is re-zeroed if
+    a call reports an error.  Mirrors the options read by the reference's
     MonoDepth2Model.__init__ (detectron2/modeling/meta_arch/MonoDepth2.py:26-46).
     """
 
@@ -70,7 +72,9 @@ class MonoLossPlan:
             d.height[i], d.width[i] = h, w
         d.full_height, d.full_width = self.full_size
         d.ssim_weight, d.c1, d.c2, d.smooth_weight = ssim_weight, c1, c2, smooth_weight
-        d.flags = (_lib.FLAG_AUTOMASK if automask else 0) | (_lib.FLAG_REDUCE_MEAN if reduce == "mean" else 0)
+        d.flags = (_lib.FLAG_AUTOMASK if automask else 0) | (_lib.FLAG_REDUCE_MEAN if reduce == "mean" else 0) | \
+                  (_lib.FLAG_NO_TMA if _lib.tma_disabled() else 0)
+        self.lib.sde_reload_env()   # developer switches are read when a plan is built, not per call
         # depth_mode "disp" / "logit": the `depth` tensors hold the decoder's disparity / pre-softplus output and the
         # kernels apply disp_to_depth(., min_depth, max_depth) (depth_decoder.py:9-18,108) themselves; the gradient comes
         # back w.r.t. that tensor
@@ -82,6 +86,11 @@ class MonoLossPlan:
             raise _lib.SdeError("invalid loss descriptor (sizes must be >= 2, 1..6 scales, 1..4 sources)")
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         self.stats = torch.empty(len(sizes) * batch * 2, dtype=torch.float32, device=self.device)
+
+    def _check_status(self, st, what):
+        if st != 0:
+            self.workspace.zero_()   # a failed call may leave tickets behind: restore the zero-filled state
+        _lib.check(st, what)
 
     # ---------------------------------------------------------------------------------
     def _buffers(self, target, source, depth, K, pose) -> _lib.MonoBuffers:
@@ -152,7 +161,7 @@ class MonoLossPlan:
                 argmin.append(a)
                 b.argmin[i] = a.data_ptr()
         st = self.lib.sde_mono_loss_forward(C.byref(self.desc), C.byref(b), torch.cuda.current_stream().cuda_stream)
-        _lib.check(st, "sde_mono_loss_forward")
+        self._check_status(st, "sde_mono_loss_forward")
         return losses, argmin
 
     def backward(self, target, source, depth, K, pose, argmin, grad_losses, grad_depth=None, grad_pose=None,
@@ -173,7 +182,7 @@ class MonoLossPlan:
         for j in range(self.n_sources):
             b.grad_pose[j] = grad_pose[j].data_ptr()
         st = self.lib.sde_mono_loss_backward(C.byref(self.desc), C.byref(b), torch.cuda.current_stream().cuda_stream)
-        _lib.check(st, "sde_mono_loss_backward")
+        self._check_status(st, "sde_mono_loss_backward")
         return grad_depth, grad_pose
 
 
@@ -395,7 +404,8 @@ class MotionLossPlan:
         d.batch, d.n_dirs, d.height, d.width = batch, n_dirs, self.size[0], self.size[1]
         d.scale_x, d.scale_y = float(scale[0]), float(scale[1])
         d.ssim_weight, d.c1, d.c2 = float(ssim_weight), float(c1), float(c2)
-        d.flags = _lib.MOTION_FLAG_FIELD if with_field else 0
+        d.flags = (_lib.MOTION_FLAG_FIELD if with_field else 0) | (_lib.MOTION_FLAG_NO_TMA if _lib.tma_disabled() else 0)
+        self.lib.sde_reload_env()
         self.desc = d
         nbytes = self.lib.sde_motion_workspace_bytes(C.byref(d))
         if nbytes == 0:
@@ -468,6 +478,8 @@ class MotionLossPlan:
                 b.coords[k] = m["coords_A_in_B"].data_ptr()
                 maps.append(m)
         st = self.lib.sde_motion_loss_forward(C.byref(self.desc), C.byref(b), torch.cuda.current_stream().cuda_stream)
+        if st != 0:
+            self.workspace.zero_()   # a failed call may leave tickets behind
         _lib.check(st, "sde_motion_loss_forward")
         return losses, maps
 
@@ -487,6 +499,8 @@ class MotionLossPlan:
             if self.with_field:
                 b.grad_field[k] = grad_field[k].data_ptr()
         st = self.lib.sde_motion_loss_backward(C.byref(self.desc), C.byref(b), torch.cuda.current_stream().cuda_stream)
+        if st != 0:
+            self.workspace.zero_()   # a failed call may leave tickets behind
         _lib.check(st, "sde_motion_loss_backward")
         return grad_depth, grad_pose, grad_field
 

@@ -15,7 +15,7 @@ import torch.nn.functional as F
 from ...functional import MotionLossPlan, motion_rgbd_smoothness_loss
 from ...geometry.camera import resize_img, resize_img_avgpool, scale_intrinsics, view_synthesis
 from ...utils.memory import to_cuda
-from ..losses.motion_loss import motion_consistency_loss, motion_smoothness_loss_fn, motion_sparsity_loss_fn
+from ..losses.motion_loss import motion_consistency_loss_split, motion_field_regularizer_losses
 from ..losses.losses import silog_loss, variance_loss
 from ..losses.ssim_loss import WeightedSSIM
 from ..nets import build_depth_net, build_pose_net
@@ -27,6 +27,28 @@ def _scaled_translation(pose, s):
     out = pose.clone()
     out[:, :3, 3] = pose[:, :3, 3] / s
     return out
+
+
+class OverallMotion:
+    """batch['overall_motion'] entry (MotionLearning.py:143-154): the translation field t = pose[:, :3, [3], None] +
+    residual field, [B,3,H,W].  The losses never need it as a tensor (the kernels add the two parts per pixel), and its
+    only reader is the periodic image logging of projects/MotionLearning/train.py:150-153, so it is formed on first
+    use: indexing, attributes and methods are those of the tensor."""
+
+    def __init__(self, pose, field, size):
+        self._pose, self._field, self._size, self._t = pose, field, size, None
+
+    def tensor(self):
+        if self._t is None:
+            t = self._pose[:, :3, 3][:, :, None, None]
+            self._t = t + self._field if self._field is not None else t.expand(-1, -1, *self._size)
+        return self._t
+
+    def __getitem__(self, i):
+        return self.tensor()[i]
+
+    def __getattr__(self, name):
+        return getattr(self.tensor(), name)
 
 
 @META_ARCH_REGISTRY.register()
@@ -114,25 +136,19 @@ class MotionLearningModel(nn.Module):
             f1, f2 = resize_img_avgpool(frame1, (H, W)).contiguous(), resize_img_avgpool(frame2, (H, W)).contiguous()
             d1, d2 = resize_img_avgpool(depth1[0], (H, W)), resize_img_avgpool(depth2[0], (H, W))
             P12, P21 = pose_1to2, pose_2to1
-            R12, R21 = P12[:, :3, :3], P21[:, :3, :3]
             with_field = motion_1to2 is not None
             m12 = m21 = None
             if with_field:
                 m12, m21 = resize_img_avgpool(motion_1to2, (H, W)), resize_img_avgpool(motion_2to1, (H, W))
-            # overall translation fields (MotionLearning.py:143-155): the output dict carries them un-normalised
-            # (:154 comes before the SCALE_NORMALIZE block), the losses use the normalised ones
-            def overall(P, m):
-                t = P[:, :3, 3][:, :, None, None]
-                return t + m if with_field else t.expand(-1, -1, H, W)
-            t12, t21 = overall(P12, m12), overall(P21, m21)
-            batch["overall_motion"].append((t12, t21))
+            # overall translation fields (MotionLearning.py:143-155): the output dict carries them un-normalised (:154 comes
+            # before the SCALE_NORMALIZE block); formed lazily, the losses take pose and residual field separately
+            batch["overall_motion"].append((OverallMotion(P12, m12, (H, W)), OverallMotion(P21, m21, (H, W))))
             if self.scale_normalize:
                 depth_mean = torch.mean(torch.cat([d1, d2], 0))
                 d1, d2 = d1 / depth_mean, d2 / depth_mean
                 P12, P21 = _scaled_translation(P12, depth_mean), _scaled_translation(P21, depth_mean)
                 if with_field:
                     m12, m21 = m12 / depth_mean, m21 / depth_mean
-                t12, t21 = overall(P12, m12), overall(P21, m21)
 
             plan = self._plan(B, (H, W), scale_w, with_field)
             out, maps = motion_rgbd_smoothness_loss(
@@ -146,24 +162,25 @@ class MotionLearningModel(nn.Module):
                 losses["smooth_loss"] += (out[0, 2] + out[1, 2]) * (scale_w * self.smooth_loss_w)
             batch["depth_proximity_weight"].append((maps[0]["depth_proximity_weight"], maps[1]["depth_proximity_weight"]))
 
-            if self.rot_cycle_loss_w > 0 or self.trans_cycle_loss_w > 0:
-                for m, Ra, Rb, ta, tb in ((maps[0], R12, R21, t12, t21), (maps[1], R21, R12, t21, t12)):
-                    rot, tr = motion_consistency_loss(m["coords_A_in_B"], m["occlusion_mask"], Ra, Rb, ta, tb)
+            if self.rot_cycle_loss_w > 0 or self.trans_cycle_loss_w > 0:   # MotionLearning.py:188-201
+                for m, Pa, Pb, ma, mb in ((maps[0], P12, P21, m12, m21), (maps[1], P21, P12, m21, m12)):
+                    rot, tr = motion_consistency_loss_split(m["coords_A_in_B"], m["occlusion_mask"], Pa, Pb, ma, mb)
                     losses["rot_loss"] += rot * scale_w * self.rot_cycle_loss_w
                     losses["trans_loss"] += tr * scale_w * self.trans_cycle_loss_w
 
-            if with_field:
-                for m, t in ((m12, t12), (m21, t21)):
-                    t_scale = t.pow(2).mean([1, 2, 3], keepdim=True) * 3.0
-                    mn = m / torch.sqrt(t_scale + 1e-12)
+            if with_field and (self.motion_smooth_loss_w > 0.0 or self.motion_sparsity_loss_w > 0.0):
+                # MotionLearning.py:203-220: both regularisers of m / sqrt(3 mean(t^2) + 1e-12), fused per direction
+                for P, m in ((P12, m12), (P21, m21)):
+                    sm, sp = motion_field_regularizer_losses(P, m)
                     if self.motion_smooth_loss_w > 0.0:
-                        losses["motion_smooth_loss"] += motion_smoothness_loss_fn(mn) * scale_w * self.motion_smooth_loss_w
+                        losses["motion_smooth_loss"] += sm * scale_w * self.motion_smooth_loss_w
                     if self.motion_sparsity_loss_w > 0.0:
-                        losses["motion_sparsity_loss"] += motion_sparsity_loss_fn(mn) * scale_w * self.motion_sparsity_loss_w
+                        losses["motion_sparsity_loss"] += sp * scale_w * self.motion_sparsity_loss_w
 
             if self.depth_l1_loss_w > 0:   # MotionLearning.py:264-267, both directions (:166-176)
                 Ki = scale_intrinsics(K.clone(), scale_w, scale_w)
-                for fb, da, db, R, t in ((f2, d1, d2, R12, t12), (f1, d2, d1, R21, t21)):
+                t12, t21 = OverallMotion(P12, m12, (H, W)).tensor(), OverallMotion(P21, m21, (H, W)).tensor()
+                for fb, da, db, R, t in ((f2, d1, d2, P12[:, :3, :3], t12), (f1, d2, d1, P21[:, :3, :3], t21)):
                     losses["depth_l1_loss"] += self._depth_l1_loss(fb, da, db, Ki, R.contiguous(), t.contiguous()) * scale_w
             if self.sup_loss_w > 0.0:   # MotionLearning.py:222-229 (on the un-normalised resized depths)
                 r1, r2 = resize_img_avgpool(depth1[0], (H, W)), resize_img_avgpool(depth2[0], (H, W))

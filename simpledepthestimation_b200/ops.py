@@ -357,6 +357,122 @@ def motion_translation_consistency(coords, mask, R_A2B, t_A2B, t_B2A):
     return _MotionConsistencyFn.apply(coords, mask, R_A2B, t_A2B, t_B2A)
 
 
+class _MotionConsistencySplitFn(torch.autograd.Function):
+    """The translation cycle term on (pose, residual field) pairs: t = pose[:, :3, 3] + field is formed per pixel inside
+    the kernels (sde_mcons_buffers.pose_ab / pose_ba), the [B,3,H,W] overall fields are never materialised."""
+
+    @staticmethod
+    def forward(ctx, coords, mask, R, pose_ab, field_ab, pose_ba, field_ba):
+        lib = _lib.load()
+        coords, mask, R = _cuda_f32(coords.detach(), "coords_A_in_B"), _cuda_f32(mask.detach(), "mask"), _cuda_f32(R, "R_A2B")
+        pose_ab, pose_ba = _cuda_f32(pose_ab, "pose_A2B"), _cuda_f32(pose_ba, "pose_B2A")
+        field_ab = None if field_ab is None else _cuda_f32(field_ab, "field_A2B")
+        field_ba = None if field_ba is None else _cuda_f32(field_ba, "field_B2A")
+        B, h, w, _ = coords.shape
+        for f in (field_ab, field_ba):
+            if f is not None and tuple(f.shape) != (B, 3, h, w):
+                raise _lib.SdeError("motion_consistency_loss: the residual fields must be [B,3,H,W]")
+        if tuple(mask.shape) != (B, 1, h, w) or tuple(R.shape) != (B, 3, 3) or tuple(pose_ab.shape) != (B, 4, 4) \
+                or tuple(pose_ba.shape) != (B, 4, 4):
+            raise _lib.SdeError("motion_consistency_loss: expected coords [B,H,W,2], mask [B,1,H,W], R [B,3,3], pose [B,4,4]")
+        d = _lib.McDesc(B, h, w)
+        nbytes = lib.sde_motion_consistency_workspace_bytes(C.byref(d))
+        if nbytes == 0:
+            raise _lib.SdeError("motion_consistency_loss: H and W must be >= 2")
+        ws = _zero_workspace("mcons", (B, h, w), nbytes, coords.device)
+        loss = torch.empty(1, device=coords.device)
+        b = _lib.McBuffers()
+        b.coords, b.mask, b.rotation, b.pose_ab, b.pose_ba = (x.data_ptr() for x in (coords, mask, R, pose_ab, pose_ba))
+        b.t_ab = None if field_ab is None else field_ab.data_ptr()
+        b.t_ba = None if field_ba is None else field_ba.data_ptr()
+        b.loss, b.workspace = loss.data_ptr(), ws.data_ptr()
+        _lib.check(lib.sde_motion_consistency_forward(C.byref(d), C.byref(b), _stream()), "sde_motion_consistency_forward")
+        ctx.has = (field_ab is not None, field_ba is not None)
+        ctx.save_for_backward(coords, mask, R, pose_ab, pose_ba, *[f for f in (field_ab, field_ba) if f is not None])
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        coords, mask, R, pose_ab, pose_ba, *fields = ctx.saved_tensors
+        field_ab = fields.pop(0) if ctx.has[0] else None
+        field_ba = fields.pop(0) if ctx.has[1] else None
+        B, h, w, _ = coords.shape
+        d = _lib.McDesc(B, h, w)
+        ws = _zero_workspace("mcons", (B, h, w), lib.sde_motion_consistency_workspace_bytes(C.byref(d)), coords.device)
+        g = g.reshape(1).contiguous().float()
+        g_R = torch.empty_like(R)
+        g_pab, g_pba = torch.empty(B, 3, device=R.device), torch.empty(B, 3, device=R.device)
+        g_fab = None if field_ab is None else torch.empty_like(field_ab)
+        g_fba = None if field_ba is None else torch.empty_like(field_ba)
+        b = _lib.McBuffers()
+        b.coords, b.mask, b.rotation, b.pose_ab, b.pose_ba = (x.data_ptr() for x in (coords, mask, R, pose_ab, pose_ba))
+        b.grad_loss, b.grad_rotation, b.workspace = g.data_ptr(), g_R.data_ptr(), ws.data_ptr()
+        b.grad_pose_t_ab, b.grad_pose_t_ba = g_pab.data_ptr(), g_pba.data_ptr()
+        if field_ab is not None:
+            b.t_ab, b.grad_t_ab = field_ab.data_ptr(), g_fab.data_ptr()
+        if field_ba is not None:
+            b.t_ba, b.grad_t_ba = field_ba.data_ptr(), g_fba.data_ptr()
+        _lib.check(lib.sde_motion_consistency_backward(C.byref(d), C.byref(b), _stream()), "sde_motion_consistency_backward")
+
+        def pose_grad(gt):   # [B,3] -> [B,4,4] with the translation column filled
+            out = torch.zeros(B, 4, 4, device=gt.device)
+            out[:, :3, 3] = gt
+            return out
+        return None, None, g_R, pose_grad(g_pab), g_fab, pose_grad(g_pba), g_fba
+
+
+def motion_translation_consistency_split(coords, mask, R_A2B, pose_A2B, field_A2B, pose_B2A, field_B2A):
+    return _MotionConsistencySplitFn.apply(coords, mask, R_A2B, pose_A2B, field_A2B, pose_B2A, field_B2A)
+
+
+class _MotionFieldRegFn(torch.autograd.Function):
+    """motion_smoothness_loss_fn + motion_sparsity_loss_fn of the normalised field m / sqrt(3 mean(t^2) + 1e-12),
+    t = pose[:, :3, 3] + m (MotionLearning.py:203-220), fused: sde_motion_field_reg_forward / _backward."""
+
+    @staticmethod
+    def forward(ctx, pose, field):
+        lib = _lib.load()
+        pose, field = _cuda_f32(pose, "pose"), _cuda_f32(field, "motion_field")
+        if field.dim() != 4 or field.shape[1] != 3 or tuple(pose.shape) != (field.shape[0], 4, 4):
+            raise _lib.SdeError("motion field regularisers: expected pose [B,4,4] and a [B,3,H,W] field")
+        B, _, h, w = field.shape
+        d = _lib.MregDesc(B, 3, h, w)
+        nbytes = lib.sde_motion_field_reg_workspace_bytes(C.byref(d))
+        if nbytes == 0:
+            raise _lib.SdeError("motion field regularisers: H and W must be >= 2")
+        ws = _zero_workspace("mfield", (B, h, w), nbytes, field.device)
+        losses = torch.empty(2, device=field.device)
+        stats = torch.empty(B * 12, device=field.device)
+        b = _lib.MfieldBuffers()
+        b.pose, b.field, b.losses, b.saved_stats, b.workspace = (x.data_ptr() for x in (pose, field, losses, stats, ws))
+        _lib.check(lib.sde_motion_field_reg_forward(C.byref(d), C.byref(b), _stream()), "sde_motion_field_reg_forward")
+        ctx.save_for_backward(pose, field, stats)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_sm, g_sp):
+        lib = _lib.load()
+        pose, field, stats = ctx.saved_tensors
+        B, _, h, w = field.shape
+        d = _lib.MregDesc(B, 3, h, w)
+        zero = torch.zeros((), device=field.device)
+        g = torch.stack([g_sm if g_sm is not None else zero, g_sp if g_sp is not None else zero]).float().contiguous()
+        gf, gt = torch.empty_like(field), torch.empty(B, 3, device=field.device)
+        b = _lib.MfieldBuffers()
+        b.pose, b.field, b.saved_stats = pose.data_ptr(), field.data_ptr(), stats.data_ptr()
+        b.grad_losses, b.grad_field, b.grad_pose_t = g.data_ptr(), gf.data_ptr(), gt.data_ptr()
+        _lib.check(lib.sde_motion_field_reg_backward(C.byref(d), C.byref(b), _stream()), "sde_motion_field_reg_backward")
+        gp = torch.zeros(B, 4, 4, device=field.device)
+        gp[:, :3, 3] = gt
+        return gp, gf
+
+
+def motion_field_regularizers(pose, field):
+    """(motion_smoothness_loss_fn(mn), motion_sparsity_loss_fn(mn)) with mn = field / sqrt(3 mean((pose_t + field)^2) + 1e-12)."""
+    return _MotionFieldRegFn.apply(pose, field)
+
+
 class _MotionRegFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, field, kind):

@@ -35,13 +35,15 @@ def shard_batch(batch_size: int, world_size: int = None, rank: int = None) -> sl
     return slice(rank * per, (rank + 1) * per)
 
 
-def reduce_dict(input_dict, average=True, async_op=False, stream=None):
+def reduce_dict(input_dict, average=True, stream=None):
     """Reduce a dict of scalar tensors to rank 0 (comm.py:235-263): keys are sorted, values stacked,
     one `dist.reduce`, divided by the world size on rank 0 when `average`.
 
-    With `stream` (a torch.cuda.Stream) the 8-byte collective is enqueued on that side stream after
-    the producing kernels, so it never stalls the compute stream (the reduction is logging-only,
-    projects/MonoDepth2/train.py:95-98)."""
+    With `stream` (a torch.cuda.Stream) the 8-byte collective is enqueued on that side stream after the producing
+    kernels, so it does not sit between two compute kernels (the reduction is logging-only,
+    projects/MonoDepth2/train.py:95-98).  The current stream then waits for the side stream, so whatever the caller does
+    with the returned tensors next (`.item()`, logging, arithmetic) is ordered after the reduction, and the stacked
+    buffer is recorded on the side stream so the caching allocator cannot reuse it while the collective is pending."""
     world_size = get_world_size()
     if world_size < 2:
         return input_dict
@@ -49,11 +51,14 @@ def reduce_dict(input_dict, average=True, async_op=False, stream=None):
         names = sorted(input_dict.keys())
         values = torch.stack([input_dict[k].detach().float().reshape(()) for k in names], dim=0)
         if stream is not None:
-            stream.wait_stream(torch.cuda.current_stream())
+            current = torch.cuda.current_stream()
+            stream.wait_stream(current)
             with torch.cuda.stream(stream):
                 dist.reduce(values, dst=0)
                 if dist.get_rank() == 0 and average:
                     values /= world_size
+            values.record_stream(stream)
+            current.wait_stream(stream)
         else:
             dist.reduce(values, dst=0)
             if dist.get_rank() == 0 and average:

@@ -464,3 +464,81 @@ def test_resize_img_avgpool_matches_adaptive_avg_pool(sde_lib, src, dst):
     assert rel_err(got.detach(), ref.detach()) < 1e-6
     assert rel_err(xg.grad, xr.grad) < 1e-6
     assert resize_img_avgpool(xg, src) is xg
+
+
+@pytest.mark.parametrize("with_fields", [(True, True), (True, False), (False, False)])
+def test_motion_consistency_on_pose_and_residual_field(sde_lib, with_fields):
+    """SURVEY.md row N1, fused form: motion_consistency_loss on (pose, residual field) pairs -- t = pose[:, :3, [3],
+    None] + field (MotionLearning.py:143-147) is formed per pixel inside the kernels -- against the oracle on the
+    materialised fields; gradients w.r.t. both poses (rotation and translation) and both residual fields."""
+    from simpledepthestimation_b200.modeling.losses.motion_loss import motion_consistency_loss_split
+
+    B, H, W = 2, 40, 72
+    inp = motion_inputs(B, H, W, seed=6)
+    T = euler_pose(inp["pose_vec"].float())
+    P_ab, P_ba = T[:B].contiguous(), T[B:].contiguous()
+    m_ab = inp["motion"][:B].contiguous() if with_fields[0] else None
+    m_ba = inp["motion"][B:].contiguous() if with_fields[1] else None
+    gen = torch.Generator().manual_seed(3)
+    coords = (torch.rand(B, H, W, 2, generator=gen) * 2.2 - 1.1)      # some samples fall outside: zeros padding
+    mask = (torch.rand(B, 1, H, W, generator=gen) > 0.3).float()
+
+    def leaves(dt, dev):
+        return [None if x is None else x.to(dt).to(dev).clone().requires_grad_() for x in (P_ab, P_ba, m_ab, m_ba)]
+
+    def run_oracle(dt):
+        pa, pb, ma, mb = leaves(dt, "cpu")
+        full = lambda P, m: P[:, :3, 3][:, :, None, None] + m if m is not None else P[:, :3, 3][:, :, None, None].expand(-1, -1, H, W)  # noqa: E731
+        rot, tr = port.motion_consistency(coords.to(dt), mask.to(dt), pa[:, :3, :3], pb[:, :3, :3], full(pa, ma), full(pb, mb))
+        (rot * 0.3 + tr * 1.7).backward()
+        return rot.detach(), tr.detach(), [None if x is None else x.grad for x in (pa, pb, ma, mb)]
+
+    rot64, tr64, g64 = run_oracle(torch.float64)
+    _, _, g32 = run_oracle(torch.float32)
+    pa, pb, ma, mb = leaves(torch.float32, DEV)
+    rot, tr = motion_consistency_loss_split(coords.to(DEV), mask.to(DEV), pa, pb, ma, mb)
+    (rot * 0.3 + tr * 1.7).backward()
+    torch.cuda.synchronize()
+    assert rel_err(rot.detach(), rot64) < 1e-4 and rel_err(tr.detach(), tr64) < 1e-5
+    for x, r64, r32, name in zip((pa, pb, ma, mb), g64, g32, ("pose_A2B", "pose_B2A", "field_A2B", "field_B2A")):
+        if x is not None:
+            _quantile_ok(x.grad[:, :3] if name.startswith("pose") else x.grad, r64[:, :3] if name.startswith("pose") else r64,
+                         r32[:, :3] if name.startswith("pose") else r32, name)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 64), (1, 50, 70), (2, 192, 320)])
+def test_fused_motion_field_regularizers(sde_lib, shape):
+    """SURVEY.md row N1, fused form: both regularisers of the normalised residual field m / sqrt(3 mean(t^2) + 1e-12),
+    t = pose[:, :3, 3] + m (MotionLearning.py:203-220; motion_loss.py:51-64), with the gradient through the normaliser
+    to the field and to the pose translation -- against the oracle on the materialised tensors."""
+    from simpledepthestimation_b200.modeling.losses.motion_loss import motion_field_regularizer_losses
+
+    B, H, W = shape
+    gen = torch.Generator().manual_seed(W)
+    m = 0.05 * torch.randn(B, 3, H, W, generator=gen)
+    m[:, :, :4] = 0.0        # exact zeros: sqrt(1e-24) / sign(0) corner cases
+    P = euler_pose(0.05 * torch.randn(B, 6, generator=gen))
+
+    def run_oracle(dt):
+        x, p = m.to(dt).clone().requires_grad_(), P.to(dt).clone().requires_grad_()
+        t = p[:, :3, 3][:, :, None, None] + x
+        mn = x / torch.sqrt(t.pow(2).mean([1, 2, 3], keepdim=True) * 3.0 + 1e-12)
+        sm, sp = port.motion_smoothness(mn), port.motion_sparsity(mn)
+        (sm * 0.8 + sp * 0.3).backward()
+        return sm.detach(), sp.detach(), x.grad, p.grad
+
+    sm64, sp64, gx64, gp64 = run_oracle(torch.float64)
+    _, _, gx32, gp32 = run_oracle(torch.float32)
+    x, p = m.to(DEV).requires_grad_(), P.to(DEV).requires_grad_()
+    sm, sp = motion_field_regularizer_losses(p, x)
+    (sm * 0.8 + sp * 0.3).backward()
+    torch.cuda.synchronize()
+    assert rel_err(sm.detach(), sm64) < 1e-5 and rel_err(sp.detach(), sp64) < 1e-5
+    _quantile_ok(x.grad, gx64, gx32, "field")
+    assert rel_err(p.grad[:, :3, 3], gp64[:, :3, 3]) < max(1e-4, 3 * rel_err(gp32[:, :3, 3], gp64[:, :3, 3]))
+    assert float(p.grad[:, :3, :3].abs().max()) == 0.0
+    # same bits on a second run (fixed-order reductions)
+    x2, p2 = m.to(DEV).requires_grad_(), P.to(DEV).requires_grad_()
+    sm2, sp2 = motion_field_regularizer_losses(p2, x2)
+    (sm2 * 0.8 + sp2 * 0.3).backward()
+    assert torch.equal(sm, sm2) and torch.equal(sp, sp2) and torch.equal(x.grad, x2.grad)
