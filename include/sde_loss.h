@@ -35,7 +35,8 @@ extern "C" {
 #define SDE_ABI_VERSION 4
 #define SDE_MAX_SCALES 6
 #define SDE_MAX_SOURCES 4
-#define SDE_MONO_SAVED_PLANES 11   /* planes per sample of sde_mono_buffers.warped[i][j] */
+#define SDE_MONO_SAVED_PLANES 9    /* planes per sample of sde_mono_buffers.warped[i][j] */
+#define SDE_MOTION_SAVED_PLANES 16 /* planes per sample of sde_motion_buffers.warped[d] */
 
 typedef enum sde_status {
   SDE_OK = 0,
@@ -113,9 +114,8 @@ typedef struct sde_mono_buffers {
    *   warped[i][j]  [B,SDE_MONO_SAVED_PLANES,h_i,w_i]: planes 0..2 the warped source; planes 3..5 / 6..8 its
    *                 derivatives d warped_c / dX and d warped_c / dY w.r.t. the sample coordinate, already divided by
    *                 the projective denominator p2 + 1e-6 (camera.py:150-151) and zero where nan_to_num / clamp gate
-   *                 the gradient (camera.py:184-188); planes 9 / 10 the sample coordinate relative to the principal
-   *                 point, X - cx and Y - cy (zero where gated) -- everything the backward kernel needs to turn
-   *                 d loss / d warped into d loss / d (depth, R, t) without projecting again; written by the warp kernel;
+   *                 the gradient (camera.py:184-188) -- with them the backward kernel turns d loss / d warped into
+   *                 d loss / d (depth, R, t) by multiply-adds, without gathering or dividing; written by the warp kernel;
    *   smooth_g[i]   [B,1,h_i,w_i]: d smoothness / d (1/depth) before the division by the per-image mean.
    * With them the loss kernels take the warped planes through TMA and the backward kernel neither re-projects
    * the halo nor re-gathers (trades 72 B/pixel/source + 4 B/pixel of HBM traffic, which this issue-bound path
@@ -176,13 +176,13 @@ typedef struct sde_motion_buffers {
   float* occlusion[SDE_MAX_DIRS];       /* optional [B,1,h,w] occlusion_mask (MotionLearning.py:257-259) */
   float* weight[SDE_MAX_DIRS];          /* optional [B,1,h,w] depth_proximity_weight (MotionLearning.py:279-282) */
   float* coords[SDE_MAX_DIRS];          /* optional [B,h,w,2] coords_A_in_B, normalised (camera.py:190-193) */
-  /* optional, forward output / backward input: [B,16,h,w] per direction = warped rgb (3), depth_error (1),
-   * valid + 2 * occlusion (1), d warped_c / dX (3) and d warped_c / dY (3) w.r.t. the sample coordinate (zero where
-   * nan_to_num / clamp gate the gradient), the local smoothness gradient d smoothness / d (1/depth_A) (1), and four
-   * planes of scratch (frame B and depth B interleaved per pixel for the gather of the forward pass).  When
-   * given (and the row pitch is a multiple of 16 bytes) the statistics pre-pass doubles as the warp kernel, the loss
-   * kernels take these planes through TMA instead of re-projecting and re-gathering, and the backward kernel never
-   * touches frame B again.  NULL = recompute. */
+  /* optional, forward output / backward input: [B,SDE_MOTION_SAVED_PLANES,h,w] per direction = warped rgb (3),
+   * depth_error (1), valid + 2 * occlusion (1), d warped_c / dX (3) and d warped_c / dY (3) w.r.t. the sample
+   * coordinate (zero where nan_to_num / clamp gate the gradient), the local smoothness gradient
+   * d smoothness / d (1/depth_A) (1), and four planes of scratch (frame B and depth B interleaved per pixel for the
+   * gather of the forward pass).  When given (and the row pitch is a multiple of 16 bytes) the statistics pre-pass
+   * doubles as the warp kernel, the loss kernels take these planes through TMA instead of re-projecting and
+   * re-gathering, and the backward kernel never touches frame B again.  NULL = recompute. */
   float* warped[SDE_MAX_DIRS];
   /* backward */
   const float* grad_losses;             /* [n_dirs][SDE_MOTION_N_LOSSES] upstream gradients (device) */

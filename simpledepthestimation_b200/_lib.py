@@ -8,7 +8,8 @@ import os
 ABI_VERSION = 4   # SDE_ABI_VERSION of include/sde_loss.h this binding was written against
 MAX_SCALES = 6
 MAX_SOURCES = 4
-MONO_SAVED_PLANES = 11   # SDE_MONO_SAVED_PLANES: planes per sample of a `warped` buffer
+MONO_SAVED_PLANES = 9   # SDE_MONO_SAVED_PLANES: planes per sample of a `warped` buffer
+MOTION_SAVED_PLANES = 16  # SDE_MOTION_SAVED_PLANES
 FLAG_AUTOMASK = 1
 FLAG_REDUCE_MEAN = 2
 FLAG_NO_TMA = 4            # SDE_MONO_NO_TMA

@@ -53,6 +53,9 @@ struct BwdShared {
   // SAVED: d depth-gradient / d (a0, a1, a2) as an affine function of the (centred) pixel coordinates, per source:
   // rows of diag-combined K^T-weights times R K^-1 (see phase 4); row 2 is stored negated
   float wmat[SDE_MAX_SOURCES][9];
+  // SAVED: the projection as p_i = depth * (N_i . [x', y', 1]) + tau_i with N = K R K^-1 re-centred on (w/2, h/2):
+  // [0..8] N, [9..11] tau = K t, [12] cx, [13] cy -- phase 4 recomputes the sample coordinate with it (packed fp32)
+  float nmat[SDE_MAX_SOURCES][14];
   double dred[12][kWarps];
   unsigned ticket;
   __align__(8) uint64_t bar;                     // TMA completion barrier
@@ -120,6 +123,15 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
         }
 #pragma unroll
         for (int r = 0; r < 3; ++r) wm[r * 3 + 2] += wm[r * 3] * x0c + wm[r * 3 + 1] * y0c;
+        float* nm = sh.nmat[tid - 32];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) nm[r * 3 + c] = pj.m[r * 3] * cam.ki[c] + pj.m[r * 3 + 1] * cam.ki[3 + c] + pj.m[r * 3 + 2] * cam.ki[6 + c];
+          nm[r * 3 + 2] += nm[r * 3] * x0c + nm[r * 3 + 1] * y0c;
+          nm[9 + r] = pj.tau[r];
+        }
+        nm[12] = cam.cx; nm[13] = cam.cy;
       }
     }
   };
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
     }
     if constexpr (SAVED) {
       // Dense form: every lane processes its own pixel pairs in packed fp32; nothing is projected or divided here --
-      // the warp kernel left q dS_c/dX, q dS_c/dY and the centred sample coordinate (ex, ey) = (X - cx, Y - cy):
+      // the warp kernel left q dS_c/dX and q dS_c/dY (gated); (ex, ey) = (X - cx, Y - cy) is re-projected in packed fp32:
       //   a0 = sum_c gS_c (q dS_c/dX), a1 = sum_c gS_c (q dS_c/dY), a2 = -(a0 ex + a1 ey)      [= g_p in camera units]
       //   K^T g_p = (fx a0, sk a0 + fy a1, a2);  d loss / d depth = a0 w0 + a1 w1 + a2 w2 with w = W [x, y, 1]^T (wmat)
       //   d loss / d [R | t] = K^T g_p (x) [P, 1] with P = depth K^-1 [x, y, 1]^T, i.e. linear in the twelve sums of
@@ -384,6 +396,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
       // Pairs outside the gradient block / the image load zeros, so they add nothing.
       const float* __restrict__ dwp = p.warped[s][j] + (size_t)b * kSavedPlanes * hw;
       const float* wm = sh.wmat[j];
+      const float* nm = sh.nmat[j];
       const bool pair = (w & 1) == 0 && (reinterpret_cast<uintptr_t>(dwp) & 7) == 0;   // gxp is even
       const float xc0 = (float)(gxp - (w >> 1));
       const f2 xc = mk2(xc0, xc0 + 1.0f);
@@ -394,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
       // (instantiated on the alignment switch, so that the loads sit in one basic block)
       auto rows = [&](auto pair_tag) {
         constexpr bool PAIR = decltype(pair_tag)::value;
-        f2 dq[kRowsPerWarp][8];
+        f2 dq[kRowsPerWarp][6];
         bool ok[kRowsPerWarp];
 #pragma unroll
         for (int o = 0; o < kRowsPerWarp; ++o) {
@@ -404,20 +417,25 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
           if (PAIR) {
             // branch-free: pairs outside the block / the image read the sample's first pixel instead (always a valid
             // address) and are switched off through gS below
+            SDE_CHECK(!ok[o] || (gy >= 0 && gy < h && gxp >= 0 && gxp + 1 < w));
             const float* q = dwp + (ok[o] ? gy * w + gxp : 0) + 3 * hw;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dq[o][i].v = __ldg(reinterpret_cast<const unsigned long long*>(q + i * hw));
+            for (int i = 0; i < 6; ++i) dq[o][i].v = __ldg(reinterpret_cast<const unsigned long long*>(q + i * hw));
           } else {
             const float* q = dwp + (gy * w + gxp) + 3 * hw;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 6; ++i)
               dq[o][i] = mk2(ok[o] ? __ldg(q + i * hw) : 0.0f, row_ok && col_ok1 ? __ldg(q + i * hw + 1) : 0.0f);
           }
         }
-        f2 wb[3];
+        f2 wb[3], nb[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) wb[k] = fma2(bc2(wm[3 * k]), xc, bc2(wm[3 * k + 2]));
+        for (int k = 0; k < 3; ++k) {
+          wb[k] = fma2(bc2(wm[3 * k]), xc, bc2(wm[3 * k + 2]));
+          nb[k] = fma2(bc2(nm[3 * k]), xc, bc2(nm[3 * k + 2]));
+        }
         const float wy0 = wm[1], wy1 = wm[4], wy2 = wm[7];
+        const f2 ncx = bc2(-nm[12]), ncy = bc2(-nm[13]);
 #pragma unroll
         for (int o = 0; o < kRowsPerWarp; ++o) {
           const int row = r0 + 1 + o, gy = oy + row;
@@ -428,8 +446,25 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
           const f2 dd = ld2(planes + kBD * kPlane + pl);
           const f2 a0 = fma2(g2, dq[o][2], fma2(g1, dq[o][1], g0 * dq[o][0]));
           const f2 a1 = fma2(g2, dq[o][5], fma2(g1, dq[o][4], g0 * dq[o][3]));
-          const f2 a2 = fma2(a1, dq[o][7], a0 * dq[o][6]);   // -a2 (the sign lives in wmat row 2 and in the final map)
           const float yc = (float)(gy - (h >> 1));
+          // the sample coordinate again, relative to the principal point: p_i = depth n_i + tau_i, X = p0 / (p2 + 1e-6)
+          // (one Newton-refined reciprocal: 2e-7 relative, the planes' own resolution).  Only pixels whose derivative
+          // planes are non-zero use it, and those project inside the image; the clamp keeps the rest finite (a NaN
+          // clamps to a bound), so 0 * (X - cx) stays 0.
+          f2 ex, ey;
+          {
+            const f2 ycc2 = bc2(yc);
+            const f2 n0 = fma2(bc2(nm[1]), ycc2, nb[0]), n1 = fma2(bc2(nm[4]), ycc2, nb[1]), n2 = fma2(bc2(nm[7]), ycc2, nb[2]);
+            const f2 p0 = fma2(dd, n0, bc2(nm[9])), p1 = fma2(dd, n1, bc2(nm[10]));
+            const f2 den = fma2(dd, n2, bc2(nm[11])) + bc2(1e-6f);
+            f2 r = mk2(rcp_approx(lo(den)), rcp_approx(hi(den)));
+            r = fma2(fma2(den * bc2(-1.0f), r, bc2(1.0f)), r, r);
+            const f2 X = p0 * r, Y = p1 * r;
+            const float big = 16777216.0f;
+            ex = mk2(fminf(fmaxf(lo(X), -big), big), fminf(fmaxf(hi(X), -big), big)) + ncx;
+            ey = mk2(fminf(fmaxf(lo(Y), -big), big), fminf(fmaxf(hi(Y), -big), big)) + ncy;
+          }
+          const f2 a2 = fma2(a1, ey, a0 * ex);   // -a2 (the sign lives in wmat row 2 and in the final map)
           const f2 b0 = a0 * dd, b1 = a1 * dd, b2 = a2 * dd;
           Sa[0] = Sa[0] + a0; Sa[1] = Sa[1] + a1; Sa[2] = Sa[2] + a2;
           Sb[0] = Sb[0] + b0; Sb[1] = Sb[1] + b1; Sb[2] = Sb[2] + b2;
@@ -473,6 +508,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
         const bool s0 = row_ok && col_ok0 && (lo(g0) != 0.0f || lo(g1) != 0.0f || lo(g2) != 0.0f);
         const bool s1 = row_ok && col_ok1 && (hi(g0) != 0.0f || hi(g1) != 0.0f || hi(g2) != 0.0f);
         const unsigned b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1);
+        SDE_CHECK(total + __popc(b0) + __popc(b1) <= kListPerWarp);
         if (s0) wlist[total + __popc(b0 & lt)] = (unsigned short)((row << 7) | (c0 + 1 + kColOff));
         total += __popc(b0);
         if (s1) wlist[total + __popc(b1 & lt)] = (unsigned short)((row << 7) | (c0 + 2 + kColOff));
@@ -628,6 +664,7 @@ __global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_cons
           g0 *= decode_depth_grad(planes[kBD * kPlane + pl], raw0, p.depth_mode, p.disp_range);
           g1 *= decode_depth_grad(planes[kBD * kPlane + pl + 1], raw1, p.depth_mode, p.disp_range);
         }
+        SDE_CHECK(gy >= 0 && gy < h && gxp >= 0 && gxp < w && (!col_ok1 || gxp + 1 < w));
         float* po = gout + gy * w + gxp;
         if (even && col_ok1) {
           *reinterpret_cast<float2*>(po) = make_float2(g0, g1);

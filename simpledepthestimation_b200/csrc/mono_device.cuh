@@ -27,7 +27,10 @@ static_assert(kPlane >= kHH * kPitch && (kPlane * 4) % 128 == 0 && (kColOff & 1)
 constexpr unsigned kPlaneBytesTma = kHH * kPitch * 4;   // bytes one {kPitch, 18, 1} box delivers
 constexpr int kPositions = kHH * kHW; // 1188 staged positions
 
-__device__ __forceinline__ int plane_index(int yy, int xx) { return yy * kPitch + xx + kColOff; }
+__device__ __forceinline__ int plane_index(int yy, int xx) {
+  SDE_CHECK(yy >= 0 && yy < kHH && xx >= -kColOff && xx + kColOff < kPitch);
+  return yy * kPitch + xx + kColOff;
+}
 
 // Row access of phase 2: centre pair (columns c0+1, c0+2) and outer pair (c0, c0+3).
 struct Row4 {
@@ -103,6 +106,7 @@ __device__ __forceinline__ Cell bilinear_cell(float X, float Y, int w, int h) {
   const float ix = fminf(fmaxf(X, 0.0f), (float)(w - 1));
   const float iy = fminf(fmaxf(Y, 0.0f), (float)(h - 1));
   const int x0 = min((int)ix, w - 2), y0 = min((int)iy, h - 2);   // ix, iy >= 0: truncation == floor
+  SDE_CHECK(x0 >= 0 && x0 + 1 < w && y0 >= 0 && y0 + 1 < h);
   Cell c;
   c.off = y0 * w + x0;
   c.ax = ix - (float)x0;
@@ -148,6 +152,7 @@ __device__ __forceinline__ int pixel_of(const StageArgs& a, int yy, int xx, int&
     gy = reflect_clamp(gy, a.h);
     gx = reflect_clamp(gx, a.w);
   }
+  SDE_CHECK(gy >= 0 && gy < a.h && gx >= 0 && gx < a.w);
   return gy * a.w + gx;
 }
 

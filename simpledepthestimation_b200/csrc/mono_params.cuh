@@ -10,7 +10,7 @@ constexpr int kTileW = 64;   // 32 lanes x 2 pixels (one f2 per lane)
 constexpr int kTileH = 16;   // 4 warps x 4 rows
 constexpr int kThreads = 128;
 constexpr int kRowsPerWarp = 4;
-// planes per sample of a `warped` buffer: warp[3], q d/dX[3], q d/dY[3], X - cx, Y - cy (include/sde_loss.h)
+// planes per sample of a `warped` buffer: warp[3], q d/dX[3], q d/dY[3] with q = 1 / (p2 + 1e-6) (include/sde_loss.h)
 constexpr int kSavedPlanes = SDE_MONO_SAVED_PLANES;
 // backward: a CTA recomputes SSIM on a kTileW x kTileH block of window centres and emits
 // gradients for its interior (the 3x3 adjoint needs one ring of neighbours)

@@ -1,9 +1,11 @@
 // Warp kernel of the MonoDepth2 loss (sm_100a): project + bilinear gather of every source at every scale,
-// one thread per target pixel, written as [B,11,h,w] planes (the `warped` buffers of sde_mono_buffers):
-// the warped source (planes 0..2); from the same four taps its derivatives w.r.t. the sample coordinate, times
+// one thread per target pixel, written as [B,9,h,w] planes (the `warped` buffers of sde_mono_buffers):
+// the warped source (planes 0..2) and, from the same four taps, its derivatives w.r.t. the sample coordinate, times
 // q = 1 / (p2 + 1e-6) (planes 3..5: q d/dX, 6..8: q d/dY; zero where nan_to_num / clamp gate the reference's
-// gradient, camera.py:184-188); and the sample coordinate relative to the principal point (planes 9, 10: X - cx,
-// Y - cy, zero where gated) -- so that the backward kernel neither touches the source frames nor projects again.
+// gradient, camera.py:184-188) -- so that the backward kernel never touches the source frames again and its warp
+// backward is a stream of multiply-adds.  (Two more planes with the sample coordinate were measured: every plane
+// costs this kernel ~4 us at cfg2 -- it writes 140 MB per step -- which is more than re-projecting in the backward
+// kernel's packed arithmetic.)
 //
 // The fused loss kernels are stencil kernels with fat threads (128-160 registers, 12-16 warps per SM),
 // which is the wrong shape for the gather: it is latency-bound and wants many thin threads.  Run on its own
@@ -52,7 +54,6 @@ __global__ void __launch_bounds__(kWarpThreads, 1024 / kWarpThreads) mono_warp_k
   __syncthreads();
   // camera-space points of this thread's pixels (independent of the source); K^-1 stays in registers meanwhile
   float P[kWarpPixPerThread][3];
-  const float ccx = sh.cam.cx, ccy = sh.cam.cy;
   {
     const Cam cam = sh.cam;
 #pragma unroll
@@ -108,9 +109,6 @@ __global__ void __launch_bounds__(kWarpThreads, 1024 / kWarpThreads) mono_warp_k
         dst[(3 + c) * hw] = gate_x ? ddx * q : 0.0f;
         dst[(6 + c) * hw] = gate_y ? ddy * q : 0.0f;
       }
-      // sample coordinate relative to the principal point (the third row of K^T g_p is formed from it)
-      dst[9 * hw] = gate_x ? X - ccx : 0.0f;
-      dst[10 * hw] = gate_y ? Y - ccy : 0.0f;
     }
   }
 }

@@ -16,6 +16,8 @@
 namespace sde {
 
 constexpr int kFieldThreads = 256;
+constexpr int kFieldPix = 8;      // pixels per thread: the block epilogue (reduction, fence, ticket) is paid once per 2048 pixels
+constexpr int kFieldChunk = kFieldThreads * kFieldPix;
 constexpr int kFieldStats = 12;   // per sample: s, sum t_c [3], abar_c [3], E_smooth, E_sparse, (3 spare)
 
 // Sums N values over the block and publishes them in the block's slot; returns true in EVERY thread of the last block
@@ -77,16 +79,20 @@ __device__ __forceinline__ float pose_t(const float* pose, int b, int c) { retur
 
 __global__ void __launch_bounds__(kFieldThreads) mfield_stats_kernel(const __grid_constant__ MfieldParams p) {
   const int b = blockIdx.y, hw = p.h * p.w;
-  const int pix = blockIdx.x * kFieldThreads + threadIdx.x;
   float v[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // sum t^2, sum t_c, sum |m_c|, spare
-  if (pix < hw) {
+  const float T[3] = {pose_t(p.pose, b, 0), pose_t(p.pose, b, 1), pose_t(p.pose, b, 2)};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float m = __ldg(p.field + ((size_t)b * 3 + c) * hw + pix);
-      const float t = pose_t(p.pose, b, c) + m;
-      v[0] += t * t;
-      v[1 + c] = t;
-      v[4 + c] = fabsf(m);
+  for (int k = 0; k < kFieldPix; ++k) {
+    const int pix = blockIdx.x * kFieldChunk + k * kFieldThreads + threadIdx.x;
+    if (pix < hw) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float m = __ldg(p.field + ((size_t)b * 3 + c) * hw + pix);
+        const float t = T[c] + m;
+        v[0] += t * t;
+        v[1 + c] += t;
+        v[4 + c] += fabsf(m);
+      }
     }
   }
   float* slots = p.slots + (size_t)b * gridDim.x * 8;
@@ -114,11 +120,13 @@ __device__ __forceinline__ float sparsity_ratio(float a, float am) {   // d/da [
 
 __global__ void __launch_bounds__(kFieldThreads) mfield_loss_kernel(const __grid_constant__ MfieldParams p) {
   const int b = blockIdx.y, hw = p.h * p.w;
-  const int pix = blockIdx.x * kFieldThreads + threadIdx.x;
   const float* st = p.stats + b * kFieldStats;
   const float s = st[0];
   float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // smoothness, E_smooth, sparsity, E_sparse
-  if (pix < hw) {
+#pragma unroll 2
+  for (int k = 0; k < kFieldPix; ++k) {
+    const int pix = blockIdx.x * kFieldChunk + k * kFieldThreads + threadIdx.x;
+    if (pix >= hw) break;
     const int y = pix / p.w, x = pix - y * p.w;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -161,42 +169,45 @@ __global__ void __launch_bounds__(kFieldThreads) mfield_loss_kernel(const __grid
 
 __global__ void __launch_bounds__(kFieldThreads) mfield_bwd_kernel(const __grid_constant__ MfieldParams p) {
   const int b = blockIdx.y, hw = p.h * p.w;
-  const int pix = blockIdx.x * kFieldThreads + threadIdx.x;
   const float* st = p.stats + b * kFieldStats;
   const float s = st[0];
   const float g_sm = __ldg(p.g_losses), g_sp = __ldg(p.g_losses + 1);
   // d loss / d t_{c,p} through the normaliser: -(g_sm E_sm + g_sp E_sp) s^2 t / (h w)
   const float kappa = (g_sm * st[7] + g_sp * st[8]) * s * s / (float)hw;
   if (blockIdx.x == 0 && threadIdx.x < 3 && p.g_pose_t) p.g_pose_t[b * 3 + threadIdx.x] = -kappa * st[1 + threadIdx.x];
-  if (pix >= hw) return;
-  const int y = pix / p.w, x = pix - y * p.w;
   const float c_sm = g_sm / ((float)p.B * 3.0f * (float)(p.h - 1) * (float)(p.w - 1));
   const float c_sp = g_sp / ((float)p.B * 3.0f * (float)p.h * (float)p.w);
+#pragma unroll 2
+  for (int k = 0; k < kFieldPix; ++k) {
+    const int pix = blockIdx.x * kFieldChunk + k * kFieldThreads + threadIdx.x;
+    if (pix >= hw) break;
+    const int y = pix / p.w, x = pix - y * p.w;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float* m = p.field + ((size_t)b * 3 + c) * hw;
-    auto term = [&](int q, float& dx, float& dy, float& rs) {   // differences of mn and 1 / f at pixel q (row, column >= 1)
-      const float cc = __ldg(m + q) * s;
-      dx = cc - __ldg(m + q - 1) * s;
-      dy = cc - __ldg(m + q - p.w) * s;
-      rs = rsqrtf(1e-24f + dx * dx + dy * dy);
-    };
-    float G = 0.0f, dx, dy, rs;
-    if (y >= 1 && x >= 1) { term(pix, dx, dy, rs); G += (dx + dy) * rs; }
-    if (y >= 1 && x + 1 < p.w) { term(pix + 1, dx, dy, rs); G -= dx * rs; }
-    if (x >= 1 && y + 1 < p.h) { term(pix + p.w, dx, dy, rs); G -= dy * rs; }
-    G *= c_sm;
-    const float mv = __ldg(m + pix);
-    const float a = fabsf(mv) * s;
-    const float sg = mv > 0.0f ? 1.0f : (mv < 0.0f ? -1.0f : 0.0f);
-    G += c_sp * sparsity_ratio(a, st[4 + c]) * sg;
-    const float t = pose_t(p.pose, b, c) + mv;
-    p.g_field[((size_t)b * 3 + c) * hw + pix] = s * G - kappa * t;
+    for (int c = 0; c < 3; ++c) {
+      const float* m = p.field + ((size_t)b * 3 + c) * hw;
+      auto term = [&](int q, float& dx, float& dy, float& rs) {   // differences of mn and 1 / f at pixel q (row, column >= 1)
+        const float cc = __ldg(m + q) * s;
+        dx = cc - __ldg(m + q - 1) * s;
+        dy = cc - __ldg(m + q - p.w) * s;
+        rs = rsqrtf(1e-24f + dx * dx + dy * dy);
+      };
+      float G = 0.0f, dx, dy, rs;
+      if (y >= 1 && x >= 1) { term(pix, dx, dy, rs); G += (dx + dy) * rs; }
+      if (y >= 1 && x + 1 < p.w) { term(pix + 1, dx, dy, rs); G -= dx * rs; }
+      if (x >= 1 && y + 1 < p.h) { term(pix + p.w, dx, dy, rs); G -= dy * rs; }
+      G *= c_sm;
+      const float mv = __ldg(m + pix);
+      const float a = fabsf(mv) * s;
+      const float sg = mv > 0.0f ? 1.0f : (mv < 0.0f ? -1.0f : 0.0f);
+      G += c_sp * sparsity_ratio(a, st[4 + c]) * sg;
+      const float t = pose_t(p.pose, b, c) + mv;
+      p.g_field[((size_t)b * 3 + c) * hw + pix] = s * G - kappa * t;
+    }
   }
 }
 
 cudaError_t launch_mfield(bool backward, const MfieldParams& p, cudaStream_t stream) {
-  const dim3 grid((p.h * p.w + kFieldThreads - 1) / kFieldThreads, p.B);
+  const dim3 grid((p.h * p.w + kFieldChunk - 1) / kFieldChunk, p.B);
   if (backward) {
     mfield_bwd_kernel<<<grid, kFieldThreads, 0, stream>>>(p);
   } else {

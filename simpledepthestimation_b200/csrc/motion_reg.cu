@@ -11,6 +11,7 @@
 namespace sde {
 
 constexpr int kRegThreads = 256;
+constexpr int kMcPix = 4;   // motion-consistency kernels: pixels per thread (one block epilogue per 1024 pixels)
 
 // block sum of `v` -> slot; the last block adds all slots of its group (fixed order, fp64) and returns true on
 // thread 0 with the total in `total`
@@ -110,17 +111,19 @@ __device__ __forceinline__ void mcons_terms(const McParams& p, int b, int pix, i
 
 __global__ void __launch_bounds__(kRegThreads) mcons_fwd_kernel(const __grid_constant__ McParams p) {
   const int b = blockIdx.y, hw = p.h * p.w;
-  const int pix = blockIdx.x * kRegThreads + threadIdx.x;
   float R[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) R[k] = __ldg(p.R + b * 9 + k);
   float e = 0.0f;
-  if (pix < hw) {
+#pragma unroll 1
+  for (int k = 0; k < kMcPix; ++k) {
+    const int pix = (blockIdx.x * kMcPix + k) * kRegThreads + threadIdx.x;
+    if (pix >= hw) break;
     TapSet taps;
     McTerms t;
     float win;
     mcons_terms(p, b, pix, hw, R, taps, t, win);
-    e = t.m * fdiv(t.n, t.dn);
+    e += t.m * fdiv(t.n, t.dn);
   }
   double total;
   if (group_sum(e, p.slots, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y, p.counters, total))
@@ -134,7 +137,6 @@ __global__ void __launch_bounds__(kRegThreads) mcons_bwd_kernel(const __grid_con
   __shared__ unsigned ticket;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int b = blockIdx.y, hw = p.h * p.w;
-  const int pix = blockIdx.x * kRegThreads + tid;
   float R[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) R[k] = __ldg(p.R + b * 9 + k);
@@ -142,7 +144,10 @@ __global__ void __launch_bounds__(kRegThreads) mcons_bwd_kernel(const __grid_con
   float gs[NS];
 #pragma unroll
   for (int k = 0; k < NS; ++k) gs[k] = 0.0f;
-  if (pix < hw) {
+#pragma unroll 1
+  for (int kk = 0; kk < kMcPix; ++kk) {
+    const int pix = (blockIdx.x * kMcPix + kk) * kRegThreads + tid;
+    if (pix >= hw) break;
     TapSet taps;
     McTerms t;
     float win;
@@ -156,11 +161,11 @@ __global__ void __launch_bounds__(kRegThreads) mcons_bwd_kernel(const __grid_con
     for (int k = 0; k < 3; ++k) {
       const float gab = cz * t.z[k] + cd * t.ta[k];
       if (p.g_t_ab) p.g_t_ab[((size_t)b * 3 + k) * hw + pix] = gab;
-      gs[9 + k] = gab;
+      gs[9 + k] += gab;
       gth[k] = cz * (R[k] * t.z[0] + R[3 + k] * t.z[1] + R[6 + k] * t.z[2]) + cd * t.th[k];   // R^T z
-      gs[12 + k] = gth[k] * win;
+      gs[12 + k] += gth[k] * win;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) gs[k * 3 + c] = cz * t.z[k] * t.th[c];
+      for (int c = 0; c < 3; ++c) gs[k * 3 + c] += cz * t.z[k] * t.th[c];
     }
     if (p.scatter) {
 #pragma unroll
@@ -229,13 +234,13 @@ __global__ void __launch_bounds__(kRegThreads) reg_fix_to_float_kernel(long long
 }
 
 cudaError_t launch_mcons_fwd(const McParams& p, cudaStream_t stream) {
-  const dim3 grid((p.h * p.w + kRegThreads - 1) / kRegThreads, p.B);
+  const dim3 grid((p.h * p.w + kRegThreads * kMcPix - 1) / (kRegThreads * kMcPix), p.B);
   mcons_fwd_kernel<<<grid, kRegThreads, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_mcons_bwd(const McParams& p, float* g_t_ba, cudaStream_t stream) {
-  const dim3 grid((p.h * p.w + kRegThreads - 1) / kRegThreads, p.B);
+  const dim3 grid((p.h * p.w + kRegThreads * kMcPix - 1) / (kRegThreads * kMcPix), p.B);
   mcons_bwd_kernel<<<grid, kRegThreads, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -486,7 +486,7 @@ static int mcons_params(const sde_mcons_desc* d, const sde_mcons_buffers* b, boo
 struct MfieldLayout { int blocks; size_t off_fin, off_slots, total; };
 static MfieldLayout mfield_layout(const sde_mreg_desc* d) {
   MfieldLayout L;
-  L.blocks = (d->height * d->width + kOpBlock - 1) / kOpBlock;
+  L.blocks = (d->height * d->width + kOpBlock - 1) / kOpBlock;   // an upper bound of the grid (2048 pixels per block)
   size_t off = align16((size_t)(1 + d->batch) * sizeof(unsigned));
   L.off_fin = off;
   off = align16(off + (size_t)d->batch * 2 * sizeof(double));

@@ -5,6 +5,23 @@
 
 #include "../../include/sde_loss.h"
 
+// Checked build (-DSDE_CHECKED; tools/build_variant.sh checked -DSDE_CHECKED): index assertions on the shared-memory
+// plane positions, the argmin / list arrays and the global pixel offsets of the tile kernels.  compute-sanitizer is not
+// available on the GPU pool, so the odd-size parity tests are run once against this build instead; a violated
+// assertion prints its location and traps (the context dies, every later test fails).
+#ifdef SDE_CHECKED
+#include <stdio.h>
+#define SDE_CHECK(cond)                                                                                          \
+  do {                                                                                                           \
+    if (!(cond)) {                                                                                               \
+      printf("SDE_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+      __trap();                                                                                                  \
+    }                                                                                                            \
+  } while (0)
+#else
+#define SDE_CHECK(cond) ((void)0)
+#endif
+
 namespace sde {
 
 // ---------------------------------------------------------------------------------------------

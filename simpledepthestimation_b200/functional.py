@@ -127,8 +127,8 @@ class MonoLossPlan:
 
     def new_warped(self):
         """What one step keeps from the forward to the backward pass (sde_mono_buffers.warped / .smooth_g), or None:
-        per (scale, source) a [B,11,h,w] buffer -- the warped source, its derivatives w.r.t. the sample coordinate
-        and the centred sample coordinate -- and per scale the [B,1,h,w] local smoothness gradient."""
+        per (scale, source) a [B,9,h,w] buffer -- the warped source and its derivatives w.r.t. the sample coordinate
+        (divided by the projective denominator) -- and per scale the [B,1,h,w] local smoothness gradient."""
         if not self.save_warped:
             return None
         new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=self.device)  # noqa: E731
@@ -439,7 +439,8 @@ class MotionLossPlan:
         if not self.save_warped:
             return None
         h, w = self.size
-        return [torch.empty(self.batch, 16, h, w, dtype=torch.float32, device=self.device) for _ in range(self.n_dirs)]
+        return [torch.empty(self.batch, _lib.MOTION_SAVED_PLANES, h, w, dtype=torch.float32, device=self.device)
+                for _ in range(self.n_dirs)]
 
     def _buffers(self, frame_a, frame_b, depth_a, depth_b, K, pose, field, warped=None):
         b = _lib.MotionBuffers()
