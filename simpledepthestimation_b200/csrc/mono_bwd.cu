@@ -63,8 +63,12 @@ struct BwdShared {
   __align__(8) uint8_t arg[kPlane];
 };
 
+#ifndef SDE_BWD_OCC
+#define SDE_BWD_OCC 4
+#endif
+
 template <bool SAVED>
-__global__ void __launch_bounds__(kThreads, 4) mono_bwd_kernel(const __grid_constant__ MonoParams p,
+__global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const __grid_constant__ MonoParams p,
                                                                const __grid_constant__ MonoTma maps) {
   extern __shared__ __align__(128) float planes[];  // [kBwdPlanes][kPlane]
   __shared__ BwdShared sh;
