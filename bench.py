@@ -3,10 +3,11 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-ours:       a "step" is one forward + one backward pass of the fused MonoDepth2 loss (three launches: warp kernel,
-            loss forward, loss backward) over one batch of synthetic KITTI-shaped input (BASELINE.json configs[1]:
-            640x192, batch 12 per GPU, 4 scales, 2 sources, automask + smoothness).  The three launches of a step
-            are captured once per input set in a CUDA graph, so the host enqueues one graph launch per step.
+ours:       a "step" is one forward + one backward pass of the fused MonoDepth2 loss (three launches -- warp kernel,
+            loss forward, loss backward -- per sub-batch; the plan runs the batch as two sub-batches of 6 on two streams)
+            over one batch of synthetic KITTI-shaped input (BASELINE.json configs[1]: 640x192, batch 12 per GPU, 4
+            scales, 2 sources, automask + smoothness).  The launches of a step are captured once per input set in a
+            CUDA graph, so the host enqueues one graph launch per step.
             `value` = warped Mpix/s with inputs resident in HBM (three input sets are rotated so that every step reads
             from HBM, not L2).  Timing: W warm-up steps, then BLOCKS of exactly K steps, each block bracketed by a
             barrier + torch.cuda.synchronize() on both sides and timed with CUDA events on the launching stream; a
@@ -250,8 +251,8 @@ def other_configs(dev, raw_cfg2):
         gd, gp = [torch.empty_like(d) for d in depth], [torch.empty_like(p) for p in pose]
 
         def mono_step():
-            plan.forward(tgt, src, depth, K, pose, out=losses, argmin_out=argm, warped=warped)
-            plan.backward(tgt, src, depth, K, pose, argm, ones, gd, gp, warped=warped)
+            plan.forward_backward(tgt, src, depth, K, pose, ones, out=losses, argmin_out=argm, grad_depth=gd, grad_pose=gp,
+                                  warped=warped)
         ms = event_time(mono_step, iters)
         px = S * sum(B * h * w for h, w in sizes)
         out[name] = {"ms_per_step": ms, "warped_mpix_s": px / (ms * 1e-3) / 1e6, "iters": iters,
@@ -395,8 +396,10 @@ def run_ours(args):
     side = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def launch_step(k):
-        plan.forward(*sets[k], out=losses[k], argmin_out=argm[k], warped=warped[k])
-        plan.backward(*sets[k], argm[k], ones, gd[k], gp[k], warped=warped[k])
+        # losses and gradients in one call (upstream gradients = ones, as in the trainer that sums the loss keys): the same
+        # launches as plan.forward() + plan.backward(), without the stream join between the two passes
+        plan.forward_backward(*sets[k], ones, out=losses[k], argmin_out=argm[k], grad_depth=gd[k], grad_pose=gp[k],
+                              warped=warped[k])
 
     # the three launches of a step as one CUDA graph per input set: the host then enqueues one graph launch per step
     graphs = None
@@ -486,12 +489,14 @@ def run_ours(args):
     ms_step = main["ms"]
     value = world * warped_px / (ms_step * 1e-3) / 1e6
 
-    # per-kernel durations (CUDA events on the launching stream) for the roofline of the dominant kernel
+    # per-kernel durations (CUDA events on the launching stream) for the roofline of the dominant kernel: every kernel as
+    # ONE launch over the whole batch (a plan with streams=1), timed alone
     k_steps = max(20, args.steps)
-    ms_fwd = timed(lambda i: plan.forward(*sets[i % nsets], out=losses[i % nsets], argmin_out=argm[i % nsets],
-                                          warped=warped[i % nsets]), k_steps, 3, 0.1)["ms"]
-    ms_bwd = timed(lambda i: plan.backward(*sets[i % nsets], argm[i % nsets], ones, gd[i % nsets], gp[i % nsets],
+    plan1 = MonoLossPlan(B_PER_GPU, sizes, S, (H, W), dev, streams=1)
+    ms_fwd = timed(lambda i: plan1.forward(*sets[i % nsets], out=losses[i % nsets], argmin_out=argm[i % nsets],
                                            warped=warped[i % nsets]), k_steps, 3, 0.1)["ms"]
+    ms_bwd = timed(lambda i: plan1.backward(*sets[i % nsets], argm[i % nsets], ones, gd[i % nsets], gp[i % nsets],
+                                            warped=warped[i % nsets]), k_steps, 3, 0.1)["ms"]
     peak, peak_src = peaks()
     dom = "mono_bwd_kernel" if ms_bwd >= ms_fwd else "mono_warp_kernel + mono_fwd_kernel"
     dom_bytes = target_px * (BYTES_BWD_PER_TARGET_PX if dom == "mono_bwd_kernel" else BYTES_FWD_PER_TARGET_PX)
@@ -507,7 +512,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
-                "fwd_ms": ms_fwd, "bwd_ms": ms_bwd,
+                "fwd_ms": ms_fwd, "bwd_ms": ms_bwd, "kernel_timing": "one launch over the whole batch, timed alone",
                 "step_frac_of_hbm_roofline": (target_px * 84.0 / (ms_step * 1e-3) / 1e9) / peak}
 
     # End to end through host buffers.  Headline leg: everything a step consumes travels from pinned host memory --
@@ -563,12 +568,14 @@ def run_ours(args):
                        "l2": f"{nsets} input sets rotated ({nsets * 86} MB > 126 MB L2)",
                        "timing": f"{n_blocks} blocks of {args.steps} steps (>= {MIN_TIMED_SECONDS} s), barrier + synchronize "
                                  "around every block, CUDA events, max over ranks per block, median block",
-                       "cuda_graph": graphs is not None},
+                       "cuda_graph": graphs is not None,
+                       "sub_batches": f"{plan.parts} sub-batches of {plan.sub_batch} samples on {plan.parts} streams "
+                                      "(MonoLossPlan(streams=...): their kernels overlap each other's start-up and drain)"},
             "per_rank_ms": main["per_rank"], "block_ms": [round(b, 5) for b in main["blocks"][:64]],
             "timed_seconds": main["seconds"],
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
-            "gpu_launches": (3 if plan.save_warped else 2) * args.steps * n_blocks,
-            "gpu_launches_per_step": 3 if plan.save_warped else 2, "clocks": clocks, "other_configs": extra,
+            "gpu_launches": (3 if plan.save_warped else 2) * plan.parts * args.steps * n_blocks,
+            "gpu_launches_per_step": (3 if plan.save_warped else 2) * plan.parts, "clocks": clocks, "other_configs": extra,
         }
         print(json.dumps(line), file=args.out)
     if world > 1:

@@ -96,6 +96,12 @@ typedef struct sde_mono_desc {
    * grad_depth[i] receives d loss / d depth[i] in the same representation. */
   int32_t depth_mode;
   float min_depth, max_depth;       /* used unless depth_mode == SDE_DEPTH_IS_DEPTH; 0 < min_depth < max_depth */
+  /* The batch size the means of the losses are taken over; 0 = `batch`.  A caller that splits a batch of N samples into
+   * sub-batches -- one call per sub-batch, e.g. on two streams so that the tail of one call's kernels overlaps the head
+   * of the other's (MonoLossPlan(streams=2)) -- passes N in every call: the losses and the gradients of the
+   * sub-batches then ADD UP to those of the whole batch (every term of the reference's losses is a mean of per-sample
+   * terms: MonoDepth2.py:119, smoothness_loss.py:62-80). */
+  int32_t norm_batch;
 } sde_mono_desc;
 
 typedef struct sde_mono_buffers {

@@ -29,7 +29,7 @@ class MonoDesc(C.Structure):
         ("full_height", C.c_int32), ("full_width", C.c_int32),
         ("ssim_weight", C.c_float), ("c1", C.c_float), ("c2", C.c_float), ("smooth_weight", C.c_float),
         ("flags", C.c_uint32),
-        ("depth_mode", C.c_int32), ("min_depth", C.c_float), ("max_depth", C.c_float),
+        ("depth_mode", C.c_int32), ("min_depth", C.c_float), ("max_depth", C.c_float), ("norm_batch", C.c_int32),
     ]
 
 

@@ -630,8 +630,8 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
   {
     const float sscale = p.smooth_scale[s];
     const float mbar = p.stats[(s * p.B + b) * 2], Lb = p.stats[(s * p.B + b) * 2 + 1];
-    const float inx = 1.0f / ((float)p.B * (float)h * (float)(w - 1));
-    const float iny = 1.0f / ((float)p.B * (float)(h - 1) * (float)w);
+    const float inx = 1.0f / ((float)p.NB * (float)h * (float)(w - 1));
+    const float iny = 1.0f / ((float)p.NB * (float)(h - 1) * (float)w);
     const float homog = mbar > 1e-6f ? Lb / ((float)h * (float)w * mbar) : 0.0f;
     const float rmbar = 1.0f / mbar;
     const float gsm = g_smooth * sscale;

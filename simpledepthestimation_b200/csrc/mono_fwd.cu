@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
     }
   }
   if (p.smooth_scale[s] > 0.0f)
-    tile_smoothness(planes, kPlD, kPlA, r0, c0, tc.x0, tc.y0, h, w, p.B, p.smooth_g[s] ? p.smooth_g[s] + (size_t)b * hw : nullptr,
+    tile_smoothness(planes, kPlD, kPlA, r0, c0, tc.x0, tc.y0, h, w, p.NB, p.smooth_g[s] ? p.smooth_g[s] + (size_t)b * hw : nullptr,
                     smx, smy, sinv);
 
   // ------------------------------------------------------------------ CTA reduction -> partial slot
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
       double t4[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) t4[k] = ((sh.dred[k][0] + sh.dred[k][1]) + sh.dred[k][2]) + sh.dred[k][3];
-      const double qh = h, qw = w, nB = p.B;
+      const double qh = h, qw = w, nB = p.NB;
       const int ncand = NC * p.S;
       double rec_q = t4[0] / (nB * qh * qw) / p.n_scales;
       if (reduce_mean) rec_q /= ncand;

@@ -30,6 +30,7 @@ constexpr int kBwdH = kTileH - 2;   // 14
 
 struct MonoParams {
   int B, n_scales, S;
+  int NB;                 // batch size the means are taken over (>= B: sde_mono_desc.norm_batch)
   int h[SDE_MAX_SCALES], w[SDE_MAX_SCALES];
   int tiles_x[SDE_MAX_SCALES], tiles_y[SDE_MAX_SCALES];
   int tile_start[SDE_MAX_SCALES + 1];  // CTA index where scale s starts; [n_scales] = grid size

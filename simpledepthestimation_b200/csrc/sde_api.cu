@@ -58,6 +58,7 @@ static int mono_check(const sde_mono_desc* d) {
   if (!(d->ssim_weight >= 0.0f) || !(d->smooth_weight >= 0.0f)) return SDE_ERR_INVALID_ARG;
   if (d->depth_mode < SDE_DEPTH_IS_DEPTH || d->depth_mode > SDE_DEPTH_IS_LOGIT) return SDE_ERR_INVALID_ARG;
   if (d->depth_mode != SDE_DEPTH_IS_DEPTH && !(d->min_depth > 0.0f && d->max_depth > d->min_depth)) return SDE_ERR_INVALID_ARG;
+  if (d->norm_batch != 0 && d->norm_batch < d->batch) return SDE_ERR_INVALID_ARG;
   return SDE_OK;
 }
 
@@ -90,6 +91,7 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
   if (!b || !b->intrinsics || !b->workspace || !b->saved_stats) return SDE_ERR_INVALID_ARG;
   memset(&p, 0, sizeof(p));
   p.B = d->batch; p.n_scales = d->n_scales; p.S = d->n_sources;
+  p.NB = d->norm_batch > 0 ? d->norm_batch : d->batch;
   int start = 0, bstart = 0;
   for (int i = 0; i < d->n_scales; ++i) {
     if (!b->target[i] || !b->depth[i]) return SDE_ERR_INVALID_ARG;
@@ -123,7 +125,7 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
     {
       const bool mean = (d->flags & SDE_MONO_REDUCE_MEAN) != 0, am = (d->flags & SDE_MONO_AUTOMASK) != 0;
       const double ncand = mean ? (double)((am ? 2 : 1) * d->n_sources) : 1.0;
-      p.inv_norm[i] = (float)(1.0 / ((double)d->n_scales * (double)d->batch * (double)p.h[i] * (double)p.w[i] * ncand));
+      p.inv_norm[i] = (float)(1.0 / ((double)d->n_scales * (double)p.NB * (double)p.h[i] * (double)p.w[i] * ncand));
     }
   }
   for (int i = d->n_scales; i <= SDE_MAX_SCALES; ++i) {

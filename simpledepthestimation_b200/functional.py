@@ -7,6 +7,7 @@ tensor or without the built library raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -42,15 +43,22 @@ class MonoLossPlan:
 
     Holds the descriptor, the zero-initialised workspace and the output buffers for one
     (B, scales, S, sizes, loss options) signature so that a training step costs three kernel
-    launches and no allocation.  A plan (its workspace: ticket counters and partial-sum slots)
-    belongs to ONE stream at a time -- use one plan per stream; the workspace is re-zeroed if
+    launches per sub-batch and no allocation.  A plan (its workspace: ticket counters and partial-sum
+    slots) belongs to ONE stream at a time -- use one plan per stream; the workspace is re-zeroed if
     a call reports an error.  Mirrors the options read by the reference's
     MonoDepth2Model.__init__ (detectron2/modeling/meta_arch/MonoDepth2.py:26-46).
+
+    streams: the batch is processed as `streams` contiguous sub-batches, each on its own side stream of the calling
+    stream (sde_mono_desc.norm_batch makes their losses and gradients add up to the whole batch's): the kernels of one
+    sub-batch fill the SMs that the other's leave idle while they start up and drain -- at 640x192 x 12 the three
+    launches of a step spend ~17 % of their time in such tails (measured: 258.8 -> 244.8 us per step with two
+    sub-batches).  None = 2 when the batch is even and >= 4, else 1.  The calling stream waits for the side streams
+    before forward() / backward() return, so callers see ordinary stream semantics.
     """
 
     def __init__(self, batch: int, sizes: Sequence[Sequence[int]], n_sources: int, full_size: Sequence[int],
                  device, ssim_weight=0.85, c1=1e-4, c2=9e-4, smooth_weight=1e-3, automask=True, reduce="min",
-                 save_warped=True, depth_mode="depth", min_depth=0.1, max_depth=80.0):
+                 save_warped=True, depth_mode="depth", min_depth=0.1, max_depth=80.0, streams=None):
         if reduce not in ("min", "mean"):
             raise NotImplementedError(reduce)  # same as MonoDepth2.py:120-121
         if depth_mode not in _lib.DEPTH_MODES:
@@ -61,13 +69,19 @@ class MonoLossPlan:
         self.device = torch.device(device)
         self.batch, self.sizes, self.n_sources = batch, [tuple(s) for s in sizes], n_sources
         self.full_size = tuple(full_size)
+        if streams is None:
+            streams = int(os.environ.get("SDE_MONO_STREAMS", "0")) or (2 if batch >= 4 and batch % 2 == 0 else 1)
+        if streams < 1 or batch % streams != 0:
+            raise _lib.SdeError(f"streams ({streams}) must divide the batch ({batch})")
+        self.parts, self.sub_batch = int(streams), batch // int(streams)
         # keep the warped sources from forward to backward (default: the backward kernel then stages them with
         # coalesced loads instead of re-projecting and re-gathering, 16 % faster per step at 640x192x12 for 24 B
         # per pixel and source of extra HBM traffic, which this issue-bound path has to spare) or recompute them
         # (save_warped=False: nothing but the argmin bytes and O(B) scalars live between the passes)
         self.save_warped = bool(save_warped)
         d = _lib.MonoDesc()
-        d.batch, d.n_scales, d.n_sources = batch, len(sizes), n_sources
+        d.batch, d.n_scales, d.n_sources = self.sub_batch, len(sizes), n_sources
+        d.norm_batch = batch
         for i, (h, w) in enumerate(self.sizes):
             d.height[i], d.width[i] = h, w
         d.full_height, d.full_width = self.full_size
@@ -84,27 +98,38 @@ class MonoLossPlan:
         nbytes = self.lib.sde_mono_workspace_bytes(C.byref(d))
         if nbytes == 0:
             raise _lib.SdeError("invalid loss descriptor (sizes must be >= 2, 1..6 scales, 1..4 sources)")
-        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self._ws_stride = (nbytes + 255) // 256 * 256
+        self.workspace = torch.zeros(self.parts * self._ws_stride, dtype=torch.uint8, device=self.device)
+        # per sub-batch a block of [n_scales * sub_batch * 2] floats: the same total as for the whole batch
         self.stats = torch.empty(len(sizes) * batch * 2, dtype=torch.float32, device=self.device)
+        self._partial = torch.empty(self.parts, 2, dtype=torch.float32, device=self.device) if self.parts > 1 else None
+        self._side = None
 
     def _check_status(self, st, what):
         if st != 0:
             self.workspace.zero_()   # a failed call may leave tickets behind: restore the zero-filled state
         _lib.check(st, what)
 
+    def _side_streams(self):
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.parts)]
+        return self._side
+
     # ---------------------------------------------------------------------------------
-    def _buffers(self, target, source, depth, K, pose) -> _lib.MonoBuffers:
+    def _buffers(self, q, target, source, depth, K, pose) -> _lib.MonoBuffers:
+        """The buffer block of sub-batch q: every per-sample tensor enters as base pointer + q * sub_batch samples."""
         b = _lib.MonoBuffers()
-        for i in range(len(self.sizes)):
-            b.target[i] = target[i].data_ptr()
-            b.depth[i] = depth[i].data_ptr()
+        n0 = q * self.sub_batch
+        for i, (h, w) in enumerate(self.sizes):
+            b.target[i] = target[i].data_ptr() + n0 * 3 * h * w * 4
+            b.depth[i] = depth[i].data_ptr() + n0 * h * w * 4
             for j in range(self.n_sources):
-                b.source[i][j] = source[i][j].data_ptr()
+                b.source[i][j] = source[i][j].data_ptr() + n0 * 3 * h * w * 4
         for j in range(self.n_sources):
-            b.pose[j] = pose[j].data_ptr()
-        b.intrinsics = K.data_ptr()
-        b.saved_stats = self.stats.data_ptr()
-        b.workspace = self.workspace.data_ptr()
+            b.pose[j] = pose[j].data_ptr() + n0 * 64
+        b.intrinsics = K.data_ptr() + n0 * 36
+        b.saved_stats = self.stats.data_ptr() + q * len(self.sizes) * self.sub_batch * 2 * 4
+        b.workspace = self.workspace.data_ptr() + q * self._ws_stride
         return b
 
     def _check(self, target, source, depth, K, pose):
@@ -113,17 +138,19 @@ class MonoLossPlan:
             _require_cuda(target[i], "target"); _require_cuda(depth[i], "depth")
             if tuple(target[i].shape) != (B, 3, h, w) or tuple(depth[i].shape) != (B, 1, h, w):
                 raise _lib.SdeError(f"scale {i}: expected target [B,3,{h},{w}] and depth [B,1,{h},{w}]")
+            if not (target[i].is_contiguous() and depth[i].is_contiguous()):
+                raise _lib.SdeError(f"scale {i}: target and depth must be contiguous")
             for j in range(self.n_sources):
                 _require_cuda(source[i][j], "source")
-                if tuple(source[i][j].shape) != (B, 3, h, w):
-                    raise _lib.SdeError(f"scale {i} source {j}: expected [B,3,{h},{w}]")
+                if tuple(source[i][j].shape) != (B, 3, h, w) or not source[i][j].is_contiguous():
+                    raise _lib.SdeError(f"scale {i} source {j}: expected contiguous [B,3,{h},{w}]")
         _require_cuda(K, "intrinsics")
-        if tuple(K.shape) != (B, 3, 3):
-            raise _lib.SdeError("intrinsics must be [B,3,3]")
+        if tuple(K.shape) != (B, 3, 3) or not K.is_contiguous():
+            raise _lib.SdeError("intrinsics must be contiguous [B,3,3]")
         for j in range(self.n_sources):
             _require_cuda(pose[j], "pose")
-            if tuple(pose[j].shape) != (B, 4, 4):
-                raise _lib.SdeError("pose must be [B,4,4]")
+            if tuple(pose[j].shape) != (B, 4, 4) or not pose[j].is_contiguous():
+                raise _lib.SdeError("pose must be contiguous [B,4,4]")
 
     def new_warped(self):
         """What one step keeps from the forward to the backward pass (sde_mono_buffers.warped / .smooth_g), or None:
@@ -135,54 +162,113 @@ class MonoLossPlan:
         return MonoSaved([[new(self.batch, _lib.MONO_SAVED_PLANES, h, w) for _ in range(self.n_sources)] for h, w in self.sizes],
                          [new(self.batch, 1, h, w) for h, w in self.sizes])
 
-    def _set_warped(self, b, saved):
+    def _set_warped(self, b, q, saved):
         if saved is not None:
-            for i in range(len(self.sizes)):
-                b.smooth_g[i] = saved.smooth_g[i].data_ptr()
+            n0 = q * self.sub_batch
+            for i, (h, w) in enumerate(self.sizes):
+                b.smooth_g[i] = saved.smooth_g[i].data_ptr() + n0 * h * w * 4
                 for j in range(self.n_sources):
-                    b.warped[i][j] = saved.warped[i][j].data_ptr()
+                    b.warped[i][j] = saved.warped[i][j].data_ptr() + n0 * _lib.MONO_SAVED_PLANES * h * w * 4
+
+    def _launch(self, fn, what, fill):
+        """Calls entry point `fn` once per sub-batch: on the current stream, or each on its own side stream, forked from
+        and joined back into the current stream."""
+        cur = torch.cuda.current_stream()
+        if self.parts == 1:
+            self._check_status(fn(C.byref(self.desc), C.byref(fill(0)), cur.cuda_stream), what)
+            return
+        side = self._side_streams()
+        for q in range(self.parts):
+            side[q].wait_stream(cur)
+            self._check_status(fn(C.byref(self.desc), C.byref(fill(q)), side[q].cuda_stream), what)
+        for q in range(self.parts):
+            cur.wait_stream(side[q])
+
+    def forward_backward(self, target, source, depth, K, pose, grad_losses, out=None, argmin_out=None, grad_depth=None,
+                         grad_pose=None, warped=None):
+        """Losses AND gradients in one call (value-and-grad), for callers that know the upstream gradients of
+        (rec_loss, smooth_loss) when they ask for the losses -- a trainer that sums the loss keys knows them to be ones
+        (projects/MonoDepth2/train.py:91-101).  Same kernels and results as forward() followed by backward(); the
+        difference is scheduling: every sub-batch runs warp -> loss forward -> loss backward on its own side stream
+        without rejoining the calling stream in between, so one sub-batch's backward kernel overlaps the other's
+        forward tail (forward() must join before it returns, because its outputs are handed to the caller).
+        Returns (losses[2], argmin list, grad_depth list, grad_pose list)."""
+        self._check(target, source, depth, K, pose)
+        losses = out if out is not None else torch.empty(2, dtype=torch.float32, device=self.device)
+        argmin = argmin_out if argmin_out is not None else \
+            [torch.empty(self.batch, h, w, dtype=torch.uint8, device=self.device) for h, w in self.sizes]
+        if grad_depth is None:
+            grad_depth = [torch.empty_like(d) for d in depth]
+        if grad_pose is None:
+            grad_pose = [torch.empty_like(p) for p in pose]
+        if warped is None:
+            warped = self.new_warped()
+
+        def fill(q):
+            b = self._buffers(q, target, source, depth, K, pose)
+            self._set_warped(b, q, warped)
+            b.losses = losses.data_ptr() if self.parts == 1 else self._partial.data_ptr() + q * 8
+            b.grad_losses = grad_losses.data_ptr()
+            for i, (h, w) in enumerate(self.sizes):
+                b.argmin[i] = argmin[i].data_ptr() + q * self.sub_batch * h * w
+                b.grad_depth[i] = grad_depth[i].data_ptr() + q * self.sub_batch * h * w * 4
+            for j in range(self.n_sources):
+                b.grad_pose[j] = grad_pose[j].data_ptr() + q * self.sub_batch * 64
+            return b
+
+        def both(desc, buf, stream):
+            st = self.lib.sde_mono_loss_forward(desc, buf, stream)
+            return st if st != 0 else self.lib.sde_mono_loss_backward(desc, buf, stream)
+        self._launch(both, "sde_mono_loss_forward + sde_mono_loss_backward", fill)
+        if self.parts > 1:
+            torch.sum(self._partial, 0, out=losses)
+        return losses, argmin, grad_depth, grad_pose
 
     def forward(self, target, source, depth, K, pose, want_argmin=True, out=None, argmin_out=None, warped=None):
         """Runs the forward kernel.  Returns (losses[2], argmin list).  All inputs contiguous fp32 CUDA.
         `warped` (from new_warped()) receives the warped sources for the backward pass."""
         self._check(target, source, depth, K, pose)
-        b = self._buffers(target, source, depth, K, pose)
-        self._set_warped(b, warped)
         losses = out if out is not None else torch.empty(2, dtype=torch.float32, device=self.device)
-        b.losses = losses.data_ptr()
         argmin = []
         if argmin_out is not None:
             argmin = argmin_out
-            for i in range(len(self.sizes)):
-                b.argmin[i] = argmin[i].data_ptr()
         elif want_argmin:
+            argmin = [torch.empty(self.batch, h, w, dtype=torch.uint8, device=self.device) for h, w in self.sizes]
+
+        def fill(q):
+            b = self._buffers(q, target, source, depth, K, pose)
+            self._set_warped(b, q, warped)
+            b.losses = losses.data_ptr() if self.parts == 1 else self._partial.data_ptr() + q * 8
             for i, (h, w) in enumerate(self.sizes):
-                a = torch.empty(self.batch, h, w, dtype=torch.uint8, device=self.device)
-                argmin.append(a)
-                b.argmin[i] = a.data_ptr()
-        st = self.lib.sde_mono_loss_forward(C.byref(self.desc), C.byref(b), torch.cuda.current_stream().cuda_stream)
-        self._check_status(st, "sde_mono_loss_forward")
+                if argmin:
+                    b.argmin[i] = argmin[i].data_ptr() + q * self.sub_batch * h * w
+            return b
+        self._launch(self.lib.sde_mono_loss_forward, "sde_mono_loss_forward", fill)
+        if self.parts > 1:
+            torch.sum(self._partial, 0, out=losses)   # the sub-batches' shares of the batch means
         return losses, argmin
 
     def backward(self, target, source, depth, K, pose, argmin, grad_losses, grad_depth=None, grad_pose=None,
                  warped=None):
         """Runs the backward kernel (reads `warped` if given, else recomputes the warp).
         Returns (grad_depth list, grad_pose list)."""
-        b = self._buffers(target, source, depth, K, pose)
-        self._set_warped(b, warped)
-        b.grad_losses = grad_losses.data_ptr()
         if grad_depth is None:
             grad_depth = [torch.empty_like(d) for d in depth]
         if grad_pose is None:
             grad_pose = [torch.empty_like(p) for p in pose]
-        for i in range(len(self.sizes)):
-            b.grad_depth[i] = grad_depth[i].data_ptr()
-            if argmin:
-                b.argmin[i] = argmin[i].data_ptr()
-        for j in range(self.n_sources):
-            b.grad_pose[j] = grad_pose[j].data_ptr()
-        st = self.lib.sde_mono_loss_backward(C.byref(self.desc), C.byref(b), torch.cuda.current_stream().cuda_stream)
-        self._check_status(st, "sde_mono_loss_backward")
+
+        def fill(q):
+            b = self._buffers(q, target, source, depth, K, pose)
+            self._set_warped(b, q, warped)
+            b.grad_losses = grad_losses.data_ptr()
+            for i, (h, w) in enumerate(self.sizes):
+                b.grad_depth[i] = grad_depth[i].data_ptr() + q * self.sub_batch * h * w * 4
+                if argmin:
+                    b.argmin[i] = argmin[i].data_ptr() + q * self.sub_batch * h * w
+            for j in range(self.n_sources):
+                b.grad_pose[j] = grad_pose[j].data_ptr() + q * self.sub_batch * 64
+            return b
+        self._launch(self.lib.sde_mono_loss_backward, "sde_mono_loss_backward", fill)
         return grad_depth, grad_pose
 
 
@@ -306,9 +392,9 @@ class HostLossRunner:
                                    for _, shape, dt in shapes)
         self.h2d_bytes, self.d2h_bytes = count(self.in_shapes), count(self.out_shapes)
         self._i = 0
-        # kernels per step: pyramid (all frames and scales in one launch), warp + loss forward, backward
+        # kernels per step: pyramid (all frames and scales in one launch); per sub-batch warp + loss forward, backward
         pyr = 1 if (self.u8_frames or len(plan.sizes) > 1) else 0
-        self.launches_per_step = pyr + (2 if plan.save_warped else 1) + 1
+        self.launches_per_step = pyr + ((2 if plan.save_warped else 1) + 1) * plan.parts
 
     def describe(self):
         frames = "uint8 frames (byte / 255 in the pyramid kernel)" if self.u8_frames else "fp32 frames"
@@ -369,10 +455,9 @@ class HostLossRunner:
         rest = self.resident if self.frames_only else sl
         if rest is None:
             raise _lib.SdeError("HostLossRunner(frames_only=True): call set_resident(depth, K, pose) first")
-        self.plan.forward(target, source, rest["depth"], rest["K"], rest["pose"], out=self.losses, argmin_out=self.argmin,
-                          warped=self.warped)
-        self.plan.backward(target, source, rest["depth"], rest["K"], rest["pose"], self.argmin, self.ones, self.grad_depth,
-                           self.grad_pose, warped=self.warped)
+        self.plan.forward_backward(target, source, rest["depth"], rest["K"], rest["pose"], self.ones, out=self.losses,
+                                   argmin_out=self.argmin, grad_depth=self.grad_depth, grad_pose=self.grad_pose,
+                                   warped=self.warped)
         sl["free"].record()
         self.h_out.copy_(self.out_arena, non_blocking=True)
 

@@ -486,3 +486,49 @@ def test_depth_decoder_tail_folded_into_the_loss(dev, mode, B, H, W, save):
         for a, b in zip(x2, xd))
     record(mode=mode, shape=[B, H, W], save_warped=save, **e)
     assert e["rec_vs_oracle"] < LOSS_TOL and e["smooth_vs_oracle"] < LOSS_TOL and e["grad_raw_vs_oracle_q999"] < GRAD_TOL, e
+
+
+def test_sub_batch_streams_reproduce_the_single_launch(dev):
+    """MonoLossPlan(streams=K): the batch as K sub-batches on K streams (sde_mono_desc.norm_batch = the whole batch)
+    gives the single-launch losses up to the summation order and the same argmin maps and gradients bit for bit
+    (every gradient element belongs to one sample), for K = 2 and 3; odd batches refuse to split."""
+    from simpledepthestimation_b200 import _lib
+    from simpledepthestimation_b200.functional import MonoLossPlan
+
+    inp = mono_inputs(6, 48, 160, seed=31)
+    ref = gpu_mono_from_vec(inp, dev, streams=1)
+    for k in (2, 3):
+        out = gpu_mono_from_vec(inp, dev, streams=k)
+        assert rel_err(out["rec_loss"], ref["rec_loss"]) < 1e-6 and rel_err(out["smooth_loss"], ref["smooth_loss"]) < 1e-6
+        for a, b in zip(out["argmin"] + out["grad_depth"], ref["argmin"] + ref["grad_depth"]):
+            assert torch.equal(a, b)
+        for a, b in zip(out["grad_pose_vec"], ref["grad_pose_vec"]):
+            assert rel_err(a, b) < 1e-6
+    with pytest.raises(_lib.SdeError):
+        MonoLossPlan(6, [(48, 160)], 2, (48, 160), dev, streams=4)
+    assert MonoLossPlan(12, [(48, 160)], 2, (48, 160), dev).parts == 2 and MonoLossPlan(3, [(48, 160)], 2, (48, 160), dev).parts == 1
+
+
+def test_forward_backward_in_one_call_matches_the_two_calls(dev):
+    """MonoLossPlan.forward_backward (losses and gradients in one call, sub-batch streams not rejoined between the
+    passes) returns the bits of forward() followed by backward()."""
+    from simpledepthestimation_b200.functional import MonoLossPlan
+
+    B, H, W = 4, 48, 160
+    inp = mono_inputs(B, H, W, seed=33)
+    tgt, src = build_pyramid(inp)
+    g = lambda t: t.to(dev).contiguous()  # noqa: E731
+    sizes = [tuple(d.shape[-2:]) for d in inp["depth"]]
+    args = ([g(t) for t in tgt], [[g(x) for x in row] for row in src], [g(d) for d in inp["depth"]], g(inp["K"]),
+            [g(euler_pose(v)) for v in inp["pose_vec"]])
+    gl = torch.tensor([0.7, 1.3], device=dev)
+    for streams in (1, 2):
+        plan = MonoLossPlan(B, sizes, 2, (H, W), dev, streams=streams)
+        saved = plan.new_warped()
+        l1, a1 = plan.forward(*args, warped=saved)
+        gd1, gp1 = plan.backward(*args, a1, gl, warped=saved)
+        l2, a2, gd2, gp2 = plan.forward_backward(*args, gl)
+        torch.cuda.synchronize()
+        assert torch.equal(l1, l2)
+        for x, y in zip(a1 + gd1 + gp1, a2 + gd2 + gp2):
+            assert torch.equal(x, y)

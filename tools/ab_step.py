@@ -69,8 +69,8 @@ if cfg in ("cfg2", "cfg3"):
         plan.backward(*sets[k], argm[k], ones, gd[k], gp[k], warped=warped[k])
 
     def step(i):
-        fwd(i)
-        bwd(i)
+        k = i % nsets
+        plan.forward_backward(*sets[k], ones, out=losses[k], argmin_out=argm[k], grad_depth=gd[k], grad_pose=gp[k], warped=warped[k])
     st, f, b = blocks(step), blocks(fwd), blocks(bwd)
     print(f"{tag:>14s} {cfg} step {st[0]:7.1f} (min {st[1]:7.1f})  fwd {f[0]:6.1f} (min {f[1]:6.1f})  bwd {b[0]:6.1f} (min {b[1]:6.1f}) us"
           f"  loss {float(losses[0][0]):.7f} gd0sum {float(gd[0][0].double().abs().sum()):.9e} gp {float(gp[0][0].double().abs().sum()):.9e}")
