@@ -291,6 +291,11 @@ def other_configs(dev, raw_cfg2):
     except Exception as exc:
         out["model_step_cfg2"] = {"error": repr(exc)[:300]}
     torch.cuda.empty_cache()
+    try:
+        out["model_step_cfg4"] = motion_model_step(dev)
+    except Exception as exc:
+        out["model_step_cfg4"] = {"error": repr(exc)[:300]}
+    torch.cuda.empty_cache()
     # the comparator SURVEY.md 2.3 / 8d names: the reference itself, eager PyTorch on the same B200
     try:
         out["eager_cuda_reference_cfg2"] = eager_cuda_reference(dev, raw_cfg2)
@@ -346,6 +351,44 @@ def model_step(dev, inp):
     px = S * sum(B_PER_GPU * (H >> i) * (W >> i) for i in range(SCALES))
     return {"ms_per_step": ms, "warped_mpix_s": px / (ms * 1e-3) / 1e6, "iters": 30,
             "path": "MonoDepth2Model.forward(batch) -> rec_loss + smooth_loss -> .backward(); depth / pose injected"}
+
+
+def motion_model_step(dev):
+    """MotionLearningModel.forward(batch) + backward of every *loss key (rgbd consistency both directions, smoothness,
+    rotation / translation cycle, field smoothness / sparsity), cfg4: 1920x1280, batch 4, residual translation field;
+    depth / pose / motion predictions injected in place of the networks."""
+    from simpledepthestimation_b200.geometry.pose_utils import pose_vec2mat
+    from simpledepthestimation_b200.modeling import DEPTH_NET_REGISTRY, POSE_NET_REGISTRY, build_model
+    from simpledepthestimation_b200.synthetic import motion_inputs
+    if "BenchInjectDepth" not in DEPTH_NET_REGISTRY:
+        DEPTH_NET_REGISTRY._do_register("BenchInjectDepth", _Inject)
+        POSE_NET_REGISTRY._do_register("BenchInjectPose", _Inject)
+    loss = _AttrDict(NUM_SCALES=1, SSIM_WEIGHT=3.0, C1="inf", C2=9e-6, CLIP=0.0, DEPTH_L1_WEIGHT=0.0, SMOOTHNESS_WEIGHT=1e-3,
+                     SUPERVISED_WEIGHT=0.0, VARIANCE_FOCUS=0.85, VAR_LOSS_WEIGHT=0.0, MOTION_SMOOTHNESS_WEIGHT=1.0,
+                     MOTION_SPARSITY_WEIGHT=0.2, ROT_CYCLE_WEIGHT=1e-3, TRANS_CYCLE_WEIGHT=5e-2, SCALE_NORMALIZE=False)
+    cfg = _AttrDict(LOSS=loss, MODEL=_AttrDict(META_ARCHITECTURE="MotionLearningModel", DEVICE=str(dev),
+                                               PIXEL_MEAN=[0.45, 0.45, 0.45], PIXEL_STD=[0.225, 0.225, 0.225],
+                                               DEPTH_NET=_AttrDict(NAME="BenchInjectDepth"),
+                                               POSE_NET=_AttrDict(NAME="BenchInjectPose", USE_DEPTH=True)))
+    model = build_model(cfg).train()
+    B4, H4, W4 = 4, 1280, 1920
+    inp = motion_inputs(B4, H4, W4, seed=0)
+    g = lambda t: t.to(dev).contiguous()  # noqa: E731
+    d = g(torch.cat([inp["depth1"], inp["depth2"]], 0)).requires_grad_()
+    vec, mo = g(inp["pose_vec"]).requires_grad_(), g(inp["motion"]).requires_grad_()
+    feed = {"img": g(inp["img1"]), "ctx_img": [g(inp["img2"])], "intrinsics": g(inp["K"])}
+
+    def step():
+        for t in (d, vec, mo):
+            t.grad = None
+        model.depth_net.payload = {"depth_pred": [d]}
+        model.pose_net.payload = {"pose_pred": pose_vec2mat(vec), "motion_pred": mo}
+        out = model(dict(feed))
+        sum(v for k, v in out.items() if "loss" in k).backward()
+    ms = event_time(step, 8, warm=2)
+    px = 2 * B4 * H4 * W4
+    return {"ms_per_step": ms, "warped_mpix_s": px / (ms * 1e-3) / 1e6, "iters": 8,
+            "path": "MotionLearningModel.forward(batch) -> all *loss keys -> .backward(); depth / pose / motion injected"}
 
 
 def eager_cuda_reference(dev, inp):
