@@ -483,7 +483,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, min_seconds=MIN_TIMED_SECONDS, max_blocks=400):
+    def timed(fn, steps, warmup, min_seconds=MIN_TIMED_SECONDS, max_blocks=400, after=None):
         """Blocks of exactly `steps` steps, barrier + synchronize on both sides of every block, CUDA events on the
         launching stream; a block's time is the MAX over ranks.  Returns per-step ms: median block, every block, and
         every rank's own median."""
@@ -496,6 +496,8 @@ def run_ours(args):
             e0.record()
             for i in range(steps):
                 fn(it + i)
+            if after is not None:
+                after()          # e.g. order the timed stream after the last device->host copy
             e1.record()
             if side is not None:
                 torch.cuda.current_stream().wait_stream(side)
@@ -568,7 +570,7 @@ def run_ours(args):
         pins = [r.pin(h) for h in host]
         if kw.get("frames_only"):
             r.set_resident(sets[0][2], sets[0][3], sets[0][4])
-        t = timed(lambda i: r.step(pins[i % nsets]), e_steps, 3, 0.3)
+        t = timed(lambda i: r.step(pins[i % nsets]), e_steps, 3, 0.3, after=r.join)
         r.finish()
         return {"value": world * warped_px / (t["ms"] * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": r.h2d_bytes,
                 "d2h_bytes_per_step": r.d2h_bytes, "ms_per_step": t["ms"], "per_rank_ms": t["per_rank"],

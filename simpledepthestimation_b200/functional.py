@@ -330,8 +330,8 @@ class HostLossRunner:
     them to the device, builds the image pyramid there (resize_img, MonoDepth2.py:82,88), runs the fused
     forward + backward and copies the losses and gradients back to pinned host memory.
 
-    Copies and compute are software-pipelined over two input slots: the H2D copy of step i+1 (copy stream)
-    overlaps the kernels and the D2H copy of step i (compute stream).  Every step still performs its own H2D
+    Copies and compute are software-pipelined over two input slots and two result slots: the H2D copy of step i+1
+    (copy stream) and the D2H copy of step i-1 (its own stream) overlap the kernels of step i (calling stream).  Every step still performs its own H2D
     and D2H; `h2d_bytes` / `d2h_bytes` count exactly the tensors copied per step.  step() is asynchronous;
     finish() waits for the last step and returns its host results.
 
@@ -373,19 +373,25 @@ class HostLossRunner:
             sl["free"].record()
             self.slots.append(sl)
         self.resident = None
-        self.out_arena = new(self.out_bytes, dt=torch.uint8)
-        ov = self._views(self.out_arena, self.out_shapes)
-        self.losses = ov["losses"]
-        self.grad_depth = [ov[f"grad_depth{i}"] for i in range(len(plan.sizes))]
-        self.grad_pose = [ov[f"grad_pose{j}"] for j in range(S)]
+        # results: two device arenas and two pinned host arenas, so that the device->host copy of step i (its own stream)
+        # overlaps the kernels of step i + 1 -- PCIe is full duplex, the copies of the two directions overlap as well
+        self.outs = []
+        for _ in range(2):
+            arena = new(self.out_bytes, dt=torch.uint8)
+            ov = self._views(arena, self.out_shapes)
+            h = torch.empty(self.out_bytes, dtype=torch.uint8, pin_memory=True)
+            hv = self._views(h, self.out_shapes)
+            o = dict(arena=arena, losses=ov["losses"], grad_depth=[ov[f"grad_depth{i}"] for i in range(len(plan.sizes))],
+                     grad_pose=[ov[f"grad_pose{j}"] for j in range(S)], host=h, h_losses=hv["losses"],
+                     h_grad_depth=[hv[f"grad_depth{i}"] for i in range(len(plan.sizes))],
+                     h_grad_pose=[hv[f"grad_pose{j}"] for j in range(S)], ready=torch.cuda.Event(), free=torch.cuda.Event())
+            o["free"].record()
+            self.outs.append(o)
+        self._last = self.outs[0]
         self.argmin = [new(B, h, w, dt=torch.uint8) for h, w in plan.sizes]
         self.ones = torch.ones(2, device=self.device)
         self.warped = plan.new_warped()
-        self.h_out = torch.empty(self.out_bytes, dtype=torch.uint8, pin_memory=True)
-        hv = self._views(self.h_out, self.out_shapes)
-        self.h_losses = hv["losses"]
-        self.h_grad_depth = [hv[f"grad_depth{i}"] for i in range(len(plan.sizes))]
-        self.h_grad_pose = [hv[f"grad_pose{j}"] for j in range(S)]
+        self.d2h_stream = torch.cuda.Stream(device=self.device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         # bytes per step, counted from the tensors (the arenas add at most 15 bytes of padding per tensor)
         count = lambda shapes: sum(int(torch.Size(shape).numel()) * torch.empty((), dtype=dt).element_size()  # noqa: E731
@@ -455,15 +461,28 @@ class HostLossRunner:
         rest = self.resident if self.frames_only else sl
         if rest is None:
             raise _lib.SdeError("HostLossRunner(frames_only=True): call set_resident(depth, K, pose) first")
-        self.plan.forward_backward(target, source, rest["depth"], rest["K"], rest["pose"], self.ones, out=self.losses,
-                                   argmin_out=self.argmin, grad_depth=self.grad_depth, grad_pose=self.grad_pose,
+        o = self.outs[(self._i - 1) % 2]
+        main.wait_event(o["free"])                        # the copy that last read this result arena is done
+        self.plan.forward_backward(target, source, rest["depth"], rest["K"], rest["pose"], self.ones, out=o["losses"],
+                                   argmin_out=self.argmin, grad_depth=o["grad_depth"], grad_pose=o["grad_pose"],
                                    warped=self.warped)
         sl["free"].record()
-        self.h_out.copy_(self.out_arena, non_blocking=True)
+        o["ready"].record()
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(o["ready"])
+            o["host"].copy_(o["arena"], non_blocking=True)
+            o["free"].record()
+        self._last = o
+
+    def join(self):
+        """Orders the calling stream after the device->host copies issued so far (for event timing on that stream)."""
+        torch.cuda.current_stream().wait_stream(self.d2h_stream)
 
     def finish(self):
-        torch.cuda.current_stream().synchronize()
-        return self.h_losses, self.h_grad_depth, self.h_grad_pose
+        """Waits for the last step (kernels and its device->host copy) and returns its host results."""
+        self.d2h_stream.synchronize()
+        o = self._last
+        return o["h_losses"], o["h_grad_depth"], o["h_grad_pose"]
 
 
 # =================================================================================================
