@@ -24,7 +24,18 @@ def dev(sde_lib):
     return torch.device("cuda", 0)
 
 
-def check_against(out, ref_rec, ref_smooth, ref_gd, ref_gv, masks=None, ref_gv32=None):
+def check_against(out, ref_rec, ref_smooth, ref_gd, ref_gv, masks=None, ref_gv32=None, tag=""):
+    from parity_log import record
+    achieved = {"rec_loss_rel": rel_err(out["rec_loss"], ref_rec), "smooth_loss_rel": rel_err(out["smooth_loss"], ref_smooth)}
+    for i, (g, r) in enumerate(zip(out["grad_depth"], ref_gd)):
+        r = torch.as_tensor(r, dtype=torch.float64)
+        e = ((g.double() - r).abs() / r.abs().max())[:, 0]
+        achieved[f"grad_depth_s{i}_max" + ("_stable" if masks is not None else "")] = float((e[masks[i]] if masks is not None else e).max())
+    for j, (g, r) in enumerate(zip(out["grad_pose_vec"], ref_gv)):
+        achieved[f"grad_pose_vec{j}_rel"] = rel_err(g, r)
+        if ref_gv32 is not None:
+            achieved[f"grad_pose_vec{j}_rel_reference_fp32"] = rel_err(ref_gv32[j], r)
+    record(**{("variant" + tag if tag else "variant_default"): achieved})
     assert rel_err(out["rec_loss"], ref_rec) < LOSS_TOL
     assert rel_err(out["smooth_loss"], ref_smooth) < LOSS_TOL
     for i, (g, r) in enumerate(zip(out["grad_depth"], ref_gd)):
@@ -60,7 +71,7 @@ def test_golden_reference_outputs(dev, name):
         check_against(out, g[f"rec_loss{tag}_f64"], g[f"smooth_loss{tag}_f64"],
                       [g[f"grad_depth{i}{tag}_f64"] for i in range(n)],
                       [g[f"grad_pose_vec{j}{tag}_f64"] for j in range(len(inp["pose_vec"]))], masks,
-                      [g[f"grad_pose_vec{j}{tag}_f32"] for j in range(len(inp["pose_vec"]))])
+                      [g[f"grad_pose_vec{j}{tag}_f32"] for j in range(len(inp["pose_vec"]))], tag=tag)
         if tag == "":
             for i, a in enumerate(out["argmin"]):
                 mism = a.numpy() != g[f"argmin{i}"]
@@ -103,12 +114,17 @@ def test_cfg1_kitti_shape_against_live_oracle(dev):
         assert bool(ok[m].all())
         assert float(torch.quantile(err64.flatten(), 0.999)) < GRAD_TOL
         assert int((err64[m] > GRAD_TOL).sum()) <= 20
+    from parity_log import record
+    ach = {"rec_loss_rel": rel_err(out["rec_loss"], ref["rec_loss"].detach()),
+           "smooth_loss_rel": rel_err(out["smooth_loss"], ref["smooth_loss"].detach())}
     for j, (gv, r) in enumerate(zip(out["grad_pose_vec"], ref["grad_pose_vec"])):
         # a handful of decision-flip pixels at the coarse scales move a pose gradient by ~1e-3 in ANY
         # fp32 implementation; bound ours by the reference's own fp32 deviation
         own = rel_err(gv, r)
         ref_dev = rel_err(ref32["grad_pose_vec"][j], r)
+        ach[f"grad_pose_vec{j}_rel"], ach[f"grad_pose_vec{j}_rel_reference_fp32"] = own, ref_dev
         assert own < max(GRAD_TOL, 5 * ref_dev), (own, ref_dev)
+    record(config="cfg1 1x192x640", **ach)
 
 
 def test_bit_identical_across_runs(dev):

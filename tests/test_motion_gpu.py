@@ -70,9 +70,11 @@ def gpu_motion(inp, with_field, c1=INF, c2=9e-6, ssim_w=3.0, dev="cuda:0", **pla
 
 def check_grad(name, got, f64, f32):
     """|got - f64| against the reference-fp32 deviation (see module docstring)."""
+    from parity_log import record
     scale = float(f64.abs().max())
     err = (got.double() - f64).abs() / scale
     ref = float((f32.double() - f64).abs().max() / scale)
+    record(**{name: {"max_err": float(err.max()), "reference_fp32_max_err": ref}})
     assert float(err.max()) <= max(1e-4, 3.0 * ref), f"{name}: max err {float(err.max()):.2e}, reference fp32 {ref:.2e}"
     if err.numel() >= 1000:
         q = float(torch.quantile(err.flatten()[:1_000_000], 0.99))
@@ -93,10 +95,12 @@ def test_motion_loss_matches_oracle(sde_lib, B, H, W, seed, field, c1, c2):
     r64 = oracle_motion(inp, torch.float64, field, c1, c2)
     r32 = oracle_motion(inp, torch.float32, field, c1, c2)
     rg = gpu_motion(inp, field, c1, c2)
+    from parity_log import record
     for d in range(2):
         for k in range(3):
             ref = float(r64["losses"][d, k])
             tol = max(1e-5, 3.0 * abs(float(r32["losses"][d, k]) - ref) / abs(ref))
+            record(**{f"loss_dir{d}_{('rgb_l1', 'ssim', 'smooth')[k]}_rel": abs(float(rg["losses"][d, k]) - ref) / abs(ref)})
             assert abs(float(rg["losses"][d, k]) - ref) / abs(ref) <= tol, (d, k)
     for k in ("gd1", "gd2", "gpose", "gmo"):
         if r64[k] is not None:

@@ -23,9 +23,11 @@ def _vs_inputs(B=2, H=40, W=72, seed=0, C=4):
 
 
 def _quantile_ok(got, ref, ref32, name):
+    from parity_log import record
     scale = float(ref.abs().max())
     err = (got.double().cpu() - ref).abs() / scale
     r32 = float((ref32.double() - ref).abs().max() / scale)
+    record(**{name: {"max_err": float(err.max()), "reference_fp32_max_err": r32}})
     assert float(err.max()) <= max(1e-4, 3 * r32), f"{name}: {float(err.max()):.2e} (reference fp32 {r32:.2e})"
     if err.numel() > 1000:
         assert float(torch.quantile(err.flatten(), 0.99)) <= 1e-4, name
