@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SDE_ABI_VERSION 4
+#define SDE_ABI_VERSION 5
 #define SDE_MAX_SCALES 6
 #define SDE_MAX_SOURCES 4
 #define SDE_MONO_SAVED_PLANES 9    /* planes per sample of sde_mono_buffers.warped[i][j] */
@@ -51,6 +51,9 @@ typedef enum sde_status {
 #define SDE_MONO_REDUCE_MEAN 2u    /* LOSS.PHOTOMETRIC_REDUCE == 'mean' (MonoDepth2.py:116-117); default 'min' */
 #define SDE_MONO_NO_TMA 4u         /* stage the tile planes with plain loads even where TMA boxes are possible (testing);
                                       part of the descriptor so that the forward and the backward call of a step agree */
+#define SDE_MONO_NO_FLOW 8u        /* whole-grid dependencies between the kernels of a call instead of tile-level ones
+                                      (see sde_mono_loss_step); set by callers that overlap several calls on several
+                                      streams themselves (MonoLossPlan(streams > 1)): measured slower when combined */
 /* values of sde_mono_desc.depth_mode */
 #define SDE_DEPTH_IS_DEPTH 0
 #define SDE_DEPTH_IS_DISP 1
@@ -141,6 +144,12 @@ size_t sde_mono_workspace_bytes(const sde_mono_desc* desc);
 int sde_mono_loss_forward(const sde_mono_desc* desc, const sde_mono_buffers* buf, void* stream);
 /* reads argmin, saved_stats, grad_losses; recomputes the warp; writes grad_depth, grad_pose */
 int sde_mono_loss_backward(const sde_mono_desc* desc, const sde_mono_buffers* buf, void* stream);
+/* forward + backward of one step in one call (value-and-grad: grad_losses is known when the losses are asked for, as for
+ * a trainer that sums the loss keys, projects/MonoDepth2/train.py:91-101).  Same kernels, same results as the two calls
+ * above; the three launches are chained with TILE-level dependencies instead of grid-level ones: a forward tile waits
+ * for the chunks of the warp kernel that hold its rows, a backward tile for the forward tiles of its image, so each
+ * kernel fills the SMs its predecessor leaves idle while it drains.  Needs every buffer of both calls. */
+int sde_mono_loss_step(const sde_mono_desc* desc, const sde_mono_buffers* buf, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * MotionLearning two-frame loss (fused).  One call covers n_dirs directions (1->2 and 2->1) of

@@ -5,7 +5,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 4   # SDE_ABI_VERSION of include/sde_loss.h this binding was written against
+ABI_VERSION = 5   # SDE_ABI_VERSION of include/sde_loss.h this binding was written against
 MAX_SCALES = 6
 MAX_SOURCES = 4
 MONO_SAVED_PLANES = 9   # SDE_MONO_SAVED_PLANES: planes per sample of a `warped` buffer
@@ -13,6 +13,7 @@ MOTION_SAVED_PLANES = 16  # SDE_MOTION_SAVED_PLANES
 FLAG_AUTOMASK = 1
 FLAG_REDUCE_MEAN = 2
 FLAG_NO_TMA = 4            # SDE_MONO_NO_TMA
+FLAG_NO_FLOW = 8
 MOTION_FLAG_NO_TMA = 2     # SDE_MOTION_NO_TMA
 DEPTH_MODES = {"depth": 0, "disp": 1, "logit": 2}   # SDE_DEPTH_IS_*
 MAX_DIRS = 2
@@ -182,7 +183,7 @@ def load():
     lib.sde_reload_env.restype = None
     lib.sde_mono_workspace_bytes.restype = C.c_size_t
     lib.sde_mono_workspace_bytes.argtypes = [C.POINTER(MonoDesc)]
-    for name in ("sde_mono_loss_forward", "sde_mono_loss_backward"):
+    for name in ("sde_mono_loss_forward", "sde_mono_loss_backward", "sde_mono_loss_step"):
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(MonoDesc), C.POINTER(MonoBuffers), C.c_void_p]

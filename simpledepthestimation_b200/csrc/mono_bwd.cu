@@ -98,7 +98,16 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
     mbar_init(&sh.bar, 1);
     mbar_init_fence();
   }
-  pdl_wait();   // the forward pass's outputs (and every other tensor) are complete and visible from here on
+  // without flow: the forward pass's outputs (and every other tensor) are complete and visible from here on.  With flow
+  // (mono_params.cuh) the forward kernel may still be running: this tile waits for its image's flag -- the image's
+  // statistics, argmin bytes, smoothness gradients and (through the forward tiles' own waits) warped planes are final.
+  const bool flow_i = (p.flow & kFlowImage) != 0;
+  SDE_TRACE_BEGIN(p, 2);
+  if (!flow_i) pdl_wait();
+  else if (tid == 0) {
+    flag_wait(p.img_flag + s * p.B + b);
+    flag_proxy_fence();   // the warped planes were written with ordinary stores; the copy engine reads them
+  }
   CamRaw raw;
   if (cam_thread) load_cam_raw(raw, p.K, p.pose[tid - 32], b);
   auto make_camera = [&]() {
@@ -151,7 +160,9 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
     }
     tma_load_plane(planes + kBD * kPlane, &maps.depth[s], &sh.bar, ox - kColOff, oy, b);
   }
-  __syncthreads();
+  __syncthreads();   // (flow: thread 0 arrives here after the image's flag)
+  const unsigned behind_flag = launder_zero();   // see ld_plane (sde_common.cuh)
+  SDE_TRACE_MARK(p, 2, 3);
 
   const float* __restrict__ depth = p.depth[s] + (size_t)b * hw;
   const float* __restrict__ tg0 = p.target[s] + (size_t)b * 3 * hw;
@@ -379,11 +390,11 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
         float G0 = 0.0f, G1 = 0.0f;
         if (row >= 2 && row <= kBwdH + 1 && gy < h && col_ok0) {
           if (pair) {
-            const float2 G = __ldg(reinterpret_cast<const float2*>(sg + gy * w + gxp));
+            const float2 G = ld_prod(reinterpret_cast<const float2*>(sg + gy * w + gxp));
             G0 = G.x; G1 = G.y;
           } else {
-            G0 = __ldg(sg + gy * w + gxp);
-            if (col_ok1) G1 = __ldg(sg + gy * w + gxp + 1);
+            G0 = ld_prod(sg + gy * w + gxp);
+            if (col_ok1) G1 = ld_prod(sg + gy * w + gxp + 1);
           }
         }
         Gs[o] = mk2(G0, G1);
@@ -398,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
       //   a_i depth x, a_i depth y, a_i depth, a_i -- the linear map is applied once per (sample, scale) in fp64 by the
       //   tile that finishes the sample.  x is fixed per lane: sum(b x) = x sum(b), formed after the rows.
       // Pairs outside the gradient block / the image load zeros, so they add nothing.
-      const float* __restrict__ dwp = p.warped[s][j] + (size_t)b * kSavedPlanes * hw;
+      const float* __restrict__ dwp = p.warped[s][j] + (size_t)b * kSavedPlanes * hw + behind_flag;
       const float* wm = sh.wmat[j];
       const float* nm = sh.nmat[j];
       const bool pair = (w & 1) == 0 && (reinterpret_cast<uintptr_t>(dwp) & 7) == 0;   // gxp is even
@@ -424,12 +435,12 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
             SDE_CHECK(!ok[o] || (gy >= 0 && gy < h && gxp >= 0 && gxp + 1 < w));
             const float* q = dwp + (ok[o] ? gy * w + gxp : 0) + 3 * hw;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) dq[o][i].v = __ldg(reinterpret_cast<const unsigned long long*>(q + i * hw));
+            for (int i = 0; i < 6; ++i) dq[o][i].v = ld_plane(reinterpret_cast<const unsigned long long*>(q + i * hw));
           } else {
             const float* q = dwp + (gy * w + gxp) + 3 * hw;
 #pragma unroll
             for (int i = 0; i < 6; ++i)
-              dq[o][i] = mk2(ok[o] ? __ldg(q + i * hw) : 0.0f, row_ok && col_ok1 ? __ldg(q + i * hw + 1) : 0.0f);
+              dq[o][i] = mk2(ok[o] ? ld_plane(q + i * hw) : 0.0f, row_ok && col_ok1 ? ld_plane(q + i * hw + 1) : 0.0f);
           }
         }
         f2 wb[3], nb[3];
@@ -523,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
       float acc[12];
 #pragma unroll
       for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
-      const float* __restrict__ dw = SAVED ? p.warped[s][j] + ((size_t)b * kSavedPlanes + 3) * hw : nullptr;
+      const float* __restrict__ dw = SAVED ? p.warped[s][j] + ((size_t)b * kSavedPlanes + 3) * hw + behind_flag : nullptr;
       const float wm1 = (float)(w - 1), hm1 = (float)(h - 1);
       // the derivative-plane loads of the NEXT listed pixel are in flight while the current one is processed
       float nd[6];
@@ -534,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
           const int row = npl >> 7, col = (npl & 127) - kColOff;
           const float* q = dw + ((oy + row) * w + (ox + col));
 #pragma unroll
-          for (int i = 0; i < 6; ++i) nd[i] = __ldg(q + i * hw);
+          for (int i = 0; i < 6; ++i) nd[i] = ld_plane(q + i * hw);
         }
       };
       if (lane < total) fetch(lane);
@@ -629,7 +640,7 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
   // ------------------------------------------------------------------ smoothness gradient + store
   {
     const float sscale = p.smooth_scale[s];
-    const float mbar = p.stats[(s * p.B + b) * 2], Lb = p.stats[(s * p.B + b) * 2 + 1];
+    const float mbar = ld_prod(p.stats + (s * p.B + b) * 2), Lb = ld_prod(p.stats + (s * p.B + b) * 2 + 1);
     const float inx = 1.0f / ((float)p.NB * (float)h * (float)(w - 1));
     const float iny = 1.0f / ((float)p.NB * (float)(h - 1) * (float)w);
     const float homog = mbar > 1e-6f ? Lb / ((float)h * (float)w * mbar) : 0.0f;
@@ -683,6 +694,7 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
   // ------------------------------------------------------------------ last tile of a sample: pose gradients
   // The tile that finishes a sample last (over all scales) adds that sample's per-CTA slots in a fixed
   // order in fp64, while other samples are still being computed.  Only the lanes that wrote pose slots fence.
+  SDE_TRACE_MARK(p, 2, 1);
   int total_b = 0;
   for (int ss = 0; ss < p.n_scales; ++ss) total_b += p.btiles_x[ss] * p.btiles_y[ss];
 #ifndef SDE_BWD_EARLY_TICKET
@@ -693,6 +705,13 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
 #endif
   if (sh.ticket != (unsigned)(total_b - 1)) return;
   publish_fence();
+  if (flow_i) {
+    // every tile of this sample has passed its image flag: leave the flags cleared for the next call.  This grid did
+    // not wait for the forward kernel as a grid; the CTAs that finish a sample do (it has long finished), so that the
+    // completion of this grid implies the completion of the grids before it.
+    if (tid < p.n_scales) p.img_flag[tid * p.B + b] = 0u;
+    pdl_wait();
+  }
   for (int tj = 0; tj < p.S; ++tj) {
     double a[12];
 #pragma unroll
@@ -760,8 +779,13 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
 
 size_t mono_bwd_smem_bytes() { return (size_t)kBwdPlanes * kPlane * sizeof(float); }
 
+cudaError_t launch_mono_bwd_pair(const MonoParams& p, const MonoTma& t, cudaStream_t stream);   // mono_bwd_pair.cu
+bool bwd_pair_enabled();                                                                          // sde_api.cu
+
 cudaError_t launch_mono_bwd(const MonoParams& p, const MonoTma& t, cudaStream_t stream) {
   const bool saved = p.warped[0][0] != nullptr;   // all-or-nothing, checked by the caller
+  // min-reprojection over an even number of sources with kept warps: two sources per pass (mono_bwd_pair.cu)
+  if (saved && (p.S & 1) == 0 && !(p.flags & SDE_MONO_REDUCE_MEAN) && bwd_pair_enabled()) return launch_mono_bwd_pair(p, t, stream);
   auto kernel = saved ? mono_bwd_kernel<true> : mono_bwd_kernel<false>;
   // 47.8 KB of dynamic shared memory (+ 4 KB static): four CTAs per SM; the opt-in attribute is per device, cheap and idempotent
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mono_bwd_smem_bytes());

@@ -322,7 +322,7 @@ __device__ __forceinline__ void stage_target(const StageArgs& a0, int tid, bool 
         const int ty = a.oy + yy, tx = a.ox + xx;
         const bool inside = ty >= 0 && ty < a.h && tx >= 0 && tx < a.w;
         // 255 never matches a candidate: windows centred outside the image do not exist
-        m[u] = inside ? (reduce_mean ? (uint8_t)254 : a.amap[pix]) : (uint8_t)255;
+        m[u] = inside ? (reduce_mean ? (uint8_t)254 : ld_prod(a.amap + pix)) : (uint8_t)255;
       }
     }
 #pragma unroll
@@ -396,6 +396,9 @@ __device__ __forceinline__ void stage_source(const StageArgs& a0, const Cam& cam
 // loads of the halo'd tile (a reflected halo position takes the warp of the reflected pixel,
 // which is what re-projecting it would give).
 template <bool INTERIOR>
+// (what another kernel of the same step produced -- argmin bytes, warped planes, smoothness gradient -- is read with
+// ld.global.cg: under flow (mono_params.cuh) the producer grid may still be running, and L1 must not keep a line that
+// straddles a finished and an unfinished image)
 __device__ __forceinline__ void stage_saved(const StageArgs& a0, const float* __restrict__ warped, int tid) {
   StageArgs a = a0;
   const float* wp = pinned(warped);
@@ -414,7 +417,7 @@ __device__ __forceinline__ void stage_saved(const StageArgs& a0, const float* __
       const int pix = pixel_of<INTERIOR>(a, yy, xx, gy, gx);
       pl[u] = plane_index(yy, xx);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[u][c] = __ldg(wp + (pix + c * a.hw));
+      for (int c = 0; c < 3; ++c) v[u][c] = ld_prod(wp + (pix + c * a.hw));
     }
 #pragma unroll
     for (int u = 0; u < kStageBatch; ++u)
@@ -481,7 +484,7 @@ __device__ __forceinline__ void stage_arg(uint8_t* arg, const uint8_t* __restric
     const int ty = oy + yy, tx = ox + xx;
     const bool inside = ty >= 0 && ty < h && tx >= 0 && tx < w;
     pl[k] = i < kPositions ? plane_index(yy, xx) : -1;
-    m[k] = inside ? (reduce_mean ? (uint8_t)254 : __ldg(amap + ty * w + tx)) : (uint8_t)255;
+    m[k] = inside ? (reduce_mean ? (uint8_t)254 : ld_prod(amap + ty * w + tx)) : (uint8_t)255;
   }
 #pragma unroll
   for (int k = 0; k < kIter; ++k)
@@ -525,7 +528,7 @@ __device__ __forceinline__ void stage_arg_words(uint8_t* arg, const uint8_t* __r
     const int yy = i / kWords, wd = i - yy * kWords;
     const int ty = oy + yy, tx = cx0 + 4 * wd;
     const bool inside = i < kTot && ty >= 0 && ty < h && tx >= 0 && tx < w;
-    v[k] = inside ? (reduce_mean ? 0xfefefefeu : __ldg(reinterpret_cast<const unsigned*>(amap + ty * w + tx))) : 0xffffffffu;
+    v[k] = inside ? (reduce_mean ? 0xfefefefeu : ld_prod(reinterpret_cast<const unsigned*>(amap + ty * w + tx))) : 0xffffffffu;
   }
 #pragma unroll
   for (int k = 0; k < kIter; ++k) {

@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   // of the last samples last, so they are still in L2 when this kernel starts; the backward kernel then runs in list
   // order and starts with what this kernel touched last.  Measured at cfg2: step 271.2 -> 266.8 us (backward kernel
   // reversed instead: 269.8, both: 268.0).
-  const int vbid = (int)(gridDim.x - 1 - blockIdx.x);
+  // flow (tile-level dependencies, mono_params.cuh): list order instead -- the chunks of the first tiles were written
+  // first, and the images the backward kernel starts with complete first.
+  const bool flow_w = (p.flow & kFlowWarp) != 0, flow_i = (p.flow & kFlowImage) != 0;
+  const int vbid = flow_w ? (int)blockIdx.x : (int)(gridDim.x - 1 - blockIdx.x);
   const TileCoord tc = decode_tile(p, vbid);
   const int s = tc.s, b = tc.b, h = p.h[s], w = p.w[s], hw = h * w;
   const bool reduce_mean = (p.flags & SDE_MONO_REDUCE_MEAN) != 0;
@@ -72,16 +75,30 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
     mbar_init(&sh.bar, 1);
     mbar_init_fence();
   }
-  pdl_wait();   // the warp kernel's planes (and every other tensor) are complete and visible from here on
+  // without flow: the warp kernel's planes (and every other tensor) are complete and visible from here on.  With flow
+  // the warp kernel may still be running: this tile's inputs are complete (the warp kernel itself was serialised behind
+  // whatever produced them), the warped planes of its rows once their chunk flags are set.
+  SDE_TRACE_BEGIN(p, 1);
+  if (!flow_w) pdl_wait();
+  if (flow_i) pdl_launch_dependents();   // backward tiles wait for image flags, not for this grid
   if (tma && tid == 0) {
     mbar_arrive_expect_tx(&sh.bar, (4 + (AUTOMASK ? 3 : 0) + (p.prewarp[s] ? 3 : 0)) * kPlaneBytesTma);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       tma_load_plane(planes + (kPlA + c) * kPlane, &maps.target[s], &sh.bar, ox - kColOff, oy, b * 3 + c);
       if (AUTOMASK) tma_load_plane(planes + (kPlI + c) * kPlane, &maps.source[s][0], &sh.bar, ox - kColOff, oy, b * 3 + c);
-      if (p.prewarp[s]) tma_load_plane(planes + (kPlS + c) * kPlane, &maps.warped[s][0], &sh.bar, ox - kColOff, oy, b * kSavedPlanes + c);
+      if (p.prewarp[s] && !flow_w) tma_load_plane(planes + (kPlS + c) * kPlane, &maps.warped[s][0], &sh.bar, ox - kColOff, oy, b * kSavedPlanes + c);
     }
     tma_load_plane(planes + kPlD * kPlane, &maps.depth[s], &sh.bar, ox - kColOff, oy, b);
+  }
+  if (flow_w) {
+    // the chunks of the warp kernel that hold rows y0 - 1 .. y0 + kTileH of this image (every tile waits, whether or not
+    // it reads the planes itself: an image's flag below then implies that all of the image's chunks are complete)
+    const int chunks = (hw + kWarpChunk - 1) / kWarpChunk;
+    const int row_lo = max(tc.y0 - 1, 0), row_hi = min(tc.y0 + kTileH, h - 1);
+    const int c_lo = (row_lo * w) / kWarpChunk, c_hi = (row_hi * w + w - 1) / kWarpChunk;
+    const unsigned* wf = p.warp_flag + p.warp_start[s] + b * chunks;
+    for (int c = c_lo + tid; c <= c_hi; c += kThreads) flag_wait(wf + c);
   }
   // camera terms: only the in-kernel gather needs them (with the warp kernel's planes the CTA never projects, and
   // nobody waits at this barrier for two threads' global-memory round trip)
@@ -93,6 +110,13 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
     load_proj(sh.proj[tid], k, p.pose[tid], b);
   }
   __syncthreads();
+  SDE_TRACE_MARK(p, 1, 3);
+  if (flow_w && tma && p.prewarp[s] && tid == 0) {
+    flag_proxy_fence();   // the chunks were written with ordinary stores; the copy engine reads them
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      tma_load_plane(planes + (kPlS + c) * kPlane, &maps.warped[s][0], &sh.bar, ox - kColOff, oy, b * kSavedPlanes + c);
+  }
 
   const float* __restrict__ depth = p.depth[s] + (size_t)b * hw;
   const float* __restrict__ tg0 = p.target[s] + (size_t)b * 3 * hw;
@@ -268,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
 
   // the heavy part of this tile is done: once that holds for every tile, the next kernel of the stream may be
   // scheduled (it waits for this grid to complete before it touches memory)
-  pdl_launch_dependents();
+  if (!flow_i) pdl_launch_dependents();
   // ------------------------------------------------------------------ per-thread sums, argmin, smoothness
   float rec = 0.0f, smx = 0.0f, smy = 0.0f, sinv = 0.0f;
   const int gx0 = tc.x0 + c0;  // image column of this lane's first pixel
@@ -295,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   // One thread publishes the slot, fences it and takes the ticket: the other threads' stores (argmin bytes,
   // smoothness gradient) are consumed by later kernels only and need no fence here.
   const int q = s * p.B + b, per = p.tiles_x[s] * p.tiles_y[s];
+  SDE_TRACE_MARK(p, 1, 1);
   if (tid == 0) {
     float4 v;
     v.x = ((sh.red[0][0] + sh.red[0][1]) + sh.red[0][2]) + sh.red[0][3];
@@ -320,6 +345,12 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
     }
+    if (flow_w) {
+      // every tile of this image has passed its chunk flags: leave them cleared for the next call
+      const int chunks = (hw + kWarpChunk - 1) / kWarpChunk;
+      unsigned* wf = p.warp_flag + p.warp_start[s] + b * chunks;
+      for (int c = tid; c < chunks; c += kThreads) wf[c] = 0u;
+    }
     __syncthreads();   // sh.red is reused below
     if (lane == 0) {
 #pragma unroll
@@ -342,6 +373,9 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
       p.fin[q * 2 + 1] = Lb * (double)p.smooth_scale[s];
       p.img_counter[q] = 0u;   // leave the workspace zeroed for the next call
       publish_fence();
+      // flow: this image's statistics are final, and so are the argmin bytes and smoothness gradients of its tiles (each
+      // tile released them with its ticket, this thread acquired them with the last one): backward tiles may start
+      if (flow_i) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.img_flag + q), "r"(1u) : "memory");
       sh.ticket = atomicAdd(p.counter, 1u);
     }
   }
@@ -349,6 +383,9 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   const int pairs = p.n_scales * p.B;
   if (sh.ticket != (unsigned)(pairs - 1)) return;
   publish_fence();
+  // flow: this grid did not wait for the warp kernel as a grid; the last CTA does (the warp kernel has long finished),
+  // so that the completion of this grid implies the completion of the one before it
+  if (flow_w) pdl_wait();
   if (wid == 0) {
     double r = 0.0, sm = 0.0;
     for (int k = lane; k < pairs; k += 32) { r += __ldcg(p.fin + k * 2); sm += __ldcg(p.fin + k * 2 + 1); }

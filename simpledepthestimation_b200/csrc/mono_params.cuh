@@ -70,7 +70,21 @@ struct MonoParams {
   int tma[SDE_MAX_SCALES];   // tile planes of this scale are staged by TMA (tensor maps in MonoTma are valid)
   int prewarp[SDE_MAX_SCALES];            // forward: the loss kernel takes warped[s][*] (filled by the warp kernel) through TMA
   int warp_start[SDE_MAX_SCALES + 1];     // warp kernel: first block of scale s (blocks of kWarpChunk pixels per sample)
+  // Tile-level dependencies between the kernels of a step (sde_api.cu: "flow"), instead of whole-grid ones:
+  //   kFlowWarp   the warp kernel publishes one flag per block (= chunk of kWarpChunk pixels of one image); a forward
+  //               tile waits for the chunks that hold its rows only, so forward tiles run while the warp kernel drains
+  //   kFlowImage  the forward tile that completes an image publishes the image's flag (its statistics, argmin bytes and
+  //               smoothness gradients are final); a backward tile waits for its image only
+  // Flags live in the workspace, are zero between calls, and are cleared by the consumer side (the forward tile that
+  // completes an image clears the image's chunk flags, the backward tile that completes a sample its image flags).
+  unsigned flow;
+  unsigned* warp_flag;    // [warp grid]
+  unsigned* img_flag;     // [n_scales*B]
+#ifdef SDE_TRACE
+  unsigned long long* trace;
+#endif
 };
+constexpr unsigned kFlowWarp = 1u, kFlowImage = 2u;
 
 // Tensor maps over the [planes, h, w] inputs of every scale, box {68, 18, 1} (tma.cuh).  Second kernel
 // parameter: the copy engine reads the descriptors straight from the parameter space.

@@ -33,7 +33,12 @@ __global__ void __launch_bounds__(kWarpThreads, 1024 / kWarpThreads) mono_warp_k
   const int chunks = (hw + kWarpChunk - 1) / kWarpChunk;
   const int b = bid / chunks, chunk = bid - b * chunks;
   const int tid = threadIdx.x;
+  SDE_TRACE_BEGIN(p, 0);
   pdl_wait();   // K, pose and depth may come from the kernel ahead; the planes written below may still be read by it
+  // flow: the forward kernel may be scheduled as soon as every block of this grid is resident -- its tiles wait for the
+  // chunk flags published below, not for the grid
+  const bool flow = (p.flow & kFlowWarp) != 0;
+  if (flow) pdl_launch_dependents();
   if (tid < p.S) {
     Cam cam;
     float k[9];
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(kWarpThreads, 1024 / kWarpThreads) mono_warp_k
     for (int it = 0; it < kWarpPixPerThread; ++it) {
       // once every block is on its last pixel, the next kernel of the stream may be scheduled (it waits for this grid
       // to complete before it touches memory): its launch latency overlaps this kernel's tail
-      if (j == p.S - 1 && it == kWarpPixPerThread - 1) pdl_launch_dependents();
+      if (!flow && j == p.S - 1 && it == kWarpPixPerThread - 1) pdl_launch_dependents();
       const int pix = pix0 + it * kWarpThreads;
       if (pix >= hw) break;
       float den, X, Y, q;
@@ -111,6 +116,11 @@ __global__ void __launch_bounds__(kWarpThreads, 1024 / kWarpThreads) mono_warp_k
       }
     }
   }
+  if (flow) {
+    __syncthreads();
+    if (tid == 0) flag_publish(p.warp_flag + blockIdx.x);
+  }
+  SDE_TRACE_MARK(p, 0, 1);
 }
 
 cudaError_t launch_mono_warp(const MonoParams& p, cudaStream_t stream) {

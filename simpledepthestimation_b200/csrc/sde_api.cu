@@ -44,8 +44,8 @@ static int cuda_fail(cudaError_t e) {
 static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 struct MonoLayout {
-  int grid, bgrid;
-  size_t off_imgc, off_smpc, off_fin, off_partials, off_pose, total;
+  int grid, bgrid, wgrid;
+  size_t off_imgc, off_smpc, off_fin, off_partials, off_pose, off_wflag, off_iflag, total;
 };
 
 static int mono_check(const sde_mono_desc* d) {
@@ -66,7 +66,9 @@ static MonoLayout mono_layout(const sde_mono_desc* d) {
   MonoLayout L;
   L.grid = 0;
   L.bgrid = 0;
+  L.wgrid = 0;
   for (int i = 0; i < d->n_scales; ++i) {
+    L.wgrid += d->batch * ((d->width[i] * d->height[i] + kWarpChunk - 1) / kWarpChunk);
     L.grid += d->batch * ((d->width[i] + kTileW - 1) / kTileW) * ((d->height[i] + kTileH - 1) / kTileH);
     L.bgrid += d->batch * ((d->width[i] + kBwdW - 1) / kBwdW) * ((d->height[i] + kBwdH - 1) / kBwdH);
   }
@@ -81,6 +83,10 @@ static MonoLayout mono_layout(const sde_mono_desc* d) {
   off = align16(off + (size_t)L.grid * 4 * sizeof(float));
   L.off_pose = off;
   off = align16(off + (size_t)L.bgrid * (kThreads / 32) * d->n_sources * 12 * sizeof(float));
+  L.off_wflag = off;   // flow: one flag per block of the warp kernel, one per (scale, image)
+  off = align16(off + (size_t)L.wgrid * sizeof(unsigned));
+  L.off_iflag = off;
+  off = align16(off + (size_t)d->n_scales * d->batch * sizeof(unsigned));
   L.total = off;
   return L;
 }
@@ -157,6 +163,8 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
   p.fin = reinterpret_cast<double*>(ws + L.off_fin);
   p.partials = reinterpret_cast<float*>(ws + L.off_partials);
   p.pose_partials = reinterpret_cast<float*>(ws + L.off_pose);
+  p.warp_flag = reinterpret_cast<unsigned*>(ws + L.off_wflag);
+  p.img_flag = reinterpret_cast<unsigned*>(ws + L.off_iflag);
   p.grad_losses = b->grad_losses;
   // what the forward pass keeps for the backward pass is all-or-nothing
   {
@@ -225,6 +233,28 @@ static int read_pdl_mask() {
 bool pdl_enabled(int which) {
   if (g_pdl_mask < 0) g_pdl_mask = read_pdl_mask();
   return (g_pdl_mask >> which) & 1;
+}
+// Tile-level dependencies between the kernels of a step (mono_params.cuh: flow): bit 0 warp -> forward (any call that
+// runs the warp kernel), bit 1 forward -> backward (sde_mono_loss_step only: a stand-alone backward call must not wait
+// for flags that a forward call may have set for another step).  SDE_FLOW_MASK=<bits> overrides the default 3.
+static int g_flow_mask = -1;
+static int read_flow_mask() {
+  const char* m = getenv("SDE_FLOW_MASK");
+  return m ? (atoi(m) & 3) : 3;
+}
+// SDE_BWD_PAIR=0: the one-source-per-pass backward kernel on every configuration (A/B timing, parity tests)
+static int g_bwd_pair = -1;
+static int read_bwd_pair() {
+  const char* m = getenv("SDE_BWD_PAIR");
+  return (m && m[0] == '0') ? 0 : 1;
+}
+bool bwd_pair_enabled() {
+  if (g_bwd_pair < 0) g_bwd_pair = read_bwd_pair();
+  return g_bwd_pair != 0;
+}
+static unsigned flow_mask() {
+  if (g_flow_mask < 0) g_flow_mask = read_flow_mask();
+  return (unsigned)g_flow_mask;
 }
 
 // Decides per scale whether the tile planes are staged by TMA (row pitch a multiple of 16 bytes, encoder
@@ -549,23 +579,66 @@ const char* sde_strerror(int status) {
 }
 
 const char* sde_last_cuda_error(void) { return g_cuda_err; }
+#ifdef SDE_TRACE
+// developer build (tools/trace_step.py): per-CTA time stamps of the last MonoDepth2 launches
+static unsigned long long* g_trace_buf = nullptr;
+extern "C" int sde_debug_trace(unsigned long long* dst) {
+  const size_t n = (size_t)3 * kTraceBlocks * 4 * sizeof(unsigned long long);
+  if (!g_trace_buf) { if (cudaMalloc(&g_trace_buf, n) != cudaSuccess) return 1; cudaMemset(g_trace_buf, 0, n); return 0; }
+  return dst && cudaMemcpy(dst, g_trace_buf, n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+}
+#endif
 
-void sde_reload_env(void) { g_pdl_mask = read_pdl_mask(); }
+void sde_reload_env(void) { g_pdl_mask = read_pdl_mask(); g_flow_mask = read_flow_mask(); g_bwd_pair = read_bwd_pair(); }
 
 size_t sde_mono_workspace_bytes(const sde_mono_desc* desc) {
   if (mono_check(desc) != SDE_OK) return 0;
   return mono_layout(desc).total;
 }
 
-int sde_mono_loss_forward(const sde_mono_desc* desc, const sde_mono_buffers* buf, void* stream) {
+// warp kernel + loss forward kernel; `step`: the backward kernel follows in the same call (sde_mono_loss_step)
+static int mono_forward_launches(const sde_mono_desc* desc, const sde_mono_buffers* buf, cudaStream_t stream, bool step, unsigned* flow_out) {
   MonoParams p;
   int st = mono_params(desc, buf, false, p);
   if (st != SDE_OK) return st;
   MonoTma t;
   mono_tma(desc, buf, false, p, t);
-  cudaError_t e = launch_mono_warp(p, static_cast<cudaStream_t>(stream));
+  // flow needs the forward kernel to be scheduled behind the warp kernel programmatically (bit 1 of the launch mask),
+  // and the warp kernel to run at all; the image flags also need the backward kernel's launch to be programmatic
+  unsigned flow = 0;
+  if (p.warp_start[p.n_scales] > 0 && pdl_enabled(1)) flow |= flow_mask() & kFlowWarp;
+  if (step && pdl_enabled(2)) flow |= flow_mask() & kFlowImage;
+  if (desc->flags & SDE_MONO_NO_FLOW) flow = 0;
+  p.flow = flow;
+#ifdef SDE_TRACE
+  p.trace = g_trace_buf;
+#endif
+  if (flow_out) *flow_out = flow;
+  cudaError_t e = launch_mono_warp(p, stream);
   if (e != cudaSuccess) return cuda_fail(e);
-  e = launch_mono_fwd(p, t, static_cast<cudaStream_t>(stream));
+  e = launch_mono_fwd(p, t, stream);
+  return e == cudaSuccess ? SDE_OK : cuda_fail(e);
+}
+
+int sde_mono_loss_forward(const sde_mono_desc* desc, const sde_mono_buffers* buf, void* stream) {
+  return mono_forward_launches(desc, buf, static_cast<cudaStream_t>(stream), false, nullptr);
+}
+
+int sde_mono_loss_step(const sde_mono_desc* desc, const sde_mono_buffers* buf, void* stream) {
+  // validate the backward side before anything is launched
+  MonoParams pb;
+  int st = mono_params(desc, buf, true, pb);
+  if (st != SDE_OK) return st;
+  unsigned flow = 0;
+  st = mono_forward_launches(desc, buf, static_cast<cudaStream_t>(stream), true, &flow);
+  if (st != SDE_OK) return st;
+  MonoTma tb;
+  mono_tma(desc, buf, true, pb, tb);
+  pb.flow = flow & kFlowImage;
+#ifdef SDE_TRACE
+  pb.trace = g_trace_buf;
+#endif
+  cudaError_t e = launch_mono_bwd(pb, tb, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SDE_OK : cuda_fail(e);
 }
 

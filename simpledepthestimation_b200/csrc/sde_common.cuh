@@ -103,6 +103,59 @@ __device__ __forceinline__ f2 ld2(const float* p) {   // 8-byte aligned
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Flags between kernels that overlap under programmatic dependent launch (mono_params.cuh: flow).  The producer's CTA
+// stores its data, synchronises, and ONE thread fences and sets the flag; a consumer thread spins with acquire loads.
+// Every CTA of the producer grid is resident (or has exited) before the consumer grid is scheduled -- that is what
+// the launch attribute guarantees once all of them have executed launch_dependents -- so the spin cannot starve the
+// producer.  A flag that stays clear for seconds means a broken protocol: trap instead of hanging the device.
+__device__ __forceinline__ void flag_publish(unsigned* f) {
+  __threadfence();
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(1u) : "memory");
+}
+__device__ __forceinline__ void flag_wait(const unsigned* f) {
+  unsigned v, spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v != 0u) return;
+    __nanosleep(100);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+// What the forward kernel of the same step produced (argmin bytes, smoothness gradient, per-image statistics) is read
+// with ld.global.cg: under flow the producer grid may still be running, and L1 must not keep a line that straddles a
+// finished and an unfinished image (these tensors are [B, h, w]: one image follows the other).
+template <class T>
+__device__ __forceinline__ T ld_prod(const T* p) { return __ldcg(p); }
+// The derivative planes of the warp kernel keep the read-only path (ld.global.nc: the compiler may issue these loads a
+// phase early, worth 8 us of the backward kernel at cfg2): a line of planes 3..8 of an image never holds another
+// image's data that is read through L1 (planes 0..2 on either side go through the copy engine), and nobody reads it
+// before the image's flag.  `launder` hides a pointer's value from the compiler at a point behind the flag wait, so
+// that no such load can be hoisted above it.
+template <class T>
+__device__ __forceinline__ T ld_plane(const T* p) { return __ldg(p); }
+__device__ __forceinline__ unsigned launder_zero() { unsigned z = 0; asm volatile("" : "+r"(z)); return z; }
+#ifdef SDE_TRACE
+// developer build (tools/trace_step.py): per-CTA %globaltimer stamps [kernel][block][start, end, SM id, after the wait]
+constexpr int kTraceBlocks = 8192;
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void trace_begin(unsigned long long* tr, int k) {
+  if (tr && threadIdx.x == 0 && blockIdx.x < kTraceBlocks) {
+    unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    tr[(k * kTraceBlocks + blockIdx.x) * 4] = gtimer(); tr[(k * kTraceBlocks + blockIdx.x) * 4 + 2] = sm;
+  }
+}
+__device__ __forceinline__ void trace_mark(unsigned long long* tr, int k, int slot) {
+  if (tr && threadIdx.x == 0 && blockIdx.x < kTraceBlocks) tr[(k * kTraceBlocks + blockIdx.x) * 4 + slot] = gtimer();
+}
+#define SDE_TRACE_BEGIN(p, k) trace_begin((p).trace, k)
+#define SDE_TRACE_MARK(p, k, slot) trace_mark((p).trace, k, slot)
+#else
+#define SDE_TRACE_BEGIN(p, k)
+#define SDE_TRACE_MARK(p, k, slot)
+#endif
+// data another SM wrote with ordinary stores is read by the copy engine (async proxy) next
+__device__ __forceinline__ void flag_proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 #ifndef __CUDACC_RTC__
 // Host side: launch with the programmatic-stream-serialization attribute (SDE_DISABLE_PDL=1: plain launch).
 bool pdl_enabled(int which);

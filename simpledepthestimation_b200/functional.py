@@ -48,12 +48,15 @@ class MonoLossPlan:
     a call reports an error.  Mirrors the options read by the reference's
     MonoDepth2Model.__init__ (detectron2/modeling/meta_arch/MonoDepth2.py:26-46).
 
-    streams: the batch is processed as `streams` contiguous sub-batches, each on its own side stream of the calling
-    stream (sde_mono_desc.norm_batch makes their losses and gradients add up to the whole batch's): the kernels of one
-    sub-batch fill the SMs that the other's leave idle while they start up and drain -- at 640x192 x 12 the three
-    launches of a step spend ~17 % of their time in such tails (measured: 258.8 -> 244.8 us per step with two
-    sub-batches).  None = 2 when the batch is even and >= 4, else 1.  The calling stream waits for the side streams
-    before forward() / backward() return, so callers see ordinary stream semantics.
+    Scheduling of a step's three kernels (warp, loss forward, loss backward).  Default (streams=1): one stream, the
+    launches chained with TILE-level dependencies (sde_mono_loss_step / sde_mono_loss_forward, include/sde_loss.h: a
+    forward tile waits for the chunks of the warp kernel that hold its rows, a backward tile for the forward tiles of
+    its image), so each kernel fills the SMs its predecessor leaves idle while it drains -- at 640x192 x 12 the three
+    launches otherwise spend ~17 % of their time in such tails.  streams=K > 1: the batch as K contiguous sub-batches,
+    each on its own side stream of the calling stream with grid-level dependencies (sde_mono_desc.norm_batch makes
+    their losses and gradients add up to the whole batch's); measured equal for forward_backward() (251 us either
+    way at cfg2) and slower for separate forward() / backward() calls (267 against 257 us), kept as an option.  The
+    calling stream waits for the side streams before a call returns, so callers see ordinary stream semantics.
     """
 
     def __init__(self, batch: int, sizes: Sequence[Sequence[int]], n_sources: int, full_size: Sequence[int],
@@ -70,7 +73,7 @@ class MonoLossPlan:
         self.batch, self.sizes, self.n_sources = batch, [tuple(s) for s in sizes], n_sources
         self.full_size = tuple(full_size)
         if streams is None:
-            streams = int(os.environ.get("SDE_MONO_STREAMS", "0")) or (2 if batch >= 4 and batch % 2 == 0 else 1)
+            streams = int(os.environ.get("SDE_MONO_STREAMS", "0")) or 1
         if streams < 1 or batch % streams != 0:
             raise _lib.SdeError(f"streams ({streams}) must divide the batch ({batch})")
         self.parts, self.sub_batch = int(streams), batch // int(streams)
@@ -87,7 +90,7 @@ class MonoLossPlan:
         d.full_height, d.full_width = self.full_size
         d.ssim_weight, d.c1, d.c2, d.smooth_weight = ssim_weight, c1, c2, smooth_weight
         d.flags = (_lib.FLAG_AUTOMASK if automask else 0) | (_lib.FLAG_REDUCE_MEAN if reduce == "mean" else 0) | \
-                  (_lib.FLAG_NO_TMA if _lib.tma_disabled() else 0)
+                  (_lib.FLAG_NO_TMA if _lib.tma_disabled() else 0) | (_lib.FLAG_NO_FLOW if self.parts > 1 else 0)
         self.lib.sde_reload_env()   # developer switches are read when a plan is built, not per call
         # depth_mode "disp" / "logit": the `depth` tensors hold the decoder's disparity / pre-softplus output and the
         # kernels apply disp_to_depth(., min_depth, max_depth) (depth_decoder.py:9-18,108) themselves; the gradient comes
@@ -98,7 +101,7 @@ class MonoLossPlan:
         nbytes = self.lib.sde_mono_workspace_bytes(C.byref(d))
         if nbytes == 0:
             raise _lib.SdeError("invalid loss descriptor (sizes must be >= 2, 1..6 scales, 1..4 sources)")
-        self._ws_stride = (nbytes + 255) // 256 * 256
+        self._ws_bytes, self._ws_stride = nbytes, (nbytes + 255) // 256 * 256
         self.workspace = torch.zeros(self.parts * self._ws_stride, dtype=torch.uint8, device=self.device)
         # per sub-batch a block of [n_scales * sub_batch * 2] floats: the same total as for the whole batch
         self.stats = torch.empty(len(sizes) * batch * 2, dtype=torch.float32, device=self.device)
@@ -216,10 +219,7 @@ class MonoLossPlan:
                 b.grad_pose[j] = grad_pose[j].data_ptr() + q * self.sub_batch * 64
             return b
 
-        def both(desc, buf, stream):
-            st = self.lib.sde_mono_loss_forward(desc, buf, stream)
-            return st if st != 0 else self.lib.sde_mono_loss_backward(desc, buf, stream)
-        self._launch(both, "sde_mono_loss_forward + sde_mono_loss_backward", fill)
+        self._launch(self.lib.sde_mono_loss_step, "sde_mono_loss_step", fill)
         if self.parts > 1:
             torch.sum(self._partial, 0, out=losses)
         return losses, argmin, grad_depth, grad_pose

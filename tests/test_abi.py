@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(sde_lib):
 def test_version_and_strerror(sde_lib):
     from simpledepthestimation_b200 import _lib
 
-    assert sde_lib.sde_version() == _lib.ABI_VERSION == 4
+    assert sde_lib.sde_version() == _lib.ABI_VERSION == 5
     assert sde_lib.sde_strerror(0) == b"ok"
     assert b"invalid" in sde_lib.sde_strerror(-1)
     assert sde_lib.sde_last_cuda_error() == b""

@@ -522,7 +522,7 @@ def test_sub_batch_streams_reproduce_the_single_launch(dev):
             assert rel_err(a, b) < 1e-6
     with pytest.raises(_lib.SdeError):
         MonoLossPlan(6, [(48, 160)], 2, (48, 160), dev, streams=4)
-    assert MonoLossPlan(12, [(48, 160)], 2, (48, 160), dev).parts == 2 and MonoLossPlan(3, [(48, 160)], 2, (48, 160), dev).parts == 1
+    assert MonoLossPlan(12, [(48, 160)], 2, (48, 160), dev).parts == 1 and MonoLossPlan(12, [(48, 160)], 2, (48, 160), dev, streams=2).parts == 2
 
 
 def test_forward_backward_in_one_call_matches_the_two_calls(dev):
@@ -548,3 +548,53 @@ def test_forward_backward_in_one_call_matches_the_two_calls(dev):
         assert torch.equal(l1, l2)
         for x, y in zip(a1 + gd1 + gp1, a2 + gd2 + gp2):
             assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("B,H,W", [(6, 96, 320), (3, 50, 70)])
+def test_tile_level_dependencies_give_the_same_bits(dev, monkeypatch, B, H, W):
+    """sde_mono_loss_step chains warp -> forward -> backward with tile-level dependencies (SDE_FLOW_MASK bit 0: a
+    forward tile waits for the chunk flags of its rows, bit 1: a backward tile for its image's flag) instead of
+    whole-grid ones.  Every output must carry the bits of the grid-level chain (mask 0) over repeated back-to-back
+    steps on alternating inputs -- one plan, one set of kept planes, so a flag left set by one step would let the next
+    one read the previous step's planes -- with and without sub-batch streams, on a TMA shape and on an odd width
+    (thread-staged planes); the flag words (the tail of the workspace) must be clear again after every step."""
+    from simpledepthestimation_b200.functional import MonoLossPlan
+
+    g = lambda t: t.to(dev).contiguous()  # noqa: E731
+    sets = []
+    for seed in (41, 42):
+        inp = mono_inputs(B, H, W, seed=seed)
+        tgt, src = build_pyramid(inp)
+        sets.append(([g(t) for t in tgt], [[g(x) for x in row] for row in src], [g(d) for d in inp["depth"]], g(inp["K"]),
+                     [g(euler_pose(v)) for v in inp["pose_vec"]]))
+    sizes = [tuple(d.shape[-2:]) for d in inp["depth"]]
+    gl = torch.tensor([0.9, 1.1], device=dev)
+    ref = None
+    for mask in ("0", "1", "2", "3"):
+        monkeypatch.setenv("SDE_FLOW_MASK", mask)
+        for streams in (1, 3):
+            plan = MonoLossPlan(B, sizes, 2, (H, W), dev, streams=streams)
+            saved = plan.new_warped()
+            sub = B // streams
+            outs = []
+            for it in range(6):
+                l, a, gd, gp = plan.forward_backward(*sets[it % 2], gl, warped=saved)
+                outs.append([t.clone() for t in [l] + a + gd + gp])
+            torch.cuda.synchronize()
+            # the flag words are the last two regions of a sub-batch's workspace (sde_api.cu: mono_layout): one word per
+            # block of the warp kernel (2048 pixels), one per (scale, image), each region padded to 16 bytes
+            a16 = lambda n: (n + 15) // 16 * 16  # noqa: E731
+            flag_bytes = a16(4 * sum(sub * (-(-h * w // 2048)) for h, w in sizes)) + a16(4 * len(sizes) * sub)
+            for q in range(streams):
+                end = q * plan._ws_stride + plan._ws_bytes
+                assert int(plan.workspace[end - flag_bytes:end].count_nonzero()) == 0, f"mask {mask} streams {streams}: flags left set"
+            for it in range(2, 6):
+                for x, y in zip(outs[it], outs[it - 2]):
+                    assert torch.equal(x, y), f"mask {mask} streams {streams}: step {it} differs from step {it - 2}"
+            if ref is None:
+                ref = outs[:2]
+            else:
+                for k in range(2):
+                    assert torch.allclose(outs[k][0], ref[k][0], rtol=1e-6, atol=0)   # losses: summation order of the sub-batches
+                    for x, y in zip(outs[k][1:], ref[k][1:]):
+                        assert torch.equal(x, y), f"mask {mask} streams {streams}"
