@@ -3,9 +3,9 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-ours:       a "step" is one forward + one backward pass of the fused MonoDepth2 loss (three launches -- warp kernel,
-            loss forward, loss backward -- per sub-batch; the plan runs the batch as two sub-batches of 6 on two streams)
-            over one batch of synthetic KITTI-shaped input (BASELINE.json configs[1]: 640x192, batch 12 per GPU, 4
+ours:       a "step" is one forward + one backward pass of the fused MonoDepth2 loss (sde_mono_loss_step: three launches
+            -- warp kernel, loss forward, loss backward -- chained with tile-level dependencies, so each kernel fills
+            the SMs its predecessor leaves idle while it drains) over one batch of synthetic KITTI-shaped input (BASELINE.json configs[1]: 640x192, batch 12 per GPU, 4
             scales, 2 sources, automask + smoothness).  The launches of a step are captured once per input set in a
             CUDA graph, so the host enqueues one graph launch per step.
             `value` = warped Mpix/s with inputs resident in HBM (three input sets are rotated so that every step reads
@@ -543,8 +543,9 @@ def run_ours(args):
     ms_bwd = timed(lambda i: plan1.backward(*sets[i % nsets], argm[i % nsets], ones, gd[i % nsets], gp[i % nsets],
                                             warped=warped[i % nsets]), k_steps, 3, 0.1)["ms"]
     peak, peak_src = peaks()
-    dom = "mono_bwd_kernel" if ms_bwd >= ms_fwd else "mono_warp_kernel + mono_fwd_kernel"
-    dom_bytes = target_px * (BYTES_BWD_PER_TARGET_PX if dom == "mono_bwd_kernel" else BYTES_FWD_PER_TARGET_PX)
+    bwd_name = "mono_bwd_pair_kernel" if (S % 2 == 0 and plan1.save_warped and os.environ.get("SDE_BWD_PAIR", "1") != "0") else "mono_bwd_kernel"
+    dom = bwd_name if ms_bwd >= ms_fwd else "mono_warp_kernel + mono_fwd_kernel"
+    dom_bytes = target_px * (BYTES_BWD_PER_TARGET_PX if dom == bwd_name else BYTES_FWD_PER_TARGET_PX)
     dom_ms = max(ms_bwd, ms_fwd)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
@@ -614,8 +615,10 @@ def run_ours(args):
                        "timing": f"{n_blocks} blocks of {args.steps} steps (>= {MIN_TIMED_SECONDS} s), barrier + synchronize "
                                  "around every block, CUDA events, max over ranks per block, median block",
                        "cuda_graph": graphs is not None,
-                       "sub_batches": f"{plan.parts} sub-batches of {plan.sub_batch} samples on {plan.parts} streams "
-                                      "(MonoLossPlan(streams=...): their kernels overlap each other's start-up and drain)"},
+                       "scheduling": ("one stream, three launches chained with tile-level dependencies (sde_mono_loss_step)"
+                                      if plan.parts == 1 else
+                                      f"{plan.parts} sub-batches of {plan.sub_batch} samples on {plan.parts} streams "
+                                      "(MonoLossPlan(streams=...): their kernels overlap each other's start-up and drain)")},
             "per_rank_ms": main["per_rank"], "block_ms": [round(b, 5) for b in main["blocks"][:64]],
             "timed_seconds": main["seconds"],
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,

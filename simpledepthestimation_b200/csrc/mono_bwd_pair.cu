@@ -38,6 +38,11 @@ struct PairShared {
 #ifndef SDE_PAIR_OCC
 #define SDE_PAIR_OCC 3
 #endif
+#ifndef SDE_PAIR_UNROLL
+#define SDE_PAIR_UNROLL 1
+#endif
+#define SDE_PRAGMA_(x) _Pragma(#x)
+#define SDE_PRAGMA_UNROLL(n) SDE_PRAGMA_(unroll n)
 
 __global__ void __launch_bounds__(kThreads, SDE_PAIR_OCC) mono_bwd_pair_kernel(const __grid_constant__ MonoParams p,
                                                                               const __grid_constant__ MonoTma maps) {
@@ -197,66 +202,88 @@ __global__ void __launch_bounds__(kThreads, SDE_PAIR_OCC) mono_bwd_pair_kernel(c
       // -------------------------------------------------------------- phase 2: SSIM coefficients of the selected source on Q
       if (use_ssim) {
         const float* pa = planes + (kPA + c) * kPlane + plane_index(r0, c0);
-        f2 hA[2], hAA[2], hX[2][2], hXX[2][2], hXA[2][2];
-#pragma unroll
-        for (int rr = 0; rr < kRowsPerWarp + 2; ++rr) {
+        // horizontal 3-sums of a row: target side (A, A^2) and, per source, (X, X^2, X A)
+        struct HRow { f2 A, AA, X[2], XX[2], XA[2]; };
+        auto hsum = [&](int rr) {
+          HRow n;
           const Row4 a = ld_row(pa + rr * kPitch);
           const f2 aa = a.c * a.c;
-          const f2 nA = (a.c + swp(a.c)) + a.o, nAA = fma2(a.o, a.o, aa + swp(aa));
-          f2 nX[2], nXX[2], nXA[2];
+          n.A = (a.c + swp(a.c)) + a.o;
+          n.AA = fma2(a.o, a.o, aa + swp(aa));
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const Row4 x = ld_row(pa + ((k ? kPS1 : kPS0) - kPA) * kPlane + rr * kPitch);
             const f2 xx2 = x.c * x.c, xa = x.c * a.c;
-            nX[k] = (x.c + swp(x.c)) + x.o;
-            nXX[k] = fma2(x.o, x.o, xx2 + swp(xx2));
-            nXA[k] = fma2(x.o, a.o, xa + swp(xa));
+            n.X[k] = (x.c + swp(x.c)) + x.o;
+            n.XX[k] = fma2(x.o, x.o, xx2 + swp(xx2));
+            n.XA[k] = fma2(x.o, a.o, xa + swp(xa));
           }
-          if (rr >= 2) {
-            const int row = r0 + rr - 1;  // plane row of the window centre
-            const uchar2 m = *reinterpret_cast<const uchar2*>(sh.arg + plane_index(row, c0 + 1));
-            const bool f0 = m.x == cand0, s0 = m.x == cand1, f1 = m.y == cand0, s1 = m.y == cand1;
-            f2 ca = bc2(0.0f), cb = bc2(0.0f), cc = bc2(0.0f);
-            if (__any_sync(0xffffffffu, f0 || s0 || f1 || s1)) {
-              const f2 sA = (hA[0] + hA[1]) + nA, sAA = (hAA[0] + hAA[1]) + nAA;
-              const f2 sXa = (hX[0][0] + hX[0][1]) + nX[0], sXXa = (hXX[0][0] + hXX[0][1]) + nXX[0], sXAa = (hXA[0][0] + hXA[0][1]) + nXA[0];
-              const f2 sXb = (hX[1][0] + hX[1][1]) + nX[1], sXXb = (hXX[1][0] + hXX[1][1]) + nXX[1], sXAb = (hXA[1][0] + hXA[1][1]) + nXA[1];
-              // the window sums of the source this window selected (either, where it selected neither: its coefficients are zeroed)
-              const f2 sX = mk2(s0 ? lo(sXb) : lo(sXa), s1 ? hi(sXb) : hi(sXa));
-              const f2 sXX = mk2(s0 ? lo(sXXb) : lo(sXXa), s1 ? hi(sXXb) : hi(sXXa));
-              const f2 sXA = mk2(s0 ? lo(sXAb) : lo(sXAa), s1 ? hi(sXAb) : hi(sXAa));
-              // same operation order as the forward kernel
-              const f2 aa2 = sA * sA, xs = sX * sX, t = sX * sA;
-              const f2 vA = fma2(aa2, bc2(-1.0f), sAA * bc2(9.0f));
-              const f2 n1 = fma2(bc2(2.0f), t, C1);
-              const f2 n2 = fma2(bc2(2.0f), fma2(t, bc2(-1.0f), sXA * bc2(9.0f)), C2);
-              const f2 d1 = (xs + aa2) + C1;
-              const f2 d2 = (fma2(xs, bc2(-1.0f), sXX * bc2(9.0f)) + vA) + C2;
-              const f2 N = n1 * n2, D = d1 * d2;
-              const f2 nssim = ndiv2(N, D);
-              const f2 ninvD = ndiv2(bc2(1.0f), D);
-              // torch.clamp passes the gradient on the closed interval 0 <= (1-ssim)/2 <= 1
-              const float h0 = fmaf(lo(nssim), 0.5f, 0.5f), h1 = fmaf(hi(nssim), 0.5f, 0.5f);
-              const f2 g = mk2(((f0 || s0) && h0 >= 0.0f && h0 <= 1.0f) ? g_ss : 0.0f,
-                               ((f1 || s1) && h1 >= 0.0f && h1 <= 1.0f) ? g_ss : 0.0f);
-              const f2 ngi = g * ninvD;
-              const f2 u = fma2(sX * nssim, d2 - d1, sA * (n2 - n1));
-              ca = (ngi * bc2(-2.0f)) * u;
-              cb = (ngi * bc2(-18.0f)) * (nssim * d1);
-              cc = (ngi * bc2(-18.0f)) * n1;
-            }
-            float* pc = planes + kPC * kPlane + plane_index(row, c0 + 1);
-            *reinterpret_cast<unsigned long long*>(pc) = ca.v;
-            *reinterpret_cast<unsigned long long*>(pc + kPlane) = cb.v;
-            *reinterpret_cast<unsigned long long*>(pc + 2 * kPlane) = cc.v;
-            // which source the window selected does not depend on the channel
-            if (c == 0) *reinterpret_cast<unsigned long long*>(pc + 3 * kPlane) = mk2(f0 ? 1.0f : 0.0f, f1 ? 1.0f : 0.0f).v;
+          return n;
+        };
+        // coefficients of the windows centred on plane row `row` from pp = the 3-sums of the two rows above it, added up,
+        // and n = the 3-sums of the row below it
+        auto coef_row = [&](int row, const HRow& pp, const HRow& n) {
+          const uchar2 m = *reinterpret_cast<const uchar2*>(sh.arg + plane_index(row, c0 + 1));
+          const bool f0 = m.x == cand0, s0 = m.x == cand1, f1 = m.y == cand0, s1 = m.y == cand1;
+          f2 ca = bc2(0.0f), cb = bc2(0.0f), cc = bc2(0.0f);
+          if (__any_sync(0xffffffffu, f0 || s0 || f1 || s1)) {
+            const f2 sA = pp.A + n.A, sAA = pp.AA + n.AA;
+            const f2 sXa = pp.X[0] + n.X[0], sXXa = pp.XX[0] + n.XX[0], sXAa = pp.XA[0] + n.XA[0];
+            const f2 sXb = pp.X[1] + n.X[1], sXXb = pp.XX[1] + n.XX[1], sXAb = pp.XA[1] + n.XA[1];
+            // the window sums of the source this window selected (either, where it selected neither: its coefficients are zeroed)
+            const f2 sX = mk2(s0 ? lo(sXb) : lo(sXa), s1 ? hi(sXb) : hi(sXa));
+            const f2 sXX = mk2(s0 ? lo(sXXb) : lo(sXXa), s1 ? hi(sXXb) : hi(sXXa));
+            const f2 sXA = mk2(s0 ? lo(sXAb) : lo(sXAa), s1 ? hi(sXAb) : hi(sXAa));
+            // same operation order as the forward kernel
+            const f2 aa2 = sA * sA, xs = sX * sX, t = sX * sA;
+            const f2 vA = fma2(aa2, bc2(-1.0f), sAA * bc2(9.0f));
+            const f2 n1 = fma2(bc2(2.0f), t, C1);
+            const f2 n2 = fma2(bc2(2.0f), fma2(t, bc2(-1.0f), sXA * bc2(9.0f)), C2);
+            const f2 d1 = (xs + aa2) + C1;
+            const f2 d2 = (fma2(xs, bc2(-1.0f), sXX * bc2(9.0f)) + vA) + C2;
+            const f2 N = n1 * n2, D = d1 * d2;
+            const f2 nssim = ndiv2(N, D);
+            const f2 ninvD = ndiv2(bc2(1.0f), D);
+            // torch.clamp passes the gradient on the closed interval 0 <= (1-ssim)/2 <= 1
+            const float h0 = fmaf(lo(nssim), 0.5f, 0.5f), h1 = fmaf(hi(nssim), 0.5f, 0.5f);
+            const f2 g = mk2(((f0 || s0) && h0 >= 0.0f && h0 <= 1.0f) ? g_ss : 0.0f,
+                             ((f1 || s1) && h1 >= 0.0f && h1 <= 1.0f) ? g_ss : 0.0f);
+            const f2 ngi = g * ninvD;
+            const f2 uu = fma2(sX * nssim, d2 - d1, sA * (n2 - n1));
+            ca = (ngi * bc2(-2.0f)) * uu;
+            cb = (ngi * bc2(-18.0f)) * (nssim * d1);
+            cc = (ngi * bc2(-18.0f)) * n1;
           }
-          hA[0] = hA[1]; hA[1] = nA; hAA[0] = hAA[1]; hAA[1] = nAA;
+          float* pc = planes + kPC * kPlane + plane_index(row, c0 + 1);
+          *reinterpret_cast<unsigned long long*>(pc) = ca.v;
+          *reinterpret_cast<unsigned long long*>(pc + kPlane) = cb.v;
+          *reinterpret_cast<unsigned long long*>(pc + 2 * kPlane) = cc.v;
+          // which source the window selected does not depend on the channel
+          if (c == 0) *reinterpret_cast<unsigned long long*>(pc + 3 * kPlane) = mk2(f0 ? 1.0f : 0.0f, f1 ? 1.0f : 0.0f).v;
+        };
+        auto add_rows = [](const HRow& u, const HRow& v) {
+          HRow r;
+          r.A = u.A + v.A; r.AA = u.AA + v.AA;
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            hX[k][0] = hX[k][1]; hX[k][1] = nX[k]; hXX[k][0] = hXX[k][1]; hXX[k][1] = nXX[k]; hXA[k][0] = hXA[k][1]; hXA[k][1] = nXA[k];
-          }
+          for (int k = 0; k < 2; ++k) { r.X[k] = u.X[k] + v.X[k]; r.XX[k] = u.XX[k] + v.XX[k]; r.XA[k] = u.XA[k] + v.XA[k]; }
+          return r;
+        };
+        // Sliding window over the rows with two row slots and the running pair sum pp = (row r-2) + (row r-1): the new
+        // row replaces the slot of row r-2 (already folded into pp), the window sum is pp + new -- the association
+        // (r-2 + r-1) + r of the forward kernel -- and pp becomes (row r-1) + new.  The slots swap roles after one row
+        // and are back after two, so a loop over row PAIRS carries no register moves and can stay rolled
+        // (SDE_PAIR_UNROLL 1): a third of the unrolled code -- three CTAs in different phases share the instruction cache.
+        HRow hx = hsum(0), hy = hsum(1);
+        HRow pp = add_rows(hx, hy);
+SDE_PRAGMA_UNROLL(SDE_PAIR_UNROLL)
+        for (int it = 0; it < kRowsPerWarp / 2; ++it) {
+          const int rr = 2 + 2 * it;
+          hx = hsum(rr);
+          coef_row(r0 + rr - 1, pp, hx);
+          pp = add_rows(hy, hx);
+          hy = hsum(rr + 1);
+          coef_row(r0 + rr, pp, hy);
+          pp = add_rows(hx, hy);
         }
       }
       __syncthreads();

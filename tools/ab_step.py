@@ -1,5 +1,6 @@
 """Same-box timing of one build of libsde_loss.so (SDE_LIB_PATH selects it): cfg2 step / forward / backward in
-microseconds, median over blocks of CUDA-event-timed launches.  usage: python tools/ab_step.py [tag] [cfg2|cfg3|cfg4]"""
+microseconds, median over blocks of CUDA-event-timed launches.  usage: python tools/ab_step.py [tag] [cfg2|cfg3|cfg4|cfg5]
+(cfg5 = the 96-sample global batch of configs[4] on one GPU)"""
 import os
 import sys
 import statistics
@@ -42,9 +43,9 @@ def blocks(fn, n_blocks=9, iters=50):
     return statistics.median(out), min(out)
 
 
-if cfg in ("cfg2", "cfg3"):
-    B, H, W = (12, 192, 640) if cfg == "cfg2" else (8, 320, 1024)
-    nsets = 3
+if cfg in ("cfg2", "cfg3", "cfg5"):
+    B, H, W = {"cfg2": (12, 192, 640), "cfg3": (8, 320, 1024), "cfg5": (96, 192, 640)}[cfg]
+    nsets = 3 if cfg != "cfg5" else 1
     sets = []
     for k in range(nsets):
         inp = cached(f"{cfg}_{k}", lambda: mono_inputs(B, H, W, 4, 2, seed=k))
