@@ -3,9 +3,10 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-ours:       a "step" is one forward + one backward pass of the fused MonoDepth2 loss (sde_mono_loss_step: three launches
-            -- warp kernel, loss forward, loss backward -- chained with tile-level dependencies, so each kernel fills
-            the SMs its predecessor leaves idle while it drains) over one batch of synthetic KITTI-shaped input (BASELINE.json configs[1]: 640x192, batch 12 per GPU, 4
+ours:       a "step" is one forward + one backward pass of the fused MonoDepth2 loss (MonoLossPlan.forward_backward ->
+            sde_mono_loss_step: three launches -- warp kernel, loss forward, loss backward -- per sub-batch; the plan's
+            default runs the batch as two sub-batches of 6 on two streams, `config.scheduling` says what ran) over one
+            batch of synthetic KITTI-shaped input (BASELINE.json configs[1]: 640x192, batch 12 per GPU, 4
             scales, 2 sources, automask + smoothness).  The launches of a step are captured once per input set in a
             CUDA graph, so the host enqueues one graph launch per step.
             `value` = warped Mpix/s with inputs resident in HBM (three input sets are rotated so that every step reads

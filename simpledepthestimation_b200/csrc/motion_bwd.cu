@@ -29,6 +29,9 @@ constexpr int kMPosPerThread = (kBwdW * kBwdH + kThreads - 1) / kThreads;  // 7
 
 struct MotionBwdShared {
   MCam cam;
+  // dense phase 4 (warp mode): the projection as p_i = depth (N_i . [x, y, 1]) + tau_i with N = K R K^-1 and
+  // tau = K (t_pose + field), and d (R P + t) / d depth = V [x, y, 1]^T with V = R K^-1
+  float nmat[9], vmat[9], kt[3];
   float red[12][kThreads / 32];
   double dred[12][kThreads / 32];
   unsigned ticket;
@@ -64,7 +67,19 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
     tma_load_plane(planes + kNW * kPlane, &maps.warped[dir], &sh.bar, bx, oy, b * kMotionSaved + 4);
     tma_load_plane(planes + kND * kPlane, &maps.depth_a[dir], &sh.bar, bx, oy, b);
   }
-  if (tid == 0) load_mcam(sh.cam, p.K, p.pose[dir], b, p.sx, p.sy);
+  if (tid == 0) {
+    load_mcam(sh.cam, p.K, p.pose[dir], b, p.sx, p.sy);
+    const MCam& c = sh.cam;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        sh.nmat[i * 3 + j] = c.m[i * 3] * c.cam.ki[j] + c.m[i * 3 + 1] * c.cam.ki[3 + j] + c.m[i * 3 + 2] * c.cam.ki[6 + j];
+        sh.vmat[i * 3 + j] = c.r[i * 3] * c.cam.ki[j] + c.r[i * 3 + 1] * c.cam.ki[3 + j] + c.r[i * 3 + 2] * c.cam.ki[6 + j];
+      }
+      sh.kt[i] = c.k[i * 3] * c.t[0] + c.k[i * 3 + 1] * c.t[1] + c.k[i * 3 + 2] * c.t[2];
+    }
+  }
   // coefficient planes 1, 2: the border ring is never written and must read as zero (plane 0 holds WZ for now)
   zero_ring<2>(planes, kNCoef + 1, tid);
   __syncthreads();
@@ -304,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
 
   // ------------------------------------------------------------------ phase 4: warp backward on P + smoothness
   {
-    const MCam mc = sh.cam;
+    const MCam& mc = sh.cam;   // camera terms are read from shared memory where they are used
     const float* __restrict__ sc0 = st.frame_b;
     const float* __restrict__ saved = tma ? p.warped[dir] + (size_t)b * kMotionSaved * hw : nullptr;
     float* __restrict__ gout = p.grad_depth[dir] + (size_t)b * hw;
@@ -317,6 +332,117 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
     float acc[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc[k] = 0.0f;
+    // Warp mode with 8-byte aligned gradient / field tensors: dense form, as phase 4 of the MonoDepth2 kernel
+    // (mono_bwd.cu).  Every lane takes its own pixel pairs (the rows of its warp, two columns) in packed fp32; the
+    // global operands of a row -- residual translation, the six derivative planes of the statistics pass (already gated
+    // as nan_to_num / clamp gate the reference's gradient), the local smoothness gradient -- are coalesced 8-byte loads,
+    // issued for two rows at a time; the sample coordinate is re-projected in packed arithmetic with one refined
+    // reciprocal, which is also the factor 1 / (p2 + 1e-6) of d (X, Y) / d p.  Pairs outside the gradient block / the
+    // image read the sample's first pixel and are switched off through gS.  (The per-pixel loop below it -- one
+    // position per thread and iteration, scalar projection with IEEE divisions -- was 42 % of this kernel's instructions.)
+    const bool dense = tma && ((reinterpret_cast<uintptr_t>(gout) | reinterpret_cast<uintptr_t>(st.field) |
+                                reinterpret_cast<uintptr_t>(gfield) | reinterpret_cast<uintptr_t>(saved)) & 7) == 0;
+    if (dense) {
+      const int gxp = ox + c0 + 1;   // even, and w % 4 == 0 in warp mode: a pair is inside the image or outside it
+      const bool col_ok = lane >= 1 && lane <= 30 && gxp < w;
+      const f2 xs = mk2((float)gxp, (float)gxp + 1.0f);
+      const float* nm = sh.nmat;
+      const float* vm = sh.vmat;
+      f2 nb[3], vb[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        nb[i] = fma2(bc2(nm[3 * i]), xs, bc2(nm[3 * i + 2]));
+        vb[i] = fma2(bc2(vm[3 * i]), xs, bc2(vm[3 * i + 2]));
+      }
+      const f2 ncx = bc2(-mc.cam.cx), ncy = bc2(-mc.cam.cy);
+      const bool smooth = g_smooth != 0.0f;
+      f2 Sa[3], Sb[3], Sy[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Sa[k] = Sb[k] = Sy[k] = bc2(0.0f);
+#pragma unroll
+      for (int o2 = 0; o2 < kRowsPerWarp; o2 += 2) {
+        f2 fq[2][3], dq[2][6], Gq[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int row = r0 + 1 + o2 + u, gy = oy + row;
+          ok[u] = row >= 2 && row <= kBwdH + 1 && gy < h && col_ok;
+          SDE_CHECK(!ok[u] || (gy >= 0 && gy < h && gxp >= 0 && gxp + 1 < w));
+          const int pix = ok[u] ? gy * w + gxp : 0;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) fq[u][k] = st.field ? ldg2(st.field + pix + k * hw) : bc2(0.0f);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) dq[u][k] = ldg2(saved + (5 + k) * hw + pix);
+          Gq[u] = smooth ? ldg2(saved + 11 * hw + pix) : bc2(0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int row = r0 + 1 + o2 + u, gy = oy + row;
+          const int pl = plane_index(row, c0 + 1);
+          f2 g0 = ld2(planes + kNG * kPlane + pl), g1 = ld2(planes + (kNG + 1) * kPlane + pl), g2 = ld2(planes + (kNG + 2) * kPlane + pl);
+          if (!ok[u]) g0 = g1 = g2 = bc2(0.0f);
+          const f2 dd = ld2(planes + kND * kPlane + pl);
+          const f2 gX = fma2(g2, dq[u][2], fma2(g1, dq[u][1], g0 * dq[u][0]));
+          const f2 gY = fma2(g2, dq[u][5], fma2(g1, dq[u][4], g0 * dq[u][3]));
+          const f2 yf = bc2((float)gy);
+          // p_i = depth n_i + tau_i, tau = K t_pose + K field
+          f2 pi[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const f2 ni = fma2(bc2(nm[3 * i + 1]), yf, nb[i]);
+            const f2 tau = fma2(bc2(mc.k[3 * i + 2]), fq[u][2], fma2(bc2(mc.k[3 * i + 1]), fq[u][1], fma2(bc2(mc.k[3 * i]), fq[u][0], bc2(sh.kt[i]))));
+            pi[i] = fma2(dd, ni, tau);
+          }
+          const f2 den = pi[2] + bc2(1e-6f);
+          f2 r = mk2(rcp_approx(lo(den)), rcp_approx(hi(den)));
+          r = fma2(fma2(den * bc2(-1.0f), r, bc2(1.0f)), r, r);
+          // pixels whose derivative planes are non-zero project inside the image (finite r, X, Y); the clamps keep the
+          // rest finite (a NaN clamps to a bound), so that their zero gradients stay zero
+          const float huge = 3.0e38f, big = 16777216.0f;
+          r = mk2(fminf(fmaxf(lo(r), -huge), huge), fminf(fmaxf(hi(r), -huge), huge));
+          const f2 X = pi[0] * r, Y = pi[1] * r;
+          const f2 ex = mk2(fminf(fmaxf(lo(X), -big), big), fminf(fmaxf(hi(X), -big), big)) + ncx;
+          const f2 ey = mk2(fminf(fmaxf(lo(Y), -big), big), fminf(fmaxf(hi(Y), -big), big)) + ncy;
+          const f2 u0 = gX * r, u1 = gY * r;
+          // K^T g_p = d loss / d (t_pose + field) of the pixels
+          const f2 gt0 = bc2(mc.cam.fx) * u0;
+          const f2 gt1 = fma2(bc2(mc.cam.sk), u0, bc2(mc.cam.fy) * u1);
+          const f2 gt2 = (fma2(gY, ey, gX * ex) * r) * bc2(-1.0f);
+          const int pix = gy * w + gxp;
+          if (gfield && ok[u]) {
+            *reinterpret_cast<unsigned long long*>(gfield + pix) = gt0.v;
+            *reinterpret_cast<unsigned long long*>(gfield + pix + hw) = gt1.v;
+            *reinterpret_cast<unsigned long long*>(gfield + pix + 2 * hw) = gt2.v;
+          }
+          // pose sums: sum gt_i [P, 1] with P = depth K^-1 [x, y, 1]^T is linear in sum gt_i depth {x, y, 1} and sum gt_i;
+          // x is fixed per lane half and applied after the rows
+          const f2 b0 = gt0 * dd, b1 = gt1 * dd, b2 = gt2 * dd;
+          Sa[0] = Sa[0] + gt0; Sa[1] = Sa[1] + gt1; Sa[2] = Sa[2] + gt2;
+          Sb[0] = Sb[0] + b0; Sb[1] = Sb[1] + b1; Sb[2] = Sb[2] + b2;
+          Sy[0] = fma2(b0, yf, Sy[0]); Sy[1] = fma2(b1, yf, Sy[1]); Sy[2] = fma2(b2, yf, Sy[2]);
+          // d/d depth: g_t . (R K^-1 [x, y, 1]^T)
+          const f2 v0 = fma2(bc2(vm[1]), yf, vb[0]), v1 = fma2(bc2(vm[4]), yf, vb[1]), v2 = fma2(bc2(vm[7]), yf, vb[2]);
+          f2 gd = fma2(gt2, v2, fma2(gt1, v1, gt0 * v0));
+          if (smooth) {
+            const float d0 = lo(dd), d1 = hi(dd);
+            const float ic0 = inv_depth(d0), ic1 = inv_depth(d1);
+            const float s0 = d0 >= 1e-6f ? -ic0 * ic0 * (lo(Gq[u]) * rmbar - homog) * g_smooth : 0.0f;
+            const float s1 = d1 >= 1e-6f ? -ic1 * ic1 * (hi(Gq[u]) * rmbar - homog) * g_smooth : 0.0f;
+            gd = gd + mk2(s0, s1);
+          }
+          if (ok[u]) *reinterpret_cast<unsigned long long*>(gout + pix) = gd.v;
+        }
+      }
+      // the twelve sums sum gt_i P_j, sum gt_i of this lane: P_j = depth (ki_j0 x + ki_j1 y + ki_j2)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const f2 sxv = Sb[i] * xs;
+        const float sx = lo(sxv) + hi(sxv), sy = lo(Sy[i]) + hi(Sy[i]), sb = lo(Sb[i]) + hi(Sb[i]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[4 * i + j] = mc.cam.ki[3 * j] * sx + mc.cam.ki[3 * j + 1] * sy + mc.cam.ki[3 * j + 2] * sb;
+        acc[4 * i + 3] = lo(Sa[i]) + hi(Sa[i]);
+      }
+    } else {
     // warp mode: the global operands of a pixel (translation field, derivative planes, smoothness gradient; all
     // coalesced) are fetched one iteration ahead
     float nx[10];
@@ -410,6 +536,7 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
         gout[pix] = gd;
         if (gfield) { gfield[pix] = gt0; gfield[pix + hw] = gt1; gfield[pix + 2 * hw] = gt2; }
       }
+    }
     }
     {
       float v16[16];

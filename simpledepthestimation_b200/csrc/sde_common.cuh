@@ -88,6 +88,11 @@ __device__ __forceinline__ f2 ndiv2(f2 a, f2 b) {
   const f2 q = a * r;                                           // -q
   return fma2(r, fma2(q, b, a), q);                             // -(q + (a - q b)/b)
 }
+__device__ __forceinline__ f2 ldg2(const float* p) {   // 8-byte aligned, global, read-only path
+  f2 r;
+  r.v = __ldg(reinterpret_cast<const unsigned long long*>(p));
+  return r;
+}
 __device__ __forceinline__ f2 ld2(const float* p) {   // 8-byte aligned
   f2 r;
   r.v = *reinterpret_cast<const unsigned long long*>(p);

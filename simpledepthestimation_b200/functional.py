@@ -48,15 +48,20 @@ class MonoLossPlan:
     a call reports an error.  Mirrors the options read by the reference's
     MonoDepth2Model.__init__ (detectron2/modeling/meta_arch/MonoDepth2.py:26-46).
 
-    Scheduling of a step's three kernels (warp, loss forward, loss backward).  Default (streams=1): one stream, the
-    launches chained with TILE-level dependencies (sde_mono_loss_step / sde_mono_loss_forward, include/sde_loss.h: a
-    forward tile waits for the chunks of the warp kernel that hold its rows, a backward tile for the forward tiles of
-    its image), so each kernel fills the SMs its predecessor leaves idle while it drains -- at 640x192 x 12 the three
-    launches otherwise spend ~17 % of their time in such tails.  streams=K > 1: the batch as K contiguous sub-batches,
-    each on its own side stream of the calling stream with grid-level dependencies (sde_mono_desc.norm_batch makes
-    their losses and gradients add up to the whole batch's); measured equal for forward_backward() (251 us either
-    way at cfg2) and slower for separate forward() / backward() calls (267 against 257 us), kept as an option.  The
-    calling stream waits for the side streams before a call returns, so callers see ordinary stream semantics.
+    Scheduling of a step's three kernels (warp, loss forward, loss backward); measured at 640x192 x 12 with the
+    two-sources-per-pass backward kernel (profiles/r2_notes.md), where the launches of a batch of 12 alone would spend
+    ~17 % of their time starting up and draining:
+      streams=1   one stream, the launches chained with TILE-level dependencies (sde_mono_loss_step /
+                  sde_mono_loss_forward, include/sde_loss.h: a forward tile waits for the chunks of the warp kernel that
+                  hold its rows, a backward tile for the forward tiles of its image), so each kernel fills the SMs its
+                  predecessor leaves idle.  forward_backward() 246 us, forward() + backward() 251 us.
+      streams=K   the batch as K contiguous sub-batches, each on its own side stream of the calling stream with
+                  grid-level dependencies (sde_mono_desc.norm_batch makes their losses and gradients add up to the whole
+                  batch's; a sub-batch's kept planes stay in L2 between its kernels).  K = 2: forward_backward() 244 us,
+                  forward() + backward() 259 us (each must rejoin the calling stream before it returns).
+      None        (default) each call in its faster form: forward_backward() on two sub-batch streams when the batch is
+                  even and >= 4, forward() / backward() through a single-stream plan (split_plan()).
+    The calling stream waits for the side streams before a call returns, so callers see ordinary stream semantics.
     """
 
     def __init__(self, batch: int, sizes: Sequence[Sequence[int]], n_sources: int, full_size: Sequence[int],
@@ -72,8 +77,9 @@ class MonoLossPlan:
         self.device = torch.device(device)
         self.batch, self.sizes, self.n_sources = batch, [tuple(s) for s in sizes], n_sources
         self.full_size = tuple(full_size)
+        auto = streams is None and not os.environ.get("SDE_MONO_STREAMS")
         if streams is None:
-            streams = int(os.environ.get("SDE_MONO_STREAMS", "0")) or 1
+            streams = int(os.environ.get("SDE_MONO_STREAMS", "0")) or (2 if batch >= 4 and batch % 2 == 0 else 1)
         if streams < 1 or batch % streams != 0:
             raise _lib.SdeError(f"streams ({streams}) must divide the batch ({batch})")
         self.parts, self.sub_batch = int(streams), batch // int(streams)
@@ -107,6 +113,16 @@ class MonoLossPlan:
         self.stats = torch.empty(len(sizes) * batch * 2, dtype=torch.float32, device=self.device)
         self._partial = torch.empty(self.parts, 2, dtype=torch.float32, device=self.device) if self.parts > 1 else None
         self._side = None
+        # streams=None: forward_backward() runs the sub-batches on two streams, separate forward() / backward() calls (the
+        # autograd path) go to a single-stream plan with tile-level dependencies -- each the faster form for its call
+        self._split = None
+        if auto and self.parts > 1:
+            self._split = MonoLossPlan(batch, sizes, n_sources, full_size, device, ssim_weight, c1, c2, smooth_weight, automask,
+                                       reduce, save_warped, depth_mode, min_depth, max_depth, streams=1)
+
+    def split_plan(self) -> "MonoLossPlan":
+        """The plan that serves separate forward() / backward() calls (its `stats` travel between them)."""
+        return self._split if self._split is not None else self
 
     def _check_status(self, st, what):
         if st != 0:
@@ -227,6 +243,8 @@ class MonoLossPlan:
     def forward(self, target, source, depth, K, pose, want_argmin=True, out=None, argmin_out=None, warped=None):
         """Runs the forward kernel.  Returns (losses[2], argmin list).  All inputs contiguous fp32 CUDA.
         `warped` (from new_warped()) receives the warped sources for the backward pass."""
+        if self._split is not None:
+            return self._split.forward(target, source, depth, K, pose, want_argmin, out, argmin_out, warped)
         self._check(target, source, depth, K, pose)
         losses = out if out is not None else torch.empty(2, dtype=torch.float32, device=self.device)
         argmin = []
@@ -252,6 +270,8 @@ class MonoLossPlan:
                  warped=None):
         """Runs the backward kernel (reads `warped` if given, else recomputes the warp).
         Returns (grad_depth list, grad_pose list)."""
+        if self._split is not None:
+            return self._split.backward(target, source, depth, K, pose, argmin, grad_losses, grad_depth, grad_pose, warped)
         if grad_depth is None:
             grad_depth = [torch.empty_like(d) for d in depth]
         if grad_pose is None:
@@ -286,7 +306,7 @@ class _MonoLossFn(torch.autograd.Function):
         ctx.plan, ctx.n_scales, ctx.n_sources = plan, n_scales, n_sources
         ctx.warped = warped
         ctx.save_for_backward(K, *depth, *pose, *target, *[s for row in source for s in row], *argmin)
-        ctx.stats = plan.stats.clone()  # the plan may be reused before backward runs
+        ctx.stats = plan.split_plan().stats.clone()  # the plan may be reused before backward runs
         for a in argmin:
             ctx.mark_non_differentiable(a)
         return (losses[0], losses[1], *argmin)
@@ -304,7 +324,7 @@ class _MonoLossFn(torch.autograd.Function):
         argmin = list(saved[1 + 2 * n + S + n * S:])
         zero = torch.zeros((), dtype=torch.float32, device=K.device)
         g = torch.stack([g_rec if g_rec is not None else zero, g_smooth if g_smooth is not None else zero]).float()
-        plan.stats.copy_(ctx.stats)
+        plan.split_plan().stats.copy_(ctx.stats)
         grad_depth, grad_pose = plan.backward(target, source, depth, K, pose, argmin, g.contiguous(),
                                               warped=ctx.warped)
         return (None, None, None, None, *grad_depth, *grad_pose, *([None] * (n + n * S)))

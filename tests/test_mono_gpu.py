@@ -522,7 +522,10 @@ def test_sub_batch_streams_reproduce_the_single_launch(dev):
             assert rel_err(a, b) < 1e-6
     with pytest.raises(_lib.SdeError):
         MonoLossPlan(6, [(48, 160)], 2, (48, 160), dev, streams=4)
-    assert MonoLossPlan(12, [(48, 160)], 2, (48, 160), dev).parts == 1 and MonoLossPlan(12, [(48, 160)], 2, (48, 160), dev, streams=2).parts == 2
+    auto = MonoLossPlan(12, [(48, 160)], 2, (48, 160), dev)
+    assert auto.parts == 2 and auto.split_plan().parts == 1 and MonoLossPlan(3, [(48, 160)], 2, (48, 160), dev).parts == 1
+    explicit = MonoLossPlan(12, [(48, 160)], 2, (48, 160), dev, streams=2)
+    assert explicit.parts == 2 and explicit.split_plan() is explicit
 
 
 def test_forward_backward_in_one_call_matches_the_two_calls(dev):
