@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kThreads, SDE_PAIR_OCC) mono_bwd_pair_kernel(c
   const int ox = tc.x0 - kPairColOff, oy = tc.y0 - 2;
   const bool interior = ox >= 0 && oy >= 0 && ox + kHW <= w && oy + kHH <= h;
   const bool lr_border = ox + 2 <= 1 || ox + kHW - 3 >= w - 2;
+  const bool tb_border = oy + 2 <= 1 || oy + kBwdH + 1 >= h - 2;   // a row of P is image row 1 or h - 2 (doubled pad row)
 
   const bool cam_thread = tid >= 32 && tid < 32 + p.S;
   // coefficient and mask planes: the coefficient pass writes every window centre, the ring around the block reads as zero
@@ -346,9 +347,67 @@ SDE_PRAGMA_UNROLL(SDE_PAIR_UNROLL)
           }
         }
       };
+      // Tiles away from the image border (no mirrored pad column, no doubled pad row: every weight of the adjoint is 1)
+      // take the same pass as a rolled loop over row pairs with running pair sums, as the coefficient pass above.
+      auto phase3_interior = [&]() {
+        struct QRow { f2 t[3], t0[3]; };   // horizontal 3-sums of a, b, c: all windows / windows of the first source
+        auto qsum = [&](int rr) {
+          QRow n;
+          const Row4 qm = ld_row(planes + kPM * kPlane + plane_index(r0 + rr, c0));
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const Row4 q = ld_row(planes + (kPC + k) * kPlane + plane_index(r0 + rr, c0));
+            const f2 mc = q.c * qm.c, mo = q.o * qm.o;
+            n.t[k] = (q.c + swp(q.c)) + q.o;
+            n.t0[k] = (mc + swp(mc)) + mo;
+          }
+          return n;
+        };
+        auto add_q = [](const QRow& u, const QRow& v) {
+          QRow r;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { r.t[k] = u.t[k] + v.t[k]; r.t0[k] = u.t0[k] + v.t0[k]; }
+          return r;
+        };
+        auto out_row = [&](int row, const QRow& pp, const QRow& n) {
+          const int pl = plane_index(row, c0 + 1);
+          const f2 Ap = ld2(planes + (kPA + c) * kPlane + pl);
+          const f2 Sp0 = ld2(planes + (kPS0 + c) * kPlane + pl), Sp1 = ld2(planes + (kPS1 + c) * kPlane + pl);
+          const f2 va = pp.t[0] + n.t[0], vb = pp.t[1] + n.t[1], vc = pp.t[2] + n.t[2];
+          const f2 va0 = pp.t0[0] + n.t0[0], vb0 = pp.t0[1] + n.t0[1], vc0 = pp.t0[2] + n.t0[2];
+          f2 gS0 = fma2(Sp0, vb0, fma2(Ap, vc0, va0));
+          f2 gS1 = fma2(Sp1, vb - vb0, fma2(Ap, vc - vc0, va - va0));
+          const uchar2 m = *reinterpret_cast<const uchar2*>(sh.arg + pl);
+          auto l1 = [&](f2 Sp, int cand) {
+            const f2 df = Sp - Ap;
+            const float d0 = lo(df), d1 = hi(df);
+            float l0 = __int_as_float(__float_as_int(g_l1) ^ (__float_as_int(d0) & 0x80000000));
+            float l1v = __int_as_float(__float_as_int(g_l1) ^ (__float_as_int(d1) & 0x80000000));
+            l0 = (m.x == cand && d0 != 0.0f) ? l0 : 0.0f;
+            l1v = (m.y == cand && d1 != 0.0f) ? l1v : 0.0f;
+            return mk2(l0, l1v);
+          };
+          gS0 = gS0 + l1(Sp0, cand0);
+          gS1 = gS1 + l1(Sp1, cand1);
+          *reinterpret_cast<unsigned long long*>(planes + (kPS0 + c) * kPlane + pl) = gS0.v;   // in place of S_c
+          *reinterpret_cast<unsigned long long*>(planes + (kPS1 + c) * kPlane + pl) = gS1.v;
+        };
+        QRow qx = qsum(0), qy = qsum(1);
+        QRow pp = add_q(qx, qy);
+SDE_PRAGMA_UNROLL(SDE_PAIR_UNROLL)
+        for (int it = 0; it < kRowsPerWarp / 2; ++it) {
+          const int rr = 2 + 2 * it;
+          qx = qsum(rr);
+          out_row(r0 + rr - 1, pp, qx);
+          pp = add_q(qy, qx);
+          qy = qsum(rr + 1);
+          out_row(r0 + rr, pp, qy);
+          pp = add_q(qx, qy);
+        }
+      };
       if (use_ssim) {
-        if (lr_border) phase3(std::true_type{}, std::true_type{});
-        else           phase3(std::false_type{}, std::true_type{});
+        if (lr_border || tb_border) phase3(std::true_type{}, std::true_type{});
+        else                        phase3_interior();
       } else {
         phase3(std::false_type{}, std::false_type{});
       }

@@ -395,10 +395,9 @@ __device__ __forceinline__ void stage_source(const StageArgs& a0, const Cam& cam
 // Phase 1 of the backward kernel when the forward pass kept the warped source: plain coalesced
 // loads of the halo'd tile (a reflected halo position takes the warp of the reflected pixel,
 // which is what re-projecting it would give).
+// (What another kernel of the same step produced -- argmin bytes, warped planes, smoothness gradient -- is read through
+// ld_prod, sde_common.cuh: under flow the producer grid may still be running.)
 template <bool INTERIOR>
-// (what another kernel of the same step produced -- argmin bytes, warped planes, smoothness gradient -- is read with
-// ld.global.cg: under flow (mono_params.cuh) the producer grid may still be running, and L1 must not keep a line that
-// straddles a finished and an unfinished image)
 __device__ __forceinline__ void stage_saved(const StageArgs& a0, const float* __restrict__ warped, int tid) {
   StageArgs a = a0;
   const float* wp = pinned(warped);
