@@ -48,34 +48,43 @@ __global__ void __launch_bounds__(kThreads, SDE_PAIR_OCC) mono_bwd_pair_kernel(c
                                                                               const __grid_constant__ MonoTma maps) {
   extern __shared__ __align__(128) float planes[];  // [kPairPlanes][kPlane]
   __shared__ PairShared sh;
+  __shared__ int next_item;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int vbid = (int)blockIdx.x;
-  const TileCoord tc = decode_btile(p, vbid);
-  const int s = tc.s, b = tc.b, h = p.h[s], w = p.w[s], hw = h * w;
   const bool automask = (p.flags & SDE_MONO_AUTOMASK) != 0;
   const bool use_ssim = p.ssim_w > 0.0f;
-  // plane (yy, xx) <-> image (oy + yy, ox + xx); Q = plane [1..16]x[1..64]; P = plane [2..15]x[3..62]
-  const int ox = tc.x0 - kPairColOff, oy = tc.y0 - 2;
-  const bool interior = ox >= 0 && oy >= 0 && ox + kHW <= w && oy + kHH <= h;
-  const bool lr_border = ox + 2 <= 1 || ox + kHW - 3 >= w - 2;
-  const bool tb_border = oy + 2 <= 1 || oy + kBwdH + 1 >= h - 2;   // a row of P is image row 1 or h - 2 (doubled pad row)
-
   const bool cam_thread = tid >= 32 && tid < 32 + p.S;
-  // coefficient and mask planes: the coefficient pass writes every window centre, the ring around the block reads as zero
+  // coefficient and mask planes: the coefficient pass writes every window centre, the ring around the block reads as
+  // zero (no tile ever writes it: once per CTA)
   zero_ring<4>(planes, kPC, tid);
-  const bool tma = p.tma[s] != 0;
-  if (tma && tid == 0) {
+  if (tid == 0) {
     mbar_init(&sh.bar, 1);
     mbar_init_fence();
   }
   const bool flow_i = (p.flow & kFlowImage) != 0;   // see mono_bwd.cu
   SDE_TRACE_BEGIN(p, 2);
   if (!flow_i) pdl_wait();
-  else if (tid == 0) {
+  const int total = p.btile_start[p.n_scales];
+  int total_b = 0;   // tiles of one sample, all scales
+  for (int ss = 0; ss < p.n_scales; ++ss) total_b += p.btiles_x[ss] * p.btiles_y[ss];
+  int vbid = 0;
+  bool first = true;
+  unsigned tma_phase = 0;   // parity of the TMA barrier: carried from tile to tile
+  // work items: gradient tiles in list order (mono_params.cuh: work_next)
+  while (work_next(p, 2, total, &next_item, vbid, first)) {
+  const TileCoord tc = decode_btile(p, vbid);
+  const int s = tc.s, b = tc.b, h = p.h[s], w = p.w[s], hw = h * w;
+  // plane (yy, xx) <-> image (oy + yy, ox + xx); Q = plane [1..16]x[1..64]; P = plane [2..15]x[3..62]
+  const int ox = tc.x0 - kPairColOff, oy = tc.y0 - 2;
+  const bool interior = ox >= 0 && oy >= 0 && ox + kHW <= w && oy + kHH <= h;
+  const bool lr_border = ox + 2 <= 1 || ox + kHW - 3 >= w - 2;
+  const bool tb_border = oy + 2 <= 1 || oy + kBwdH + 1 >= h - 2;   // a row of P is image row 1 or h - 2 (doubled pad row)
+  const bool tma = p.tma[s] != 0;
+  if (flow_i && tid == 0) {
     flag_wait(p.img_flag + s * p.B + b);
     flag_proxy_fence();
   }
+  if (tma && tid == 0 && ((p.persist >> 2) & 1)) proxy_fence();   // the planes were last written by this CTA's own stores
   CamRaw raw;
   if (cam_thread) load_cam_raw(raw, p.K, p.pose[tid - 32], b);
   auto load_pair = [&](int j0, bool first) {   // thread 0: target + depth (first pair only) and the pair's warped planes
@@ -123,7 +132,6 @@ __global__ void __launch_bounds__(kThreads, SDE_PAIR_OCC) mono_bwd_pair_kernel(c
   sa.planes = planes; sa.arg = sh.arg; sa.oy = oy; sa.ox = ox; sa.h = h; sa.w = w; sa.hw = hw;
   sa.plS = kPS0; sa.plI = 0; sa.plA = kPA; sa.plD = kPD;
   // ------------------------------------------------------------------ phase 0: argmin bytes (+ depth, target without TMA)
-  unsigned tma_phase = 0;
   if (tma) {
     if ((reinterpret_cast<uintptr_t>(amap) & 3) == 0) stage_arg_words(sh.arg, amap, oy, ox, h, w, false, tid);
     else stage_arg(sh.arg, amap, oy, ox, h, w, false, tid);
@@ -532,7 +540,7 @@ SDE_PRAGMA_UNROLL(SDE_PAIR_UNROLL)
     }
   }
 
-  pdl_launch_dependents();
+  if (!((p.persist >> 2) & 1)) pdl_launch_dependents();
   // ------------------------------------------------------------------ smoothness gradient + store (mono_bwd.cu)
   {
     const float sscale = p.smooth_scale[s];
@@ -578,13 +586,11 @@ SDE_PRAGMA_UNROLL(SDE_PAIR_UNROLL)
 
   // ------------------------------------------------------------------ last tile of a sample: pose gradients (mono_bwd.cu)
   SDE_TRACE_MARK(p, 2, 1);
-  int total_b = 0;
-  for (int ss = 0; ss < p.n_scales; ++ss) total_b += p.btiles_x[ss] * p.btiles_y[ss];
   if ((lane & 1) == 0 && warp_slot(lane) < 12) publish_fence();
   __syncthreads();
   if (tid == 0) sh.ticket = atomicAdd(p.smp_counter + b, 1u);
   __syncthreads();
-  if (sh.ticket != (unsigned)(total_b - 1)) return;
+  if (sh.ticket != (unsigned)(total_b - 1)) continue;
   publish_fence();
   if (flow_i) {
     if (tid < p.n_scales) p.img_flag[tid * p.B + b] = 0u;
@@ -645,6 +651,9 @@ SDE_PRAGMA_UNROLL(SDE_PAIR_UNROLL)
     }
   }
   if (tid == 0) p.smp_counter[b] = 0u;   // leave the workspace zeroed for the next call
+  }   // work items
+  if (((p.persist >> 2) & 1)) pdl_launch_dependents();
+  work_leave(p, 2);
 }
 
 size_t mono_bwd_pair_smem_bytes() { return (size_t)kPairPlanes * kPlane * sizeof(float); }
@@ -652,7 +661,13 @@ size_t mono_bwd_pair_smem_bytes() { return (size_t)kPairPlanes * kPlane * sizeof
 cudaError_t launch_mono_bwd_pair(const MonoParams& p, const MonoTma& t, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(mono_bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mono_bwd_pair_smem_bytes());
   if (e != cudaSuccess) return e;
-  return launch_chained(2, mono_bwd_pair_kernel, (unsigned)p.btile_start[p.n_scales], kThreads, mono_bwd_pair_smem_bytes(), stream, p, t);
+  unsigned grid = (unsigned)p.btile_start[p.n_scales];
+  if (((p.persist >> 2) & 1)) {
+    static unsigned slots = 0;
+    if (!slots) slots = resident_ctas(mono_bwd_pair_kernel, kThreads, mono_bwd_pair_smem_bytes());
+    if (slots && grid > slots) grid = slots;
+  }
+  return launch_chained(2, mono_bwd_pair_kernel, grid, kThreads, mono_bwd_pair_smem_bytes(), stream, p, t);
 }
 
 }  // namespace sde

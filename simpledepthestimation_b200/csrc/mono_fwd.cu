@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
                                                                        const __grid_constant__ MonoTma maps) {
   extern __shared__ __align__(128) float planes[];  // [kFwdPlanes][kPlane]
   __shared__ FwdShared sh;
+  __shared__ int next_item;
   constexpr int NC = AUTOMASK ? 2 : 1;             // candidates per source: warp [+ identity]
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -62,25 +63,32 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   // flow (tile-level dependencies, mono_params.cuh): list order instead -- the chunks of the first tiles were written
   // first, and the images the backward kernel starts with complete first.
   const bool flow_w = (p.flow & kFlowWarp) != 0, flow_i = (p.flow & kFlowImage) != 0;
-  const int vbid = flow_w ? (int)blockIdx.x : (int)(gridDim.x - 1 - blockIdx.x);
-  const TileCoord tc = decode_tile(p, vbid);
-  const int s = tc.s, b = tc.b, h = p.h[s], w = p.w[s], hw = h * w;
   const bool reduce_mean = (p.flags & SDE_MONO_REDUCE_MEAN) != 0;
-  // TMA path (row pitch a multiple of 16 bytes): target, depth and the first source's unwarped frame (the
-  // identity candidate) are handed to the copy engine before anything else happens in the CTA
-  const bool tma = p.tma[s] != 0;
-  const bool prewarp = p.prewarp[s] != 0;   // the warped sources come from the warp kernel (mono_warp.cu)
-  const int ox = tc.x0 - 1, oy = tc.y0 - 1;
-  if (tma && tid == 0) {
+  if (tid == 0) {
     mbar_init(&sh.bar, 1);
     mbar_init_fence();
   }
   // without flow: the warp kernel's planes (and every other tensor) are complete and visible from here on.  With flow
-  // the warp kernel may still be running: this tile's inputs are complete (the warp kernel itself was serialised behind
+  // the warp kernel may still be running: a tile's inputs are complete (the warp kernel itself was serialised behind
   // whatever produced them), the warped planes of its rows once their chunk flags are set.
   SDE_TRACE_BEGIN(p, 1);
   if (!flow_w) pdl_wait();
   if (flow_i) pdl_launch_dependents();   // backward tiles wait for image flags, not for this grid
+  const int total = p.tile_start[p.n_scales];
+  int item = 0;
+  bool first = true;
+  unsigned tma_phase = 0;   // parity of the TMA barrier: carried from tile to tile
+  // work items: tiles (mono_params.cuh: work_next)
+  while (work_next(p, 1, total, &next_item, item, first)) {
+  const int vbid = flow_w ? item : total - 1 - item;
+  const TileCoord tc = decode_tile(p, vbid);
+  const int s = tc.s, b = tc.b, h = p.h[s], w = p.w[s], hw = h * w;
+  // TMA path (row pitch a multiple of 16 bytes): target, depth and the first source's unwarped frame (the
+  // identity candidate) are handed to the copy engine before anything else happens for the tile
+  const bool tma = p.tma[s] != 0;
+  const bool prewarp = p.prewarp[s] != 0;   // the warped sources come from the warp kernel (mono_warp.cu)
+  const int ox = tc.x0 - 1, oy = tc.y0 - 1;
+  if (tma && tid == 0 && ((p.persist >> 1) & 1)) proxy_fence();   // the planes were last written by this CTA's own stores
   if (tma && tid == 0) {
     mbar_arrive_expect_tx(&sh.bar, (4 + (AUTOMASK ? 3 : 0) + (p.prewarp[s] ? 3 : 0)) * kPlaneBytesTma);
 #pragma unroll
@@ -144,7 +152,6 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   sa.planes = planes; sa.arg = nullptr; sa.oy = tc.y0 - 1; sa.ox = tc.x0 - 1; sa.h = h; sa.w = w; sa.hw = hw;
   sa.plS = kPlS; sa.plI = kPlI; sa.plA = kPlA; sa.plD = kPlD;
   // ------------------------------------------------------------------ phase 0: depth + target
-  unsigned tma_phase = 0;
   if (tma) {
     mbar_wait(&sh.bar, tma_phase);
     tma_phase ^= 1u;
@@ -292,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
 
   // the heavy part of this tile is done: once that holds for every tile, the next kernel of the stream may be
   // scheduled (it waits for this grid to complete before it touches memory)
-  if (!flow_i) pdl_launch_dependents();
+  if (!flow_i && !((p.persist >> 1) & 1)) pdl_launch_dependents();
   // ------------------------------------------------------------------ per-thread sums, argmin, smoothness
   float rec = 0.0f, smx = 0.0f, smy = 0.0f, sinv = 0.0f;
   const int gx0 = tc.x0 + c0;  // image column of this lane's first pixel
@@ -331,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
     sh.ticket = atomicAdd(p.img_counter + q, 1u);
   }
   __syncthreads();
-  if (sh.ticket != (unsigned)(per - 1)) return;
+  if (sh.ticket != (unsigned)(per - 1)) continue;
   publish_fence();
   {
     const float* part = p.partials + ((size_t)p.tile_start[s] + (size_t)b * per) * 4;
@@ -381,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
   }
   __syncthreads();
   const int pairs = p.n_scales * p.B;
-  if (sh.ticket != (unsigned)(pairs - 1)) return;
+  if (sh.ticket != (unsigned)(pairs - 1)) continue;
   publish_fence();
   // flow: this grid did not wait for the warp kernel as a grid; the last CTA does (the warp kernel has long finished),
   // so that the completion of this grid implies the completion of the one before it
@@ -397,6 +404,9 @@ __global__ void __launch_bounds__(kThreads, SDE_FWD_OCC) mono_fwd_kernel(const _
       *p.counter = 0u;
     }
   }
+  }   // work items
+  if (!flow_i && ((p.persist >> 1) & 1)) pdl_launch_dependents();
+  work_leave(p, 1);
 }
 
 size_t mono_fwd_smem_bytes() { return (size_t)kFwdPlanes * kPlane * sizeof(float); }
@@ -408,7 +418,14 @@ cudaError_t launch_mono_fwd(const MonoParams& p, const MonoTma& t, cudaStream_t 
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mono_fwd_smem_bytes());
   if (e != cudaSuccess) return e;
   if (SDE_FWD_CARVEOUT >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, SDE_FWD_CARVEOUT);
-  return launch_chained(1, kernel, (unsigned)p.tile_start[p.n_scales], kThreads, mono_fwd_smem_bytes(), stream, p, t);
+  unsigned grid = (unsigned)p.tile_start[p.n_scales];
+  if (((p.persist >> 1) & 1)) {
+    static unsigned slots[2] = {0, 0};
+    unsigned& sl = slots[automask ? 1 : 0];
+    if (!sl) sl = resident_ctas(kernel, kThreads, mono_fwd_smem_bytes());
+    if (sl && grid > sl) grid = sl;
+  }
+  return launch_chained(1, kernel, grid, kThreads, mono_fwd_smem_bytes(), stream, p, t);
 }
 
 }  // namespace sde

@@ -80,11 +80,45 @@ struct MonoParams {
   unsigned flow;
   unsigned* warp_flag;    // [warp grid]
   unsigned* img_flag;     // [n_scales*B]
+  // Persistent CTAs (bit k of `persist`: 0 warp, 1 forward, 2 backward kernel): the grid is one CTA per resident slot
+  // (occupancy x SMs) and every CTA takes work items -- chunks of the warp kernel, tiles of the loss kernels, in list
+  // order -- from a queue in the workspace until it is empty.  queue[2k] = next item, queue[2k + 1] = CTAs that have
+  // left (the last one clears both).  Bit clear: one item per CTA, grid = number of items.
+  // Measured (profiles/r2_notes.md): per-CTA time stamps show a slot empty for 2.1-2.3 us between a CTA's last
+  // instruction and its successor's first, but most of that is the CTA's other warps finishing and its stores draining,
+  // which a loop pays as well -- persistent CTAs gain 3.6 % for the backward kernel at batch 96, nothing at batch 12,
+  // and cost the warp / forward kernels 2 % (queue atomics and a barrier per item).  Default: backward only.
+  int persist;
+  unsigned* queue;        // [6]
 #ifdef SDE_TRACE
   unsigned long long* trace;
 #endif
 };
 constexpr unsigned kFlowWarp = 1u, kFlowImage = 2u;
+
+// Work-item loop of the three kernels: `persist` -- take the next item of queue k (thread 0 fetches, `slot` broadcasts
+// it; the barrier also separates the previous item's shared-memory traffic from the next one's), else the one item
+// blockIdx.x.  Returns false when there is nothing left; the caller then calls work_leave().
+__device__ __forceinline__ bool work_next(const MonoParams& p, int k, int total, int* slot, int& item, bool& first) {
+  if ((p.persist >> k) & 1) {
+    if (threadIdx.x == 0) *slot = (int)atomicAdd(p.queue + 2 * k, 1u);
+    __syncthreads();
+    item = *slot;
+  } else {
+    if (!first) return false;
+    item = (int)blockIdx.x;
+  }
+  first = false;
+  return item < total;
+}
+__device__ __forceinline__ void work_leave(const MonoParams& p, int k) {
+  if (((p.persist >> k) & 1) && threadIdx.x == 0) {
+    if (atomicAdd(p.queue + 2 * k + 1, 1u) == gridDim.x - 1) {   // every CTA has fetched its last (out-of-range) item
+      p.queue[2 * k] = 0u;
+      p.queue[2 * k + 1] = 0u;
+    }
+  }
+}
 
 // Tensor maps over the [planes, h, w] inputs of every scale, box {68, 18, 1} (tma.cuh).  Second kernel
 // parameter: the copy engine reads the descriptors straight from the parameter space.

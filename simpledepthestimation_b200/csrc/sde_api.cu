@@ -45,7 +45,7 @@ static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 struct MonoLayout {
   int grid, bgrid, wgrid;
-  size_t off_imgc, off_smpc, off_fin, off_partials, off_pose, off_wflag, off_iflag, total;
+  size_t off_imgc, off_smpc, off_fin, off_partials, off_pose, off_queue, off_wflag, off_iflag, total;
 };
 
 static int mono_check(const sde_mono_desc* d) {
@@ -83,12 +83,27 @@ static MonoLayout mono_layout(const sde_mono_desc* d) {
   off = align16(off + (size_t)L.grid * 4 * sizeof(float));
   L.off_pose = off;
   off = align16(off + (size_t)L.bgrid * (kThreads / 32) * d->n_sources * 12 * sizeof(float));
+  L.off_queue = off;   // persistent CTAs: (next item, CTAs gone) per kernel
+  off = align16(off + 6 * sizeof(unsigned));
   L.off_wflag = off;   // flow: one flag per block of the warp kernel, one per (scale, image)
   off = align16(off + (size_t)L.wgrid * sizeof(unsigned));
   L.off_iflag = off;
   off = align16(off + (size_t)d->n_scales * d->batch * sizeof(unsigned));
   L.total = off;
   return L;
+}
+
+// Which kernels run persistent CTAs (mono_params.cuh: persist): bit 0 warp, 1 forward, 2 backward.  SDE_PERSIST=<bits>
+// overrides the default 4; calls with SDE_MONO_NO_FLOW never do (two calls on two streams would take the machine in
+// turns instead of sharing it).
+static int g_persist = -1;
+static int read_persist() {
+  const char* m = getenv("SDE_PERSIST");
+  return m ? (atoi(m) & 7) : 4;
+}
+static int persist_mask() {
+  if (g_persist < 0) g_persist = read_persist();
+  return g_persist;
 }
 
 static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool backward, MonoParams& p) {
@@ -163,6 +178,8 @@ static int mono_params(const sde_mono_desc* d, const sde_mono_buffers* b, bool b
   p.fin = reinterpret_cast<double*>(ws + L.off_fin);
   p.partials = reinterpret_cast<float*>(ws + L.off_partials);
   p.pose_partials = reinterpret_cast<float*>(ws + L.off_pose);
+  p.queue = reinterpret_cast<unsigned*>(ws + L.off_queue);
+  p.persist = (d->flags & SDE_MONO_NO_FLOW) ? 0 : persist_mask();
   p.warp_flag = reinterpret_cast<unsigned*>(ws + L.off_wflag);
   p.img_flag = reinterpret_cast<unsigned*>(ws + L.off_iflag);
   p.grad_losses = b->grad_losses;
@@ -589,7 +606,7 @@ extern "C" int sde_debug_trace(unsigned long long* dst) {
 }
 #endif
 
-void sde_reload_env(void) { g_pdl_mask = read_pdl_mask(); g_flow_mask = read_flow_mask(); g_bwd_pair = read_bwd_pair(); }
+void sde_reload_env(void) { g_pdl_mask = read_pdl_mask(); g_flow_mask = read_flow_mask(); g_bwd_pair = read_bwd_pair(); g_persist = read_persist(); }
 
 size_t sde_mono_workspace_bytes(const sde_mono_desc* desc) {
   if (mono_check(desc) != SDE_OK) return 0;

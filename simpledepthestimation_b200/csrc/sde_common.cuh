@@ -181,6 +181,18 @@ inline cudaError_t launch_chained(int which, void (*kernel)(KArgs...), unsigned 
 }
 #endif
 
+#ifndef __CUDACC_RTC__
+// CTAs of `kernel` that are resident at once on the current device (occupancy x SMs): the grid of a persistent launch
+template <class K>
+inline unsigned resident_ctas(K kernel, int threads, size_t smem) {
+  int dev = 0, sms = 0, occ = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess)
+    return 0;
+  return (unsigned)(occ * sms);
+}
+#endif
+
 // Fence between publishing a partial-result slot and taking the ticket (and, on the reading side, between the ticket and
 // the slots).  SDE_FENCE_ACQREL: the release / acquire form instead of the sequentially consistent __threadfence().
 __device__ __forceinline__ void publish_fence() {

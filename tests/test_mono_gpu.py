@@ -601,3 +601,43 @@ def test_tile_level_dependencies_give_the_same_bits(dev, monkeypatch, B, H, W):
                     assert torch.allclose(outs[k][0], ref[k][0], rtol=1e-6, atol=0)   # losses: summation order of the sub-batches
                     for x, y in zip(outs[k][1:], ref[k][1:]):
                         assert torch.equal(x, y), f"mask {mask} streams {streams}"
+
+
+def test_persistent_work_queues_give_the_same_bits(dev, monkeypatch):
+    """SDE_PERSIST selects which kernels run one CTA per resident slot over a work queue in the workspace (bit 0 warp,
+    1 forward, 2 backward; default 4) instead of one CTA per chunk / tile.  Same tiles, same arithmetic: every output
+    must carry the bits of the plain launches, over repeated steps on alternating inputs (a queue that was not cleared
+    would leave the next step without work), with and without tile-level dependencies, for both calling forms."""
+    from simpledepthestimation_b200.functional import MonoLossPlan
+
+    B, H, W = 4, 96, 320
+    g = lambda t: t.to(dev).contiguous()  # noqa: E731
+    sets = []
+    for seed in (51, 52):
+        inp = mono_inputs(B, H, W, seed=seed)
+        tgt, src = build_pyramid(inp)
+        sets.append(([g(t) for t in tgt], [[g(x) for x in row] for row in src], [g(d) for d in inp["depth"]], g(inp["K"]),
+                     [g(euler_pose(v)) for v in inp["pose_vec"]]))
+    sizes = [tuple(d.shape[-2:]) for d in inp["depth"]]
+    gl = torch.tensor([1.0, 1.0], device=dev)
+    ref = None
+    for flow in ("3", "0"):
+        monkeypatch.setenv("SDE_FLOW_MASK", flow)
+        for persist in ("0", "4", "7"):
+            monkeypatch.setenv("SDE_PERSIST", persist)
+            plan = MonoLossPlan(B, sizes, 2, (H, W), dev, streams=1)
+            saved = plan.new_warped()
+            outs = []
+            for it in range(4):
+                if it < 2:
+                    l, a, gd, gp = plan.forward_backward(*sets[it % 2], gl, warped=saved)
+                else:
+                    l, a = plan.forward(*sets[it % 2], warped=saved)
+                    gd, gp = plan.backward(*sets[it % 2], a, gl, warped=saved)
+                outs.append([t.clone() for t in [l] + a + gd + gp])
+            torch.cuda.synchronize()
+            if ref is None:
+                ref = outs
+            for it in range(4):
+                for x, y in zip(outs[it], ref[it % 2]):
+                    assert torch.equal(x, y), f"flow {flow} persist {persist} step {it}"

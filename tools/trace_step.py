@@ -49,6 +49,25 @@ for k in range(3):
     print(f"{names[k]:5s} {n:5d} CTAs  first start {st.min():7.1f}  last start {st.max():7.1f}  last end {en.max():7.1f} us  "
           f"CTA life mean {np.mean(en - st):6.1f} p10 {np.percentile(en - st, 10):6.1f} p90 {np.percentile(en - st, 90):6.1f}  "
           f"start->past wait mean {np.mean(wt - st):5.2f} max {np.max(wt - st):6.1f}")
+# refill gaps: on every SM, the time between a CTA's exit and the start of the CTA that takes its slot
+for k in range(3):
+    n = int((buf[k, :, 0] > 0).sum())
+    st = (buf[k, :n, 0].astype(np.int64) - t0) / 1e3
+    en = (buf[k, :n, 1].astype(np.int64) - t0) / 1e3
+    sm = buf[k, :n, 2].astype(np.int64)
+    gaps = []
+    for m in np.unique(sm):
+        idx = np.where(sm == m)[0]
+        ev = sorted([(st[i], 1) for i in idx] + [(en[i], -1) for i in idx])
+        free_since = []
+        for t, kind in ev:
+            if kind == -1:
+                free_since.append(t)
+            elif free_since:
+                gaps.append(t - free_since.pop(0))
+    gaps = np.array(gaps) if gaps else np.zeros(1)
+    print(f"{names[k]:5s} refill gap per CTA: mean {gaps.mean():5.2f} us  p50 {np.percentile(gaps, 50):5.2f}  p90 {np.percentile(gaps, 90):5.2f}  "
+          f"sum {gaps.sum() / 1e3:6.2f} ms over {len(gaps)} refills = {gaps.sum() / max(len(np.unique(sm)), 1):6.1f} us per SM")
 end = max(en.max() for _, en in spans)
 print("resident CTAs per 5 us bin (warp / fwd / bwd):")
 for lo in np.arange(0, end, 5.0):
