@@ -131,11 +131,14 @@ __device__ __forceinline__ void flag_wait(const unsigned* f) {
 // finished and an unfinished image (these tensors are [B, h, w]: one image follows the other).
 template <class T>
 __device__ __forceinline__ T ld_prod(const T* p) { return __ldcg(p); }
-// The derivative planes of the warp kernel keep the read-only path (ld.global.nc: the compiler may issue these loads a
-// phase early, worth 8 us of the backward kernel at cfg2): a line of planes 3..8 of an image never holds another
-// image's data that is read through L1 (planes 0..2 on either side go through the copy engine), and nobody reads it
-// before the image's flag.  `launder` hides a pointer's value from the compiler at a point behind the flag wait, so
-// that no such load can be hoisted above it.
+// The derivative planes of the warp kernel keep the L1-allocating read-only path (ld.global.nc).  Measured at cfg2: the
+// backward kernel takes 130.8 us with it, 138.3 us with ld.global.nc.L1::no_allocate (SASS LDG.E.NA) and 138-140 us with
+// ld.global.cg -- the 60-wide gradient tiles share 128-byte lines with their neighbours, and the compiler issues these
+// loads a phase early.  Why no stale line can be hit under flow: a step's warp kernel is an ordinary launch behind the
+// previous step's backward kernel, so L1 is invalidated before the planes are rewritten; within the step nobody reads a
+// line of planes 3..8 of an image before the image's flag, and such a line never holds another image's L1-read data
+// (planes 0..2 on either side go through the copy engine).  `launder` hides a pointer's value from the compiler at a
+// point behind the flag wait, so that no such load can be hoisted above it.
 template <class T>
 __device__ __forceinline__ T ld_plane(const T* p) { return __ldg(p); }
 __device__ __forceinline__ unsigned launder_zero() { unsigned z = 0; asm volatile("" : "+r"(z)); return z; }
