@@ -56,6 +56,9 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
     // warp mode: warped rgb, depth error, valid/occlusion from the forward pass, frame A and depth A by TMA
     mbar_init(&sh.bar, 1);
     mbar_init_fence();
+  }
+  pdl_wait();   // the forward pass's planes and statistics (and every other tensor) are complete from here on
+  if (tma && tid == 0) {
     mbar_arrive_expect_tx(&sh.bar, 9 * kPlaneBytesTma);
     const int bx = ox - kColOff;
 #pragma unroll
@@ -538,6 +541,7 @@ __global__ void __launch_bounds__(kThreads, 4) motion_bwd_kernel(const __grid_co
       }
     }
     }
+    pdl_launch_dependents();
     {
       float v16[16];
 #pragma unroll
@@ -600,8 +604,7 @@ cudaError_t launch_motion_bwd(const MotionParams& p, const MotionTma& t, cudaStr
   cudaError_t e = cudaFuncSetAttribute(motion_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)motion_bwd_smem_bytes());
   if (e != cudaSuccess) return e;
-  motion_bwd_kernel<<<p.n_dirs * p.btiles_per_dir, kThreads, motion_bwd_smem_bytes(), stream>>>(p, t);
-  return cudaGetLastError();
+  return launch_chained(2, motion_bwd_kernel, (unsigned)(p.n_dirs * p.btiles_per_dir), kThreads, motion_bwd_smem_bytes(), stream, p, t);
 }
 
 }  // namespace sde

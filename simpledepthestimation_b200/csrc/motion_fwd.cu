@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kStatThreads, 3) motion_stats_kernel(const __g
   const int img = blockIdx.x / p.stat_blocks, chunk = blockIdx.x - img * p.stat_blocks;
   const int dir = img / p.B, b = img - dir * p.B;
   const int hw = p.h * p.w;
+  pdl_wait();   // (plain launch unless bit 1 of SDE_PDL_MASK's motion half is set: see launch_motion_fwd)
   if (tid == 0) load_mcam(s_cam, p.K, p.pose[dir], b, p.sx, p.sy);
   __syncthreads();
   const MCam mc = s_cam;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(kStatThreads, 3) motion_stats_kernel(const __g
       }
     }
   }
+  pdl_launch_dependents();   // the heavy part of this block is done (mono_fwd.cu)
   socc = warp_sum(socc); serr = warp_sum(serr);
   if (lane == 0) { red[0][wid] = socc; red[1][wid] = serr; }
   __syncthreads();
@@ -171,6 +173,9 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
     // brings them in together with frame A and depth A (U and WZ are computed in place of the last two)
     mbar_init(&sh.bar, 1);
     mbar_init_fence();
+  }
+  pdl_wait();   // the statistics pass's planes and per-sample moments (and every other tensor) are complete from here on
+  if (tma && tid == 0) {
     mbar_arrive_expect_tx(&sh.bar, 9 * kPlaneBytesTma);
     const int bx = tx0 - 1 - kColOff, by = ty0 - 1;
 #pragma unroll
@@ -359,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
     }
   }
 
+  pdl_launch_dependents();
   // ------------------------------------------------------------------ smoothness(depth_A, frame_A)
   float smx = 0.0f, smy = 0.0f, sinv = 0.0f;
   // warp mode: the local smoothness gradient goes to plane 11 of `warped` for the backward pass
@@ -447,13 +453,14 @@ cudaError_t launch_motion_fwd(const MotionParams& p, const MotionTma& t, cudaStr
     cudaError_t e0 = cudaGetLastError();
     if (e0 != cudaSuccess) return e0;
   }
+  // the statistics pass is a plain launch (a gather kernel whose blocks start in lock-step behind a chained launch loses more
+  // than the launch latency, cf. mono_warp.cu); the loss kernel is chained behind it (bit 1 of the launch mask)
   motion_stats_kernel<<<p.n_dirs * p.B * p.stat_blocks, kStatThreads, 0, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(motion_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)motion_fwd_smem_bytes());
   if (e != cudaSuccess) return e;
-  motion_fwd_kernel<<<p.n_dirs * p.tiles_per_dir, kThreads, motion_fwd_smem_bytes(), stream>>>(p, t);
-  return cudaGetLastError();
+  return launch_chained(1, motion_fwd_kernel, (unsigned)(p.n_dirs * p.tiles_per_dir), kThreads, motion_fwd_smem_bytes(), stream, p, t);
 }
 
 }  // namespace sde
