@@ -235,7 +235,10 @@ __global__ void __launch_bounds__(kThreads, SDE_PAIR_OCC) mono_bwd_pair_kernel(c
           const uchar2 m = *reinterpret_cast<const uchar2*>(sh.arg + plane_index(row, c0 + 1));
           const bool f0 = m.x == cand0, s0 = m.x == cand1, f1 = m.y == cand0, s1 = m.y == cand1;
           f2 ca = bc2(0.0f), cb = bc2(0.0f), cc = bc2(0.0f);
-          if (__any_sync(0xffffffffu, f0 || s0 || f1 || s1)) {
+#ifdef SDE_PAIR_SKIP
+          if (__any_sync(0xffffffffu, f0 || s0 || f1 || s1))   // skip rows of 64 unselected windows: rare, and the branch
+#endif                                                         // keeps the scheduler from interleaving the two rows of a trip
+          {
             const f2 sA = pp.A + n.A, sAA = pp.AA + n.AA;
             const f2 sXa = pp.X[0] + n.X[0], sXXa = pp.XX[0] + n.XX[0], sXAa = pp.XA[0] + n.XA[0];
             const f2 sXb = pp.X[1] + n.X[1], sXXb = pp.XX[1] + n.XX[1], sXAb = pp.XA[1] + n.XA[1];
