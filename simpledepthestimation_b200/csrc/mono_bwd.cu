@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(kThreads, SDE_BWD_OCC) mono_bwd_kernel(const _
             const uchar2 m = *reinterpret_cast<const uchar2*>(sh.arg + plane_index(row, c0 + 1));
             const bool sel0 = m.x == cand, sel1 = m.y == cand;
             f2 ca = bc2(0.0f), cb = bc2(0.0f), cc = bc2(0.0f);
-            if (__any_sync(0xffffffffu, sel0 || sel1)) {
+            {   // (no skip of rows of 64 unselected windows: the branch kept the scheduler from interleaving the unrolled rows,
+                //  measured in mono_bwd_pair.cu: -1.6 %; unselected windows get zero coefficients through g)
               const f2 sA = (hA[0] + hA[1]) + nA, sAA = (hAA[0] + hAA[1]) + nAA;
               const f2 sX = (hX[0] + hX[1]) + nX, sXX = (hXX[0] + hXX[1]) + nXX, sXA = (hXA[0] + hXA[1]) + nXA;
               // same operation order as the forward kernel
