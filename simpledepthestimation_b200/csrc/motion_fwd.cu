@@ -18,6 +18,8 @@
 // image column tile_x0 - 4 (TMA boxes must start 16-byte aligned)
 #define SDE_PITCH 72
 #define SDE_COL_OFF 3
+#include <type_traits>
+
 #include "motion_device.cuh"
 
 namespace sde {
@@ -310,6 +312,10 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
         hW[0] = hW[1]; hW[1] = nW;
       }
     }
+    // instantiated per C1/C2 mode (ssim_loss.py:97-105), as in the backward kernel: a run-time switch inside the unrolled
+    // rows would put every row's formula into its own basic block and keep the scheduler from interleaving the rows
+    auto channels = [&](auto mode_tag) {
+    constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
       const float* pa = planes + (kMA + c) * kPlane + plane_index(r0, c0);
@@ -335,10 +341,10 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
           const f2 sx = fma2(mx * bc2(-1.0f), mx, exx), sy = fma2(my * bc2(-1.0f), my, eaa);
           const f2 sxy = fma2(mx * bc2(-1.0f), my, exa);
           f2 n, d;
-          if (p.mode == 1) {            // C1 == inf
+          if (MODE == 1) {            // C1 == inf
             n = fma2(bc2(2.0f), sxy, C2);
             d = (sx + sy) + C2;
-          } else if (p.mode == 2) {     // C2 == inf
+          } else if (MODE == 2) {     // C2 == inf
             n = fma2(bc2(2.0f), mx * my, C1);
             d = fma2(mx, mx, my * my) + C1;
           } else {
@@ -353,6 +359,10 @@ __global__ void __launch_bounds__(kThreads, 4) motion_fwd_kernel(const __grid_co
         hXX[0] = hXX[1]; hXX[1] = nXX; hAA[0] = hAA[1]; hAA[1] = nAA; hXA[0] = hXA[1]; hXA[1] = nXA;
       }
     }
+    };
+    if (p.mode == 1) channels(std::integral_constant<int, 1>{});
+    else if (p.mode == 2) channels(std::integral_constant<int, 2>{});
+    else channels(std::integral_constant<int, 0>{});
     const int gx0 = tx0 + c0;
 #pragma unroll
     for (int o = 0; o < kRowsPerWarp; ++o) {
